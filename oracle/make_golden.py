@@ -1,0 +1,167 @@
+"""TEST INFRASTRUCTURE — golden-vector generator.  Runs the UNMODIFIED reference (/root/reference/ladcast) on
+CPU fp32 with oracle/shim standing in for diffusers/xarray, on deterministic weights/inputs that
+oracle/ladcast_oracle.py can rebuild from (key, shape) alone, and writes small fixtures to tests/golden/.
+Run in the builder container only:  python oracle/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "shim"))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, ROOT)
+
+from diffusers import EDMDPMSolverMultistepScheduler  # noqa: E402  (shim)
+from ladcast.evaluate.utils import (  # noqa: E402
+    get_normalized_lat_weights_based_on_cos,
+    pointwise_crps_skill,
+    pointwise_crps_spread,
+)
+from ladcast.models.DCAE import AutoencoderDC  # noqa: E402
+from ladcast.models.embeddings import LaDCastRotaryPosEmbed_from_grid, get_year_sincos_embedding  # noqa: E402
+from ladcast.models.LaDCast_3D_model import LaDCastTransformer3DModel  # noqa: E402
+from ladcast.models.sphere_conv import SphereConv2d  # noqa: E402
+from ladcast.pipelines.pipeline_AR import AutoRegressive2DPipeline  # noqa: E402
+from ladcast.pipelines.utils import decode_latent_ens, ensemble_AR_sampler  # noqa: E402
+
+from oracle import ladcast_oracle as O  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+torch.set_grad_enabled(False)
+
+
+def seeded(shape, seed, scale=1.0):
+    return torch.randn(shape, generator=torch.Generator("cpu").manual_seed(seed)) * scale
+
+
+def summary(x: torch.Tensor):
+    """Size-independent fingerprints of a big tensor: per-channel (dim 1) sum and abs-sum in float64."""
+    xd = x.double()
+    dims = [d for d in range(x.ndim) if d != 1]
+    return xd.sum(dim=dims).numpy(), xd.abs().sum(dim=dims).numpy()
+
+
+def build_denoiser(name, salt):
+    cfg = O.denoiser_config(name)
+    m = LaDCastTransformer3DModel.from_config(cfg).eval()
+    sd = O.make_state_dict(O.denoiser_param_shapes(cfg), salt)
+    m.load_state_dict(sd, strict=True)  # strict: pins key names + shapes
+    return cfg, m
+
+
+def golden_denoiser():
+    for name, salt, B, T_out in (("tiny", 11, 2, 2), ("375M", 12, 1, 1)):
+        cfg, m = build_denoiser(name, salt)
+        x = seeded((B, 84, T_out, 15, 30), 100)
+        cond = seeded((B, 84, 1, 15, 30), 101, 0.5)
+        t = torch.tensor([0.8, -0.4][:B])
+        ts = torch.tensor([2018022906 if False else 2020022906])  # leap-year date
+        out = m(x, t, cond, time_elapsed=ts, return_dict=False)[0]
+        s, a = summary(out)
+        np.savez(os.path.join(OUT, f"denoiser_{name}.npz"), salt=salt, B=B, T_out=T_out, t=t.numpy(), ts=ts.numpy(),
+                 out=out.numpy().astype(np.float32), ch_sum=s, ch_abs=a)
+        print("denoiser", name, out.shape, float(out.abs().mean()))
+
+
+def golden_samplers():
+    cfg, m = build_denoiser("tiny", 11)
+    sched = EDMDPMSolverMultistepScheduler()
+    pipe = AutoRegressive2DPipeline(m, sched)
+    known = seeded((1, 84, 1, 15, 30), 102, 0.5)
+    ts = torch.tensor([2018010100])
+    res = {}
+    for sampler, n in (("pipeline", 5), ("pipeline", 16), ("edm", 4)):
+        s = ensemble_AR_sampler(pipe, sample_size=2, return_seq_len=1, num_inference_steps=n, known_latents=known,
+                                timestamps=ts, sampler_type=sampler, device="cpu")
+        res[f"{sampler}_{n}"] = s.numpy().astype(np.float32)
+        print("sampler", sampler, n, float(s.abs().mean()))
+    sched.set_timesteps(20)
+    np.savez(os.path.join(OUT, "samplers_tiny.npz"), sigmas20=sched.sigmas.numpy(), timesteps20=sched.timesteps.numpy(),
+             **res)
+
+
+def golden_dcae():
+    cfg = O.dcae_config("tiny")
+    full = dict(cfg, encoder_block_types=cfg["decoder_block_types"],
+                encoder_block_out_channels=cfg["decoder_block_out_channels"],
+                encoder_layers_per_block=cfg["decoder_layers_per_block"],
+                encoder_qkv_multiscales=cfg["decoder_qkv_multiscales"],
+                upsample_block_type="pixel_shuffle", downsample_block_type="pixel_unshuffle")
+    ae = AutoencoderDC.from_config(full).eval()
+    sd = O.make_state_dict(O.dcae_decoder_param_shapes(cfg), 21)
+    missing = ae.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and all(k.startswith("encoder.") for k in missing.missing_keys)
+    z = seeded((2, 84, 5, 8), 103)
+    out = ae.decode(z).sample
+    lat = seeded((1, 84, 2, 5, 8), 104)
+    mean, std = seeded((84,), 105), seeded((84,), 106).abs() + 0.5
+    ens = decode_latent_ens(ae, lat, mean, std)
+    s, a = summary(out)
+    np.savez(os.path.join(OUT, "dcae_tiny.npz"), salt=21, out_sub=out[:, ::7].numpy().astype(np.float32), ch_sum=s,
+             ch_abs=a, ens_sub=ens[:, ::7].numpy().astype(np.float32))
+    print("dcae", out.shape, float(out.abs().mean()))
+
+
+def golden_sphere():
+    conv = SphereConv2d(6, 8, 3, 1, 1)
+    conv.weight.data = O.det_tensor("sphere3.weight", (8, 6, 3, 3), 31)
+    conv.bias.data = O.det_tensor("sphere3.bias", (8,), 31)
+    x = seeded((2, 6, 7, 10), 107)
+    y3 = conv(x)
+    dw = SphereConv2d(6, 6, 5, 1, 2, groups=6, bias=False)
+    dw.weight.data = O.det_tensor("sphere5.weight", (6, 1, 5, 5), 31)
+    y5 = dw(x)
+    np.savez(os.path.join(OUT, "sphere_conv.npz"), y3=y3.numpy(), y5=y5.numpy())
+
+
+def golden_embeddings():
+    ts = torch.tensor([2018010100, 2020022906, 2019123118, 2016070112])
+    ye = get_year_sincos_embedding(ts, embedding_dim=256)
+    cfg = O.denoiser_config("375M")
+    rope = LaDCastRotaryPosEmbed_from_grid(cfg["rope_axes_dim"], [1, 1, 1], theta=cfg["rope_theta"])
+    lat = torch.linspace(float(np.deg2rad(-499.5)), float(np.deg2rad(508.5)), 15)
+    lon = torch.linspace(float(np.deg2rad(5.25)), float(np.deg2rad(353.25)), 30)
+    cos_p, sin_p = rope(torch.zeros(1, 84, 4, 15, 30), [torch.arange(1, 5).float(), lat, lon])
+    cos_c, sin_c = rope(torch.zeros(1, 84, 1, 15, 30), [torch.arange(0, 1).float(), lat, lon])
+    rows = np.arange(0, 1800, 37)
+    np.savez(os.path.join(OUT, "embeddings.npz"), ts=ts.numpy(), year=ye.numpy(), rows=rows,
+             cos_p=cos_p[rows].numpy(), sin_p=sin_p[rows].numpy(), cos_c=cos_c[::9].numpy(), sin_c=sin_c[::9].numpy(),
+             cos_p_colsum=cos_p.double().sum(0).numpy(), sin_p_colsum=sin_p.double().sum(0).numpy())
+
+
+def golden_metrics():
+    """evaluate/evaluate_ens_gpu.py:339-415 transcribed around the reference's own pointwise functions."""
+    M, C, T, H, W = 5, 84, 2, 120, 16
+    dec = seeded((M, C, T, H, W), 108)
+    ref = seeded((C, T, H, W), 109)
+    ref[82, :, 5:9, 3:7] = float("nan")
+    lat_weight = torch.from_numpy(get_normalized_lat_weights_based_on_cos(np.linspace(-88.5, 90, 120)))
+    SST = 82
+    tabs = {k: torch.zeros(C, T, dtype=torch.float64) for k in ("ens_mse", "crps_skill", "crps_spread", "crps")}
+    for t in range(T):
+        dec_t, ref_t = dec[:, :, t], ref[:, t]
+        weights = lat_weight.view(1, -1, 1)
+        mean_t = dec_t.mean(dim=0)
+        se_t = (mean_t - ref_t) ** 2 * weights
+        spread_t = pointwise_crps_spread(dec_t, ensemble_dim=0) * weights
+        skill_t = pointwise_crps_skill(dec_t, ref_t.unsqueeze(0), 0) * weights
+        crps_t = skill_t - 0.5 * spread_t
+        for name, v in (("ens_mse", se_t), ("crps_spread", spread_t), ("crps_skill", skill_t), ("crps", crps_t)):
+            tabs[name][:SST, t] = v[:SST].mean(dim=(1, 2))
+            tabs[name][SST : SST + 1, t] = torch.nanmean(v[SST : SST + 1], dim=(1, 2))
+            tabs[name][SST + 1 :, t] = v[SST + 1 :].mean(dim=(1, 2))
+    np.savez(os.path.join(OUT, "metrics.npz"), lat_weight=lat_weight.numpy(), **{k: v.numpy() for k, v in tabs.items()})
+
+
+if __name__ == "__main__":
+    golden_sphere()
+    golden_embeddings()
+    golden_metrics()
+    golden_dcae()
+    golden_samplers()
+    golden_denoiser()
+    print("golden vectors written to", OUT)
