@@ -1,0 +1,111 @@
+/* ladcast_b200 — C ABI of the B200-native (sm_100a) LaDCast ensemble-rollout hot path.
+ *
+ * The reference (tonyzyl/ladcast) is pure Python/PyTorch and has no FFI boundary; its boundary for this path is the
+ * set of Python call signatures listed next to each entry point below (paths relative to the reference's
+ * `ladcast/` package).  The Python drop-ins in `ladcast_b200/` bind these symbols with ctypes
+ * (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative code on failure; lc_last_error() returns a thread-local
+ *     human-readable message for the last failure on the calling thread;
+ *   - all tensor arguments are DEVICE pointers unless the name ends in `_host`; the caller owns every I/O buffer;
+ *     the library owns weights and workspace;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, no host synchronisation and no
+ *     allocation happens inside *_forward / *_step / *_decode / *_accumulate calls;
+ *   - a handle is not thread-safe; distinct handles are independent.
+ */
+#ifndef LADCAST_B200_H_
+#define LADCAST_B200_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define LC_API __attribute__((visibility("default")))
+#else
+#define LC_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LC_PRECISION_BF16 0 /* tcgen05 bf16 x bf16 -> f32 tensor-core path (production) */
+#define LC_PRECISION_F32 1  /* SIMT fp32 validation path (rel-L2 <= 1e-4 vs the reference) */
+
+LC_API int lc_version(void);
+LC_API const char* lc_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Denoiser — replaces LaDCastTransformer3DModel.__init__/forward (models/LaDCast_3D_model.py:624-650, 833-1071)
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct lc_denoiser lc_denoiser;
+
+typedef struct {
+  int in_channels;        /* 84 */
+  int out_channels;       /* 84 */
+  int cond_channels;      /* conditioning_tensor_in_channels, 84 */
+  int num_heads;          /* 12 (375M) / 16 (1.6B) */
+  int head_dim;           /* 128 */
+  int num_layers;         /* dual-stream blocks   */
+  int num_single_layers;  /* single-stream blocks */
+  int num_refiner_layers; /* context refiner blocks */
+  int mlp_dim;            /* int(hidden * mlp_ratio) */
+  int incl_time_elapsed;  /* 1 if time_elapsed_embed exists */
+  int precision;          /* LC_PRECISION_* */
+} lc_denoiser_cfg;
+
+LC_API int lc_denoiser_create(const lc_denoiser_cfg* cfg, lc_denoiser** out);
+LC_API void lc_denoiser_destroy(lc_denoiser* h);
+
+/* Checkpoint loading: one call per state-dict entry of the V0.1.X diffusers-format checkpoint (fp32 tensors,
+ * key names as in the reference's state_dict), then finalize() re-packs them into fused,
+ * padded library-owned buffers (q|k|v fused, all AdaLN linears fused into one modulation matrix, ...). */
+LC_API int lc_denoiser_load(lc_denoiser* h, const char* key, const float* data, const int64_t* shape, int ndim, void* stream);
+LC_API int lc_denoiser_finalize(lc_denoiser* h, void* stream);
+
+/* Geometry + RoPE tables (LaDCastRotaryPosEmbed_from_grid, models/embeddings.py:252-327; forward :885-938).
+ * cos/sin tables are [T*H*W, head_dim] fp32 for pred (T_out) and cond (T_in) tokens.  Allocates the workspace
+ * for up to max_batch members (the only allocating call besides create/load/finalize). */
+LC_API int lc_denoiser_set_geometry(lc_denoiser* h, int max_batch, int t_in, int t_out, int height, int width,
+                             const float* cos_pred, const float* sin_pred, const float* cos_cond,
+                             const float* sin_cond, void* stream);
+
+/* Step-invariant work of one AR step (hoisted out of the num_inference_steps loop): context_embedder(known),
+ * its token mean, refiner proj_in, the refiner's text embedder, and the date MLP of
+ * get_year_sincos_embedding -> time_elapsed_embed (forward :943-969).  known: [B, C, T_in, H, W] fp32;
+ * year_emb: [n_ts, 256] fp32 (n_ts = 1 broadcast or B) or NULL when time_elapsed is None. */
+LC_API int lc_denoiser_prepare(lc_denoiser* h, const float* known, int batch, const float* year_emb, int n_ts, void* stream);
+
+/* One denoiser evaluation F(x_in, c_noise | known, date).  x_in/out: [B, C, T_out, H, W] fp32; c_noise: [n_t]
+ * fp32 with n_t = B (pipeline_AR.py:92) or 1 (edm_sampler.py:87, broadcast).  out must not alias x_in. */
+LC_API int lc_denoiser_forward(lc_denoiser* h, const float* x_in, const float* c_noise, int n_t, float* out, void* stream);
+
+/* Debug tap: copies an internal buffer after a forward ("h", "e", "temb", "mod") to `out` as fp32. */
+LC_API int lc_denoiser_debug_read(lc_denoiser* h, const char* name, float* out, int64_t max_elems, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Scheduler — replaces diffusers.EDMDPMSolverMultistepScheduler.step (+ scale_model_input of the next step)
+ * as called at pipelines/pipeline_AR.py:87-102, and the Heun update of pipelines/edm_sampler.py:65-113.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* x0 = c_skip*x + c_out*f ; x <- a_x*x + a_x0*x0 + a_d*(x0 - x0_prev) ; x0_prev <- x0 ;
+ * x_in_next <- x*c_in_next (skipped when x_in_next is NULL).  n elements, n % 4 == 0. */
+LC_API int lc_sched_dpmpp2m_step(const float* f, float* x, float* x0_prev, float* x_in_next, int64_t n, float c_skip,
+                          float c_out, float a_x, float a_x0, float a_d, float c_in_next, void* stream);
+/* phase 0: Euler predictor from x (saved to x_hat) ; phase 1: trapezoid corrector.  State in fp64. */
+LC_API int lc_sched_heun_step(const float* f, double* x, double* x_hat, double* d_cur, float* x_in_next, int64_t n, int phase,
+                       double t_cur, double t_next, double c_skip, double c_out, double c_in_next, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Low-level ops exported for parity tests (same kernels the handles use)
+ * ---------------------------------------------------------------------------------------------------------- */
+/* C[M,N] = A[M,K] W[N,K]^T + bias, act in {0 none, 1 gelu-tanh, 2 silu}.  precision BF16: A, W bf16 (raw uint16
+ * storage), C fp32; precision F32: everything fp32. */
+LC_API int lc_gemm(int precision, const void* a, const void* w, const float* bias, float* c, int m, int n, int k, int act,
+            void* stream);
+/* qkv: [B, S, 3*heads*128] (q|k|v) fp32 (F32) or bf16 (BF16); out: [B, S, heads*128] same dtype. */
+LC_API int lc_attention(int precision, const void* qkv, void* out, int batch, int seq, int heads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LADCAST_B200_H_ */

@@ -1,0 +1,55 @@
+// Remaining C-ABI entry points: version/error, scheduler steps, low-level op exports used by the parity tests.
+#include <string>
+
+#include "../../include/ladcast_b200.h"
+#include "kernels.h"
+
+namespace lc {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* last_error() { return g_err.c_str(); }
+}  // namespace lc
+
+using namespace lc;
+
+extern "C" {
+
+int lc_version(void) { return 100; }
+const char* lc_last_error(void) { return lc::last_error(); }
+
+int lc_sched_dpmpp2m_step(const float* f, float* x, float* x0_prev, float* x_in_next, int64_t n, float c_skip,
+                          float c_out, float a_x, float a_x0, float a_d, float c_in_next, void* stream) {
+  LC_REQUIRE(f && x && x0_prev, "null argument");
+  SchedCoef c;
+  c.c_skip = c_skip; c.c_out = c_out; c.a_x = a_x; c.a_x0 = a_x0; c.a_d = a_d; c.c_in_next = c_in_next;
+  return sched_dpmpp2m_step(f, x, x0_prev, x_in_next, n, c, static_cast<cudaStream_t>(stream));
+}
+
+int lc_sched_heun_step(const float* f, double* x, double* x_hat, double* d_cur, float* x_in_next, int64_t n, int phase,
+                       double t_cur, double t_next, double c_skip, double c_out, double c_in_next, void* stream) {
+  LC_REQUIRE(f && x && x_hat && d_cur, "null argument");
+  return sched_heun_step(f, x, x_hat, d_cur, x_in_next, n, phase, t_cur, t_next, c_skip, c_out, c_in_next,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int lc_gemm(int precision, const void* a, const void* w, const float* bias, float* c, int m, int n, int k, int act,
+            void* stream) {
+  LC_REQUIRE(a && w && c, "null argument");
+  GemmArgs g;
+  g.A0 = a; g.lda0 = k; g.K0 = k; g.W = w; g.ldw = k; g.M = m; g.N = n; g.K = k;
+  g.epi.mode = EPI_STORE; g.epi.act = act; g.epi.bias = bias; g.epi.out = c; g.epi.ldo = n; g.epi.out_f32 = 1;
+  return precision == LC_PRECISION_F32 ? gemm_f32(g, static_cast<cudaStream_t>(stream))
+                                       : gemm_bf16(g, static_cast<cudaStream_t>(stream));
+}
+
+int lc_attention(int precision, const void* qkv, void* out, int batch, int seq, int heads, void* stream) {
+  LC_REQUIRE(qkv && out, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (precision == LC_PRECISION_F32)
+    return attention_f32(reinterpret_cast<const float*>(qkv), batch, seq, heads, 128, reinterpret_cast<float*>(out), seq,
+                         nullptr, st);
+  return attention_bf16(reinterpret_cast<const bf16*>(qkv), batch, seq, heads, 128, reinterpret_cast<bf16*>(out), seq,
+                        nullptr, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+// Shared declarations for the ladcast_b200 CUDA library (internal; the public C ABI is include/ladcast_b200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <string>
+
+namespace lc {
+
+// ---------------------------------------------------------------- errors (thread-local message, C-ABI style)
+void set_error(const std::string& msg);
+const char* last_error();
+
+#define LC_CHECK_CUDA(expr)                                                                       \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      ::lc::set_error(std::string(#expr) + " -> " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                      std::to_string(__LINE__) + ")");                                            \
+      return -2;                                                                                  \
+    }                                                                                             \
+  } while (0)
+
+#define LC_REQUIRE(cond, msg)                                                               \
+  do {                                                                                      \
+    if (!(cond)) {                                                                          \
+      ::lc::set_error(std::string(msg) + " [" #cond "] (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+      return -1;                                                                            \
+    }                                                                                       \
+  } while (0)
+
+#define LC_TRY(expr)          \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != 0) return _r;   \
+  } while (0)
+
+// ---------------------------------------------------------------- element types
+typedef __nv_bfloat16 bf16;
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float gelu_tanh(float x) {
+  // torch F.gelu(approximate="tanh"): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float u = k0 * (x + k1 * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(u));
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+enum Act { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_SILU = 2, ACT_RELU = 3 };
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case ACT_GELU_TANH: return gelu_tanh(v);
+    case ACT_SILU: return silu(v);
+    case ACT_RELU: return fmaxf(v, 0.0f);
+    default: return v;
+  }
+}
+
+// ---------------------------------------------------------------- GEMM epilogue description
+// C[M,N] = A[M,K] * W[N,K]^T (+bias) -> act -> one of the output modes.  Rows are "tokens"/"pixels"; a
+// sample = `rows_per_sample` consecutive rows; per-sample vectors (gates) are indexed by row / rows_per_sample.
+enum EpiMode {
+  EPI_STORE = 0,       // out[orow, n] = act(acc + bias)                  (out dtype: bf16 or f32)
+  EPI_GATED_RESID = 1, // out_f32[orow, n] += gate[b, n] * (acc + bias)   (gate may be null -> 1)
+  EPI_UNPATCHIFY = 2,  // out_f32[b, n, row % rows_per_sample] = acc + bias   (token-major -> channel-major)
+  EPI_RESID_STORE = 3, // out[orow, n] = act(acc + bias) + resid_f32[orow, n]  (conv shortcut adds)
+};
+
+struct EpiParams {
+  int mode = EPI_STORE;
+  int act = ACT_NONE;
+  int out_f32 = 0;            // EPI_STORE / EPI_RESID_STORE: 1 -> float output, 0 -> bf16 output
+  const float* bias = nullptr;
+  void* out = nullptr;
+  long long ldo = 0;          // elements between consecutive output rows
+  // output row remap: orow = (row / rows_per_sample) * out_rows_per_sample + out_row_offset + row % rows_per_sample
+  int rows_per_sample = 1 << 30;
+  int out_rows_per_sample = 1 << 30;
+  int out_row_offset = 0;
+  const float* gate = nullptr;  // [n_samples, gate_stride]
+  long long gate_stride = 0;
+  const float* resid = nullptr;  // EPI_RESID_STORE
+  long long ldr = 0;
+  int n_valid = 0;  // EPI_UNPATCHIFY: number of real output channels (<= N)
+};
+
+__device__ __forceinline__ long long epi_out_row(const EpiParams& ep, int row, int& sample) {
+  sample = row / ep.rows_per_sample;
+  int r = row - sample * ep.rows_per_sample;
+  return static_cast<long long>(sample) * ep.out_rows_per_sample + ep.out_row_offset + r;
+}
+
+// GEMM problem: A is [M, K] row-major split in up to two K-segments (A0: k < K0, A1: K0 <= k < K);
+// W is [N, K] row-major (nn.Linear layout).  bf16 path: A/W bf16, fp32 path: A/W float.
+struct GemmArgs {
+  const void* A0 = nullptr;
+  long long lda0 = 0;
+  int K0 = 0;
+  const void* A1 = nullptr;
+  long long lda1 = 0;
+  const void* W = nullptr;
+  long long ldw = 0;
+  int M = 0, N = 0, K = 0;
+  EpiParams epi;
+};
+
+int gemm_f32(const GemmArgs& g, cudaStream_t stream);   // SIMT fp32 validation path
+int gemm_bf16(const GemmArgs& g, cudaStream_t stream);  // tcgen05 / TMEM / TMA path
+int gemm_bf16_selftest_smem_bytes();
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+int num_sms();
+
+}  // namespace lc

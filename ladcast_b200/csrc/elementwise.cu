@@ -1,0 +1,384 @@
+// HBM-bound kernels of the denoiser: LayerNorm + modulation, QK RMSNorm + RoPE, patchify, timestep embedding,
+// token pooling, gated residual, temb combine; and the fused scheduler steps.  All vectorised (128-bit) with
+// warp-shuffle reductions; fp32 statistics regardless of the storage type.
+#include "kernels.h"
+
+namespace lc {
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__device__ __forceinline__ void store4(T* p, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <>
+__device__ __forceinline__ void store4<bf16>(bf16* p, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+template <typename T>
+__device__ __forceinline__ float4 load4(const T* p);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <>
+__device__ __forceinline__ float4 load4<bf16>(const bf16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+  const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// ---------------------------------------------------------------- LayerNorm (+ AdaLN modulation | affine)
+// One warp per row; the row (d = NV*128 floats) lives in registers; two-pass variance (biased), as nn.LayerNorm.
+// Reference: AdaLayerNormZero/ZeroSingle/Continuous (diffusers), LaDCast_3D_model.py:287-302, 524-552, 1044.
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, T* __restrict__ out, int M, int d,
+                                                        float eps, int rows_per_sample, const float* __restrict__ scale,
+                                                        const float* __restrict__ shift, long long mod_stride,
+                                                        const float* __restrict__ w, const float* __restrict__ b) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + static_cast<long long>(row) * d;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) / d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / d + eps);
+  const int sample = row / rows_per_sample;
+  T* orow = out + static_cast<long long>(row) * d;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    float4 y = make_float4(v[i].x * rstd, v[i].y * rstd, v[i].z * rstd, v[i].w * rstd);
+    if (scale != nullptr) {
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + sample * mod_stride + c));
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + sample * mod_stride + c));
+      y.x = y.x * (1.f + sc.x) + sh.x; y.y = y.y * (1.f + sc.y) + sh.y;
+      y.z = y.z * (1.f + sc.z) + sh.z; y.w = y.w * (1.f + sc.w) + sh.w;
+    } else if (w != nullptr) {
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w + c));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
+      y.x = y.x * ww.x + bb.x; y.y = y.y * ww.y + bb.y; y.z = y.z * ww.z + bb.z; y.w = y.w * ww.w + bb.w;
+    }
+    store4<T>(orow + c, y.x, y.y, y.z, y.w);
+  }
+}
+
+// ---------------------------------------------------------------- per-head RMSNorm(q,k) + RoPE, in place
+// One warp per (token row, q|k, head); lane owns 4 consecutive features = 2 rotation pairs (head_dim == 128).
+// Reference: LaDCast_3D_model.py:103-169 + diffusers RMSNorm / apply_rotary_emb (interleaved pairs).
+template <typename T>
+__global__ void __launch_bounds__(256) qk_norm_rope_kernel(T* __restrict__ qkv, long long ld, int B, int S, int heads,
+                                                           float eps, RopeSeg s0, RopeSeg s1, int nseg) {
+  const long long gw = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const long long total = static_cast<long long>(B) * S * 2 * heads;
+  if (gw >= total) return;
+  const int head = static_cast<int>(gw % heads);
+  const int which = static_cast<int>((gw / heads) % 2);  // 0 = q, 1 = k
+  const long long row = gw / (2 * heads);
+  const int tok = static_cast<int>(row % S);
+  const RopeSeg& sg = (nseg > 1 && tok >= s1.start) ? s1 : s0;
+  T* p = qkv + row * ld + static_cast<long long>(which) * heads * 128 + head * 128 + lane * 4;
+  float4 v = load4<T>(p);
+  const float ss = warp_sum((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
+  const float r = rsqrtf(ss * (1.0f / 128.0f) + eps);
+  const float4 w = __ldg(reinterpret_cast<const float4*>((which ? sg.wk : sg.wq) + lane * 4));
+  v.x = v.x * r * w.x; v.y = v.y * r * w.y; v.z = v.z * r * w.z; v.w = v.w * r * w.w;
+  if (sg.cos != nullptr) {
+    const long long t = static_cast<long long>(tok - sg.start) * 128 + lane * 4;
+    const float4 c = __ldg(reinterpret_cast<const float4*>(sg.cos + t));
+    const float4 s = __ldg(reinterpret_cast<const float4*>(sg.sin + t));
+    const float4 o = make_float4(v.x * c.x - v.y * s.x, v.y * c.y + v.x * s.y, v.z * c.z - v.w * s.z,
+                                 v.w * c.w + v.z * s.w);
+    v = o;
+  }
+  store4<T>(p, v.x, v.y, v.z, v.w);
+}
+
+// ---------------------------------------------------------------- patchify: [B,C,THW] f32 -> [B*THW, Kp] T (zero pad)
+// Reference: HunyuanVideoPatchEmbed flatten(2).transpose(1,2) with patch (1,1,1): token n = t*HW + h*W + w
+// (embeddings.py:56-59).  Pure index permutation -> bit-exact in the fp32 mode.
+template <typename T>
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ x, T* __restrict__ out, int C, int THW,
+                                                       int Kp) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, n = n0 + tx;
+    tile[i][tx] = (c < C && n < THW) ? x[(static_cast<long long>(b) * C + c) * THW + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int n = n0 + i, c = c0 + tx;
+    if (n < THW && c < Kp) out[(static_cast<long long>(b) * THW + n) * Kp + c] = from_f32<T>(tile[tx][i]);
+  }
+}
+
+// ---------------------------------------------------------------- Timesteps(256, flip_sin_to_cos, shift 0): [cos | sin]
+template <typename T>
+__global__ void timestep_embed_kernel(const float* __restrict__ t, int n_t, int B, T* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 128) return;
+  const int b = i >> 7, k = i & 127;
+  const float f = expf(-logf(10000.0f) * static_cast<float>(k) / 128.0f);
+  const float arg = t[n_t == 1 ? 0 : b] * f;
+  out[b * 256 + k] = from_f32<T>(cosf(arg));
+  out[b * 256 + 128 + k] = from_f32<T>(sinf(arg));
+}
+
+// ---------------------------------------------------------------- mean over tokens: [B,N,d] f32 -> [B,d] T
+template <typename T>
+__global__ void __launch_bounds__(256) token_mean_kernel(const float* __restrict__ x, int N, int d, T* __restrict__ out) {
+  __shared__ float part[8][32 * 4 + 4];
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 128 + (threadIdx.x & 31) * 4;
+  const int ty = threadIdx.x >> 5;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < d) {
+    const float* p = x + static_cast<long long>(b) * N * d + c;
+    for (int n = ty; n < N; n += 8) {
+      const float4 v = *reinterpret_cast<const float4*>(p + static_cast<long long>(n) * d);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  float* pp = &part[ty][(threadIdx.x & 31) * 4];
+  pp[0] = acc.x; pp[1] = acc.y; pp[2] = acc.z; pp[3] = acc.w;
+  __syncthreads();
+  if (ty == 0 && c < d) {
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < 8; ++j)
+      for (int q = 0; q < 4; ++q) r[q] += part[j][(threadIdx.x & 31) * 4 + q];
+    const float inv = 1.0f / N;
+    for (int q = 0; q < 4; ++q) out[static_cast<long long>(b) * d + c + q] = from_f32<T>(r[q] * inv);
+  }
+}
+
+// ---------------------------------------------------------------- h += a * gate[b]  (refiner attention has no out-proj)
+template <typename T>
+__global__ void __launch_bounds__(256) gated_add_kernel(float* __restrict__ h, const T* __restrict__ a,
+                                                        const float* __restrict__ gate, long long gate_stride,
+                                                        long long n4, int d, int rows_per_sample) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const long long e = i * 4;
+  const long long row = e / d;
+  const int c = static_cast<int>(e - row * d);
+  const int sample = static_cast<int>(row / rows_per_sample);
+  float4 hv = *reinterpret_cast<float4*>(h + e);
+  const float4 av = load4<T>(a + e);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gate + sample * gate_stride + c));
+  hv.x += av.x * g.x; hv.y += av.y * g.y; hv.z += av.z * g.z; hv.w += av.w * g.w;
+  *reinterpret_cast<float4*>(h + e) = hv;
+}
+
+template <typename T>
+__global__ void temb_combine_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                    const float* __restrict__ sc, const float* __restrict__ sh, long long sc_stride,
+                                    int B, int d, float* __restrict__ out_f32, T* __restrict__ out_silu) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * d) return;
+  const int r = i / d, c = i - r * d;
+  float v = a[i] + (b ? b[i] : 0.f);
+  if (sc) v = v * (1.f + sc[r * sc_stride + c]) + sh[r * sc_stride + c];
+  if (out_f32) out_f32[i] = v;
+  if (out_silu) out_silu[i] = from_f32<T>(v / (1.f + expf(-v)));
+}
+
+template <typename T>
+__global__ void cast_kernel(const float* __restrict__ x, T* __restrict__ out, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = from_f32<T>(x[i]);
+}
+
+// ---------------------------------------------------------------- scheduler steps
+// DPM-Solver++ (1st order / 2M midpoint) of diffusers' EDMDPMSolverMultistepScheduler.step with
+// precondition_outputs and the NEXT step's scale_model_input fused (pipeline_AR.py:87-102).
+__global__ void __launch_bounds__(256) dpmpp2m_kernel(const float* __restrict__ f, float* __restrict__ x,
+                                                      float* __restrict__ x0_prev, float* __restrict__ x_in_next,
+                                                      long long n4, SchedCoef c) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 fv = reinterpret_cast<const float4*>(f)[i];
+  float4 xv = reinterpret_cast<float4*>(x)[i];
+  float4 x0 = make_float4(c.c_skip * xv.x + c.c_out * fv.x, c.c_skip * xv.y + c.c_out * fv.y,
+                          c.c_skip * xv.z + c.c_out * fv.z, c.c_skip * xv.w + c.c_out * fv.w);
+  float4 xn = make_float4(c.a_x * xv.x + c.a_x0 * x0.x, c.a_x * xv.y + c.a_x0 * x0.y, c.a_x * xv.z + c.a_x0 * x0.z,
+                          c.a_x * xv.w + c.a_x0 * x0.w);
+  if (c.a_d != 0.f) {
+    const float4 p = reinterpret_cast<const float4*>(x0_prev)[i];
+    xn.x += c.a_d * (x0.x - p.x); xn.y += c.a_d * (x0.y - p.y); xn.z += c.a_d * (x0.z - p.z); xn.w += c.a_d * (x0.w - p.w);
+  }
+  reinterpret_cast<float4*>(x0_prev)[i] = x0;
+  reinterpret_cast<float4*>(x)[i] = xn;
+  if (x_in_next != nullptr)
+    reinterpret_cast<float4*>(x_in_next)[i] =
+        make_float4(xn.x * c.c_in_next, xn.y * c.c_in_next, xn.z * c.c_in_next, xn.w * c.c_in_next);
+}
+
+// EDM Heun sampler in float64 (edm_sampler.py:65-113).  phase 0 = Euler predictor, phase 1 = trapezoid corrector.
+__global__ void __launch_bounds__(256) heun_kernel(const float* __restrict__ f, double* __restrict__ x,
+                                                   double* __restrict__ x_hat, double* __restrict__ d_cur,
+                                                   float* __restrict__ x_in_next, long long n, int phase, double t_cur,
+                                                   double t_next, double c_skip, double c_out, double c_in_next) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double fv = static_cast<double>(f[i]);
+  double xn;
+  if (phase == 0) {
+    const double xh = x[i];
+    const double den = c_skip * xh + c_out * fv;
+    const double dc = (xh - den) / t_cur;
+    xn = xh + (t_next - t_cur) * dc;
+    x_hat[i] = xh;
+    d_cur[i] = dc;
+  } else {
+    const double xc = x[i];
+    const double den = c_skip * xc + c_out * fv;
+    const double dp = (xc - den) / t_next;
+    xn = x_hat[i] + (t_next - t_cur) * (0.5 * d_cur[i] + 0.5 * dp);
+  }
+  x[i] = xn;
+  if (x_in_next != nullptr) x_in_next[i] = static_cast<float>(xn * c_in_next);
+}
+
+}  // namespace
+
+template <typename T>
+int layernorm_modulate(const float* x, T* out, int M, int d, float eps, int rows_per_sample, const float* scale,
+                       const float* shift, long long mod_stride, const float* w, const float* b, cudaStream_t s) {
+  LC_REQUIRE(d % 128 == 0 && d <= 2048, "layernorm: d must be a multiple of 128, <= 2048");
+  const int nv = d / 128;
+  dim3 grid(ceil_div(M, 8));
+#define LC_LN_CASE(NV)                                                                                            \
+  case NV:                                                                                                        \
+    layernorm_kernel<T, NV><<<grid, 256, 0, s>>>(x, out, M, d, eps, rows_per_sample, scale, shift, mod_stride, w, b); \
+    break;
+  switch (nv) {
+    LC_LN_CASE(1) LC_LN_CASE(2) LC_LN_CASE(3) LC_LN_CASE(4) LC_LN_CASE(5) LC_LN_CASE(6) LC_LN_CASE(7) LC_LN_CASE(8)
+    LC_LN_CASE(9) LC_LN_CASE(10) LC_LN_CASE(11) LC_LN_CASE(12) LC_LN_CASE(13) LC_LN_CASE(14) LC_LN_CASE(15)
+    LC_LN_CASE(16)
+  }
+#undef LC_LN_CASE
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int qk_norm_rope(T* qkv, long long ld, int B, int S, int heads, int head_dim, float eps, const RopeSeg* segs, int nseg,
+                 cudaStream_t s) {
+  LC_REQUIRE(head_dim == 128, "qk_norm_rope: head_dim must be 128");
+  LC_REQUIRE(nseg == 1 || nseg == 2, "qk_norm_rope: 1 or 2 segments");
+  const long long total = static_cast<long long>(B) * S * 2 * heads;
+  RopeSeg s1 = nseg > 1 ? segs[1] : segs[0];
+  qk_norm_rope_kernel<T><<<static_cast<unsigned>(ceil_div_ll(total, 8)), 256, 0, s>>>(qkv, ld, B, S, heads, eps, segs[0],
+                                                                                     s1, nseg);
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int patchify(const float* x, T* out, int B, int C, int THW, int Kp, cudaStream_t s) {
+  dim3 grid(ceil_div(THW, 32), ceil_div(Kp, 32), B);
+  patchify_kernel<T><<<grid, 256, 0, s>>>(x, out, C, THW, Kp);
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int timestep_embed(const float* t, int n_t, int B, T* out, cudaStream_t s) {
+  timestep_embed_kernel<T><<<ceil_div(B * 128, 128), 128, 0, s>>>(t, n_t, B, out);
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int token_mean(const float* x, int B, int N, int d, T* out, cudaStream_t s) {
+  dim3 grid(ceil_div(d, 128), B);
+  token_mean_kernel<T><<<grid, 256, 0, s>>>(x, N, d, out);
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int gated_add(float* h, const T* a, const float* gate, long long gate_stride, int M, int d, int rows_per_sample,
+              cudaStream_t s) {
+  const long long n4 = static_cast<long long>(M) * d / 4;
+  gated_add_kernel<T><<<static_cast<unsigned>(ceil_div_ll(n4, 256)), 256, 0, s>>>(h, a, gate, gate_stride, n4, d,
+                                                                                rows_per_sample);
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int temb_combine(const float* a, const float* b, const float* sc, const float* sh, long long sc_stride, int B, int d,
+                 float* out_f32, T* out_silu, cudaStream_t s) {
+  temb_combine_kernel<T><<<ceil_div(B * d, 256), 256, 0, s>>>(a, b, sc, sh, sc_stride, B, d, out_f32, out_silu);
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int cast_rows(const float* x, T* out, long long n, cudaStream_t s) {
+  cast_kernel<T><<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s>>>(x, out, n);
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sched_dpmpp2m_step(const float* f, float* x, float* x0_prev, float* x_in_next, long long n, SchedCoef c,
+                       cudaStream_t s) {
+  LC_REQUIRE(n % 4 == 0, "scheduler: element count must be a multiple of 4");
+  const long long n4 = n / 4;
+  dpmpp2m_kernel<<<static_cast<unsigned>(ceil_div_ll(n4, 256)), 256, 0, s>>>(f, x, x0_prev, x_in_next, n4, c);
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sched_heun_step(const float* f, double* x, double* x_hat, double* d_cur, float* x_in_next, long long n, int phase,
+                    double t_cur, double t_next, double c_skip, double c_out, double c_in_next, cudaStream_t s) {
+  heun_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s>>>(f, x, x_hat, d_cur, x_in_next, n, phase, t_cur,
+                                                                       t_next, c_skip, c_out, c_in_next);
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+#define LC_INST(T)                                                                                                    \
+  template int layernorm_modulate<T>(const float*, T*, int, int, float, int, const float*, const float*, long long,   \
+                                     const float*, const float*, cudaStream_t);                                       \
+  template int qk_norm_rope<T>(T*, long long, int, int, int, int, float, const RopeSeg*, int, cudaStream_t);          \
+  template int patchify<T>(const float*, T*, int, int, int, int, cudaStream_t);                                       \
+  template int timestep_embed<T>(const float*, int, int, T*, cudaStream_t);                                           \
+  template int token_mean<T>(const float*, int, int, int, T*, cudaStream_t);                                          \
+  template int gated_add<T>(float*, const T*, const float*, long long, int, int, int, cudaStream_t);                  \
+  template int temb_combine<T>(const float*, const float*, const float*, const float*, long long, int, int, float*,   \
+                               T*, cudaStream_t);                                                                     \
+  template int cast_rows<T>(const float*, T*, long long, cudaStream_t);
+LC_INST(float)
+LC_INST(bf16)
+#undef LC_INST
+
+}  // namespace lc

@@ -1,0 +1,56 @@
+// Internal launch functions of the non-GEMM kernels.  T = activation storage type (bf16 in the production
+// mode, float in the FP32 validation mode); all statistics/accumulation are fp32.
+#pragma once
+#include "common.cuh"
+
+namespace lc {
+
+struct RopeSeg {
+  int start = 0, len = 0;         // token range [start, start+len) inside a sample's sequence
+  const float* wq = nullptr;      // RMSNorm weights [head_dim]
+  const float* wk = nullptr;
+  const float* cos = nullptr;     // [len, head_dim] or null (no rotation: dual-stream cond tokens)
+  const float* sin = nullptr;
+};
+
+template <typename T>
+int layernorm_modulate(const float* x, T* out, int M, int d, float eps, int rows_per_sample, const float* scale,
+                       const float* shift, long long mod_stride, const float* w, const float* b, cudaStream_t s);
+template <typename T>
+int qk_norm_rope(T* qkv, long long ld, int B, int S, int heads, int head_dim, float eps, const RopeSeg* segs, int nseg,
+                 cudaStream_t s);
+template <typename T>
+int patchify(const float* x, T* out, int B, int C, int THW, int Kp, cudaStream_t s);
+template <typename T>
+int timestep_embed(const float* t, int n_t, int B, T* out, cudaStream_t s);
+template <typename T>
+int token_mean(const float* x, int B, int N, int d, T* out, cudaStream_t s);
+template <typename T>
+int gated_add(float* h, const T* a, const float* gate, long long gate_stride, int M, int d, int rows_per_sample,
+              cudaStream_t s);
+// out = (a + b) * (1 + sc) + sh (sc/sh optional, row stride sc_stride, 0 = broadcast); writes f32 and/or silu() as T
+template <typename T>
+int temb_combine(const float* a, const float* b, const float* sc, const float* sh, long long sc_stride, int B, int d,
+                 float* out_f32, T* out_silu, cudaStream_t s);
+template <typename T>
+int cast_rows(const float* x, T* out, long long n, cudaStream_t s);
+
+// attention over a joint sequence stored token-major as [B, S, 3*d] (q | k | v); the output is written
+// token-major and split: tokens [0, Np) -> out_p [B*Np, d], tokens [Np, S) -> out_c [B*(S-Np), d].
+int attention_f32(const float* qkv, int B, int S, int heads, int head_dim, float* out_p, int Np, float* out_c,
+                  cudaStream_t s);
+int attention_bf16(const bf16* qkv, int B, int S, int heads, int head_dim, bf16* out_p, int Np, bf16* out_c,
+                   cudaStream_t s);
+
+// scheduler (diffusers EDMDPMSolverMultistepScheduler.step + scale_model_input of the NEXT step, fused)
+struct SchedCoef {
+  float c_skip, c_out;     // x0 = c_skip*x + c_out*F
+  float a_x, a_x0, a_d;    // x' = a_x*x + a_x0*x0 + a_d*(x0 - x0_prev)   (a_d = 0 for first-order steps)
+  float c_in_next;         // x_in' = x' * c_in_next (0 -> not written)
+};
+int sched_dpmpp2m_step(const float* f, float* x, float* x0_prev, float* x_in_next, long long n, SchedCoef c,
+                       cudaStream_t s);
+int sched_heun_step(const float* f, double* x, double* x_hat, double* d_cur, float* x_in_next, long long n, int phase,
+                    double t_cur, double t_next, double c_skip, double c_out, double c_in_next, cudaStream_t s);
+
+}  // namespace lc

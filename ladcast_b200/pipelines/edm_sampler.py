@@ -1,0 +1,61 @@
+"""Drop-in for `ladcast.pipelines.edm_sampler.edm_AR_sampler` (reference pipelines/edm_sampler.py:11-120): EDM Heun
+sampler, sampler state in float64, 2N-1 denoiser calls.  The fp64 predictor/corrector updates run in
+`lc_sched_heun_step`; stochastic churn (deterministic=False) is not part of the reference's call sites."""
+from typing import List, Optional, Union
+
+import torch
+
+from .. import _lib
+from .utils import randn_tensor
+
+
+@torch.no_grad()
+def edm_AR_sampler(net, noise_scheduler, batch_size=1, return_seq_len=1, randn_like=torch.randn_like,
+                   num_inference_steps=18, S_churn=0, S_min=0, S_max=float("inf"), S_noise=0, deterministic=True,
+                   known_latents=None, timestamps: Optional[torch.LongTensor] = None,
+                   generator: Optional[Union[torch.Generator, List[torch.Generator]]] = None, device="cpu"):
+    if isinstance(generator, list) and len(generator) != batch_size:
+        raise ValueError(
+            f"You have passed a list of generators of length {len(generator)}, but requested an effective batch"
+            f" size of {batch_size}. Make sure the batch size matches the length of the generators.")
+    assert known_latents is not None, "known_latents must be provided"
+    if not deterministic:
+        raise NotImplementedError("stochastic churn is not implemented (the reference always samples deterministically)")
+    if isinstance(device, str):
+        device = torch.device(device)
+    shape = (batch_size, net.config.out_channels, return_seq_len, *known_latents.shape[-2:])
+    latents = randn_tensor(shape, generator=generator, device=device, dtype=net.dtype)
+    noise_scheduler.set_timesteps(num_inference_steps, device=device)
+    t_steps = noise_scheduler.sigmas.to(torch.float64)  # CPU, float32 values widened
+    sd = float(noise_scheduler.config.sigma_data)
+    lib = _lib.load()
+
+    def coef(t):
+        t32 = t.to(torch.float32)
+        c_in = 1 / ((t32**2 + sd**2) ** 0.5)
+        c_skip = sd**2 / (t32**2 + sd**2)
+        c_out = t32 * sd / (t32**2 + sd**2) ** 0.5
+        return float(c_in), float(c_skip), float(c_out), (0.25 * torch.log(t32)).reshape(1)
+
+    x = (latents.to(torch.float64) * t_steps[0]).contiguous()
+    x_hat, d_cur = torch.empty_like(x), torch.empty_like(x)
+    x_in = torch.empty(shape, device=device, dtype=torch.float32)
+    n = num_inference_steps
+    with net.cached_conditioning(known_latents, timestamps, t_out=return_seq_len):
+        c_in, c_skip, c_out, c_noise = coef(t_steps[0])
+        x_in.copy_((x * c_in).to(torch.float32))
+        for i in range(n):
+            t_cur, t_next = float(t_steps[i]), float(t_steps[i + 1])
+            f = net(x_in, c_noise.to(device), known_latents, time_elapsed=timestamps).sample
+            second = i < n - 1
+            c_in_n, c_skip_n, c_out_n, c_noise_n = coef(t_steps[i + 1]) if second else (0.0, 0.0, 0.0, None)
+            _lib.check(lib.lc_sched_heun_step(_lib.ptr(f), _lib.ptr(x), _lib.ptr(x_hat), _lib.ptr(d_cur),
+                                              _lib.ptr(x_in) if second else None, x.numel(), 0, t_cur, t_next, c_skip,
+                                              c_out, c_in_n, _lib.stream()), "lc_sched_heun_step")
+            if second:
+                f2 = net(x_in, c_noise_n.to(device), known_latents, time_elapsed=timestamps).sample
+                _lib.check(lib.lc_sched_heun_step(_lib.ptr(f2), _lib.ptr(x), _lib.ptr(x_hat), _lib.ptr(d_cur),
+                                                  _lib.ptr(x_in), x.numel(), 1, t_cur, t_next, c_skip_n, c_out_n, c_in_n,
+                                                  _lib.stream()), "lc_sched_heun_step")
+                c_in, c_skip, c_out, c_noise = c_in_n, c_skip_n, c_out_n, c_noise_n
+    return x.float()

@@ -1,0 +1,99 @@
+"""Drop-ins for the hot-path helpers of `ladcast.pipelines.utils` (reference pipelines/utils.py): `ensemble_AR_sampler`
+(:665-742), `decode_latent_ens` (:52-80), `Fields2DPipelineOutput` (:26-35), plus `randn_tensor` (diffusers
+utils/torch_utils.py) and the member-sharding helper the multi-GPU driver uses."""
+import copy
+from dataclasses import dataclass
+from typing import Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+
+@dataclass
+class Fields2DPipelineOutput:
+    fields: Union[torch.Tensor, np.ndarray]
+
+    def __getitem__(self, i):
+        return (self.fields,)[i]
+
+
+def randn_tensor(shape, generator=None, device=None, dtype=None):
+    """Per-sample CPU generators -> one draw of (1, *shape[1:]) each, concatenated, then moved to `device`."""
+    device = torch.device(device) if device is not None else torch.device("cpu")
+    if isinstance(generator, list) and len(generator) == 1:
+        generator = generator[0]
+    if isinstance(generator, list):
+        one = (1,) + tuple(shape[1:])
+        parts = [torch.randn(one, generator=g, device=g.device, dtype=dtype) for g in generator]
+        return torch.cat(parts, dim=0).to(device)
+    gdev = generator.device if generator is not None else device
+    return torch.randn(tuple(shape), generator=generator, device=gdev, dtype=dtype).to(device)
+
+
+def member_shard(sample_size: int, rank: int, world_size: int) -> range:
+    """Contiguous block of global member indices owned by `rank`: [ceil(r*M/W), ceil((r+1)*M/W))."""
+    lo = -(-rank * sample_size // world_size)
+    hi = -(-(rank + 1) * sample_size // world_size)
+    return range(lo, hi)
+
+
+@torch.no_grad()
+def ensemble_AR_sampler(pipeline, sample_size: int, return_seq_len: int, num_inference_steps: int, sampler_kwargs=None,
+                        known_latents: torch.Tensor = None, timestamps: Optional[torch.LongTensor] = None,
+                        batch_size: int = 64, sampler_type: Optional[str] = "edm", device="cpu",
+                        member_indices: Optional[Sequence[int]] = None):
+    """timestamps: (1,) or (B,) int YYYYMMDDHH; known_latents: (1 or B, C, T, H, W); returns (sample_size, C, T, H, W).
+    Member m always draws its noise from torch.Generator('cpu').manual_seed(m) — at every AR step (reference quirk).
+    `member_indices` (extension) selects which GLOBAL members this process samples (default 0..sample_size-1), so
+    that ranks of a multi-GPU job reproduce exactly the members a single process would."""
+    from .edm_sampler import edm_AR_sampler
+
+    if member_indices is None:
+        member_indices = list(range(sample_size))
+    member_indices = list(member_indices)
+    assert len(member_indices) == sample_size, "member_indices must list sample_size members"
+    sizes = [batch_size] * (sample_size // batch_size)
+    if sample_size % batch_size:
+        sizes.append(sample_size % batch_size)
+    samples = torch.empty(sample_size, pipeline.ar_model.config.out_channels, return_seq_len, *known_latents.shape[-2:],
+                          device=device, dtype=pipeline.ar_model.dtype)
+    sampler_kwargs = sampler_kwargs or {}
+    scheduler = copy.deepcopy(pipeline.scheduler) if sampler_type == "edm" else pipeline.scheduler
+    count = 0
+    for n in sizes:
+        gens = [torch.Generator("cpu").manual_seed(int(m) % (1 << 32)) for m in member_indices[count : count + n]]
+        if known_latents.shape[0] == 1:
+            known = known_latents.expand(n, *known_latents.shape[1:]).contiguous()
+        else:
+            known = known_latents[count : count + n] if known_latents.shape[0] == sample_size else known_latents
+        if sampler_type == "edm":
+            out = edm_AR_sampler(pipeline.ar_model, scheduler, batch_size=n, return_seq_len=return_seq_len,
+                                 num_inference_steps=num_inference_steps, generator=gens, device=device,
+                                 known_latents=known, timestamps=timestamps, **sampler_kwargs)
+        elif sampler_type == "pipeline":
+            out = pipeline(batch_size=n, return_seq_len=return_seq_len, num_inference_steps=num_inference_steps,
+                           generator=gens, known_latents=known, timestamps=timestamps, return_dict=False,
+                           do_edm_style=True, **sampler_kwargs)[0]
+        else:
+            raise ValueError(f"unknown sampler_type {sampler_type!r}")
+        samples[count : count + n] = out
+        count += n
+    return samples
+
+
+@torch.no_grad()
+def decode_latent_ens(encdec_model, latents: torch.Tensor, mean_tensor: Optional[torch.Tensor] = None,
+                      std_tensor: Optional[torch.Tensor] = None, extract_first: Optional[int] = None) -> torch.Tensor:
+    """latents: (B, C, T, H, W) -> decoded fields (B, 84, T, 8H, 8W), de-normalised with mean/std if given."""
+    B, C, T, H, W = latents.shape
+    if extract_first is None:
+        extract_first = T
+    z = latents[:, :, :extract_first].to(encdec_model.device).permute(0, 2, 1, 3, 4).reshape(B * extract_first, C, H, W)
+    if hasattr(encdec_model, "decode_fused"):
+        y = encdec_model.decode_fused(z.contiguous(), mean_tensor, std_tensor)
+    else:
+        y = encdec_model.decode(z.contiguous()).sample
+        if mean_tensor is not None:
+            y = y * std_tensor.to(y.device)[None, :, None, None] + mean_tensor.to(y.device)[None, :, None, None]
+    y = y.reshape(B, extract_first, *y.shape[1:]).permute(0, 2, 1, 3, 4)
+    return y
