@@ -1,0 +1,394 @@
+// HBM-bound kernels of the DC-AE decoder (NHWC internal layout): sphere padding, depthwise sphere convolutions,
+// grouped 1x1, ReLU linear attention, channel RMSNorm (+residual), pixel-shuffle (+shortcut).
+// Reference: models/sphere_conv.py:62-192, models/DCAE.py:96-324, 327-377, 493-536, 717-732.
+#include "dcae_kernels.h"
+
+namespace lc {
+namespace {
+
+// Source pixel of padded position (py, px) for a sphere pad of p rows/cols (sphere_conv.py:62-91):
+// longitude circular; pole rows = first/last p rows flipped vertically and rolled by W/2.
+__device__ __forceinline__ void sphere_src(int py, int px, int p, int H, int W, int& sy, int& sx) {
+  int cx = px - p;
+  cx = (cx % W + W) % W;
+  if (py < p) {
+    sy = p - 1 - py;
+    sx = (cx - W / 2 + W) % W;
+  } else if (py >= H + p) {
+    sy = H - 1 - (py - (H + p));
+    sx = (cx - W / 2 + W) % W;
+  } else {
+    sy = py - p;
+    sx = cx;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ float ld(const T* p) { return to_f32<T>(*p); }
+
+// ---------------------------------------------------------------- NCHW f32 latent -> padded NHWC T  (conv_in input)
+template <typename T>
+__global__ void pad_from_nchw_kernel(const float* __restrict__ z, T* __restrict__ out, int n, int C, int H, int W,
+                                     int Cp) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n) * (H + 2) * (W + 2) * Cp;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % Cp);
+  long long r = i / Cp;
+  const int px = static_cast<int>(r % (W + 2));
+  r /= (W + 2);
+  const int py = static_cast<int>(r % (H + 2));
+  const int f = static_cast<int>(r / (H + 2));
+  float v = 0.f;
+  if (c < C) {
+    int sy, sx;
+    sphere_src(py, px, 1, H, W, sy, sx);
+    v = z[((static_cast<long long>(f) * C + c) * H + sy) * W + sx];
+  }
+  out[i] = from_f32<T>(v);
+}
+
+// ---------------------------------------------------------------- NHWC f32 [n,H,W,C] -> padded NHWC T [n,H+2,W+2,Cp]
+template <typename T>
+__global__ void pad_from_nhwc_kernel(const float* __restrict__ x, T* __restrict__ out, int n, int C, int H, int W,
+                                     int Cp) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // one thread per 4 channels
+  const int c4 = Cp / 4;
+  const long long total = static_cast<long long>(n) * (H + 2) * (W + 2) * c4;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % c4) * 4;
+  long long r = i / c4;
+  const int px = static_cast<int>(r % (W + 2));
+  r /= (W + 2);
+  const int py = static_cast<int>(r % (H + 2));
+  const int f = static_cast<int>(r / (H + 2));
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+    int sy, sx;
+    sphere_src(py, px, 1, H, W, sy, sx);
+    v = *reinterpret_cast<const float4*>(x + ((static_cast<long long>(f) * H + sy) * W + sx) * C + c);
+  }
+  T* o = out + i * 4;
+  o[0] = from_f32<T>(v.x); o[1] = from_f32<T>(v.y); o[2] = from_f32<T>(v.z); o[3] = from_f32<T>(v.w);
+}
+
+// ---------------------------------------------------------------- fill the 1-pixel halo of a padded NHWC buffer
+// from its own interior (after a conv epilogue wrote the interior directly).
+template <typename T>
+__global__ void halo_fill_kernel(T* __restrict__ buf, int n, int H, int W, int Cp) {
+  // halo positions per frame: 2 full rows (W+2) + 2 columns x H
+  const int per_frame = 2 * (W + 2) + 2 * H;
+  const int c8 = Cp / 8;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n) * per_frame * c8;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % c8) * 8;
+  long long r = i / c8;
+  const int hidx = static_cast<int>(r % per_frame);
+  const int f = static_cast<int>(r / per_frame);
+  int py, px;
+  if (hidx < W + 2) { py = 0; px = hidx; }
+  else if (hidx < 2 * (W + 2)) { py = H + 1; px = hidx - (W + 2); }
+  else { const int k = hidx - 2 * (W + 2); py = 1 + (k >> 1); px = (k & 1) ? W + 1 : 0; }
+  int sy, sx;
+  sphere_src(py, px, 1, H, W, sy, sx);
+  const long long fs = static_cast<long long>(f) * (H + 2) * (W + 2);
+  const T* src = buf + (fs + static_cast<long long>(sy + 1) * (W + 2) + (sx + 1)) * Cp + c;
+  T* dst = buf + (fs + static_cast<long long>(py) * (W + 2) + px) * Cp + c;
+  if (sizeof(T) == 2) {
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+  } else {
+    reinterpret_cast<float4*>(dst)[0] = reinterpret_cast<const float4*>(src)[0];
+    reinterpret_cast<float4*>(dst)[1] = reinterpret_cast<const float4*>(src)[1];
+  }
+}
+
+// ---------------------------------------------------------------- depthwise KxK sphere conv on NHWC (unpadded input)
+// out[p, c] = bias[c] + sum_{ky,kx} w[c, ky, kx'] * in[src(y+ky, x+kx)], kx' mirrored in the pole pad rows of output
+// rows 0 / H-1 (sphere_conv.py:93-129).  If GLU: channels are [value | gate] halves, output = v * silu(g).
+template <typename TI, typename TO, int K, bool GLU>
+__global__ void __launch_bounds__(256) dwconv_kernel(const TI* __restrict__ in, const float* __restrict__ w,
+                                                     const float* __restrict__ bias, TO* __restrict__ out, int n, int H,
+                                                     int W, int C) {
+  constexpr int P = K / 2;
+  const int Co = GLU ? C / 2 : C;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n) * H * W * Co;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % Co);
+  long long r = i / Co;
+  const int x = static_cast<int>(r % W);
+  r /= W;
+  const int y = static_cast<int>(r % H);
+  const int f = static_cast<int>(r / H);
+  const TI* base = in + static_cast<long long>(f) * H * W * C;
+  float acc0 = bias ? bias[c] : 0.f;
+  float acc1 = (GLU && bias) ? bias[c + Co] : 0.f;
+#pragma unroll
+  for (int ky = 0; ky < K; ++ky) {
+    const bool flip = (y == 0 && ky < P) || (y == H - 1 && ky >= K - P);
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+      int sy, sx;
+      sphere_src(y + ky, x + kx, P, H, W, sy, sx);
+      const int wk = ky * K + (flip ? K - 1 - kx : kx);
+      const TI* px = base + (static_cast<long long>(sy) * W + sx) * C;
+      acc0 = fmaf(w[c * K * K + wk], ld<TI>(px + c), acc0);
+      if (GLU) acc1 = fmaf(w[(c + Co) * K * K + wk], ld<TI>(px + c + Co), acc1);
+    }
+  }
+  const float v = GLU ? acc0 * silu(acc1) : acc0;
+  out[i] = from_f32<TO>(v);
+}
+
+// ---------------------------------------------------------------- grouped 1x1 conv, 32 -> 32 per group (DCAE.py:86-88)
+__global__ void __launch_bounds__(256) grouped1x1_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                         float* __restrict__ out, long long P, int C) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= P * C) return;
+  const int c = static_cast<int>(i % C);
+  const long long p = i / C;
+  const float* src = in + p * C + (c & ~31);
+  const float* wr = w + static_cast<long long>(c) * 32;
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) acc = fmaf(wr[k], src[k], acc);
+  out[i] = acc;
+}
+
+// ---------------------------------------------------------------- ReLU linear attention (DCAE.py:155-175, 226-262)
+// One CTA per (frame, head).  Head g of scale s reads channels [g*96, g*96+96) of qkv (s=0) or of the multiscale
+// branch (s=1): 32 q | 32 k | 32 v.  S = [V;1] relu(K)^T (33x32, fp32), out = S relu(Q), out[:32] / (out[32] + eps).
+template <typename TO>
+__global__ void __launch_bounds__(256) linear_attn_kernel(const float* __restrict__ qkv, const float* __restrict__ ms,
+                                                          TO* __restrict__ out, int HW, int heads, float eps) {
+  __shared__ float S[33][33];
+  __shared__ float kt[64][33];
+  __shared__ float vt[64][33];
+  const int g = blockIdx.x % (2 * heads);
+  const int f = blockIdx.x / (2 * heads);
+  const int scale = g / heads, hg = g % heads;
+  const int C3 = heads * 96;
+  const float* src = (scale ? ms : qkv) + static_cast<long long>(f) * HW * C3 + hg * 96;
+  // phase 1: S[c][c'] = sum_p v1[p][c] * relu(k[p][c'])
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // entries e = tid + 256*j of the 33x32 matrix
+  for (int p0 = 0; p0 < HW; p0 += 64) {
+    for (int i = threadIdx.x; i < 64 * 32; i += 256) {
+      const int pp = i >> 5, c = i & 31;
+      const bool ok = p0 + pp < HW;
+      const float* row = src + static_cast<long long>(p0 + pp) * C3;
+      kt[pp][c] = ok ? fmaxf(row[32 + c], 0.f) : 0.f;
+      vt[pp][c] = ok ? row[64 + c] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 64; i += 256) vt[i][32] = (p0 + i < HW) ? 1.f : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int e = threadIdx.x + 256 * j;
+      if (e < 33 * 32) {
+        const int c = e >> 5, cp = e & 31;
+        float a = acc[j];
+        for (int pp = 0; pp < 64; ++pp) a = fmaf(vt[pp][c], kt[pp][cp], a);
+        acc[j] = a;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const int e = threadIdx.x + 256 * j;
+    if (e < 33 * 32) S[e >> 5][e & 31] = acc[j];
+  }
+  __syncthreads();
+  // phase 2: per pixel, out[c] = (S[c] . relu(q)) / (S[32] . relu(q) + eps)
+  const int Co = 2 * heads * 32;
+  for (int p = threadIdx.x; p < HW; p += 256) {
+    const float* row = src + static_cast<long long>(p) * C3;
+    float q[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) q[c] = fmaxf(row[c], 0.f);
+    float den = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) den = fmaf(S[32][c], q[c], den);
+    const float inv = 1.0f / (den + eps);
+    TO* o = out + (static_cast<long long>(f) * HW + p) * Co + g * 32;
+#pragma unroll 4
+    for (int c = 0; c < 32; ++c) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) a = fmaf(S[c][k], q[k], a);
+      o[c] = from_f32<TO>(a * inv);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- channel RMSNorm (+residual) on [P, C] rows
+// y = x_in * rsqrt(mean(x_in^2) + eps) * w + b ; if resid: resid += y (in place) and the result is also written as T.
+template <typename T>
+__global__ void __launch_bounds__(256) rmsnorm_rows_kernel(const float* __restrict__ y, const float* __restrict__ w,
+                                                           const float* __restrict__ b, float eps, float* __restrict__ resid,
+                                                           float* __restrict__ out_f32, T* __restrict__ out_t, long long P,
+                                                           int C, int relu) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= P) return;
+  const float* yr = y + row * C;
+  const int c4 = C / 4;
+  float ss = 0.f;
+  for (int i = lane; i < c4; i += 32) {
+    const float4 v = *reinterpret_cast<const float4*>(yr + i * 4);
+    ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float r = rsqrtf(ss / C + eps);
+  for (int i = lane; i < c4; i += 32) {
+    const int c = i * 4;
+    const float4 v = *reinterpret_cast<const float4*>(yr + c);
+    const float4 ww = __ldg(reinterpret_cast<const float4*>(w + c));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
+    float4 o = make_float4(v.x * r * ww.x + bb.x, v.y * r * ww.y + bb.y, v.z * r * ww.z + bb.z, v.w * r * ww.w + bb.w);
+    if (resid != nullptr) {
+      float4 h = *reinterpret_cast<float4*>(resid + row * C + c);
+      o.x += h.x; o.y += h.y; o.z += h.z; o.w += h.w;
+      *reinterpret_cast<float4*>(resid + row * C + c) = o;
+    }
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + row * C + c) = o;
+    if (out_t != nullptr) {
+      T* ot = out_t + row * C + c;
+      ot[0] = from_f32<T>(o.x); ot[1] = from_f32<T>(o.y); ot[2] = from_f32<T>(o.z); ot[3] = from_f32<T>(o.w);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- pixel_shuffle(2) of conv output + shortcut
+// out[f, 2y+i, 2x+j, c] = conv[f, y, x, 4c+2i+j] + x_in[f, y, x, (4c+2i+j) / rep]     (DCAE.py:519-536)
+template <typename T>
+__global__ void __launch_bounds__(256) pixel_shuffle_kernel(const float* __restrict__ conv, const float* __restrict__ xin,
+                                                            float* __restrict__ out, T* __restrict__ out_t, int n, int H,
+                                                            int W, int Cin, int Cout, int rep) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n) * 2 * H * 2 * W * Cout;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % Cout);
+  long long r = i / Cout;
+  const int X = static_cast<int>(r % (2 * W));
+  r /= (2 * W);
+  const int Y = static_cast<int>(r % (2 * H));
+  const int f = static_cast<int>(r / (2 * H));
+  const int y = Y >> 1, ii = Y & 1, x = X >> 1, jj = X & 1;
+  const int ch = 4 * c + 2 * ii + jj;
+  const long long pin = (static_cast<long long>(f) * H + y) * W + x;
+  const float v = conv[pin * (4 * Cout) + ch] + xin[pin * Cin + ch / rep];
+  out[i] = v;
+  if (out_t != nullptr) out_t[i] = from_f32<T>(v);
+}
+
+// ---------------------------------------------------------------- conv_in shortcut: x[p, c] += z[f, c / rep, y, x]
+template <typename T>
+__global__ void in_shortcut_kernel(float* __restrict__ x, T* __restrict__ x_t, const float* __restrict__ z, int n, int HW,
+                                   int C, int Cz, int rep) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n) * HW * C;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % C);
+  const long long p = i / C;
+  const int f = static_cast<int>(p / HW), pix = static_cast<int>(p % HW);
+  const float v = x[i] + z[(static_cast<long long>(f) * Cz + c / rep) * HW + pix];
+  x[i] = v;
+  if (x_t != nullptr) x_t[i] = from_f32<T>(v);
+}
+
+inline unsigned blocks(long long n, int t = 256) { return static_cast<unsigned>((n + t - 1) / t); }
+
+}  // namespace
+
+template <typename T>
+int pad_from_nchw(const float* z, T* out, int n, int C, int H, int W, int Cp, cudaStream_t s) {
+  const long long total = static_cast<long long>(n) * (H + 2) * (W + 2) * Cp;
+  pad_from_nchw_kernel<T><<<blocks(total), 256, 0, s>>>(z, out, n, C, H, W, Cp);
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+template <typename T>
+int pad_from_nhwc(const float* x, T* out, int n, int C, int H, int W, int Cp, cudaStream_t s) {
+  LC_REQUIRE(C % 4 == 0 && Cp % 4 == 0, "pad: channels must be multiples of 4");
+  const long long total = static_cast<long long>(n) * (H + 2) * (W + 2) * (Cp / 4);
+  pad_from_nhwc_kernel<T><<<blocks(total), 256, 0, s>>>(x, out, n, C, H, W, Cp);
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+template <typename T>
+int halo_fill(T* buf, int n, int H, int W, int Cp, cudaStream_t s) {
+  LC_REQUIRE(Cp % 8 == 0, "halo_fill: Cp must be a multiple of 8");
+  const long long total = static_cast<long long>(n) * (2 * (W + 2) + 2 * H) * (Cp / 8);
+  halo_fill_kernel<T><<<blocks(total), 256, 0, s>>>(buf, n, H, W, Cp);
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int dwconv5(const float* in, const float* w, float* out, int n, int H, int W, int C, cudaStream_t s) {
+  const long long total = static_cast<long long>(n) * H * W * C;
+  dwconv_kernel<float, float, 5, false><<<blocks(total), 256, 0, s>>>(in, w, nullptr, out, n, H, W, C);
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+template <typename T>
+int dwconv3_glu(const T* in, const float* w, const float* bias, T* out, int n, int H, int W, int C, cudaStream_t s) {
+  const long long total = static_cast<long long>(n) * H * W * (C / 2);
+  dwconv_kernel<T, T, 3, true><<<blocks(total), 256, 0, s>>>(in, w, bias, out, n, H, W, C);
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int grouped1x1(const float* in, const float* w, float* out, long long P, int C, cudaStream_t s) {
+  LC_REQUIRE(C % 32 == 0, "grouped 1x1: channels must be a multiple of 32");
+  grouped1x1_kernel<<<blocks(P * C), 256, 0, s>>>(in, w, out, P, C);
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+template <typename T>
+int linear_attention(const float* qkv, const float* ms, T* out, int n, int HW, int heads, float eps, cudaStream_t s) {
+  linear_attn_kernel<T><<<n * 2 * heads, 256, 0, s>>>(qkv, ms, out, HW, heads, eps);
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+template <typename T>
+int rmsnorm_rows(const float* y, const float* w, const float* b, float eps, float* resid, float* out_f32, T* out_t,
+                 long long P, int C, int relu, cudaStream_t s) {
+  LC_REQUIRE(C % 4 == 0, "rmsnorm: C must be a multiple of 4");
+  rmsnorm_rows_kernel<T><<<blocks(P, 8), 256, 0, s>>>(y, w, b, eps, resid, out_f32, out_t, P, C, relu);
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+template <typename T>
+int pixel_shuffle_shortcut(const float* conv, const float* xin, float* out, T* out_t, int n, int H, int W, int Cin,
+                           int Cout, cudaStream_t s) {
+  const long long total = static_cast<long long>(n) * 4 * H * W * Cout;
+  pixel_shuffle_kernel<T><<<blocks(total), 256, 0, s>>>(conv, xin, out, out_t, n, H, W, Cin, Cout, 4 * Cout / Cin);
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+template <typename T>
+int in_shortcut(float* x, T* x_t, const float* z, int n, int HW, int C, int Cz, cudaStream_t s) {
+  const long long total = static_cast<long long>(n) * HW * C;
+  in_shortcut_kernel<T><<<blocks(total), 256, 0, s>>>(x, x_t, z, n, HW, C, Cz, C / Cz);
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+#define LC_INST(T)                                                                                                   \
+  template int pad_from_nchw<T>(const float*, T*, int, int, int, int, int, cudaStream_t);                            \
+  template int pad_from_nhwc<T>(const float*, T*, int, int, int, int, int, cudaStream_t);                            \
+  template int halo_fill<T>(T*, int, int, int, int, cudaStream_t);                                                   \
+  template int dwconv3_glu<T>(const T*, const float*, const float*, T*, int, int, int, int, cudaStream_t);           \
+  template int linear_attention<T>(const float*, const float*, T*, int, int, int, float, cudaStream_t);              \
+  template int rmsnorm_rows<T>(const float*, const float*, const float*, float, float*, float*, T*, long long, int,  \
+                               int, cudaStream_t);                                                                   \
+  template int pixel_shuffle_shortcut<T>(const float*, const float*, float*, T*, int, int, int, int, int,            \
+                                         cudaStream_t);                                                              \
+  template int in_shortcut<T>(float*, T*, const float*, int, int, int, int, cudaStream_t);
+LC_INST(float)
+LC_INST(bf16)
+#undef LC_INST
+
+}  // namespace lc
