@@ -96,6 +96,37 @@ LC_API int lc_sched_heun_step(const float* f, double* x, double* x_hat, double* 
                        double t_cur, double t_next, double c_skip, double c_out, double c_in_next, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * DC-AE decoder — replaces AutoencoderDC.decode / Decoder.forward (models/DCAE.py:1018-1056, 717-732) and the
+ * de-normalisation of decode_latent_ens (pipelines/utils.py:71-79).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct lc_dcae lc_dcae;
+
+typedef struct {
+  int latent_channels; /* 84 */
+  int out_channels;    /* decoder conv_out channels, 89 */
+  int head_dim;        /* EfficientViT attention_head_dim, 32 */
+  int n_stages;        /* len(decoder_block_out_channels), 4 */
+  int precision;       /* LC_PRECISION_* */
+  int stage_channels[8]; /* decoder_block_out_channels, index 0 = highest resolution: 252, 504, 504, 1008 */
+  int stage_layers[8];   /* decoder_layers_per_block */
+  int stage_is_evit[8];  /* 1 where decoder_block_types[i] == "EfficientViTBlock" */
+} lc_dcae_cfg;
+
+LC_API int lc_dcae_create(const lc_dcae_cfg* cfg, lc_dcae** out);
+LC_API void lc_dcae_destroy(lc_dcae* h);
+/* state-dict entries with prefix "decoder." (reference key names); encoder.* are ignored */
+LC_API int lc_dcae_load(lc_dcae* h, const char* key, const float* data, const int64_t* shape, int ndim, void* stream);
+LC_API int lc_dcae_finalize(lc_dcae* h, void* stream);
+/* allocates the workspace for up to max_frames latents of size h x w (the only allocating call after finalize) */
+LC_API int lc_dcae_reserve(lc_dcae* h, int max_frames, int height, int width, void* stream);
+/* z: [n, latent_channels, h, w] fp32 -> out: [n, keep_channels, 8h, 8w] fp32 (NCHW); keep_channels =
+ * out_channels - static_channels (84) drops the static channels exactly like DCAE.py:1050-1052.  If mean/std
+ * ([keep_channels] fp32) are given the output is out*std + mean (inverse_normalize_transform_3D,
+ * dataloader/utils.py:233-240). */
+LC_API int lc_dcae_decode(lc_dcae* h, const float* z, int n, int height, int width, float* out, int keep_channels,
+                          const float* mean, const float* std, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Low-level ops exported for parity tests (same kernels the handles use)
  * ---------------------------------------------------------------------------------------------------------- */
 /* C[M,N] = A[M,K] W[N,K]^T + bias, act in {0 none, 1 gelu-tanh, 2 silu}.  precision BF16: A, W bf16 (raw uint16
@@ -104,6 +135,11 @@ LC_API int lc_gemm(int precision, const void* a, const void* w, const float* bia
             void* stream);
 /* qkv: [B, S, 3*heads*128] (q|k|v) fp32 (F32) or bf16 (BF16); out: [B, S, heads*128] same dtype. */
 LC_API int lc_attention(int precision, const void* qkv, void* out, int batch, int seq, int heads, void* stream);
+
+/* One SphereConv2d 3x3 (models/sphere_conv.py:138-192), NCHW fp32 in/out, through the implicit-GEMM path.
+ * w: [cout, cin, 3, 3], bias: [cout] or NULL.  Test helper: allocates and synchronises internally. */
+LC_API int lc_sphere_conv3x3(int precision, const float* x, const float* w, const float* bias, float* out, int n, int cin,
+                             int height, int width, int cout, int act, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ class DenoiserCfg(ctypes.Structure):
 
 class DcaeCfg(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in (
-        "latent_channels", "out_channels", "keep_channels", "head_dim", "n_stages", "precision")] + [
+        "latent_channels", "out_channels", "head_dim", "n_stages", "precision")] + [
         ("stage_channels", ctypes.c_int * 8), ("stage_layers", ctypes.c_int * 8), ("stage_is_evit", ctypes.c_int * 8)]
 
 
@@ -58,7 +58,7 @@ _OPTIONAL = {
     "lc_dcae_load": ([_vp, _cp, _vp, ctypes.POINTER(_i64), _i, _vp], _i),
     "lc_dcae_finalize": ([_vp, _vp], _i),
     "lc_dcae_reserve": ([_vp, _i, _i, _i, _vp], _i),
-    "lc_dcae_decode": ([_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp], _i),
+    "lc_dcae_decode": ([_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp], _i),
     "lc_dcae_debug_read": ([_vp, _cp, _vp, _i64, _vp], _i),
     "lc_sphere_conv3x3": ([_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "lc_metrics_accumulate": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp], _i),

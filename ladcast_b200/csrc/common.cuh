@@ -99,12 +99,19 @@ struct EpiParams {
   const float* resid = nullptr;  // EPI_RESID_STORE
   long long ldr = 0;
   int n_valid = 0;  // EPI_UNPATCHIFY: number of real output channels (<= N)
+  // second-level remap (padded image buffers): orow += (row / rows_per_group) * group_extra_rows
+  int rows_per_group = 1 << 30;
+  int group_extra_rows = 0;
+  // EPI_UNPATCHIFY only: out = v * ch_scale[n] + ch_shift[n]  (decoder: fields * std + mean fused)
+  const float* ch_scale = nullptr;
+  const float* ch_shift = nullptr;
 };
 
 __device__ __forceinline__ long long epi_out_row(const EpiParams& ep, int row, int& sample) {
   sample = row / ep.rows_per_sample;
   int r = row - sample * ep.rows_per_sample;
-  return static_cast<long long>(sample) * ep.out_rows_per_sample + ep.out_row_offset + r;
+  return static_cast<long long>(sample) * ep.out_rows_per_sample + ep.out_row_offset + r +
+         static_cast<long long>(row / ep.rows_per_group) * ep.group_extra_rows;
 }
 
 // GEMM problem: A is [M, K] row-major split in up to two K-segments (A0: k < K0, A1: K0 <= k < K);

@@ -1,0 +1,454 @@
+// DC-AE decoder handle: weight re-packing + Decoder.forward (reference models/DCAE.py:717-732 via
+// AutoencoderDC.decode :1018-1056) as a fixed kernel sequence.  Internal layout is NHWC:
+//   x    [n*H*W, C] f32  residual stream            padA/padB [n, H+2, W+2, Cp] T  sphere-padded conv inputs
+//   y    [n*H*W, *] f32  raw conv / 1x1 outputs     xb [n*H*W, C] T                1x1-GEMM operand copy of x
+// 3x3 sphere convolutions are implicit GEMMs on the tcgen05 kernel (gemm_tc.cu); 1x1 convolutions are plain
+// GEMMs over pixels; depthwise/grouped/linear-attention/norm kernels are in dcae_kernels.cu.
+#include <algorithm>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/ladcast_b200.h"
+#include "dcae_kernels.h"
+#include "gemm_tc.h"
+#include "kernels.h"
+
+namespace lc {
+namespace {
+
+struct Buf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int alloc(size_t n) {
+    if (n <= bytes) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    LC_CHECK_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
+};
+
+struct St { float* p = nullptr; int64_t numel = 0; };
+
+struct ConvW { void* w = nullptr; float* bias = nullptr; int cin = 0, cp = 0, cout = 0; };
+struct MatW { void* w = nullptr; float* bias = nullptr; int out = 0, in = 0; };
+struct EvitW {
+  MatW qkv, to_out, inv, point;
+  float *dw5 = nullptr, *g1 = nullptr, *no_w = nullptr, *no_b = nullptr, *dw3 = nullptr, *dw3_b = nullptr, *n_w = nullptr, *n_b = nullptr;
+  int heads = 0, inner = 0;
+};
+struct ResW { ConvW c1, c2; float *n_w = nullptr, *n_b = nullptr; };
+struct Block { int kind = 0; /*0 up, 1 res, 2 evit*/ int cin = 0, cout = 0; ConvW up; ResW res; EvitW ev; };
+
+inline int r64(int c) { return (c + 63) / 64 * 64; }
+
+__global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin, int cp, void* __restrict__ dst, int to_bf16) {
+  // w [cout, cin, 3, 3] -> dst [cout, 9*cp], k = (ky*3+kx)*cp + c
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long K = 9LL * cp;
+  if (i >= cout * K) return;
+  const int o = static_cast<int>(i / K);
+  const int k = static_cast<int>(i % K);
+  const int tap = k / cp, c = k % cp;
+  const float v = c < cin ? w[(static_cast<long long>(o) * cin + c) * 9 + tap] : 0.f;
+  if (to_bf16) reinterpret_cast<bf16*>(dst)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(dst)[i] = v;
+}
+
+__global__ void pack_mat_kernel(const float* __restrict__ w, long long n, void* __restrict__ dst, long long off, int to_bf16) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (to_bf16) reinterpret_cast<bf16*>(dst)[off + i] = __float2bfloat16_rn(w[i]);
+  else reinterpret_cast<float*>(dst)[off + i] = w[i];
+}
+
+}  // namespace
+}  // namespace lc
+
+using namespace lc;
+
+struct lc_dcae {
+  lc_dcae_cfg cfg;
+  bool f32 = false;
+  size_t esz = 2;
+  bool finalized = false;
+  std::map<std::string, St> staged;
+  std::vector<void*> owned;
+  ConvW conv_in, conv_out;
+  float *no_w = nullptr, *no_b = nullptr;
+  std::vector<Block> blocks;
+  int max_frames = 0, h0 = 0, w0 = 0;
+  Buf x, x2, y, padA, padB, xb, qkv, ms1, ms, att, hid, glu;
+};
+
+namespace lc {
+namespace {
+
+int find(lc_dcae* D, const std::string& k, const St** out) {
+  auto it = D->staged.find(k);
+  LC_REQUIRE(it != D->staged.end(), "missing checkpoint tensor '" + k + "'");
+  *out = &it->second;
+  return 0;
+}
+int fvec(lc_dcae* D, const std::string& k, int64_t n, float** out, cudaStream_t st, int64_t take = -1) {
+  const St* s;
+  LC_TRY(find(D, k, &s));
+  LC_REQUIRE(s->numel == n, "unexpected size for '" + k + "'");
+  const int64_t cnt = take > 0 ? take : n;
+  LC_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(out), static_cast<size_t>(cnt) * 4));
+  D->owned.push_back(*out);
+  LC_CHECK_CUDA(cudaMemcpyAsync(*out, s->p, static_cast<size_t>(cnt) * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+int make_conv(lc_dcae* D, const std::string& name, int cout_full, int cin, bool bias, ConvW* W, cudaStream_t st, int cout_keep = -1) {
+  const St* w;
+  LC_TRY(find(D, name + ".weight", &w));
+  LC_REQUIRE(w->numel == static_cast<int64_t>(cout_full) * cin * 9, "unexpected conv weight shape for '" + name + "'");
+  const int cout = cout_keep > 0 ? cout_keep : cout_full;
+  W->cin = cin; W->cp = r64(cin); W->cout = cout;
+  const long long n = static_cast<long long>(cout) * 9 * W->cp;
+  LC_CHECK_CUDA(cudaMalloc(&W->w, static_cast<size_t>(n) * D->esz));
+  D->owned.push_back(W->w);
+  pack_conv_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(w->p, cout, cin, W->cp, W->w, D->f32 ? 0 : 1);
+  LC_CHECK_CUDA(cudaGetLastError());
+  if (bias) LC_TRY(fvec(D, name + ".bias", cout_full, &W->bias, st, cout));
+  return 0;
+}
+int make_mat(lc_dcae* D, const std::vector<std::string>& names, int in, bool bias, MatW* M, cudaStream_t st) {
+  int total = 0;
+  std::vector<const St*> ws;
+  for (const auto& n : names) {
+    const St* w;
+    LC_TRY(find(D, n + ".weight", &w));
+    LC_REQUIRE(w->numel % in == 0, "unexpected weight shape for '" + n + "'");
+    ws.push_back(w);
+    total += static_cast<int>(w->numel / in);
+  }
+  M->out = total; M->in = in;
+  LC_CHECK_CUDA(cudaMalloc(&M->w, static_cast<size_t>(total) * in * D->esz));
+  D->owned.push_back(M->w);
+  long long off = 0;
+  for (const St* w : ws) {
+    pack_mat_kernel<<<static_cast<unsigned>((w->numel + 255) / 256), 256, 0, st>>>(w->p, w->numel, M->w, off, D->f32 ? 0 : 1);
+    LC_CHECK_CUDA(cudaGetLastError());
+    off += w->numel;
+  }
+  if (bias) {
+    LC_REQUIRE(names.size() == 1, "fused biased matrices unsupported");
+    LC_TRY(fvec(D, names[0] + ".bias", total, &M->bias, st));
+  }
+  return 0;
+}
+
+template <typename T>
+struct Run {
+  lc_dcae* D;
+  cudaStream_t st;
+  int n;
+  bool xb_valid = false;  // xb == T(x)?
+
+  int conv(const T* xpad, int H, int W, const ConvW& cw, const EpiParams& ep) const {
+    if (sizeof(T) == 2) return conv3x3_bf16(xpad, n, H, W, cw.cp, cw.w, cw.cout, ep, st);
+    return conv3x3_f32(reinterpret_cast<const float*>(xpad), n, H, W, cw.cp, reinterpret_cast<const float*>(cw.w), cw.cout, ep, st);
+  }
+  int gemm(const void* A, long long lda, long long M, const MatW& mw, void* out, bool out_f32, int act) const {
+    GemmArgs g;
+    g.A0 = A; g.lda0 = lda; g.K0 = mw.in; g.W = mw.w; g.ldw = mw.in; g.M = static_cast<int>(M); g.N = mw.out; g.K = mw.in;
+    g.epi.mode = EPI_STORE; g.epi.act = act; g.epi.bias = mw.bias; g.epi.out = out; g.epi.ldo = mw.out;
+    g.epi.out_f32 = (out_f32 || sizeof(T) == 4) ? 1 : 0;
+    return sizeof(T) == 2 ? gemm_bf16(g, st) : gemm_f32(g, st);
+  }
+  EpiParams store_f32(float* out, int ld, const float* bias) const {
+    EpiParams e;
+    e.mode = EPI_STORE; e.out_f32 = 1; e.out = out; e.ldo = ld; e.bias = bias;
+    return e;
+  }
+
+  int res_block(const Block& b, int H, int W) {
+    xb_valid = false;
+    const ResW& w = b.res;
+    const int C = b.cin;
+    const long long P = static_cast<long long>(n) * H * W;
+    T* padA = D->padA.as<T>();
+    T* padB = D->padB.as<T>();
+    float* x = D->x.as<float>();
+    LC_TRY(pad_from_nhwc<T>(x, padA, n, C, H, W, w.c1.cp, st));
+    // conv1 + bias + SiLU written straight into the interior of padB (conv2's padded input)
+    EpiParams e;
+    e.mode = EPI_STORE; e.act = ACT_SILU; e.bias = w.c1.bias; e.out = padB; e.ldo = w.c2.cp; e.out_f32 = sizeof(T) == 4;
+    e.rows_per_sample = W; e.out_rows_per_sample = W + 2; e.out_row_offset = (W + 2) + 1;
+    e.rows_per_group = H * W; e.group_extra_rows = 2 * (W + 2);
+    LC_TRY(conv(padA, H, W, w.c1, e));
+    LC_TRY(halo_fill<T>(padB, n, H, W, w.c2.cp, st));
+    LC_TRY(conv(padB, H, W, w.c2, store_f32(D->y.as<float>(), C, nullptr)));
+    return rmsnorm_rows<T>(D->y.as<float>(), w.n_w, w.n_b, 1e-5f, x, nullptr, static_cast<T*>(nullptr), P, C, 0, st);
+  }
+
+  int evit_block(const Block& b, int H, int W) {
+    const EvitW& w = b.ev;
+    const int C = b.cin, HW = H * W;
+    const long long P = static_cast<long long>(n) * HW;
+    LC_REQUIRE(HW > D->cfg.head_dim, "quadratic-attention branch (H*W <= head_dim) is not implemented");
+    float* x = D->x.as<float>();
+    T* xb = D->xb.as<T>();
+    float* y = D->y.as<float>();
+    if (!xb_valid) LC_TRY(cast_rows<T>(x, xb, P * C, st));
+    xb_valid = true;
+    LC_TRY(gemm(xb, C, P, w.qkv, D->qkv.p, true, ACT_NONE));
+    LC_TRY(dwconv5(D->qkv.as<float>(), w.dw5, D->ms1.as<float>(), n, H, W, 3 * w.inner, st));
+    LC_TRY(grouped1x1(D->ms1.as<float>(), w.g1, D->ms.as<float>(), P, 3 * w.inner, st));
+    LC_TRY(linear_attention<T>(D->qkv.as<float>(), D->ms.as<float>(), D->att.as<T>(), n, HW, w.heads, 1e-15f, st));
+    LC_TRY(gemm(D->att.p, 2 * w.inner, P, w.to_out, y, true, ACT_NONE));
+    LC_TRY(rmsnorm_rows<T>(y, w.no_w, w.no_b, 1e-5f, x, nullptr, xb, P, C, 0, st));
+    LC_TRY(gemm(xb, C, P, w.inv, D->hid.p, false, ACT_SILU));
+    LC_TRY(dwconv3_glu<T>(D->hid.as<T>(), w.dw3, w.dw3_b, D->glu.as<T>(), n, H, W, 8 * C, st));
+    LC_TRY(gemm(D->glu.p, 4 * C, P, w.point, y, true, ACT_NONE));
+    return rmsnorm_rows<T>(y, w.n_w, w.n_b, 1e-7f, x, nullptr, xb, P, C, 0, st);
+  }
+
+  int up_block(const Block& b, int& H, int& W) {
+    xb_valid = true;
+    const long long P = static_cast<long long>(n) * H * W;
+    (void)P;
+    LC_TRY(pad_from_nhwc<T>(D->x.as<float>(), D->padA.as<T>(), n, b.cin, H, W, b.up.cp, st));
+    LC_TRY(conv(D->padA.as<T>(), H, W, b.up, store_f32(D->y.as<float>(), 4 * b.cout, b.up.bias)));
+    LC_TRY(pixel_shuffle_shortcut<T>(D->y.as<float>(), D->x.as<float>(), D->x2.as<float>(), D->xb.as<T>(), n, H, W, b.cin,
+                                     b.cout, st));
+    std::swap(D->x, D->x2);
+    H *= 2; W *= 2;
+    return 0;
+  }
+
+  int decode(const float* z, int h, int w, float* out, int keep, const float* mean, const float* stdv) {
+    int H = h, W = w;
+    const int C0 = D->conv_in.cout;
+    LC_TRY(pad_from_nchw<T>(z, D->padA.as<T>(), n, D->cfg.latent_channels, H, W, D->conv_in.cp, st));
+    LC_TRY(conv(D->padA.as<T>(), H, W, D->conv_in, store_f32(D->x.as<float>(), C0, D->conv_in.bias)));
+    LC_TRY(in_shortcut<T>(D->x.as<float>(), D->xb.as<T>(), z, n, H * W, C0, D->cfg.latent_channels, st));
+    xb_valid = true;
+    for (const Block& b : D->blocks) {
+      if (b.kind == 0) LC_TRY(up_block(b, H, W));
+      else if (b.kind == 1) LC_TRY(res_block(b, H, W));
+      else LC_TRY(evit_block(b, H, W));
+    }
+    const int C = D->conv_out.cin;
+    const long long P = static_cast<long long>(n) * H * W;
+    LC_TRY(rmsnorm_rows<T>(D->x.as<float>(), D->no_w, D->no_b, 1e-7f, nullptr, D->y.as<float>(), static_cast<T*>(nullptr), P, C, 1, st));
+    LC_TRY(pad_from_nhwc<T>(D->y.as<float>(), D->padA.as<T>(), n, C, H, W, D->conv_out.cp, st));
+    EpiParams e;
+    e.mode = EPI_UNPATCHIFY; e.bias = D->conv_out.bias; e.out = out; e.rows_per_sample = H * W;
+    e.n_valid = keep; e.ch_scale = stdv; e.ch_shift = mean;
+    return conv(D->padA.as<T>(), H, W, D->conv_out, e);
+  }
+};
+
+int finalize_impl(lc_dcae* D, cudaStream_t st) {
+  const lc_dcae_cfg& c = D->cfg;
+  const int ns = c.n_stages;
+  const int Ctop = c.stage_channels[ns - 1];
+  LC_TRY(make_conv(D, "decoder.conv_in", Ctop, c.latent_channels, true, &D->conv_in, st));
+  int j = 0;
+  for (int i = ns - 1; i >= 0; --i) {
+    const int C = c.stage_channels[i];
+    if (i < ns - 1 && c.stage_layers[i] > 0) {
+      Block b;
+      b.kind = 0; b.cin = c.stage_channels[i + 1]; b.cout = C;
+      LC_REQUIRE((4 * b.cout) % b.cin == 0, "up-block shortcut needs 4*C_out divisible by C_in");
+      LC_TRY(make_conv(D, "decoder.up_blocks." + std::to_string(j) + ".conv", 4 * C, b.cin, true, &b.up, st));
+      D->blocks.push_back(b);
+      ++j;
+    }
+    for (int l = 0; l < c.stage_layers[i]; ++l) {
+      const std::string p = "decoder.up_blocks." + std::to_string(j);
+      Block b;
+      b.cin = b.cout = C;
+      if (!c.stage_is_evit[i]) {
+        b.kind = 1;
+        LC_TRY(make_conv(D, p + ".conv1", C, C, true, &b.res.c1, st));
+        LC_TRY(make_conv(D, p + ".conv2", C, C, false, &b.res.c2, st));
+        LC_TRY(fvec(D, p + ".norm.weight", C, &b.res.n_w, st));
+        LC_TRY(fvec(D, p + ".norm.bias", C, &b.res.n_b, st));
+      } else {
+        b.kind = 2;
+        EvitW& e = b.ev;
+        e.heads = C / c.head_dim;
+        e.inner = e.heads * c.head_dim;
+        LC_REQUIRE(c.head_dim == 32, "EfficientViT attention_head_dim must be 32");
+        LC_TRY(make_mat(D, {p + ".attn.to_q", p + ".attn.to_k", p + ".attn.to_v"}, C, false, &e.qkv, st));
+        LC_TRY(fvec(D, p + ".attn.to_qkv_multiscale.0.proj_in.weight", 3LL * e.inner * 25, &e.dw5, st));
+        LC_TRY(fvec(D, p + ".attn.to_qkv_multiscale.0.proj_out.weight", 3LL * e.inner * 32, &e.g1, st));
+        LC_TRY(make_mat(D, {p + ".attn.to_out"}, 2 * e.inner, false, &e.to_out, st));
+        LC_TRY(fvec(D, p + ".attn.norm_out.weight", C, &e.no_w, st));
+        LC_TRY(fvec(D, p + ".attn.norm_out.bias", C, &e.no_b, st));
+        LC_TRY(make_mat(D, {p + ".conv_out.conv_inverted"}, C, true, &e.inv, st));
+        LC_TRY(fvec(D, p + ".conv_out.conv_depth.weight", 8LL * C * 9, &e.dw3, st));
+        LC_TRY(fvec(D, p + ".conv_out.conv_depth.bias", 8LL * C, &e.dw3_b, st));
+        LC_TRY(make_mat(D, {p + ".conv_out.conv_point"}, 4 * C, false, &e.point, st));
+        LC_TRY(fvec(D, p + ".conv_out.norm.weight", C, &e.n_w, st));
+        LC_TRY(fvec(D, p + ".conv_out.norm.bias", C, &e.n_b, st));
+      }
+      D->blocks.push_back(b);
+      ++j;
+    }
+  }
+  const int C0 = c.stage_channels[0];
+  LC_TRY(fvec(D, "decoder.norm_out.weight", C0, &D->no_w, st));
+  LC_TRY(fvec(D, "decoder.norm_out.bias", C0, &D->no_b, st));
+  LC_TRY(make_conv(D, "decoder.conv_out", c.out_channels, C0, true, &D->conv_out, st));
+  LC_CHECK_CUDA(cudaStreamSynchronize(st));
+  for (auto& kv : D->staged) cudaFree(kv.second.p);
+  D->staged.clear();
+  D->finalized = true;
+  return 0;
+}
+
+}  // namespace
+}  // namespace lc
+
+extern "C" {
+
+int lc_dcae_create(const lc_dcae_cfg* cfg, lc_dcae** out) {
+  LC_REQUIRE(cfg && out, "null argument");
+  LC_REQUIRE(cfg->n_stages >= 1 && cfg->n_stages <= 8, "n_stages out of range");
+  LC_REQUIRE(cfg->out_channels > 0 && cfg->out_channels <= 128, "decoder out_channels must be <= 128");
+  if (cfg->precision == LC_PRECISION_BF16)
+    for (int i = 0; i < cfg->n_stages; ++i)
+      LC_REQUIRE(cfg->stage_channels[i] % 8 == 0, "bf16 decoder needs stage channels divisible by 8 (TMA 16-byte pitch)");
+  for (int i = 0; i < cfg->n_stages; ++i) LC_REQUIRE(cfg->stage_channels[i] % 4 == 0, "stage channels must be multiples of 4");
+  LC_REQUIRE(cfg->stage_channels[cfg->n_stages - 1] % cfg->latent_channels == 0, "in_shortcut needs C_top divisible by latent_channels");
+  lc_dcae* D = new lc_dcae();
+  D->cfg = *cfg;
+  D->f32 = cfg->precision == LC_PRECISION_F32;
+  D->esz = D->f32 ? 4 : 2;
+  *out = D;
+  return 0;
+}
+
+void lc_dcae_destroy(lc_dcae* D) {
+  if (!D) return;
+  for (void* p : D->owned) cudaFree(p);
+  for (auto& kv : D->staged) cudaFree(kv.second.p);
+  Buf* bufs[] = {&D->x, &D->x2, &D->y, &D->padA, &D->padB, &D->xb, &D->qkv, &D->ms1, &D->ms, &D->att, &D->hid, &D->glu};
+  for (Buf* b : bufs) b->release();
+  delete D;
+}
+
+int lc_dcae_load(lc_dcae* D, const char* key, const float* data, const int64_t* shape, int ndim, void* stream) {
+  LC_REQUIRE(D && key && data && shape, "null argument");
+  LC_REQUIRE(!D->finalized, "lc_dcae_load after finalize");
+  St s;
+  s.numel = 1;
+  for (int i = 0; i < ndim; ++i) s.numel *= shape[i];
+  LC_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.p), static_cast<size_t>(s.numel) * 4));
+  LC_CHECK_CUDA(cudaMemcpyAsync(s.p, data, static_cast<size_t>(s.numel) * 4, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  auto it = D->staged.find(key);
+  if (it != D->staged.end()) cudaFree(it->second.p);
+  D->staged[key] = s;
+  return 0;
+}
+
+int lc_dcae_finalize(lc_dcae* D, void* stream) {
+  LC_REQUIRE(D && !D->finalized, "finalize called twice or on null handle");
+  return finalize_impl(D, static_cast<cudaStream_t>(stream));
+}
+
+int lc_dcae_reserve(lc_dcae* D, int max_frames, int h, int w, void* stream) {
+  LC_REQUIRE(D && D->finalized, "reserve before finalize");
+  LC_REQUIRE(max_frames > 0 && h > 0 && w > 0 && w % 2 == 0, "bad decoder geometry (width must be even)");
+  const lc_dcae_cfg& c = D->cfg;
+  const int ns = c.n_stages;
+  size_t mx_x = 0, mx_y = 0, mx_pad = 0, mx_xb = 0, mx_qkv = 0, mx_att = 0, mx_hid = 0, mx_glu = 0;
+  // stage i (0 = highest resolution) has spatial size (h, w) << (ns-1-i)
+  for (int i = ns - 1; i >= 0; --i) {
+    const size_t H = static_cast<size_t>(h) << (ns - 1 - i), W = static_cast<size_t>(w) << (ns - 1 - i);
+    const size_t C = c.stage_channels[i], P = H * W;
+    mx_x = std::max(mx_x, P * C);
+    mx_y = std::max(mx_y, P * C);
+    mx_pad = std::max(mx_pad, (H + 2) * (W + 2) * static_cast<size_t>(r64(static_cast<int>(C))));
+    if (i < ns - 1) {  // up-block conv runs at the coarser resolution, producing 4*C channels
+      const size_t Hc = H / 2, Wc = W / 2, Cc = c.stage_channels[i + 1];
+      mx_y = std::max(mx_y, Hc * Wc * 4 * C);
+      mx_pad = std::max(mx_pad, (Hc + 2) * (Wc + 2) * static_cast<size_t>(r64(static_cast<int>(Cc))));
+    }
+    if (c.stage_is_evit[i] && c.stage_layers[i] > 0) {
+      const size_t inner = (C / c.head_dim) * c.head_dim;
+      mx_qkv = std::max(mx_qkv, P * 3 * inner);
+      mx_att = std::max(mx_att, P * 2 * inner);
+      mx_hid = std::max(mx_hid, P * 8 * C);
+      mx_glu = std::max(mx_glu, P * 4 * C);
+    }
+    mx_xb = std::max(mx_xb, P * C);
+  }
+  {
+    const size_t H = h, W = w;
+    mx_pad = std::max(mx_pad, (H + 2) * (W + 2) * static_cast<size_t>(r64(c.latent_channels)));
+  }
+  const size_t n = max_frames, e = D->esz;
+  LC_TRY(D->x.alloc(n * mx_x * 4)); LC_TRY(D->x2.alloc(n * mx_x * 4)); LC_TRY(D->y.alloc(n * mx_y * 4));
+  LC_TRY(D->padA.alloc(n * mx_pad * e)); LC_TRY(D->padB.alloc(n * mx_pad * e));
+  LC_TRY(D->xb.alloc(n * mx_xb * e));
+  LC_TRY(D->qkv.alloc(n * std::max<size_t>(mx_qkv, 1) * 4)); LC_TRY(D->ms1.alloc(n * std::max<size_t>(mx_qkv, 1) * 4));
+  LC_TRY(D->ms.alloc(n * std::max<size_t>(mx_qkv, 1) * 4));
+  LC_TRY(D->att.alloc(n * std::max<size_t>(mx_att, 1) * e)); LC_TRY(D->hid.alloc(n * std::max<size_t>(mx_hid, 1) * e));
+  LC_TRY(D->glu.alloc(n * std::max<size_t>(mx_glu, 1) * e));
+  // padB's channel padding is never written by a conv epilogue: keep it zero
+  LC_CHECK_CUDA(cudaMemsetAsync(D->padB.p, 0, D->padB.bytes, static_cast<cudaStream_t>(stream)));
+  D->max_frames = max_frames; D->h0 = h; D->w0 = w;
+  return 0;
+}
+
+int lc_dcae_decode(lc_dcae* D, const float* z, int n, int h, int w, float* out, int keep_channels, const float* mean,
+                   const float* stdv, void* stream) {
+  LC_REQUIRE(D && D->max_frames > 0, "decode before reserve");
+  LC_REQUIRE(n > 0 && n <= D->max_frames && h == D->h0 && w == D->w0, "decode geometry differs from lc_dcae_reserve");
+  LC_REQUIRE(z && out, "null argument");
+  LC_REQUIRE(keep_channels > 0 && keep_channels <= D->cfg.out_channels, "keep_channels out of range");
+  LC_REQUIRE((mean == nullptr) == (stdv == nullptr), "mean and std must be given together");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // the halo/channel padding of padB must be zero where conv epilogues do not write; re-zero is not needed between
+  // calls because epilogues only ever write real channels and halo_fill rewrites the halo.
+  if (D->f32) {
+    Run<float> r;
+    r.D = D; r.st = st; r.n = n;
+    return r.decode(z, h, w, out, keep_channels, mean, stdv);
+  }
+  Run<bf16> r;
+  r.D = D; r.st = st; r.n = n;
+  return r.decode(z, h, w, out, keep_channels, mean, stdv);
+}
+
+// Test export: one 3x3 sphere convolution (+bias, act) NCHW f32 -> NCHW f32 through the implicit-GEMM path.
+int lc_sphere_conv3x3(int precision, const float* x, const float* w, const float* bias, float* out, int n, int cin, int H,
+                      int W, int cout, int act, void* stream) {
+  LC_REQUIRE(x && w && out, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool f32 = precision == LC_PRECISION_F32;
+  const size_t e = f32 ? 4 : 2;
+  const int cp = r64(cin);
+  void *xpad = nullptr, *wm = nullptr;
+  LC_CHECK_CUDA(cudaMalloc(&xpad, static_cast<size_t>(n) * (H + 2) * (W + 2) * cp * e));
+  LC_CHECK_CUDA(cudaMalloc(&wm, static_cast<size_t>(cout) * 9 * cp * e));
+  const long long nw = static_cast<long long>(cout) * 9 * cp;
+  pack_conv_kernel<<<static_cast<unsigned>((nw + 255) / 256), 256, 0, st>>>(w, cout, cin, cp, wm, f32 ? 0 : 1);
+  EpiParams ep;
+  ep.mode = EPI_UNPATCHIFY; ep.act = act; ep.bias = bias; ep.out = out; ep.rows_per_sample = H * W; ep.n_valid = cout;
+  int rc;
+  if (f32) {
+    rc = pad_from_nchw<float>(x, reinterpret_cast<float*>(xpad), n, cin, H, W, cp, st);
+    if (rc == 0) rc = conv3x3_f32(reinterpret_cast<float*>(xpad), n, H, W, cp, reinterpret_cast<float*>(wm), cout, ep, st);
+  } else {
+    rc = pad_from_nchw<bf16>(x, reinterpret_cast<bf16*>(xpad), n, cin, H, W, cp, st);
+    if (rc == 0) rc = conv3x3_bf16(xpad, n, H, W, cp, wm, cout, ep, st);
+  }
+  cudaStreamSynchronize(st);
+  cudaFree(xpad);
+  cudaFree(wm);
+  return rc;
+}
+
+}  // extern "C"

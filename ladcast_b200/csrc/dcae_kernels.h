@@ -1,0 +1,30 @@
+// Launch functions of the DC-AE decoder's non-GEMM kernels (NHWC internal layout).
+#pragma once
+#include "common.cuh"
+
+namespace lc {
+template <typename T>
+int pad_from_nchw(const float* z, T* out, int n, int C, int H, int W, int Cp, cudaStream_t s);
+template <typename T>
+int pad_from_nhwc(const float* x, T* out, int n, int C, int H, int W, int Cp, cudaStream_t s);
+template <typename T>
+int halo_fill(T* buf, int n, int H, int W, int Cp, cudaStream_t s);
+int dwconv5(const float* in, const float* w, float* out, int n, int H, int W, int C, cudaStream_t s);
+template <typename T>
+int dwconv3_glu(const T* in, const float* w, const float* bias, T* out, int n, int H, int W, int C, cudaStream_t s);
+int grouped1x1(const float* in, const float* w, float* out, long long P, int C, cudaStream_t s);
+template <typename T>
+int linear_attention(const float* qkv, const float* ms, T* out, int n, int HW, int heads, float eps, cudaStream_t s);
+template <typename T>
+int rmsnorm_rows(const float* y, const float* w, const float* b, float eps, float* resid, float* out_f32, T* out_t,
+                 long long P, int C, int relu, cudaStream_t s);
+template <typename T>
+int pixel_shuffle_shortcut(const float* conv, const float* xin, float* out, T* out_t, int n, int H, int W, int Cin,
+                           int Cout, cudaStream_t s);
+template <typename T>
+int in_shortcut(float* x, T* x_t, const float* z, int n, int HW, int C, int Cz, cudaStream_t s);
+
+// fp32 SIMT implicit 3x3 sphere conv on a padded NHWC f32 buffer (validation mode)
+int conv3x3_f32(const float* xpad, int n_frames, int H, int W, int Cp, const float* wmat, int C_out,
+                const EpiParams& epi, cudaStream_t stream);
+}  // namespace lc

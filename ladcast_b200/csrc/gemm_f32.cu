@@ -1,6 +1,7 @@
 // FP32 SIMT GEMM — the "FP32 validation mode" of the denoiser/decoder (north star: rel-L2 <= 1e-4 vs the oracle).
 // Same problem statement and epilogues as the tensor-core GEMM (common.cuh), plain shared-memory tiling.
 #include "common.cuh"
+#include "dcae_kernels.h"
 
 namespace lc {
 namespace {
@@ -30,16 +31,21 @@ __device__ __forceinline__ void epi_one(const EpiParams& ep, float v, int row, i
     case EPI_UNPATCHIFY:
       if (n < ep.n_valid) {
         const int r_in = row - sample * ep.rows_per_sample;
+        if (ep.ch_scale != nullptr) v = v * __ldg(ep.ch_scale + n) + __ldg(ep.ch_shift + n);
         reinterpret_cast<float*>(ep.out)[(static_cast<long long>(sample) * ep.n_valid + n) * ep.rows_per_sample + r_in] = v;
       }
       break;
   }
 }
 
+struct ConvF32 {
+  int enabled = 0, H = 0, W = 0, Cp = 0;
+};
+
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A0, long long lda0, int K0,
                                                        const float* __restrict__ A1, long long lda1,
                                                        const float* __restrict__ W, long long ldw, int M, int N, int K,
-                                                       EpiParams ep) {
+                                                       EpiParams ep, ConvF32 cv) {
   __shared__ float As[TK][TM + 4];
   __shared__ float Ws[TK][TN + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -51,7 +57,19 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
       const int r = i / TK, c = i % TK;
       const int gr = m0 + r, gk = k0 + c;
       float v = 0.f;
-      if (gr < M && gk < K) v = (gk < K0) ? A0[gr * lda0 + gk] : A1[gr * lda1 + (gk - K0)];
+      if (gr < M && gk < K) {
+        if (!cv.enabled) {
+          v = (gk < K0) ? A0[gr * lda0 + gk] : A1[gr * lda1 + (gk - K0)];
+        } else {
+          // implicit 3x3 sphere conv: row -> (frame, y, x); k -> (tap, channel); pole rows mirror the pad kernel row
+          const int x = gr % cv.W, y = (gr / cv.W) % cv.H, f = gr / (cv.W * cv.H);
+          const int tap = gk / cv.Cp, ch = gk - tap * cv.Cp;
+          const int ky = tap / 3;
+          int kx = tap - ky * 3;
+          if ((y == 0 && ky == 0) || (y == cv.H - 1 && ky == 2)) kx = 2 - kx;
+          v = A0[((static_cast<long long>(f) * (cv.H + 2) + y + ky) * (cv.W + 2) + x + kx) * cv.Cp + ch];
+        }
+      }
       As[c][r] = v;
       const int gn = n0 + r;
       Ws[c][r] = (gn < N && gk < K) ? W[gn * ldw + gk] : 0.f;
@@ -91,7 +109,19 @@ int gemm_f32(const GemmArgs& g, cudaStream_t stream) {
   dim3 grid(ceil_div(g.N, TN), ceil_div(g.M, TM));
   gemm_f32_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(g.A0), g.lda0, K0,
                                             reinterpret_cast<const float*>(g.A1), g.lda1,
-                                            reinterpret_cast<const float*>(g.W), g.ldw, g.M, g.N, g.K, g.epi);
+                                            reinterpret_cast<const float*>(g.W), g.ldw, g.M, g.N, g.K, g.epi,
+                                            ConvF32());
+  LC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int conv3x3_f32(const float* xpad, int n_frames, int H, int W, int Cp, const float* wmat, int C_out,
+                const EpiParams& epi, cudaStream_t stream) {
+  ConvF32 cv;
+  cv.enabled = 1; cv.H = H; cv.W = W; cv.Cp = Cp;
+  const int M = n_frames * H * W, K = 9 * Cp;
+  dim3 grid(ceil_div(C_out, TN), ceil_div(M, TM));
+  gemm_f32_kernel<<<grid, 256, 0, stream>>>(xpad, 0, K, nullptr, 0, wmat, K, M, C_out, K, epi, cv);
   LC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

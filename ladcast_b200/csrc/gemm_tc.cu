@@ -151,7 +151,11 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, const uint32
                   (static_cast<long long>(sample) * ep.n_valid + n0) * ep.rows_per_sample + r_in;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (n0 + j < ep.n_valid) op[static_cast<long long>(j) * ep.rows_per_sample] = v[j];
+        if (n0 + j < ep.n_valid) {
+          float o = v[j];
+          if (ep.ch_scale != nullptr) o = o * __ldg(ep.ch_scale + n0 + j) + __ldg(ep.ch_shift + n0 + j);
+          op[static_cast<long long>(j) * ep.rows_per_sample] = o;
+        }
       break;
     }
   }

@@ -1,0 +1,100 @@
+"""GPU parity of the DC-AE decoder path (sphere conv implicit GEMM, decoder handle, decode_latent_ens)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from ladcast_b200 import _lib
+from oracle import ladcast_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _seeded(shape, seed, scale=1.0):
+    return torch.randn(shape, generator=torch.Generator("cpu").manual_seed(seed)) * scale
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("n,cin,H,W,cout", [(3, 64, 5, 8, 48), (2, 84, 15, 30, 1008), (5, 168, 15, 30, 96),
+                                            (3, 40, 30, 60, 300), (1, 252, 120, 240, 252), (2, 100, 60, 120, 89)])
+@pytest.mark.parametrize("prec", ["f32", "bf16"])
+def test_sphere_conv3x3(n, cin, H, W, cout, prec):
+    lib = _lib.load()
+    x = _seeded((n, cin, H, W), 1 + cin)
+    w = O.det_tensor("t.weight", (cout, cin, 3, 3), cin)
+    b = O.det_tensor("t.bias", (cout,), cin)
+    if prec == "bf16":
+        xr, wr, tol = x.bfloat16().float(), w.bfloat16().float(), 1e-4
+    else:
+        xr, wr, tol = x, w, 1e-5
+    want = torch.nn.functional.silu(O.sphere_conv(xr.double(), wr.double(), b.double()))
+    out = torch.full((n, cout, H, W), float("nan"), device="cuda")
+    _lib.check(lib.lc_sphere_conv3x3(_lib.PRECISION_F32 if prec == "f32" else _lib.PRECISION_BF16, _lib.ptr(x.cuda()),
+                                     _lib.ptr(w.cuda()), _lib.ptr(b.cuda()), _lib.ptr(out), n, cin, H, W, cout, 2,
+                                     _lib.stream()), "lc_sphere_conv3x3")
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert _rel(out, want) < tol
+
+
+def _ae(name, salt, precision):
+    from ladcast_b200.models import AutoencoderDC
+
+    cfg = O.dcae_config(name) if isinstance(name, str) else name
+    sd = O.make_state_dict(O.dcae_decoder_param_shapes(cfg), salt)
+    ae = AutoencoderDC(**cfg)
+    ae.load_state_dict(sd, strict=True)
+    return cfg, sd, ae.to("cuda").set_precision(precision)
+
+
+def test_dcae_tiny_vs_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "dcae_tiny.npz"))
+    cfg, sd, ae = _ae("tiny", int(g["salt"]), "fp32")
+    out = ae.decode(_seeded((2, 84, 5, 8), 103).cuda()).sample
+    torch.cuda.synchronize()
+    assert out.shape == (2, 84, 40, 64)
+    assert _rel(out[:, ::7], g["out_sub"]) < 1e-4
+    assert np.allclose(out.double().sum(dim=(0, 2, 3)).cpu().numpy(), g["ch_sum"], rtol=1e-3, atol=5e-2)
+    from ladcast_b200.pipelines.utils import decode_latent_ens
+
+    mean, std = _seeded((84,), 105), _seeded((84,), 106).abs() + 0.5
+    ens = decode_latent_ens(ae, _seeded((1, 84, 2, 5, 8), 104).cuda(), mean, std)
+    assert ens.shape == (1, 84, 2, 40, 64)
+    assert _rel(ens[:, ::7], g["ens_sub"]) < 1e-4
+
+
+SMALL = O.dcae_config("tiny", decoder_block_out_channels=[168, 168, 168, 336])
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_dcae_small_vs_oracle(precision, tol):
+    cfg, sd, ae = _ae(SMALL, 22, precision)
+    z = _seeded((3, 84, 15, 30), 500)
+    taps = {}
+    want = O.dcae_decode(sd, cfg, z, taps=taps)
+    out = ae.decode(z.cuda()).sample
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    r = _rel(out, want)
+    print("dcae small", precision, "rel-L2", r)
+    assert r < tol
+
+
+def test_dcae_full_bf16_vs_oracle():
+    """V0.1.X decoder architecture (143.2 M parameters), one frame, bf16 tensor-core path vs the fp32 oracle."""
+    cfg, sd, ae = _ae("V0.1.X", 23, "bf16")
+    z = _seeded((1, 84, 15, 30), 600)
+    want = O.dcae_decode(sd, cfg, z)
+    mean, std = _seeded((84,), 105), _seeded((84,), 106).abs() + 0.5
+    out = ae.decode(z.cuda()).sample
+    fused = ae.decode_fused(z.cuda(), mean, std)
+    torch.cuda.synchronize()
+    r = _rel(out, want)
+    print("dcae full bf16 rel-L2", r)
+    assert r < 2e-2
+    assert _rel(fused, want * std[None, :, None, None] + mean[None, :, None, None]) < 2e-2
