@@ -318,7 +318,8 @@ int lc_dcae_create(const lc_dcae_cfg* cfg, lc_dcae** out) {
   LC_REQUIRE(cfg->out_channels > 0 && cfg->out_channels <= 128, "decoder out_channels must be <= 128");
   if (cfg->precision == LC_PRECISION_BF16)
     for (int i = 0; i < cfg->n_stages; ++i)
-      LC_REQUIRE(cfg->stage_channels[i] % 8 == 0, "bf16 decoder needs stage channels divisible by 8 (TMA 16-byte pitch)");
+      LC_REQUIRE(!cfg->stage_is_evit[i] || cfg->stage_layers[i] == 0 || cfg->stage_channels[i] % 8 == 0,
+                 "bf16 decoder needs EfficientViT stage channels divisible by 8 (TMA 16-byte row pitch)");
   for (int i = 0; i < cfg->n_stages; ++i) LC_REQUIRE(cfg->stage_channels[i] % 4 == 0, "stage channels must be multiples of 4");
   LC_REQUIRE(cfg->stage_channels[cfg->n_stages - 1] % cfg->latent_channels == 0, "in_shortcut needs C_top divisible by latent_channels");
   lc_dcae* D = new lc_dcae();

@@ -52,7 +52,7 @@ def dcae_config(name: str = "V0.1.X", **over) -> dict:
         decoder_qkv_multiscales=[[], [], [5], [5]], static_channels=5,
     )
     if name == "tiny":  # test-only: same topology, 1 layer per stage, narrow channels
-        cfg.update(decoder_block_out_channels=[42, 84, 84, 168], decoder_layers_per_block=[1, 1, 1, 1])
+        cfg.update(decoder_block_out_channels=[84, 168, 168, 336], decoder_layers_per_block=[1, 1, 1, 1])
     elif name != "V0.1.X":
         raise ValueError(name)
     cfg.update(over)

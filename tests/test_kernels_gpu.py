@@ -82,7 +82,8 @@ def test_dpmpp2m_step(lib):
     xin = torch.empty_like(x)
     for i in range(6):
         c = dpmpp2m_coefficients(6, i)
-        _lib.check(lib.lc_sched_dpmpp2m_step(_lib.ptr(fs[i].cuda()), _lib.ptr(x), _lib.ptr(x0p), _lib.ptr(xin), x.numel(),
+        fd = fs[i].cuda()
+        _lib.check(lib.lc_sched_dpmpp2m_step(_lib.ptr(fd), _lib.ptr(x), _lib.ptr(x0p), _lib.ptr(xin), x.numel(),
                                              c["c_skip"], c["c_out"], c["a_x"], c["a_x0"], c["a_d"], c["c_in_next"],
                                              _lib.stream()), "sched")
     torch.cuda.synchronize()
