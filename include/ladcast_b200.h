@@ -34,6 +34,13 @@ extern "C" {
 
 LC_API int lc_version(void);
 LC_API const char* lc_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+LC_API long long lc_launch_count(void);
+/* bench instrumentation: bracket every tensor-core launch (class 0 GEMM, 1 attention, 2 sphere-conv) with CUDA
+ * events on its stream; lc_prof_collect sums per-class milliseconds, algorithmic FLOPs and launch counts (arrays of
+ * 3) and synchronises on the recorded events. */
+LC_API int lc_prof_enable(int on);
+LC_API int lc_prof_collect(double* ms, double* flops, long long* launches);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Denoiser — replaces LaDCastTransformer3DModel.__init__/forward (models/LaDCast_3D_model.py:624-650, 833-1071)

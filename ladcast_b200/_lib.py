@@ -38,6 +38,9 @@ _vp, _i, _i64, _f, _d, _cp = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, cty
 _SIGNATURES = {
     "lc_version": ([], _i),
     "lc_last_error": ([], _cp),
+    "lc_launch_count": ([], ctypes.c_longlong),
+    "lc_prof_enable": ([_i], _i),
+    "lc_prof_collect": ([ctypes.POINTER(_d), ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_longlong)], _i),
     "lc_denoiser_create": ([ctypes.POINTER(DenoiserCfg), ctypes.POINTER(_vp)], _i),
     "lc_denoiser_destroy": ([_vp], None),
     "lc_denoiser_load": ([_vp, _cp, _vp, ctypes.POINTER(_i64), _i, _vp], _i),

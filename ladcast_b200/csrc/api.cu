@@ -4,10 +4,38 @@
 #include "../../include/ladcast_b200.h"
 #include "kernels.h"
 
+#include <atomic>
+#include <vector>
+
 namespace lc {
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 const char* last_error() { return g_err.c_str(); }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct ProfRec { cudaEvent_t a, b; int cls; double flops; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static cudaEvent_t g_pending[PROF_NUM];
+void prof_begin(int cls, cudaStream_t s) {
+  if (!g_prof_on) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, s);
+  g_pending[cls] = e;
+}
+void prof_end(int cls, double flops, cudaStream_t s) {
+  if (!g_prof_on) return;
+  ProfRec r;
+  r.a = g_pending[cls];
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.b, s);
+  r.cls = cls;
+  r.flops = flops;
+  g_prof.push_back(r);
+}
 }  // namespace lc
 
 using namespace lc;
@@ -15,6 +43,29 @@ using namespace lc;
 extern "C" {
 
 int lc_version(void) { return 100; }
+
+long long lc_launch_count(void) { return lc::g_launches.load(); }
+
+int lc_prof_enable(int on) {
+  for (auto& r : lc::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  lc::g_prof.clear();
+  lc::g_prof_on = on != 0;
+  return 0;
+}
+
+int lc_prof_collect(double* ms, double* flops, long long* launches) {
+  LC_REQUIRE(ms && flops && launches, "null argument");
+  for (int i = 0; i < PROF_NUM; ++i) { ms[i] = 0; flops[i] = 0; launches[i] = 0; }
+  for (auto& r : lc::g_prof) {
+    LC_CHECK_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    LC_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.cls] += t;
+    flops[r.cls] += r.flops;
+    launches[r.cls] += 1;
+  }
+  return 0;
+}
 const char* lc_last_error(void) { return lc::last_error(); }
 
 int lc_sched_dpmpp2m_step(const float* f, float* x, float* x0_prev, float* x_in_next, int64_t n, float c_skip,

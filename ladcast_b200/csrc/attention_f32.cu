@@ -113,7 +113,7 @@ int attention_f32(const float* qkv, int B, int S, int heads, int head_dim, float
   LC_REQUIRE(head_dim == HD, "attention: head_dim must be 128");
   dim3 grid(ceil_div(S, BQ), heads, B);
   attention_f32_kernel<<<grid, 128, 0, s>>>(qkv, S, heads, out_p, Np, out_c);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 

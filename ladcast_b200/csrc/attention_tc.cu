@@ -264,8 +264,10 @@ int attention_bf16(const bf16* qkv, int B, int S, int heads, int head_dim, bf16*
   LC_TRY(make_tmap_2d_bf16(&tm, qkv, static_cast<uint64_t>(3) * d, static_cast<uint64_t>(B) * S,
                            static_cast<uint64_t>(3) * d * 2, 64, 128));
   dim3 grid(ceil_div(S, BQ), heads, B);
+  prof_begin(PROF_ATTN, s);
   attention_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(tm, S, heads, out_p, Np, out_c);
-  LC_CHECK_CUDA(cudaGetLastError());
+  prof_end(PROF_ATTN, 4.0 * B * heads * static_cast<double>(S) * S * HD, s);
+  LC_LAUNCH_CHECK();
   return 0;
 }
 

@@ -32,6 +32,14 @@ const char* last_error();
     }                                                                                       \
   } while (0)
 
+// every kernel launch in the library is followed by exactly one LC_LAUNCH_CHECK(): error check + launch counter
+void count_launch();
+#define LC_LAUNCH_CHECK()              \
+  do {                                 \
+    ::lc::count_launch();              \
+    LC_CHECK_CUDA(cudaGetLastError()); \
+  } while (0)
+
 #define LC_TRY(expr)          \
   do {                        \
     int _r = (expr);          \
@@ -136,5 +144,12 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 
 int num_sms();
+
+// ---------------------------------------------------------------- lightweight per-class kernel timing (bench only)
+// When enabled, tensor-core launches are bracketed with CUDA events on their stream; durations and algorithmic
+// FLOPs are accumulated per class at collect time.  Disabled by default (zero overhead: one branch per launch).
+enum ProfClass { PROF_GEMM = 0, PROF_ATTN = 1, PROF_CONV = 2, PROF_NUM = 3 };
+void prof_begin(int cls, cudaStream_t s);
+void prof_end(int cls, double flops, cudaStream_t s);
 
 }  // namespace lc

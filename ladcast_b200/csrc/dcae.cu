@@ -115,7 +115,7 @@ int make_conv(lc_dcae* D, const std::string& name, int cout_full, int cin, bool 
   LC_CHECK_CUDA(cudaMalloc(&W->w, static_cast<size_t>(n) * D->esz));
   D->owned.push_back(W->w);
   pack_conv_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(w->p, cout, cin, W->cp, W->w, D->f32 ? 0 : 1);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   if (bias) LC_TRY(fvec(D, name + ".bias", cout_full, &W->bias, st, cout));
   return 0;
 }
@@ -135,7 +135,7 @@ int make_mat(lc_dcae* D, const std::vector<std::string>& names, int in, bool bia
   long long off = 0;
   for (const St* w : ws) {
     pack_mat_kernel<<<static_cast<unsigned>((w->numel + 255) / 256), 256, 0, st>>>(w->p, w->numel, M->w, off, D->f32 ? 0 : 1);
-    LC_CHECK_CUDA(cudaGetLastError());
+    LC_LAUNCH_CHECK();
     off += w->numel;
   }
   if (bias) {
@@ -153,7 +153,7 @@ struct Run {
   bool xb_valid = false;  // xb == T(x)?
 
   int conv(const T* xpad, int H, int W, const ConvW& cw, const EpiParams& ep) const {
-    if (sizeof(T) == 2) return conv3x3_bf16(xpad, n, H, W, cw.cp, cw.w, cw.cout, ep, st);
+    if (sizeof(T) == 2) return conv3x3_bf16(xpad, n, H, W, cw.cp, cw.w, cw.cout, ep, st, cw.cin);
     return conv3x3_f32(reinterpret_cast<const float*>(xpad), n, H, W, cw.cp, reinterpret_cast<const float*>(cw.w), cw.cout, ep, st);
   }
   int gemm(const void* A, long long lda, long long M, const MatW& mw, void* out, bool out_f32, int act) const {

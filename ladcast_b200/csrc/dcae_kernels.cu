@@ -308,7 +308,7 @@ template <typename T>
 int pad_from_nchw(const float* z, T* out, int n, int C, int H, int W, int Cp, cudaStream_t s) {
   const long long total = static_cast<long long>(n) * (H + 2) * (W + 2) * Cp;
   pad_from_nchw_kernel<T><<<blocks(total), 256, 0, s>>>(z, out, n, C, H, W, Cp);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 template <typename T>
@@ -316,7 +316,7 @@ int pad_from_nhwc(const float* x, T* out, int n, int C, int H, int W, int Cp, cu
   LC_REQUIRE(C % 4 == 0 && Cp % 4 == 0, "pad: channels must be multiples of 4");
   const long long total = static_cast<long long>(n) * (H + 2) * (W + 2) * (Cp / 4);
   pad_from_nhwc_kernel<T><<<blocks(total), 256, 0, s>>>(x, out, n, C, H, W, Cp);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 template <typename T>
@@ -324,32 +324,32 @@ int halo_fill(T* buf, int n, int H, int W, int Cp, cudaStream_t s) {
   LC_REQUIRE(Cp % 8 == 0, "halo_fill: Cp must be a multiple of 8");
   const long long total = static_cast<long long>(n) * (2 * (W + 2) + 2 * H) * (Cp / 8);
   halo_fill_kernel<T><<<blocks(total), 256, 0, s>>>(buf, n, H, W, Cp);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 int dwconv5(const float* in, const float* w, float* out, int n, int H, int W, int C, cudaStream_t s) {
   const long long total = static_cast<long long>(n) * H * W * C;
   dwconv_kernel<float, float, 5, false><<<blocks(total), 256, 0, s>>>(in, w, nullptr, out, n, H, W, C);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 template <typename T>
 int dwconv3_glu(const T* in, const float* w, const float* bias, T* out, int n, int H, int W, int C, cudaStream_t s) {
   const long long total = static_cast<long long>(n) * H * W * (C / 2);
   dwconv_kernel<T, T, 3, true><<<blocks(total), 256, 0, s>>>(in, w, bias, out, n, H, W, C);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 int grouped1x1(const float* in, const float* w, float* out, long long P, int C, cudaStream_t s) {
   LC_REQUIRE(C % 32 == 0, "grouped 1x1: channels must be a multiple of 32");
   grouped1x1_kernel<<<blocks(P * C), 256, 0, s>>>(in, w, out, P, C);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 template <typename T>
 int linear_attention(const float* qkv, const float* ms, T* out, int n, int HW, int heads, float eps, cudaStream_t s) {
   linear_attn_kernel<T><<<n * 2 * heads, 256, 0, s>>>(qkv, ms, out, HW, heads, eps);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 template <typename T>
@@ -357,7 +357,7 @@ int rmsnorm_rows(const float* y, const float* w, const float* b, float eps, floa
                  long long P, int C, int relu, cudaStream_t s) {
   LC_REQUIRE(C % 4 == 0, "rmsnorm: C must be a multiple of 4");
   rmsnorm_rows_kernel<T><<<blocks(P, 8), 256, 0, s>>>(y, w, b, eps, resid, out_f32, out_t, P, C, relu);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 template <typename T>
@@ -365,14 +365,14 @@ int pixel_shuffle_shortcut(const float* conv, const float* xin, float* out, T* o
                            int Cout, cudaStream_t s) {
   const long long total = static_cast<long long>(n) * 4 * H * W * Cout;
   pixel_shuffle_kernel<T><<<blocks(total), 256, 0, s>>>(conv, xin, out, out_t, n, H, W, Cin, Cout, 4 * Cout / Cin);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 template <typename T>
 int in_shortcut(float* x, T* x_t, const float* z, int n, int HW, int C, int Cz, cudaStream_t s) {
   const long long total = static_cast<long long>(n) * HW * C;
   in_shortcut_kernel<T><<<blocks(total), 256, 0, s>>>(x, x_t, z, n, HW, C, Cz, C / Cz);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 

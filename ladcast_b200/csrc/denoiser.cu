@@ -145,7 +145,7 @@ int make_lin(lc_denoiser* D, const std::vector<std::string>& names, int in, int 
     const long long n = static_cast<long long>(rows) * ldw;
     pack_rows_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, st>>>(ws[i]->p, rows, in, wbuf, ldw, off,
                                                                                D->f32 ? 0 : 1);
-    LC_CHECK_CUDA(cudaGetLastError());
+    LC_LAUNCH_CHECK();
     if (has_bias) {
       LC_REQUIRE(bs[i]->numel == rows, "bias shape mismatch for '" + names[i] + "'");
       LC_CHECK_CUDA(cudaMemcpyAsync(L->bias + off, bs[i]->p, static_cast<size_t>(rows) * 4, cudaMemcpyDeviceToDevice, st));

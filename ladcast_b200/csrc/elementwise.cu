@@ -284,7 +284,7 @@ int layernorm_modulate(const float* x, T* out, int M, int d, float eps, int rows
     LC_LN_CASE(16)
   }
 #undef LC_LN_CASE
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 
@@ -297,7 +297,7 @@ int qk_norm_rope(T* qkv, long long ld, int B, int S, int heads, int head_dim, fl
   RopeSeg s1 = nseg > 1 ? segs[1] : segs[0];
   qk_norm_rope_kernel<T><<<static_cast<unsigned>(ceil_div_ll(total, 8)), 256, 0, s>>>(qkv, ld, B, S, heads, eps, segs[0],
                                                                                      s1, nseg);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 
@@ -305,14 +305,14 @@ template <typename T>
 int patchify(const float* x, T* out, int B, int C, int THW, int Kp, cudaStream_t s) {
   dim3 grid(ceil_div(THW, 32), ceil_div(Kp, 32), B);
   patchify_kernel<T><<<grid, 256, 0, s>>>(x, out, C, THW, Kp);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 
 template <typename T>
 int timestep_embed(const float* t, int n_t, int B, T* out, cudaStream_t s) {
   timestep_embed_kernel<T><<<ceil_div(B * 128, 128), 128, 0, s>>>(t, n_t, B, out);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 
@@ -320,7 +320,7 @@ template <typename T>
 int token_mean(const float* x, int B, int N, int d, T* out, cudaStream_t s) {
   dim3 grid(ceil_div(d, 128), B);
   token_mean_kernel<T><<<grid, 256, 0, s>>>(x, N, d, out);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 
@@ -330,7 +330,7 @@ int gated_add(float* h, const T* a, const float* gate, long long gate_stride, in
   const long long n4 = static_cast<long long>(M) * d / 4;
   gated_add_kernel<T><<<static_cast<unsigned>(ceil_div_ll(n4, 256)), 256, 0, s>>>(h, a, gate, gate_stride, n4, d,
                                                                                 rows_per_sample);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 
@@ -338,14 +338,14 @@ template <typename T>
 int temb_combine(const float* a, const float* b, const float* sc, const float* sh, long long sc_stride, int B, int d,
                  float* out_f32, T* out_silu, cudaStream_t s) {
   temb_combine_kernel<T><<<ceil_div(B * d, 256), 256, 0, s>>>(a, b, sc, sh, sc_stride, B, d, out_f32, out_silu);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 
 template <typename T>
 int cast_rows(const float* x, T* out, long long n, cudaStream_t s) {
   cast_kernel<T><<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s>>>(x, out, n);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 
@@ -354,7 +354,7 @@ int sched_dpmpp2m_step(const float* f, float* x, float* x0_prev, float* x_in_nex
   LC_REQUIRE(n % 4 == 0, "scheduler: element count must be a multiple of 4");
   const long long n4 = n / 4;
   dpmpp2m_kernel<<<static_cast<unsigned>(ceil_div_ll(n4, 256)), 256, 0, s>>>(f, x, x0_prev, x_in_next, n4, c);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 
@@ -362,7 +362,7 @@ int sched_heun_step(const float* f, double* x, double* x_hat, double* d_cur, flo
                     double t_cur, double t_next, double c_skip, double c_out, double c_in_next, cudaStream_t s) {
   heun_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s>>>(f, x, x_hat, d_cur, x_in_next, n, phase, t_cur,
                                                                        t_next, c_skip, c_out, c_in_next);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 

@@ -111,7 +111,7 @@ int gemm_f32(const GemmArgs& g, cudaStream_t stream) {
                                             reinterpret_cast<const float*>(g.A1), g.lda1,
                                             reinterpret_cast<const float*>(g.W), g.ldw, g.M, g.N, g.K, g.epi,
                                             ConvF32());
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 
@@ -122,7 +122,7 @@ int conv3x3_f32(const float* xpad, int n_frames, int H, int W, int Cp, const flo
   const int M = n_frames * H * W, K = 9 * Cp;
   dim3 grid(ceil_div(C_out, TN), ceil_div(M, TM));
   gemm_f32_kernel<<<grid, 256, 0, stream>>>(xpad, 0, K, nullptr, 0, wmat, K, M, C_out, K, epi, cv);
-  LC_CHECK_CUDA(cudaGetLastError());
+  LC_LAUNCH_CHECK();
   return 0;
 }
 

@@ -337,8 +337,12 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, i
   sched.group_m = 8;
   const int tiles = sched.num_m * sched.num_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  const int cls = cv.enabled ? PROF_CONV : PROF_GEMM;
+  const double flops = 2.0 * M * N * (cv.enabled ? 9.0 * cv.c_real : static_cast<double>(K));
+  prof_begin(cls, stream);
   gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM, stream>>>(a0, a1, w, M, N, K, K0, ep, sched, cv);
-  LC_CHECK_CUDA(cudaGetLastError());
+  prof_end(cls, flops, stream);
+  LC_LAUNCH_CHECK();
   return 0;
 }
 
@@ -381,7 +385,7 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
 // multiple of 64), wmat: [C_out, 9*Cp] bf16 (tap-major: k = (ky*3+kx)*Cp + c).  Output rows are pixels
 // (f*H + y)*W + x, columns are output channels; epilogue as for GEMMs.
 int conv3x3_bf16(const void* xpad, int n_frames, int H, int W, int Cp, const void* wmat, int C_out,
-                 const EpiParams& epi, cudaStream_t stream) {
+                 const EpiParams& epi, cudaStream_t stream, int c_real) {
   LC_REQUIRE(Cp % BK == 0, "conv input channels must be padded to a multiple of 64");
   ConvLoad cv;
   cv.enabled = 1;
@@ -394,6 +398,7 @@ int conv3x3_bf16(const void* xpad, int n_frames, int H, int W, int Cp, const voi
   cv.tiles_x = ceil_div(W, cv.Wt);
   cv.kb_per_tap = Cp / BK;
   cv.a_bytes = BK * 2 * cv.Wt * cv.Nt;
+  cv.c_real = c_real > 0 ? c_real : Cp;
   const int frame_groups = ceil_div(n_frames, cv.Nt);
   const int m_tiles = frame_groups * H * cv.tiles_x;
   const int M = n_frames * H * W;

@@ -12,9 +12,10 @@ struct ConvLoad {
   int tiles_x = 0;      // ceil(W / Wt)
   int kb_per_tap = 0;   // Cp / 64
   int a_bytes = 0;      // bytes one A box delivers (64*2*Wt*Nt)
+  int c_real = 0;       // un-padded input channels (algorithmic FLOP count only)
 };
 
 int conv3x3_bf16(const void* xpad, int n_frames, int H, int W, int Cp, const void* wmat, int C_out,
-                 const EpiParams& epi, cudaStream_t stream);
+                 const EpiParams& epi, cudaStream_t stream, int c_real = 0);
 
 }  // namespace lc

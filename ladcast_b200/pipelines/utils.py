@@ -97,3 +97,67 @@ def decode_latent_ens(encdec_model, latents: torch.Tensor, mean_tensor: Optional
             y = y * std_tensor.to(y.device)[None, :, None, None] + mean_tensor.to(y.device)[None, :, None, None]
     y = y.reshape(B, extract_first, *y.shape[1:]).permute(0, 2, 1, 3, 4)
     return y
+
+
+def advance_timestamp(stamp: int, hours: int) -> int:
+    """YYYYMMDDHH + hours -> YYYYMMDDHH (roll_out_serial's `current_time + Timedelta(...)`, pipelines/utils.py:538-541)."""
+    from datetime import datetime, timedelta
+
+    s = str(int(stamp))
+    t = datetime(int(s[:4]), int(s[4:6]), int(s[6:8]), int(s[8:10])) + timedelta(hours=hours)
+    return int(t.strftime("%Y%m%d%H"))
+
+
+@torch.no_grad()
+def roll_out_latent(pipeline, encdec_model, known_latents: torch.Tensor, init_timestamp: int, ensemble_size: int,
+                    latent_mean: torch.Tensor, latent_std: torch.Tensor, field_mean: Optional[torch.Tensor] = None,
+                    field_std: Optional[torch.Tensor] = None, num_inference_steps: int = 20, return_seq_len: int = 4,
+                    total_lead_time_hour: int = 240, step_size_hour: int = 6, sampler_type: str = "pipeline",
+                    member_indices: Optional[Sequence[int]] = None, return_latent: bool = False, target_std: float = 0.5,
+                    out: Optional[torch.Tensor] = None, max_ar_steps: Optional[int] = None):
+    """Tensor-in / tensor-out core of `roll_out_serial` (reference pipelines/utils.py:533-654): the AR loop
+    [sample -> feed the last T_in frames back -> de-normalise -> decode] from already encoded, normalised
+    `known_latents` (1, C, T_in, h, w).  Returns a HOST tensor (ensemble, C, n_lead, H, W) of decoded fields in
+    physical units (or de-normalised latents when return_latent) for lead steps 1..n_lead; each AR step's result
+    is copied device->host asynchronously (pinned `out`), overlapping the next AR step.
+    `member_indices`: global member ids owned by this process (multi-GPU member sharding)."""
+    import math
+
+    dev = pipeline._execution_device
+    total = total_lead_time_hour // step_size_hour
+    if total_lead_time_hour % step_size_hour != 0:
+        raise ValueError("total_lead_time_hour must be divisible by step_size_hour.")
+    reps = math.ceil(total / return_seq_len)
+    if max_ar_steps is not None:
+        reps = min(reps, max_ar_steps)
+    t_in = known_latents.shape[2]
+    known = known_latents.to(dev, torch.float32)
+    lm = latent_mean.to(dev, torch.float32)[None, :, None, None, None]
+    ls = latent_std.to(dev, torch.float32)[None, :, None, None, None]
+    n_lead = min(total, reps * return_seq_len)
+    copy_stream = torch.cuda.Stream(device=dev)
+    pending = []
+    for step in range(reps):
+        cur = min(1 + (step + 1) * return_seq_len, total + 1)
+        sel = cur - (1 + step * return_seq_len)
+        stamp = torch.tensor([advance_timestamp(init_timestamp, step * step_size_hour * return_seq_len)])
+        samples = ensemble_AR_sampler(pipeline, sample_size=ensemble_size, return_seq_len=return_seq_len,
+                                      num_inference_steps=num_inference_steps, known_latents=known, timestamps=stamp,
+                                      sampler_type=sampler_type, device=dev, member_indices=member_indices)
+        known = samples[:, :, -t_in:].clone()
+        phys = (samples / target_std) * ls + lm  # latent inverse transform (dataloader/utils.py:233-240)
+        if return_latent:
+            res = phys[:, :, :sel].contiguous()
+        else:
+            res = decode_latent_ens(encdec_model, phys[:, :, :sel], field_mean, field_std).contiguous()
+        if out is None:
+            out = torch.empty((ensemble_size, res.shape[1], n_lead, *res.shape[-2:]), dtype=torch.float32, pin_memory=True)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done)
+            lo = step * return_seq_len
+            out[:, :, lo : lo + sel].copy_(res, non_blocking=True)
+        pending.append(res)  # keep alive until the copy stream is drained
+    copy_stream.synchronize()
+    return out
