@@ -140,6 +140,9 @@ LC_API int lc_dcae_decode(lc_dcae* h, const float* z, int n, int height, int wid
  * storage), C fp32; precision F32: everything fp32. */
 LC_API int lc_gemm(int precision, const void* a, const void* w, const float* bias, float* c, int m, int n, int k, int act,
             void* stream);
+/* same product on the tensor-core path with a bf16 output matrix (the denoiser's activation storage type) */
+LC_API int lc_gemm_bf16out(const void* a, const void* w, const float* bias, void* c, int m, int n, int k, int act,
+                           void* stream);
 /* qkv: [B, S, 3*heads*128] (q|k|v) fp32 (F32) or bf16 (BF16); out: [B, S, heads*128] same dtype. */
 LC_API int lc_attention(int precision, const void* qkv, void* out, int batch, int seq, int heads, void* stream);
 

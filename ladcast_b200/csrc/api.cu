@@ -93,6 +93,14 @@ int lc_gemm(int precision, const void* a, const void* w, const float* bias, floa
                                        : gemm_bf16(g, static_cast<cudaStream_t>(stream));
 }
 
+int lc_gemm_bf16out(const void* a, const void* w, const float* bias, void* c, int m, int n, int k, int act, void* stream) {
+  LC_REQUIRE(a && w && c, "null argument");
+  GemmArgs g;
+  g.A0 = a; g.lda0 = k; g.K0 = k; g.W = w; g.ldw = k; g.M = m; g.N = n; g.K = k;
+  g.epi.mode = EPI_STORE; g.epi.act = act; g.epi.bias = bias; g.epi.out = c; g.epi.ldo = n; g.epi.out_f32 = 0;
+  return gemm_bf16(g, static_cast<cudaStream_t>(stream));
+}
+
 int lc_attention(int precision, const void* qkv, void* out, int batch, int seq, int heads, void* stream) {
   LC_REQUIRE(qkv && out, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);

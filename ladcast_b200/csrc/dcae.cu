@@ -60,6 +60,14 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin,
   else reinterpret_cast<float*>(dst)[i] = v;
 }
 
+__global__ void transpose_taps_kernel(const float* __restrict__ w, int C, int taps, float* __restrict__ dst) {
+  // depthwise weight [C, taps] -> tap-major [taps, C]
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * taps) return;
+  const int c = i / taps, t = i % taps;
+  dst[static_cast<long long>(t) * C + c] = w[i];
+}
+
 __global__ void pack_mat_kernel(const float* __restrict__ w, long long n, void* __restrict__ dst, long long off, int to_bf16) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -103,6 +111,16 @@ int fvec(lc_dcae* D, const std::string& k, int64_t n, float** out, cudaStream_t 
   LC_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(out), static_cast<size_t>(cnt) * 4));
   D->owned.push_back(*out);
   LC_CHECK_CUDA(cudaMemcpyAsync(*out, s->p, static_cast<size_t>(cnt) * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+int fvec_taps(lc_dcae* D, const std::string& k, int C, int taps, float** out, cudaStream_t st) {
+  const St* s;
+  LC_TRY(find(D, k, &s));
+  LC_REQUIRE(s->numel == static_cast<int64_t>(C) * taps, "unexpected size for '" + k + "'");
+  LC_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(out), static_cast<size_t>(C) * taps * 4));
+  D->owned.push_back(*out);
+  transpose_taps_kernel<<<(C * taps + 255) / 256, 256, 0, st>>>(s->p, C, taps, *out);
+  LC_LAUNCH_CHECK();
   return 0;
 }
 int make_conv(lc_dcae* D, const std::string& name, int cout_full, int cin, bool bias, ConvW* W, cudaStream_t st, int cout_keep = -1) {
@@ -280,13 +298,13 @@ int finalize_impl(lc_dcae* D, cudaStream_t st) {
         e.inner = e.heads * c.head_dim;
         LC_REQUIRE(c.head_dim == 32, "EfficientViT attention_head_dim must be 32");
         LC_TRY(make_mat(D, {p + ".attn.to_q", p + ".attn.to_k", p + ".attn.to_v"}, C, false, &e.qkv, st));
-        LC_TRY(fvec(D, p + ".attn.to_qkv_multiscale.0.proj_in.weight", 3LL * e.inner * 25, &e.dw5, st));
+        LC_TRY(fvec_taps(D, p + ".attn.to_qkv_multiscale.0.proj_in.weight", 3 * e.inner, 25, &e.dw5, st));
         LC_TRY(fvec(D, p + ".attn.to_qkv_multiscale.0.proj_out.weight", 3LL * e.inner * 32, &e.g1, st));
         LC_TRY(make_mat(D, {p + ".attn.to_out"}, 2 * e.inner, false, &e.to_out, st));
         LC_TRY(fvec(D, p + ".attn.norm_out.weight", C, &e.no_w, st));
         LC_TRY(fvec(D, p + ".attn.norm_out.bias", C, &e.no_b, st));
         LC_TRY(make_mat(D, {p + ".conv_out.conv_inverted"}, C, true, &e.inv, st));
-        LC_TRY(fvec(D, p + ".conv_out.conv_depth.weight", 8LL * C * 9, &e.dw3, st));
+        LC_TRY(fvec_taps(D, p + ".conv_out.conv_depth.weight", 8 * C, 9, &e.dw3, st));
         LC_TRY(fvec(D, p + ".conv_out.conv_depth.bias", 8LL * C, &e.dw3_b, st));
         LC_TRY(make_mat(D, {p + ".conv_out.conv_point"}, 4 * C, false, &e.point, st));
         LC_TRY(fvec(D, p + ".conv_out.norm.weight", C, &e.n_w, st));

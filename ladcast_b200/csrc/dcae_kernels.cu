@@ -104,56 +104,151 @@ __global__ void halo_fill_kernel(T* __restrict__ buf, int n, int H, int W, int C
 }
 
 // ---------------------------------------------------------------- depthwise KxK sphere conv on NHWC (unpadded input)
-// out[p, c] = bias[c] + sum_{ky,kx} w[c, ky, kx'] * in[src(y+ky, x+kx)], kx' mirrored in the pole pad rows of output
-// rows 0 / H-1 (sphere_conv.py:93-129).  If GLU: channels are [value | gate] halves, output = v * silu(g).
-template <typename TI, typename TO, int K, bool GLU>
-__global__ void __launch_bounds__(256) dwconv_kernel(const TI* __restrict__ in, const float* __restrict__ w,
-                                                     const float* __restrict__ bias, TO* __restrict__ out, int n, int H,
-                                                     int W, int C) {
-  constexpr int P = K / 2;
-  const int Co = GLU ? C / 2 : C;
+// out[p, c] = bias[c] + sum_{ky,kx} w[ky, kx', c] * in[src(y+ky, x+kx), c], kx' mirrored in the pole pad rows of
+// output rows 0 / H-1 (sphere_conv.py:93-129).  Weights are tap-major [K*K, C] so channel vectors load coalesced.
+__device__ __forceinline__ void sphere_row(int py, int p, int H, int& sy, bool& rolled) {
+  if (py < p) { sy = p - 1 - py; rolled = true; }
+  else if (py >= H + p) { sy = H - 1 - (py - (H + p)); rolled = true; }
+  else { sy = py - p; rolled = false; }
+}
+__device__ __forceinline__ int sphere_col(int px, int p, int W, bool rolled) {
+  int cx = px - p;
+  if (cx < 0) cx += W;
+  if (cx >= W) cx -= W;
+  if (rolled) { cx += W / 2; if (cx >= W) cx -= W; }
+  return cx;
+}
+
+// 5x5, fp32 in/out, 4 channels per thread (multiscale projection, DCAE.py:76-85)
+__global__ void __launch_bounds__(256) dwconv5_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                      float* __restrict__ out, int n, int H, int W, int C) {
+  const int c4n = C / 4;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(n) * H * W * Co;
+  const long long total = static_cast<long long>(n) * H * W * c4n;
   if (i >= total) return;
-  const int c = static_cast<int>(i % Co);
-  long long r = i / Co;
+  const int c = static_cast<int>(i % c4n) * 4;
+  long long r = i / c4n;
   const int x = static_cast<int>(r % W);
   r /= W;
   const int y = static_cast<int>(r % H);
   const int f = static_cast<int>(r / H);
-  const TI* base = in + static_cast<long long>(f) * H * W * C;
-  float acc0 = bias ? bias[c] : 0.f;
-  float acc1 = (GLU && bias) ? bias[c + Co] : 0.f;
+  const float* base = in + static_cast<long long>(f) * H * W * C + c;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int ky = 0; ky < K; ++ky) {
-    const bool flip = (y == 0 && ky < P) || (y == H - 1 && ky >= K - P);
+  for (int ky = 0; ky < 5; ++ky) {
+    int sy;
+    bool rolled;
+    sphere_row(y + ky, 2, H, sy, rolled);
+    const bool flip = (y == 0 && ky < 2) || (y == H - 1 && ky >= 3);
+    const float* rowp = base + static_cast<long long>(sy) * W * C;
 #pragma unroll
-    for (int kx = 0; kx < K; ++kx) {
-      int sy, sx;
-      sphere_src(y + ky, x + kx, P, H, W, sy, sx);
-      const int wk = ky * K + (flip ? K - 1 - kx : kx);
-      const TI* px = base + (static_cast<long long>(sy) * W + sx) * C;
-      acc0 = fmaf(w[c * K * K + wk], ld<TI>(px + c), acc0);
-      if (GLU) acc1 = fmaf(w[(c + Co) * K * K + wk], ld<TI>(px + c + Co), acc1);
+    for (int kx = 0; kx < 5; ++kx) {
+      const int sx = sphere_col(x + kx, 2, W, rolled);
+      const float4 v = *reinterpret_cast<const float4*>(rowp + static_cast<long long>(sx) * C);
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w + (ky * 5 + (flip ? 4 - kx : kx)) * C + c));
+      acc.x = fmaf(ww.x, v.x, acc.x); acc.y = fmaf(ww.y, v.y, acc.y);
+      acc.z = fmaf(ww.z, v.z, acc.z); acc.w = fmaf(ww.w, v.w, acc.w);
     }
   }
-  const float v = GLU ? acc0 * silu(acc1) : acc0;
-  out[i] = from_f32<TO>(v);
+  *reinterpret_cast<float4*>(out + i * 4) = acc;
+}
+
+// 3x3 + bias + GLU: channels [value | gate] halves -> value * silu(gate); T in/out, 4 channels per thread
+// (GLUMBConv.conv_depth + chunk + nonlinearity, DCAE.py:312-315)
+template <typename T>
+__device__ __forceinline__ float4 ld4(const T* p);
+template <>
+__device__ __forceinline__ float4 ld4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <>
+__device__ __forceinline__ float4 ld4<bf16>(const bf16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T>
+__device__ __forceinline__ void st4(T* p, float4 v);
+template <>
+__device__ __forceinline__ void st4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <>
+__device__ __forceinline__ void st4<bf16>(bf16* p, float4 v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv3_glu_kernel(const T* __restrict__ in, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, T* __restrict__ out, int n,
+                                                          int H, int W, int C) {
+  const int Co = C / 2, c4n = Co / 4;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n) * H * W * c4n;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % c4n) * 4;
+  long long r = i / c4n;
+  const int x = static_cast<int>(r % W);
+  r /= W;
+  const int y = static_cast<int>(r % H);
+  const int f = static_cast<int>(r / H);
+  const T* base = in + static_cast<long long>(f) * H * W * C + c;
+  float4 a0 = __ldg(reinterpret_cast<const float4*>(bias + c));
+  float4 a1 = __ldg(reinterpret_cast<const float4*>(bias + Co + c));
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    int sy;
+    bool rolled;
+    sphere_row(y + ky, 1, H, sy, rolled);
+    const bool flip = (y == 0 && ky == 0) || (y == H - 1 && ky == 2);
+    const T* rowp = base + static_cast<long long>(sy) * W * C;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int sx = sphere_col(x + kx, 1, W, rolled);
+      const T* px = rowp + static_cast<long long>(sx) * C;
+      const float4 v = ld4<T>(px), g = ld4<T>(px + Co);
+      const float* wt = w + (ky * 3 + (flip ? 2 - kx : kx)) * C + c;
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(wt));
+      const float4 wg = __ldg(reinterpret_cast<const float4*>(wt + Co));
+      a0.x = fmaf(wv.x, v.x, a0.x); a0.y = fmaf(wv.y, v.y, a0.y); a0.z = fmaf(wv.z, v.z, a0.z); a0.w = fmaf(wv.w, v.w, a0.w);
+      a1.x = fmaf(wg.x, g.x, a1.x); a1.y = fmaf(wg.y, g.y, a1.y); a1.z = fmaf(wg.z, g.z, a1.z); a1.w = fmaf(wg.w, g.w, a1.w);
+    }
+  }
+  st4<T>(out + i * 4, make_float4(a0.x * silu(a1.x), a0.y * silu(a1.y), a0.z * silu(a1.z), a0.w * silu(a1.w)));
 }
 
 // ---------------------------------------------------------------- grouped 1x1 conv, 32 -> 32 per group (DCAE.py:86-88)
+// One warp per (4-pixel strip, group): lane = output channel, its 32 weights live in registers, inputs are
+// broadcast with shuffles.  All global accesses are 128 B row segments.
 __global__ void __launch_bounds__(256) grouped1x1_kernel(const float* __restrict__ in, const float* __restrict__ w,
-                                                         float* __restrict__ out, long long P, int C) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= P * C) return;
-  const int c = static_cast<int>(i % C);
-  const long long p = i / C;
-  const float* src = in + p * C + (c & ~31);
-  const float* wr = w + static_cast<long long>(c) * 32;
-  float acc = 0.f;
+                                                         float* __restrict__ out, long long P, int C, int pix_per_warp) {
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.y;
+  const long long wid = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const long long p0 = wid * pix_per_warp;
+  if (p0 >= P) return;
+  float wr[32];
+  const float* wp = w + (static_cast<long long>(g) * 32 + lane) * 32;
 #pragma unroll
-  for (int k = 0; k < 32; ++k) acc = fmaf(wr[k], src[k], acc);
-  out[i] = acc;
+  for (int k = 0; k < 32; k += 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(wp + k));
+    wr[k] = t.x; wr[k + 1] = t.y; wr[k + 2] = t.z; wr[k + 3] = t.w;
+  }
+  const long long pend = (p0 + pix_per_warp < P) ? p0 + pix_per_warp : P;
+  for (long long p = p0; p < pend; p += 4) {
+    float xv[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) xv[q] = (p + q < pend) ? in[(p + q) * C + g * 32 + lane] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fmaf(wr[k], __shfl_sync(0xffffffffu, xv[q], k), acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (p + q < pend) out[(p + q) * C + g * 32 + lane] = acc[q];
+  }
 }
 
 // ---------------------------------------------------------------- ReLU linear attention (DCAE.py:155-175, 226-262)
@@ -328,21 +423,25 @@ int halo_fill(T* buf, int n, int H, int W, int Cp, cudaStream_t s) {
   return 0;
 }
 int dwconv5(const float* in, const float* w, float* out, int n, int H, int W, int C, cudaStream_t s) {
-  const long long total = static_cast<long long>(n) * H * W * C;
-  dwconv_kernel<float, float, 5, false><<<blocks(total), 256, 0, s>>>(in, w, nullptr, out, n, H, W, C);
+  LC_REQUIRE(C % 4 == 0, "dwconv5: channels must be a multiple of 4");
+  const long long total = static_cast<long long>(n) * H * W * (C / 4);
+  dwconv5_kernel<<<blocks(total), 256, 0, s>>>(in, w, out, n, H, W, C);
   LC_LAUNCH_CHECK();
   return 0;
 }
 template <typename T>
 int dwconv3_glu(const T* in, const float* w, const float* bias, T* out, int n, int H, int W, int C, cudaStream_t s) {
-  const long long total = static_cast<long long>(n) * H * W * (C / 2);
-  dwconv_kernel<T, T, 3, true><<<blocks(total), 256, 0, s>>>(in, w, bias, out, n, H, W, C);
+  LC_REQUIRE(C % 8 == 0, "dwconv3_glu: channels must be a multiple of 8");
+  const long long total = static_cast<long long>(n) * H * W * (C / 8);
+  dwconv3_glu_kernel<T><<<blocks(total), 256, 0, s>>>(in, w, bias, out, n, H, W, C);
   LC_LAUNCH_CHECK();
   return 0;
 }
 int grouped1x1(const float* in, const float* w, float* out, long long P, int C, cudaStream_t s) {
   LC_REQUIRE(C % 32 == 0, "grouped 1x1: channels must be a multiple of 32");
-  grouped1x1_kernel<<<blocks(P * C), 256, 0, s>>>(in, w, out, P, C);
+  const int ppw = 32;
+  dim3 grid(static_cast<unsigned>((P + ppw * 8 - 1) / (ppw * 8)), C / 32);
+  grouped1x1_kernel<<<grid, 256, 0, s>>>(in, w, out, P, C, ppw);
   LC_LAUNCH_CHECK();
   return 0;
 }

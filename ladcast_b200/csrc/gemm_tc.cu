@@ -22,8 +22,10 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
+constexpr int NUM_EPI_WARPS = 8;  // two per TMEM lane quarter, each owning half of the tile's columns
+constexpr int NUM_THREADS = (EPI_WARP0 + NUM_EPI_WARPS) * 32;
+constexpr int EPI_SMEM = NUM_EPI_WARPS * 32 * 33 * 4;  // per-warp padded 32x32 transpose tiles
 
 template <int BN>
 struct Cfg {
@@ -32,7 +34,7 @@ struct Cfg {
   static constexpr int STAGE = STAGE_A + STAGE_B;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM = STAGES * STAGE + EPI_SMEM + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct TileSched {
@@ -48,117 +50,129 @@ struct TileSched {
   }
 };
 
-template <int BN>
-__device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, const uint32_t (&r)[32], int row, int n0, int M,
-                                               int N) {
-  if (row >= M) return;
-  int sample;
-  const long long orow = epi_out_row(ep, row, sample);
-  const bool full = (n0 + 32 <= N);
-  float v[32];
+// Fast activations for the bf16 path (MUFU tanh / ex2): the epilogue runs on 8 warps next to a saturated tensor
+// pipe, so it must stay a few instructions per element.  (The FP32 validation path uses the precise versions.)
+template <int ACT>
+__device__ __forceinline__ float act_fast(float v) {
+  if (ACT == ACT_GELU_TANH) {
+    const float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+    return 0.5f * v * (1.0f + t);
+  }
+  if (ACT == ACT_SILU) return __fdividef(v, 1.0f + __expf(-v));
+  if (ACT == ACT_RELU) return fmaxf(v, 0.0f);
+  return v;
+}
+
+enum EpiKind { K_STORE_BF16 = 0, K_STORE_F32 = 1, K_GATED = 2, K_RESID = 3, K_UNPATCH = 4 };
+
+// One 32x32 accumulator block (lane = row, r[j] = column n0+j).  K_UNPATCH keeps this layout (consecutive rows are
+// contiguous in the channel-major output); every other kind transposes the block through a padded smem tile so
+// that lanes run along the columns and each global access is a contiguous 64-128 B row segment.  Kind and
+// activation are template parameters: the row loops are branch-free.
+template <int KIND, int ACT>
+__device__ __forceinline__ void epilogue_block(const EpiParams& ep, const uint32_t (&r)[32], float* tbuf, int lane,
+                                               int row_mine, long long orow_mine, int sample_mine, int n0, int M, int N) {
+  if (KIND == K_UNPATCH) {
+    if (row_mine >= M) return;
+    const int r_in = row_mine - sample_mine * ep.rows_per_sample;
+    float* op = reinterpret_cast<float*>(ep.out) +
+                (static_cast<long long>(sample_mine) * ep.n_valid + n0) * ep.rows_per_sample + r_in;
+    const bool has_bias = ep.bias != nullptr, has_scale = ep.ch_scale != nullptr;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-  if (ep.bias != nullptr) {
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
-        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+    for (int j = 0; j < 32; ++j) {
+      if (n0 + j < ep.n_valid) {
+        float o = __uint_as_float(r[j]);
+        if (has_bias) o += __ldg(ep.bias + n0 + j);
+        o = act_fast<ACT>(o);
+        if (has_scale) o = o * __ldg(ep.ch_scale + n0 + j) + __ldg(ep.ch_shift + n0 + j);
+        op[static_cast<long long>(j) * ep.rows_per_sample] = o;
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < N) v[j] += __ldg(ep.bias + n0 + j);
     }
+    return;
   }
-  if (ep.act != ACT_NONE) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
-  }
-  switch (ep.mode) {
-    case EPI_STORE:
-    case EPI_RESID_STORE: {
-      if (ep.mode == EPI_RESID_STORE) {
-        const float* rp = ep.resid + orow * ep.ldr + n0;
-        if (full) {
+  for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
+  __syncwarp();
+  if (KIND == K_STORE_BF16) {
+    // half-warps cover two rows per instruction, each lane packs two adjacent columns (64 B per row)
+    const int cc = (lane & 15) * 2;
+    const int col = n0 + cc;
+    const float b0 = (ep.bias != nullptr && col < N) ? __ldg(ep.bias + col) : 0.f;
+    const float b1 = (ep.bias != nullptr && col + 1 < N) ? __ldg(ep.bias + col + 1) : 0.f;
+    bf16* outp = reinterpret_cast<bf16*>(ep.out) + col;
+    const long long ldo = ep.ldo;
+    const bool pair_ok = col + 1 < N, one_ok = col < N;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 q = *reinterpret_cast<const float4*>(rp + j);
-            v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+    for (int i = 0; i < 16; ++i) {
+      const int rr = 2 * i + (lane >> 4);
+      const int row = __shfl_sync(0xffffffffu, row_mine, rr);
+      const long long orow = __shfl_sync(0xffffffffu, orow_mine, rr);
+      const float v0 = act_fast<ACT>(tbuf[rr * 33 + cc] + b0);
+      const float v1 = act_fast<ACT>(tbuf[rr * 33 + cc + 1] + b1);
+      if (row < M) {
+        if (pair_ok) *reinterpret_cast<__nv_bfloat162*>(outp + orow * ldo) = __floats2bfloat162_rn(v0, v1);
+        else if (one_ok) outp[orow * ldo] = __float2bfloat16_rn(v0);
+      }
+    }
+  } else {
+    const int col = n0 + lane;
+    const bool col_ok = col < N;
+    const float bias = (ep.bias != nullptr && col_ok) ? __ldg(ep.bias + col) : 0.f;
+    float* outp = reinterpret_cast<float*>(ep.out) + col;
+    const long long ldo = ep.ldo;
+#pragma unroll
+    for (int r0 = 0; r0 < 32; r0 += 8) {
+      // issue the 8 residual/gate loads of this row group first (memory-level parallelism), then combine + store
+      float prev[8], gq[8];
+      bool ok[8];
+      long long orows[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        ok[q] = (__shfl_sync(0xffffffffu, row_mine, r0 + q) < M) && col_ok;
+        orows[q] = __shfl_sync(0xffffffffu, orow_mine, r0 + q);
+        prev[q] = 0.f;
+        gq[q] = 1.f;
+        if (KIND == K_GATED) {
+          const int smp = __shfl_sync(0xffffffffu, sample_mine, r0 + q);
+          if (ok[q]) {
+            prev[q] = outp[orows[q] * ldo];
+            if (ep.gate != nullptr) gq[q] = __ldg(ep.gate + static_cast<long long>(smp) * ep.gate_stride + col);
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + j < N) v[j] += rp[j];
+        } else if (KIND == K_RESID) {
+          if (ok[q]) prev[q] = ep.resid[orows[q] * ep.ldr + col];
         }
       }
-      if (ep.out_f32) {
-        float* op = reinterpret_cast<float*>(ep.out) + orow * ep.ldo + n0;
-        if (full) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + j < N) op[j] = v[j];
-        }
-      } else {
-        bf16* op = reinterpret_cast<bf16*>(ep.out) + orow * ep.ldo + n0;
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 pk;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&t0);
-            pk.y = *reinterpret_cast<uint32_t*>(&t1);
-            pk.z = *reinterpret_cast<uint32_t*>(&t2);
-            pk.w = *reinterpret_cast<uint32_t*>(&t3);
-            *reinterpret_cast<uint4*>(op + j) = pk;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + j < N) op[j] = __float2bfloat16_rn(v[j]);
+      for (int q = 0; q < 8; ++q) {
+        const float t = tbuf[(r0 + q) * 33 + lane] + bias;
+        if (ok[q]) {
+          if (KIND == K_GATED) outp[orows[q] * ldo] = fmaf(gq[q], t, prev[q]);
+          else outp[orows[q] * ldo] = act_fast<ACT>(t) + prev[q];
         }
       }
-      break;
-    }
-    case EPI_GATED_RESID: {
-      float* op = reinterpret_cast<float*>(ep.out) + orow * ep.ldo + n0;
-      const float* gp = ep.gate ? ep.gate + static_cast<long long>(sample) * ep.gate_stride + n0 : nullptr;
-      if (full) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 h = *reinterpret_cast<float4*>(op + j);
-          float4 g = gp ? __ldg(reinterpret_cast<const float4*>(gp + j)) : make_float4(1.f, 1.f, 1.f, 1.f);
-          h.x += g.x * v[j]; h.y += g.y * v[j + 1]; h.z += g.z * v[j + 2]; h.w += g.w * v[j + 3];
-          *reinterpret_cast<float4*>(op + j) = h;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + j < N) op[j] += (gp ? __ldg(gp + j) : 1.f) * v[j];
-      }
-      break;
-    }
-    case EPI_UNPATCHIFY: {
-      const int r_in = row - sample * ep.rows_per_sample;
-      float* op = reinterpret_cast<float*>(ep.out) +
-                  (static_cast<long long>(sample) * ep.n_valid + n0) * ep.rows_per_sample + r_in;
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < ep.n_valid) {
-          float o = v[j];
-          if (ep.ch_scale != nullptr) o = o * __ldg(ep.ch_scale + n0 + j) + __ldg(ep.ch_shift + n0 + j);
-          op[static_cast<long long>(j) * ep.rows_per_sample] = o;
-        }
-      break;
     }
   }
+  __syncwarp();
+}
+
+template <int KIND>
+__device__ __forceinline__ void epilogue_act_dispatch(const EpiParams& ep, const uint32_t (&r)[32], float* tbuf, int lane,
+                                                      int row, long long orow, int sample, int n0, int M, int N) {
+  switch (ep.act) {
+    case ACT_GELU_TANH: epilogue_block<KIND, ACT_GELU_TANH>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
+    case ACT_SILU: epilogue_block<KIND, ACT_SILU>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
+    case ACT_RELU: epilogue_block<KIND, ACT_RELU>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
+    default: epilogue_block<KIND, ACT_NONE>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
+  }
+}
+
+__device__ __forceinline__ int epi_kind(const EpiParams& ep) {
+  if (ep.mode == EPI_GATED_RESID) return K_GATED;
+  if (ep.mode == EPI_UNPATCHIFY) return K_UNPATCH;
+  if (ep.mode == EPI_RESID_STORE) return K_RESID;  // f32 output only on the tensor-core path
+  return ep.out_f32 ? K_STORE_F32 : K_STORE_BF16;
 }
 
 template <int BN>
@@ -172,7 +186,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::STAGES * C::STAGE_A;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
+  float* epi_smem = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE + EPI_SMEM);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::STAGES;
   uint64_t* tmem_full = bars + 2 * C::STAGES;
@@ -196,7 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
-      ptx::mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_empty[i], NUM_EPI_WARPS);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -278,15 +293,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= EPI_WARP0) {
-    // ===================== epilogue =====================
-    const int quarter = warp & 3;
+    // ===================== epilogue (8 warps) =====================
+    const int ew = warp - EPI_WARP0;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access (= warp id % 4)
+    const int half = ew >> 2;      // which half of the tile's columns
+    float* tbuf = epi_smem + ew * (32 * 33);
+    const int kind = epi_kind(ep);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
       sched.decode(tile, m_blk, n_blk);
-      ptx::mbar_wait(&tmem_full[acc], acc_phase);
-      ptx::tc_fence_after();
       const int t = quarter * 32 + lane;
       int row = m_blk * BM + t;
       if (cv.enabled) {
@@ -301,14 +318,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int f = fg * cv.Nt + fi;
         row = (fi < cv.Nt && x < cv.W && f < cv.n_frames) ? (f * cv.H + y) * cv.W + x : M;
       }
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      if (row > M) row = M;
+      int sample = 0;
+      const long long orow = epi_out_row(ep, row, sample);
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                              static_cast<uint32_t>(acc * BN + half * (BN / 2));
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < BN / 64; ++c) {
         uint32_t r[32];
         ptx::tmem_ld32(t_addr + c * 32, r);
         ptx::tmem_ld_wait();
-        const int n0 = n_blk * BN + c * 32;
-        if (n0 < N) epilogue_chunk<BN>(ep, r, row, n0, M, N);
+        const int n0 = n_blk * BN + half * (BN / 2) + c * 32;
+        if (n0 < N) {
+          switch (kind) {
+            case K_STORE_BF16: epilogue_act_dispatch<K_STORE_BF16>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
+            case K_STORE_F32: epilogue_act_dispatch<K_STORE_F32>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
+            case K_GATED: epilogue_block<K_GATED, ACT_NONE>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
+            case K_RESID: epilogue_act_dispatch<K_RESID>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
+            default: epilogue_act_dispatch<K_UNPATCH>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
+          }
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
