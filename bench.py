@@ -284,8 +284,7 @@ def main():
     if not args.no_e2e:
         k_e2e = min(args.steps, 3)
         host_known = known0.clone().pin_memory()
-        n_lead = k_e2e * args.t_out
-        host_out = torch.empty((args.ens, 84, n_lead, 120, 240), dtype=torch.float32, pin_memory=True)
+        host_out = torch.empty((k_e2e, args.ens, 84, args.t_out, 120, 240), dtype=torch.float32, pin_memory=True)
         barrier()
         t0 = time.perf_counter()
         roll_out_latent(pipe, ae, host_known, 2018010100, args.ens, lat_mean, lat_std, fld_mean, fld_std,

@@ -134,6 +134,21 @@ LC_API int lc_dcae_decode(lc_dcae* h, const float* z, int n, int height, int wid
                           const float* mean, const float* std, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Ensemble metrics — replaces pointwise_crps_skill / pointwise_crps_spread / get_crps (evaluate/utils.py:52-118)
+ * and the per-lead-time assembly of evaluate/evaluate_ens_gpu.py:339-415.
+ * fields: [members, planes, H*W] fp32 (planes = (channel, lead) pairs), truth: [planes, H*W] fp32 (NaN allowed),
+ * lat_weights: [H] fp64 (get_normalized_lat_weights_based_on_cos, evaluate/utils.py:40-48).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* sums/counts: [4, planes] fp64 — latitude-weighted spatial SUMS and non-NaN pixel counts of
+ * {ens-mean squared error, CRPS skill, CRPS spread, CRPS = skill - 0.5 spread}; mean = sum/count (nanmean) or
+ * sum/(H*W) with NaN propagation is formed by the caller.  Zeroes the outputs itself. */
+LC_API int lc_metrics_accumulate(const float* fields, const float* truth, const double* lat_weights, int members,
+                                 long long planes, int height, int width, double* sums, double* counts, void* stream);
+/* per-pixel outputs [planes, H*W] fp32 (any may be NULL): CRPS skill, CRPS spread, ensemble mean */
+LC_API int lc_metrics_pointwise(const float* fields, const float* truth, int members, long long planes, int height,
+                                int width, float* out_skill, float* out_spread, float* out_mean, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Low-level ops exported for parity tests (same kernels the handles use)
  * ---------------------------------------------------------------------------------------------------------- */
 /* C[M,N] = A[M,K] W[N,K]^T + bias, act in {0 none, 1 gelu-tanh, 2 silu}.  precision BF16: A, W bf16 (raw uint16

@@ -65,8 +65,8 @@ _OPTIONAL = {
     "lc_dcae_decode": ([_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp], _i),
     "lc_dcae_debug_read": ([_vp, _cp, _vp, _i64, _vp], _i),
     "lc_sphere_conv3x3": ([_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
-    "lc_metrics_accumulate": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp], _i),
-    "lc_metrics_crps_local": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp], _i),
+    "lc_metrics_accumulate": ([_vp, _vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, _vp, _vp], _i),
+    "lc_metrics_pointwise": ([_vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, _vp, _vp, _vp], _i),
 }
 
 

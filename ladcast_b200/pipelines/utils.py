@@ -117,9 +117,12 @@ def roll_out_latent(pipeline, encdec_model, known_latents: torch.Tensor, init_ti
                     out: Optional[torch.Tensor] = None, max_ar_steps: Optional[int] = None):
     """Tensor-in / tensor-out core of `roll_out_serial` (reference pipelines/utils.py:533-654): the AR loop
     [sample -> feed the last T_in frames back -> de-normalise -> decode] from already encoded, normalised
-    `known_latents` (1, C, T_in, h, w).  Returns a HOST tensor (ensemble, C, n_lead, H, W) of decoded fields in
-    physical units (or de-normalised latents when return_latent) for lead steps 1..n_lead; each AR step's result
-    is copied device->host asynchronously (pinned `out`), overlapping the next AR step.
+    `known_latents` (1, C, T_in, h, w) given on the HOST or the device.
+
+    Returns a pinned HOST tensor of shape (n_ar_steps, ensemble, C, T_out, H, W): block s holds lead steps
+    s*T_out+1 .. (s+1)*T_out (decoded fields in physical units, or de-normalised latents when return_latent).
+    `rollout_as_lead_major(out)` gives the reference's (ensemble, C, lead, H, W) view.  Each AR step's block is one
+    contiguous asynchronous device->host copy on a side stream that overlaps the next AR step's compute.
     `member_indices`: global member ids owned by this process (multi-GPU member sharding)."""
     import math
 
@@ -131,33 +134,36 @@ def roll_out_latent(pipeline, encdec_model, known_latents: torch.Tensor, init_ti
     if max_ar_steps is not None:
         reps = min(reps, max_ar_steps)
     t_in = known_latents.shape[2]
-    known = known_latents.to(dev, torch.float32)
+    known = known_latents.to(dev, torch.float32, non_blocking=True)
     lm = latent_mean.to(dev, torch.float32)[None, :, None, None, None]
     ls = latent_std.to(dev, torch.float32)[None, :, None, None, None]
-    n_lead = min(total, reps * return_seq_len)
     copy_stream = torch.cuda.Stream(device=dev)
-    pending = []
+    keep = []
     for step in range(reps):
-        cur = min(1 + (step + 1) * return_seq_len, total + 1)
-        sel = cur - (1 + step * return_seq_len)
         stamp = torch.tensor([advance_timestamp(init_timestamp, step * step_size_hour * return_seq_len)])
         samples = ensemble_AR_sampler(pipeline, sample_size=ensemble_size, return_seq_len=return_seq_len,
                                       num_inference_steps=num_inference_steps, known_latents=known, timestamps=stamp,
                                       sampler_type=sampler_type, device=dev, member_indices=member_indices)
         known = samples[:, :, -t_in:].clone()
         phys = (samples / target_std) * ls + lm  # latent inverse transform (dataloader/utils.py:233-240)
-        if return_latent:
-            res = phys[:, :, :sel].contiguous()
-        else:
-            res = decode_latent_ens(encdec_model, phys[:, :, :sel], field_mean, field_std).contiguous()
+        res = phys if return_latent else decode_latent_ens(encdec_model, phys, field_mean, field_std)
+        res = res.contiguous()  # (ens, C, T_out, H, W)
         if out is None:
-            out = torch.empty((ensemble_size, res.shape[1], n_lead, *res.shape[-2:]), dtype=torch.float32, pin_memory=True)
+            out = torch.empty((reps, *res.shape), dtype=torch.float32, pin_memory=True)
         done = torch.cuda.Event()
         done.record(torch.cuda.current_stream(dev))
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(done)
-            lo = step * return_seq_len
-            out[:, :, lo : lo + sel].copy_(res, non_blocking=True)
-        pending.append(res)  # keep alive until the copy stream is drained
+            out[step].copy_(res, non_blocking=True)
+        res.record_stream(copy_stream)
+        keep.append(res)
     copy_stream.synchronize()
     return out
+
+
+def rollout_as_lead_major(out: torch.Tensor, n_lead: Optional[int] = None) -> torch.Tensor:
+    """(n_ar, ens, C, T_out, H, W) -> the reference's (ens, C, n_ar*T_out, H, W) ordering (a copy), optionally cut to
+    the first n_lead lead steps (roll_out_serial's `pred_selection` when T_out does not divide the lead count)."""
+    n_ar, ens, C, T, H, W = out.shape
+    y = out.permute(1, 2, 0, 3, 4, 5).reshape(ens, C, n_ar * T, H, W)
+    return y if n_lead is None else y[:, :, :n_lead]

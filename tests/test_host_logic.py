@@ -1,0 +1,180 @@
+"""CPU tests (-m "not gpu"): host-side logic of the drop-ins, the C-ABI surface, and the world_size-2 gloo path."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ladcast_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads on a GPU-less host and exports every symbol include/ladcast_b200.h declares."""
+    from ladcast_b200 import _lib
+
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "ladcast_b200.h")).read()
+    names = re.findall(r"LC_API\s+[\w\s\*]+?\b(lc_\w+)\s*\(", hdr)
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert lib.lc_version() >= 100
+    assert lib.lc_launch_count() == 0
+
+
+def test_product_path_fails_loudly_without_cuda():
+    from ladcast_b200 import _lib
+    from ladcast_b200.models import LaDCastTransformer3DModel
+
+    m = LaDCastTransformer3DModel.from_config(O.denoiser_config("tiny"))
+    x = torch.zeros(1, 84, 1, 15, 30)
+    with pytest.raises(_lib.LadcastB200Error):
+        m(x, torch.zeros(1), x)  # CPU model: no fallback, must raise
+
+
+def test_state_dict_contract_matches_reference_keys():
+    from ladcast_b200.models import AutoencoderDC, LaDCastTransformer3DModel
+
+    for name in ("tiny", "375M", "1.6B"):
+        cfg = O.denoiser_config(name)
+        m = LaDCastTransformer3DModel.from_config(cfg)
+        assert m.param_shapes() == O.denoiser_param_shapes(cfg)
+    assert LaDCastTransformer3DModel.from_config(O.denoiser_config("375M")).num_parameters() == 374_938_452
+    ae = AutoencoderDC(**O.dcae_config())
+    assert ae.decoder_param_shapes() == O.dcae_decoder_param_shapes(O.dcae_config())
+    with pytest.raises(RuntimeError):
+        LaDCastTransformer3DModel.from_config(O.denoiser_config("tiny")).load_state_dict({"bogus": torch.zeros(1)})
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    from ladcast_b200.models import LaDCastTransformer3DModel
+
+    cfg = O.denoiser_config("tiny")
+    sd = O.make_state_dict(O.denoiser_param_shapes(cfg), 3)
+    m = LaDCastTransformer3DModel.from_config(cfg)
+    m.load_state_dict(sd)
+    m.save_pretrained(str(tmp_path / "ar"))
+    assert sorted(os.listdir(tmp_path / "ar")) == ["config.json", "diffusion_pytorch_model.safetensors"]
+    m2 = LaDCastTransformer3DModel.from_pretrained(str(tmp_path), subfolder="ar")
+    assert m2.config.num_attention_heads == cfg["num_attention_heads"]
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, sd[k])
+
+
+def test_host_tables_vs_reference_golden(golden_dir):
+    from ladcast_b200.models.embeddings import rope_tables, year_sincos_embedding
+
+    g = np.load(os.path.join(golden_dir, "embeddings.npz"))
+    assert np.allclose(year_sincos_embedding(g["ts"].tolist()).numpy(), g["year"], atol=1e-6)
+    (cp, sp), (cc, sc) = rope_tables(O.denoiser_config("375M"), 1, 4, 15, 30)
+    assert np.allclose(cp[g["rows"]].numpy(), g["cos_p"], atol=1e-6) and np.allclose(sp[g["rows"]].numpy(), g["sin_p"], atol=1e-6)
+    assert np.allclose(cc[::9].numpy(), g["cos_c"], atol=1e-6) and np.allclose(sc[::9].numpy(), g["sin_c"], atol=1e-6)
+
+
+def test_scheduler_schedule_and_coefficients(golden_dir):
+    from ladcast_b200.pipelines.scheduler import EDMDPMSolverMultistepScheduler, dpmpp2m_coefficients
+
+    g = np.load(os.path.join(golden_dir, "samplers_tiny.npz"))
+    s = EDMDPMSolverMultistepScheduler()
+    s.set_timesteps(20)
+    assert np.array_equal(s.sigmas.numpy(), g["sigmas20"]) and np.allclose(s.timesteps.numpy(), g["timesteps20"], rtol=1e-7)
+    assert abs(s.init_noise_sigma - (80.0**2 + 1) ** 0.5) < 1e-9
+    # the fused-kernel coefficients reproduce the oracle's DPM-Solver++ trajectory (emulated here in torch on CPU)
+    gen = torch.Generator("cpu").manual_seed(5)
+    noise = torch.randn((2, 84, 1, 15, 30), generator=gen)
+    fs = [torch.randn(noise.shape, generator=gen) for _ in range(7)]
+    it = iter(fs)
+    want = O.dpmpp2m_sample(lambda xin, cn: next(it), noise, 7)
+    x, prev = noise.clone(), torch.zeros_like(noise)
+    for i in range(7):
+        c = dpmpp2m_coefficients(7, i)
+        x0 = c["c_skip"] * x + c["c_out"] * fs[i]
+        x = c["a_x"] * x + c["a_x0"] * x0 + c["a_d"] * (x0 - prev)
+        prev = x0
+    assert float((x - want).norm() / want.norm()) < 1e-6
+
+
+def test_member_noise_and_sharding():
+    from ladcast_b200.evaluate.utils import plane_shard
+    from ladcast_b200.pipelines.utils import advance_timestamp, member_shard, randn_tensor
+
+    gens = [torch.Generator("cpu").manual_seed(m) for m in (3, 4)]
+    assert torch.equal(randn_tensor((2, 84, 1, 15, 30), generator=gens, dtype=torch.float32), O.member_noise([3, 4], (84, 1, 15, 30)))
+    for total, world in ((20, 8), (50, 8), (20, 1), (7, 4)):
+        got = [m for r in range(world) for m in member_shard(total, r, world)]
+        assert got == list(range(total))
+        sizes = [len(member_shard(total, r, world)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
+        assert [p for r in range(world) for p in plane_shard(336, r, world)] == list(range(336))
+    assert advance_timestamp(2018123118, 24) == 2019010118 and advance_timestamp(2020022818, 6) == 2020022900
+    assert advance_timestamp(2018010100, 24) == O.advance_timestamp(2018010100, 24)
+
+
+def test_pipeline_argument_errors():
+    from ladcast_b200.models import LaDCastTransformer3DModel
+    from ladcast_b200.pipelines import AutoRegressive2DPipeline, EDMDPMSolverMultistepScheduler
+
+    m = LaDCastTransformer3DModel.from_config(O.denoiser_config("tiny"))
+    pipe = AutoRegressive2DPipeline(m, EDMDPMSolverMultistepScheduler())
+    known = torch.zeros(1, 84, 1, 15, 30)
+    with pytest.raises(ValueError):
+        pipe(batch_size=2, known_latents=known, generator=[torch.Generator("cpu")])
+    with pytest.raises(AssertionError):
+        pipe(batch_size=1, known_latents=None)
+    with pytest.raises(NotImplementedError):
+        pipe(batch_size=1, known_latents=known, do_edm_style=False)
+
+
+# ---------------------------------------------------------------------------------------------------- gloo, world 2
+def _oracle_local_sums(fields, truth, lat_w):
+    """CPU stand-in for the CUDA reduction kernel (test only): same [4, N] sums / counts contract."""
+    M, N, H, W = fields.shape
+    w = lat_w.double().view(1, H, 1)
+    mean = fields.mean(0)
+    se = ((mean - truth) ** 2) * w
+    skill = torch.abs(truth.unsqueeze(0) - fields).mean(0) * w
+    spread = O.crps_spread_pointwise(fields) * w
+    vals = [se, skill, spread, skill - 0.5 * spread]
+    sums = torch.stack([torch.nan_to_num(v, nan=0.0).sum(dim=(1, 2)) for v in vals])
+    counts = torch.stack([(~torch.isnan(v)).double().sum(dim=(1, 2)) for v in vals])
+    return sums, counts
+
+
+def _dist_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from ladcast_b200.evaluate.utils import ensemble_metrics_distributed
+    from ladcast_b200.pipelines.utils import member_shard
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator("cpu").manual_seed(99)
+    fields = torch.randn((5, 84, 2, 12, 8), generator=g)  # 5 members: ranks get 3 and 2 (uneven on purpose)
+    truth = torch.randn((84, 2, 12, 8), generator=g)
+    truth[82, 0, 2:4] = float("nan")
+    mine = list(member_shard(5, rank, world))
+    lat_w = torch.from_numpy(O.lat_weights(12))
+    tabs = ensemble_metrics_distributed(fields[mine].contiguous(), truth, lat_weights=lat_w, local_sums_fn=_oracle_local_sums)
+    want = O.ensemble_metrics(fields, truth)
+    ok = all(np.allclose(tabs[k].numpy(), want[k].numpy(), rtol=1e-10, atol=1e-12, equal_nan=True) for k in want)
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_member_sharded_metrics_world2_gloo():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_dist_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

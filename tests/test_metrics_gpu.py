@@ -1,0 +1,65 @@
+"""GPU parity of the on-device metric reduction (lc_metrics_*) against the oracle and the reference-generated golden."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ladcast_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _seeded(shape, seed, scale=1.0):
+    return torch.randn(shape, generator=torch.Generator("cpu").manual_seed(seed)) * scale
+
+
+def test_metrics_vs_golden(golden_dir):
+    from ladcast_b200.evaluate.utils import ensemble_metrics
+
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    dec = _seeded((5, 84, 2, 120, 16), 108)
+    ref = _seeded((84, 2, 120, 16), 109)
+    ref[82, :, 5:9, 3:7] = float("nan")
+    tabs = ensemble_metrics(dec.cuda(), ref.cuda())
+    for k in ("ens_mse", "crps_skill", "crps_spread", "crps"):
+        got = tabs[k].cpu().numpy()
+        assert np.allclose(got, g[k], rtol=2e-6, atol=1e-9), k
+
+
+@pytest.mark.parametrize("M", [1, 2, 20, 50])
+def test_metrics_members(M):
+    from ladcast_b200.evaluate.utils import ensemble_metrics, get_crps, pointwise_crps_skill, pointwise_crps_spread
+
+    f = _seeded((M, 84, 1, 120, 24), 7 + M)
+    t = _seeded((84, 1, 120, 24), 8 + M)
+    t[82, 0, :3] = float("nan")
+    want = O.ensemble_metrics(f, t)
+    got = ensemble_metrics(f.cuda(), t.cuda())
+    for k in want:
+        assert np.allclose(got[k].cpu().numpy(), want[k].numpy(), rtol=5e-6, atol=1e-9, equal_nan=True), (k, M)
+    # pointwise drop-ins (evaluate/utils.py:52-118)
+    fc, tc = f[:, :, 0].cuda(), t[:, 0].cuda()
+    sp = pointwise_crps_spread(fc, ensemble_dim=0)
+    assert torch.allclose(sp.cpu(), O.crps_spread_pointwise(f[:, :, 0]), rtol=1e-5, atol=1e-6)
+    sk = pointwise_crps_skill(fc, tc.unsqueeze(0), 0)
+    assert torch.allclose(sk.cpu(), torch.abs(t[:, 0].unsqueeze(0) - f[:, :, 0]).mean(0), rtol=1e-5, atol=1e-6, equal_nan=True)
+    cr = get_crps(fc, tc.unsqueeze(0), 0)
+    assert torch.allclose(cr.cpu(), sk.cpu() - 0.5 * sp.cpu(), rtol=1e-5, atol=1e-6, equal_nan=True)
+
+
+def test_metrics_full_size_properties():
+    """BASELINE-size planes (120x240), ens=20: spread is translation invariant and scales linearly; skill of a
+    forecast equal to the truth is 0; identical members give zero spread and crps == skill == |error|."""
+    from ladcast_b200.evaluate.utils import ensemble_metrics
+
+    f = _seeded((20, 84, 2, 120, 240), 11).cuda()
+    t = _seeded((84, 2, 120, 240), 12).cuda()
+    a = ensemble_metrics(f, t)
+    b = ensemble_metrics(f * 3.0 + 5.0, t * 3.0 + 5.0)
+    assert torch.allclose(b["crps_spread"], 3.0 * a["crps_spread"], rtol=1e-5)
+    assert torch.allclose(b["crps"], 3.0 * a["crps"], rtol=1e-4)
+    assert torch.allclose(b["ens_mse"], 9.0 * a["ens_mse"], rtol=1e-4)
+    same = t.unsqueeze(0).expand(20, -1, -1, -1, -1).contiguous()
+    z = ensemble_metrics(same, t)
+    assert float(z["crps_spread"].abs().max()) == 0.0 and float(z["crps_skill"].abs().max()) == 0.0
