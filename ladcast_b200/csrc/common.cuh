@@ -40,6 +40,17 @@ void count_launch();
     LC_CHECK_CUDA(cudaGetLastError()); \
   } while (0)
 
+// All kernels ask for the maximum shared-memory carveout: the tensor-core kernels need ~225 KB, and alternating
+// between carveouts forces the SMs to drain and reconfigure between consecutive launches of a stream.
+#define LC_PREFER_SMEM(...)                                                                                        \
+  do {                                                                                                             \
+    static bool _lc_done = false;                                                                                  \
+    if (!_lc_done) {                                                                                               \
+      cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+      _lc_done = true;                                                                                             \
+    }                                                                                                              \
+  } while (0)
+
 #define LC_TRY(expr)          \
   do {                        \
     int _r = (expr);          \
@@ -113,6 +124,15 @@ struct EpiParams {
   // EPI_UNPATCHIFY only: out = v * ch_scale[n] + ch_shift[n]  (decoder: fields * std + mean fused)
   const float* ch_scale = nullptr;
   const float* ch_shift = nullptr;
+  // fused per-head RMSNorm(q, k) + RoPE for qkv projections on the tensor-core path (head_dim 128): columns
+  // [0, qk_cols) are q|k heads, normalised with qk_wq / qk_wk ([128] each) and rotated with the [tokens, 128]
+  // cos/sin tables (token = row % rows_per_sample; tables may be null = no rotation).  0 = disabled.
+  int qk_cols = 0;
+  float qk_eps = 0.f;
+  const float* qk_wq = nullptr;
+  const float* qk_wk = nullptr;
+  const float* rope_cos = nullptr;
+  const float* rope_sin = nullptr;
 };
 
 __device__ __forceinline__ long long epi_out_row(const EpiParams& ep, int row, int& sample) {

@@ -402,6 +402,7 @@ inline unsigned blocks(long long n, int t = 256) { return static_cast<unsigned>(
 template <typename T>
 int pad_from_nchw(const float* z, T* out, int n, int C, int H, int W, int Cp, cudaStream_t s) {
   const long long total = static_cast<long long>(n) * (H + 2) * (W + 2) * Cp;
+  LC_PREFER_SMEM(pad_from_nchw_kernel<T>);
   pad_from_nchw_kernel<T><<<blocks(total), 256, 0, s>>>(z, out, n, C, H, W, Cp);
   LC_LAUNCH_CHECK();
   return 0;
@@ -410,6 +411,7 @@ template <typename T>
 int pad_from_nhwc(const float* x, T* out, int n, int C, int H, int W, int Cp, cudaStream_t s) {
   LC_REQUIRE(C % 4 == 0 && Cp % 4 == 0, "pad: channels must be multiples of 4");
   const long long total = static_cast<long long>(n) * (H + 2) * (W + 2) * (Cp / 4);
+  LC_PREFER_SMEM(pad_from_nhwc_kernel<T>);
   pad_from_nhwc_kernel<T><<<blocks(total), 256, 0, s>>>(x, out, n, C, H, W, Cp);
   LC_LAUNCH_CHECK();
   return 0;
@@ -418,6 +420,7 @@ template <typename T>
 int halo_fill(T* buf, int n, int H, int W, int Cp, cudaStream_t s) {
   LC_REQUIRE(Cp % 8 == 0, "halo_fill: Cp must be a multiple of 8");
   const long long total = static_cast<long long>(n) * (2 * (W + 2) + 2 * H) * (Cp / 8);
+  LC_PREFER_SMEM(halo_fill_kernel<T>);
   halo_fill_kernel<T><<<blocks(total), 256, 0, s>>>(buf, n, H, W, Cp);
   LC_LAUNCH_CHECK();
   return 0;
@@ -425,6 +428,7 @@ int halo_fill(T* buf, int n, int H, int W, int Cp, cudaStream_t s) {
 int dwconv5(const float* in, const float* w, float* out, int n, int H, int W, int C, cudaStream_t s) {
   LC_REQUIRE(C % 4 == 0, "dwconv5: channels must be a multiple of 4");
   const long long total = static_cast<long long>(n) * H * W * (C / 4);
+  LC_PREFER_SMEM(dwconv5_kernel);
   dwconv5_kernel<<<blocks(total), 256, 0, s>>>(in, w, out, n, H, W, C);
   LC_LAUNCH_CHECK();
   return 0;
@@ -433,6 +437,7 @@ template <typename T>
 int dwconv3_glu(const T* in, const float* w, const float* bias, T* out, int n, int H, int W, int C, cudaStream_t s) {
   LC_REQUIRE(C % 8 == 0, "dwconv3_glu: channels must be a multiple of 8");
   const long long total = static_cast<long long>(n) * H * W * (C / 8);
+  LC_PREFER_SMEM(dwconv3_glu_kernel<T>);
   dwconv3_glu_kernel<T><<<blocks(total), 256, 0, s>>>(in, w, bias, out, n, H, W, C);
   LC_LAUNCH_CHECK();
   return 0;
@@ -441,12 +446,14 @@ int grouped1x1(const float* in, const float* w, float* out, long long P, int C, 
   LC_REQUIRE(C % 32 == 0, "grouped 1x1: channels must be a multiple of 32");
   const int ppw = 32;
   dim3 grid(static_cast<unsigned>((P + ppw * 8 - 1) / (ppw * 8)), C / 32);
+  LC_PREFER_SMEM(grouped1x1_kernel);
   grouped1x1_kernel<<<grid, 256, 0, s>>>(in, w, out, P, C, ppw);
   LC_LAUNCH_CHECK();
   return 0;
 }
 template <typename T>
 int linear_attention(const float* qkv, const float* ms, T* out, int n, int HW, int heads, float eps, cudaStream_t s) {
+  LC_PREFER_SMEM(linear_attn_kernel<T>);
   linear_attn_kernel<T><<<n * 2 * heads, 256, 0, s>>>(qkv, ms, out, HW, heads, eps);
   LC_LAUNCH_CHECK();
   return 0;
@@ -455,6 +462,7 @@ template <typename T>
 int rmsnorm_rows(const float* y, const float* w, const float* b, float eps, float* resid, float* out_f32, T* out_t,
                  long long P, int C, int relu, cudaStream_t s) {
   LC_REQUIRE(C % 4 == 0, "rmsnorm: C must be a multiple of 4");
+  LC_PREFER_SMEM(rmsnorm_rows_kernel<T>);
   rmsnorm_rows_kernel<T><<<blocks(P, 8), 256, 0, s>>>(y, w, b, eps, resid, out_f32, out_t, P, C, relu);
   LC_LAUNCH_CHECK();
   return 0;
@@ -463,6 +471,7 @@ template <typename T>
 int pixel_shuffle_shortcut(const float* conv, const float* xin, float* out, T* out_t, int n, int H, int W, int Cin,
                            int Cout, cudaStream_t s) {
   const long long total = static_cast<long long>(n) * 4 * H * W * Cout;
+  LC_PREFER_SMEM(pixel_shuffle_kernel<T>);
   pixel_shuffle_kernel<T><<<blocks(total), 256, 0, s>>>(conv, xin, out, out_t, n, H, W, Cin, Cout, 4 * Cout / Cin);
   LC_LAUNCH_CHECK();
   return 0;
@@ -470,6 +479,7 @@ int pixel_shuffle_shortcut(const float* conv, const float* xin, float* out, T* o
 template <typename T>
 int in_shortcut(float* x, T* x_t, const float* z, int n, int HW, int C, int Cz, cudaStream_t s) {
   const long long total = static_cast<long long>(n) * HW * C;
+  LC_PREFER_SMEM(in_shortcut_kernel<T>);
   in_shortcut_kernel<T><<<blocks(total), 256, 0, s>>>(x, x_t, z, n, HW, C, Cz, C / Cz);
   LC_LAUNCH_CHECK();
   return 0;

@@ -7,6 +7,7 @@
 //   att_* [rows, d] T   attention output, split         mlp_* [rows, 4d] T  MLP hidden
 //   mod [B, 12d*n_dual + 3d*n_single + 2d] f32          all AdaLN modulation vectors from ONE GEMM per call
 // T = bf16 (tensor-core mode) or float (FP32 validation mode).  The residual streams stay fp32 in both modes.
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -80,6 +81,10 @@ struct lc_denoiser {
   std::vector<DualW> dual;
   std::vector<SingleW> single;
   int mod_dim = 0, kp_in = 96;
+  // RMSNorm(q,k)+RoPE fused into the qkv GEMM epilogue (gemm_tc.cu K_QKV).  Measured slower than the separate
+  // HBM-bound kernel on the K=1536 projections (their epilogue is already the critical path), so off by default;
+  // LADCAST_B200_FUSE_QK=1 turns it on.
+  bool fuse_qk = false;
 
   // geometry
   int maxB = 0, T_in = 0, T_out = 0, H = 0, W = 0, Np = 0, Nc = 0, S = 0;
@@ -170,6 +175,7 @@ struct Ctx {
   lc_denoiser* D;
   cudaStream_t st;
   int run(const GemmArgs& g) const { return D->f32 ? gemm_f32(g, st) : gemm_bf16(g, st); }
+  bool fused_qk() const { return !D->f32 && D->fuse_qk; }
 
   GemmArgs base(const void* A, long long lda, int M, const Lin& L) const {
     GemmArgs g;
@@ -190,10 +196,17 @@ struct Ctx {
     return run(g);
   }
   // qkv projection into the joint [B, S, 3d] buffer at token offset `tok_off`
-  int lin_qkv(const void* A, int M, int rows_per_sample, const Lin& L, void* qkv, int S, int tok_off) const {
+  // On the tensor-core path the per-head RMSNorm(q,k) + RoPE of this stream's tokens is fused into the epilogue
+  // (seg gives the norm weights and cos/sin tables); the FP32 validation path runs qk_norm_rope afterwards.
+  int lin_qkv(const void* A, int M, int rows_per_sample, const Lin& L, void* qkv, int S, int tok_off,
+              const RopeSeg* seg) const {
     GemmArgs g = base(A, D->d, M, L);
     g.epi.mode = EPI_STORE; g.epi.out = qkv; g.epi.ldo = 3LL * D->d; g.epi.out_f32 = D->f32 ? 1 : 0;
     g.epi.rows_per_sample = rows_per_sample; g.epi.out_rows_per_sample = S; g.epi.out_row_offset = tok_off;
+    if (!D->f32 && seg != nullptr && D->fuse_qk) {
+      g.epi.qk_cols = 2 * D->d; g.epi.qk_eps = 1e-7f; g.epi.qk_wq = seg->wq; g.epi.qk_wk = seg->wk;
+      g.epi.rope_cos = seg->cos; g.epi.rope_sin = seg->sin;
+    }
     return run(g);
   }
   // resid[row] += gate[sample] * (A W^T + b);  A may be two K-segments
@@ -278,10 +291,10 @@ int forward_impl(lc_denoiser* D, const float* x_in, const float* c_noise, int n_
     const float* g_mlp = g_msa + d;
     const long long gs = 2LL * d * n_ref;
     LC_TRY(layernorm_modulate<T>(e, n_c, Mc, d, 1e-7f, Nc, nullptr, nullptr, 0, w.n1w, w.n1b, st));
-    LC_TRY(c.lin_qkv(n_c, Mc, Nc, w.qkv, qkv, Nc, 0));
     RopeSeg seg;
     seg.start = 0; seg.len = Nc; seg.wq = w.nq; seg.wk = w.nk; seg.cos = D->cos_c.as<float>(); seg.sin = D->sin_c.as<float>();
-    LC_TRY(qk_norm_rope<T>(qkv, 3LL * d, B, Nc, heads, 128, 1e-7f, &seg, 1, st));
+    LC_TRY(c.lin_qkv(n_c, Mc, Nc, w.qkv, qkv, Nc, 0, &seg));
+    if (!c.fused_qk()) LC_TRY(qk_norm_rope<T>(qkv, 3LL * d, B, Nc, heads, 128, 1e-7f, &seg, 1, st));
     LC_TRY(attention<T>(D, B, Nc, 0, st));  // all tokens -> att_c
     LC_TRY(gated_add<T>(e, D->att_c.as<T>(), g_msa, gs, Mc, d, Nc, st));
     LC_TRY(layernorm_modulate<T>(e, n_c, Mc, d, 1e-7f, Nc, nullptr, nullptr, 0, w.n2w, w.n2b, st));
@@ -311,13 +324,13 @@ int forward_impl(lc_denoiser* D, const float* x_in, const float* c_noise, int n_
     const float* mc = mh + 6LL * d;
     LC_TRY(layernorm_modulate<T>(h, n_p, Mp, d, 1e-6f, Np, mh + d, mh, md, nullptr, nullptr, st));
     LC_TRY(layernorm_modulate<T>(e, n_c, Mc, d, 1e-6f, Nc, mc + d, mc, md, nullptr, nullptr, st));
-    LC_TRY(c.lin_qkv(n_p, Mp, Np, w.qkv, qkv, S, 0));
-    LC_TRY(c.lin_qkv(n_c, Mc, Nc, w.add_qkv, qkv, S, Np));
     RopeSeg segs[2];
     segs[0].start = 0; segs[0].len = Np; segs[0].wq = w.nq; segs[0].wk = w.nk;
     segs[0].cos = D->cos_p.as<float>(); segs[0].sin = D->sin_p.as<float>();
     segs[1].start = Np; segs[1].len = Nc; segs[1].wq = w.naq; segs[1].wk = w.nak;  // no RoPE on cond (quirk C-3)
-    LC_TRY(qk_norm_rope<T>(qkv, 3LL * d, B, S, heads, 128, 1e-7f, segs, 2, st));
+    LC_TRY(c.lin_qkv(n_p, Mp, Np, w.qkv, qkv, S, 0, &segs[0]));
+    LC_TRY(c.lin_qkv(n_c, Mc, Nc, w.add_qkv, qkv, S, Np, &segs[1]));
+    if (!c.fused_qk()) LC_TRY(qk_norm_rope<T>(qkv, 3LL * d, B, S, heads, 128, 1e-7f, segs, 2, st));
     LC_TRY(attention<T>(D, B, S, Np, st));
     LC_TRY(c.lin_gated(D->att_p.p, d, 0, nullptr, 0, Mp, Np, w.to_out, h, mh + 2 * d, md));
     LC_TRY(c.lin_gated(D->att_c.p, d, 0, nullptr, 0, Mc, Nc, w.to_add_out, e, mc + 2 * d, md));
@@ -336,16 +349,16 @@ int forward_impl(lc_denoiser* D, const float* x_in, const float* c_noise, int n_
     const float* ms = ms_base + 3LL * d * i;  // shift, scale, gate
     LC_TRY(layernorm_modulate<T>(h, n_p, Mp, d, 1e-6f, Np, ms + d, ms, md, nullptr, nullptr, st));
     LC_TRY(layernorm_modulate<T>(e, n_c, Mc, d, 1e-6f, Nc, ms + d, ms, md, nullptr, nullptr, st));
-    LC_TRY(c.lin_qkv(n_p, Mp, Np, w.qkv, qkv, S, 0));
-    LC_TRY(c.lin_qkv(n_c, Mc, Nc, w.qkv, qkv, S, Np));
-    LC_TRY(c.lin_T(n_p, d, Mp, w.mlp, D->mlp_p.p, w.mlp.out, ACT_GELU_TANH));
-    LC_TRY(c.lin_T(n_c, d, Mc, w.mlp, D->mlp_c.p, w.mlp.out, ACT_GELU_TANH));
     RopeSeg segs[2];
     segs[0].start = 0; segs[0].len = Np; segs[0].wq = w.nq; segs[0].wk = w.nk;
     segs[0].cos = D->cos_p.as<float>(); segs[0].sin = D->sin_p.as<float>();
     segs[1].start = Np; segs[1].len = Nc; segs[1].wq = w.nq; segs[1].wk = w.nk;
     segs[1].cos = D->cos_c.as<float>(); segs[1].sin = D->sin_c.as<float>();
-    LC_TRY(qk_norm_rope<T>(qkv, 3LL * d, B, S, heads, 128, 1e-7f, segs, 2, st));
+    LC_TRY(c.lin_qkv(n_p, Mp, Np, w.qkv, qkv, S, 0, &segs[0]));
+    LC_TRY(c.lin_qkv(n_c, Mc, Nc, w.qkv, qkv, S, Np, &segs[1]));
+    LC_TRY(c.lin_T(n_p, d, Mp, w.mlp, D->mlp_p.p, w.mlp.out, ACT_GELU_TANH));
+    LC_TRY(c.lin_T(n_c, d, Mc, w.mlp, D->mlp_c.p, w.mlp.out, ACT_GELU_TANH));
+    if (!c.fused_qk()) LC_TRY(qk_norm_rope<T>(qkv, 3LL * d, B, S, heads, 128, 1e-7f, segs, 2, st));
     LC_TRY(attention<T>(D, B, S, Np, st));
     // proj_out over [attn | mlp] (K = d + mlp_dim) read from two buffers, gate, + residual
     LC_TRY(c.lin_gated(D->att_p.p, d, d, D->mlp_p.p, w.mlp.out, Mp, Np, w.proj_out, h, ms + 2 * d, md));
@@ -457,6 +470,8 @@ int lc_denoiser_create(const lc_denoiser_cfg* cfg, lc_denoiser** out) {
   D->f32 = cfg->precision == LC_PRECISION_F32;
   D->esz = D->f32 ? 4 : 2;
   D->d = cfg->num_heads * cfg->head_dim;
+  const char* fq = getenv("LADCAST_B200_FUSE_QK");
+  D->fuse_qk = fq != nullptr && fq[0] == '1';
   *out = D;
   return 0;
 }

@@ -65,7 +65,7 @@ __device__ __forceinline__ float act_fast(float v) {
   return v;
 }
 
-enum EpiKind { K_STORE_BF16 = 0, K_STORE_F32 = 1, K_GATED = 2, K_RESID = 3, K_UNPATCH = 4 };
+enum EpiKind { K_STORE_BF16 = 0, K_STORE_F32 = 1, K_GATED = 2, K_RESID = 3, K_UNPATCH = 4, K_QKV = 5 };
 
 // One 32x32 accumulator block (lane = row, r[j] = column n0+j).  K_UNPATCH keeps this layout (consecutive rows are
 // contiguous in the channel-major output); every other kind transposes the block through a padded smem tile so
@@ -157,6 +157,49 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& ep, const uint32
   __syncwarp();
 }
 
+// qkv projection block: bias, then (q/k heads only) per-head RMSNorm with the row's precomputed rstd and RoPE on
+// interleaved pairs, bf16 store.  Lanes own adjacent column pairs == rotation pairs; cos/sin rows load coalesced.
+// Reference: LaDCast_3D_model.py:92-169 (to_q/k/v, norm_q/k, apply_rotary_emb).
+__device__ __forceinline__ void epilogue_qkv_block(const EpiParams& ep, const uint32_t (&r)[32], float* tbuf, int lane,
+                                                   int row_mine, long long orow_mine, int tok_mine, float rstd_mine,
+                                                   int n0, int col_in_head0, bool is_qk, const float* nw, int M) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
+  __syncwarp();
+  const int cc = (lane & 15) * 2;
+  const int col = n0 + cc;
+  const int colh = col_in_head0 + cc;
+  const float2 b2 = ep.bias != nullptr ? __ldg(reinterpret_cast<const float2*>(ep.bias + col)) : make_float2(0.f, 0.f);
+  const float2 w2 = is_qk ? __ldg(reinterpret_cast<const float2*>(nw + colh)) : make_float2(1.f, 1.f);
+  const bool rope = is_qk && ep.rope_cos != nullptr;
+  bf16* outp = reinterpret_cast<bf16*>(ep.out) + col;
+  const long long ldo = ep.ldo;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int rr = 2 * i + (lane >> 4);
+    const int row = __shfl_sync(0xffffffffu, row_mine, rr);
+    const long long orow = __shfl_sync(0xffffffffu, orow_mine, rr);
+    const float rs = __shfl_sync(0xffffffffu, rstd_mine, rr);
+    const int tok = __shfl_sync(0xffffffffu, tok_mine, rr);
+    float v0 = tbuf[rr * 33 + cc] + b2.x, v1 = tbuf[rr * 33 + cc + 1] + b2.y;
+    if (is_qk) {
+      v0 *= rs * w2.x;
+      v1 *= rs * w2.y;
+    }
+    if (row < M) {
+      if (rope) {
+        const float2 c2 = __ldg(reinterpret_cast<const float2*>(ep.rope_cos + static_cast<long long>(tok) * 128 + colh));
+        const float2 s2 = __ldg(reinterpret_cast<const float2*>(ep.rope_sin + static_cast<long long>(tok) * 128 + colh));
+        const float o0 = v0 * c2.x - v1 * s2.x, o1 = v1 * c2.y + v0 * s2.y;
+        v0 = o0;
+        v1 = o1;
+      }
+      *reinterpret_cast<__nv_bfloat162*>(outp + orow * ldo) = __floats2bfloat162_rn(v0, v1);
+    }
+  }
+  __syncwarp();
+}
+
 template <int KIND>
 __device__ __forceinline__ void epilogue_act_dispatch(const EpiParams& ep, const uint32_t (&r)[32], float* tbuf, int lane,
                                                       int row, long long orow, int sample, int n0, int M, int N) {
@@ -169,6 +212,7 @@ __device__ __forceinline__ void epilogue_act_dispatch(const EpiParams& ep, const
 }
 
 __device__ __forceinline__ int epi_kind(const EpiParams& ep) {
+  if (ep.qk_cols > 0) return K_QKV;
   if (ep.mode == EPI_GATED_RESID) return K_GATED;
   if (ep.mode == EPI_UNPATCHIFY) return K_UNPATCH;
   if (ep.mode == EPI_RESID_STORE) return K_RESID;  // f32 output only on the tensor-core path
@@ -325,6 +369,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                               static_cast<uint32_t>(acc * BN + half * (BN / 2));
+      if (kind == K_QKV) {
+        // this warp owns one 128-column head of the tile: pass 1 = sum of squares per row (q/k heads), pass 2 =
+        // normalise + rotate + store.  TMEM is read twice; the accumulator never leaves the SM in fp32.
+        const int head0 = n_blk * BN + half * (BN / 2);
+        const bool is_qk = head0 < ep.qk_cols;
+        const float* nw = (head0 < ep.qk_cols / 2) ? ep.qk_wq : ep.qk_wk;
+        float rstd = 1.f;
+        if (is_qk && head0 < N) {
+          float ss = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            ptx::tmem_ld32(t_addr + c * 32, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float t2 = __uint_as_float(r[j]) + (ep.bias != nullptr ? __ldg(ep.bias + head0 + c * 32 + j) : 0.f);
+              ss = fmaf(t2, t2, ss);
+            }
+          }
+          rstd = rsqrtf(ss * (1.0f / 128.0f) + ep.qk_eps);
+        }
+        const int tok = row % ep.rows_per_sample;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld32(t_addr + c * 32, r);
+          ptx::tmem_ld_wait();
+          const int n0 = head0 + c * 32;
+          if (n0 < N) epilogue_qkv_block(ep, r, tbuf, lane, row, orow, tok, rstd, n0, c * 32, is_qk, nw, M);
+        }
+      } else
 #pragma unroll 1
       for (int c = 0; c < BN / 64; ++c) {
         uint32_t r[32];
@@ -393,6 +469,8 @@ static int pick_bn(int N) { return (N > 128) ? 256 : 128; }
 
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   LC_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "empty GEMM");
+  LC_REQUIRE(g.epi.qk_cols == 0 || (g.N > 128 && g.N % 128 == 0 && g.epi.qk_cols % 256 == 0 && !g.epi.out_f32),
+             "fused qk-norm/rope epilogue needs head-aligned (128) columns and bf16 output");
   const int K0 = (g.A1 != nullptr) ? g.K0 : g.K;
   LC_REQUIRE(g.A1 == nullptr || (K0 % BK == 0 && K0 > 0 && K0 < g.K), "split-K source boundary must be a multiple of 64");
   const int bn = pick_bn(g.N);

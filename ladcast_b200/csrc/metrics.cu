@@ -113,6 +113,7 @@ int lc_metrics_accumulate(const float* fields, const float* truth, const double*
   LC_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * planes, st));
   LC_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(double) * 4 * planes, st));
   dim3 grid(ceil_div(height * width, THREADS), static_cast<unsigned>(planes));
+  LC_PREFER_SMEM(metrics_kernel<true>);
   metrics_kernel<true><<<grid, THREADS, smem, st>>>(fields, truth, latw, members, planes, height, width, sums, counts,
                                                     nullptr, nullptr, nullptr);
   LC_LAUNCH_CHECK();
@@ -133,6 +134,7 @@ int lc_metrics_pointwise(const float* fields, const float* truth, int members, l
     attr = smem;
   }
   dim3 grid(ceil_div(height * width, THREADS), static_cast<unsigned>(planes));
+  LC_PREFER_SMEM(metrics_kernel<false>);
   metrics_kernel<false><<<grid, THREADS, smem, st>>>(fields, truth, nullptr, members, planes, height, width, nullptr,
                                                      nullptr, out_skill, out_spread, out_mean);
   LC_LAUNCH_CHECK();
