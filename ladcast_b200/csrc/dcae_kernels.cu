@@ -122,16 +122,12 @@ __device__ __forceinline__ int sphere_col(int px, int p, int W, bool rolled) {
 // 5x5, fp32 in/out, 4 channels per thread (multiscale projection, DCAE.py:76-85)
 __global__ void __launch_bounds__(256) dwconv5_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                       float* __restrict__ out, int n, int H, int W, int C) {
-  const int c4n = C / 4;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(n) * H * W * c4n;
-  if (i >= total) return;
-  const int c = static_cast<int>(i % c4n) * 4;
-  long long r = i / c4n;
-  const int x = static_cast<int>(r % W);
-  r /= W;
-  const int y = static_cast<int>(r % H);
-  const int f = static_cast<int>(r / H);
+  // block = 32 consecutive x of one image row x 8 channel quads: the K taps along x re-use L1 lines within the block
+  const int c = (blockIdx.x * 8 + (threadIdx.x & 7)) * 4;
+  const int x = blockIdx.y * 32 + (threadIdx.x >> 3);
+  const int y = blockIdx.z % H, f = blockIdx.z / H;
+  if (c >= C || x >= W) return;
+  const long long i = ((static_cast<long long>(f) * H + y) * W + x) * (C / 4) + c / 4;
   const float* base = in + static_cast<long long>(f) * H * W * C + c;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -183,16 +179,12 @@ template <typename T>
 __global__ void __launch_bounds__(256) dwconv3_glu_kernel(const T* __restrict__ in, const float* __restrict__ w,
                                                           const float* __restrict__ bias, T* __restrict__ out, int n,
                                                           int H, int W, int C) {
-  const int Co = C / 2, c4n = Co / 4;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(n) * H * W * c4n;
-  if (i >= total) return;
-  const int c = static_cast<int>(i % c4n) * 4;
-  long long r = i / c4n;
-  const int x = static_cast<int>(r % W);
-  r /= W;
-  const int y = static_cast<int>(r % H);
-  const int f = static_cast<int>(r / H);
+  const int Co = C / 2;
+  const int c = (blockIdx.x * 8 + (threadIdx.x & 7)) * 4;
+  const int x = blockIdx.y * 32 + (threadIdx.x >> 3);
+  const int y = blockIdx.z % H, f = blockIdx.z / H;
+  if (c >= Co || x >= W) return;
+  const long long i = ((static_cast<long long>(f) * H + y) * W + x) * (Co / 4) + c / 4;
   const T* base = in + static_cast<long long>(f) * H * W * C + c;
   float4 a0 = __ldg(reinterpret_cast<const float4*>(bias + c));
   float4 a1 = __ldg(reinterpret_cast<const float4*>(bias + Co + c));
@@ -427,18 +419,18 @@ int halo_fill(T* buf, int n, int H, int W, int Cp, cudaStream_t s) {
 }
 int dwconv5(const float* in, const float* w, float* out, int n, int H, int W, int C, cudaStream_t s) {
   LC_REQUIRE(C % 4 == 0, "dwconv5: channels must be a multiple of 4");
-  const long long total = static_cast<long long>(n) * H * W * (C / 4);
+  dim3 grid((C / 4 + 7) / 8, (W + 31) / 32, n * H);
   LC_PREFER_SMEM(dwconv5_kernel);
-  dwconv5_kernel<<<blocks(total), 256, 0, s>>>(in, w, out, n, H, W, C);
+  dwconv5_kernel<<<grid, 256, 0, s>>>(in, w, out, n, H, W, C);
   LC_LAUNCH_CHECK();
   return 0;
 }
 template <typename T>
 int dwconv3_glu(const T* in, const float* w, const float* bias, T* out, int n, int H, int W, int C, cudaStream_t s) {
   LC_REQUIRE(C % 8 == 0, "dwconv3_glu: channels must be a multiple of 8");
-  const long long total = static_cast<long long>(n) * H * W * (C / 8);
+  dim3 grid((C / 8 + 7) / 8, (W + 31) / 32, n * H);
   LC_PREFER_SMEM(dwconv3_glu_kernel<T>);
-  dwconv3_glu_kernel<T><<<blocks(total), 256, 0, s>>>(in, w, bias, out, n, H, W, C);
+  dwconv3_glu_kernel<T><<<grid, 256, 0, s>>>(in, w, bias, out, n, H, W, C);
   LC_LAUNCH_CHECK();
   return 0;
 }

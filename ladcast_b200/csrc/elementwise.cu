@@ -118,6 +118,64 @@ __global__ void __launch_bounds__(256) qk_norm_rope_kernel(T* __restrict__ qkv, 
   store4<T>(p, v.x, v.y, v.z, v.w);
 }
 
+// bf16 production variant: 16 lanes per head, 8 features (16 B) per lane -> 128-bit loads/stores, half the
+// instructions per byte of the generic kernel above.
+__global__ void __launch_bounds__(256) qk_norm_rope_bf16_kernel(bf16* __restrict__ qkv, long long ld, int B, int S,
+                                                                int heads, float eps, RopeSeg s0, RopeSeg s1, int nseg) {
+  const long long gt = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  const long long unit = gt >> 4;  // (row, q|k, head)
+  const int sub = static_cast<int>(gt & 15);
+  const long long total = static_cast<long long>(B) * S * 2 * heads;
+  const bool live = unit < total;  // no early return: every lane takes part in the shuffles below
+  const long long u = live ? unit : total - 1;
+  const int head = static_cast<int>(u % heads);
+  const int which = static_cast<int>((u / heads) % 2);
+  const long long row = u / (2 * heads);
+  const int tok = static_cast<int>(row % S);
+  const RopeSeg& sg = (nseg > 1 && tok >= s1.start) ? s1 : s0;
+  bf16* p = qkv + row * ld + static_cast<long long>(which) * heads * 128 + head * 128 + sub * 8;
+  const uint4 raw = *reinterpret_cast<const uint4*>(p);
+  float v[8];
+  {
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h2[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ss = fmaf(v[i], v[i], ss);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float r = rsqrtf(ss * (1.0f / 128.0f) + eps);
+  const float* wp = (which ? sg.wk : sg.wq) + sub * 8;
+  const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp)), w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+  const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] *= r * w[i];
+  if (sg.cos != nullptr) {
+    const long long t = static_cast<long long>(tok - sg.start) * 128 + sub * 8;
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(sg.cos + t)), c1 = __ldg(reinterpret_cast<const float4*>(sg.cos + t + 4));
+    const float4 n0 = __ldg(reinterpret_cast<const float4*>(sg.sin + t)), n1 = __ldg(reinterpret_cast<const float4*>(sg.sin + t + 4));
+    const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float sn[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      const float a = v[i], b = v[i + 1];
+      v[i] = a * cs[i] - b * sn[i];
+      v[i + 1] = b * cs[i + 1] + a * sn[i + 1];
+    }
+  }
+  uint4 o;
+  __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  if (live) *reinterpret_cast<uint4*>(p) = o;
+}
+
 // ---------------------------------------------------------------- patchify: [B,C,THW] f32 -> [B*THW, Kp] T (zero pad)
 // Reference: HunyuanVideoPatchEmbed flatten(2).transpose(1,2) with patch (1,1,1): token n = t*HW + h*W + w
 // (embeddings.py:56-59).  Pure index permutation -> bit-exact in the fp32 mode.
@@ -297,6 +355,13 @@ int qk_norm_rope(T* qkv, long long ld, int B, int S, int heads, int head_dim, fl
   LC_REQUIRE(nseg == 1 || nseg == 2, "qk_norm_rope: 1 or 2 segments");
   const long long total = static_cast<long long>(B) * S * 2 * heads;
   RopeSeg s1 = nseg > 1 ? segs[1] : segs[0];
+  if (sizeof(T) == 2) {
+    LC_PREFER_SMEM(qk_norm_rope_bf16_kernel);
+    qk_norm_rope_bf16_kernel<<<static_cast<unsigned>(ceil_div_ll(total * 16, 256)), 256, 0, s>>>(
+        reinterpret_cast<bf16*>(qkv), ld, B, S, heads, eps, segs[0], s1, nseg);
+    LC_LAUNCH_CHECK();
+    return 0;
+  }
   LC_PREFER_SMEM(qk_norm_rope_kernel<T>);
   qk_norm_rope_kernel<T><<<static_cast<unsigned>(ceil_div_ll(total, 8)), 256, 0, s>>>(qkv, ld, B, S, heads, eps, segs[0],
                                                                                      s1, nseg);

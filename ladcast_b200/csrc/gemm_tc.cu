@@ -219,6 +219,86 @@ __device__ __forceinline__ int epi_kind(const EpiParams& ep) {
   return ep.out_f32 ? K_STORE_F32 : K_STORE_BF16;
 }
 
+// Row bookkeeping of one epilogue thread for tile (m_blk, .): global row (or M when the tile row is padding), remapped
+// output row and sample index.
+__device__ __forceinline__ void epilogue_row(const EpiParams& ep, const ConvLoad& cv, int m_blk, int quarter, int lane, int M,
+                                             int& row, long long& orow, int& sample) {
+  const int t = quarter * 32 + lane;
+  row = m_blk * BM + t;
+  if (cv.enabled) {
+    // tile row t -> (frame, x) within the tile; invalid rows (t >= Wt*Nt, x >= W, frame >= n) are dropped
+    const int per_group = cv.tiles_x * cv.H;
+    const int fg = m_blk / per_group;
+    const int rem = m_blk - fg * per_group;
+    const int y = rem / cv.tiles_x;
+    const int x0 = (rem - y * cv.tiles_x) * cv.Wt;
+    const int fi = t / cv.Wt;
+    const int x = x0 + (t - fi * cv.Wt);
+    const int f = fg * cv.Nt + fi;
+    row = (fi < cv.Nt && x < cv.W && f < cv.n_frames) ? (f * cv.H + y) * cv.W + x : M;
+  }
+  if (row > M) row = M;
+  sample = 0;
+  orow = epi_out_row(ep, row, sample);
+}
+
+// Drain one accumulator stage: this warp's 32 rows x (BN/2) columns, TMEM -> registers -> fused epilogue -> global.
+template <int BN>
+__device__ __forceinline__ void epilogue_drain(const EpiParams& ep, int kind, int n_blk, int quarter, int half, int lane,
+                                               float* tbuf, uint32_t tmem_base, int acc, int row, long long orow,
+                                               int sample, int M, int N) {
+  const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                          static_cast<uint32_t>(acc * BN + half * (BN / 2));
+  if (kind == K_QKV) {
+    // this warp owns one 128-column head of the tile: pass 1 = sum of squares per row (q/k heads), pass 2 =
+    // normalise + rotate + store.  TMEM is read twice; the accumulator never leaves the SM in fp32.
+    const int head0 = n_blk * BN + half * (BN / 2);
+    const bool is_qk = head0 < ep.qk_cols;
+    const float* nw = (head0 < ep.qk_cols / 2) ? ep.qk_wq : ep.qk_wk;
+    float rstd = 1.f;
+    if (is_qk && head0 < N) {
+      float ss = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld32(t_addr + c * 32, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float t2 = __uint_as_float(r[j]) + (ep.bias != nullptr ? __ldg(ep.bias + head0 + c * 32 + j) : 0.f);
+          ss = fmaf(t2, t2, ss);
+        }
+      }
+      rstd = rsqrtf(ss * (1.0f / 128.0f) + ep.qk_eps);
+    }
+    const int tok = row % ep.rows_per_sample;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      ptx::tmem_ld32(t_addr + c * 32, r);
+      ptx::tmem_ld_wait();
+      const int n0 = head0 + c * 32;
+      if (n0 < N) epilogue_qkv_block(ep, r, tbuf, lane, row, orow, tok, rstd, n0, c * 32, is_qk, nw, M);
+    }
+  } else
+#pragma unroll 1
+  for (int c = 0; c < BN / 64; ++c) {
+    uint32_t r[32];
+    ptx::tmem_ld32(t_addr + c * 32, r);
+    ptx::tmem_ld_wait();
+    const int n0 = n_blk * BN + half * (BN / 2) + c * 32;
+    if (n0 < N) {
+      switch (kind) {
+        case K_STORE_BF16: epilogue_act_dispatch<K_STORE_BF16>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
+        case K_STORE_F32: epilogue_act_dispatch<K_STORE_F32>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
+        case K_GATED: epilogue_block<K_GATED, ACT_NONE>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
+        case K_RESID: epilogue_act_dispatch<K_RESID>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
+        default: epilogue_act_dispatch<K_UNPATCH>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
+      }
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -348,75 +428,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
       sched.decode(tile, m_blk, n_blk);
-      const int t = quarter * 32 + lane;
-      int row = m_blk * BM + t;
-      if (cv.enabled) {
-        // tile row t -> (frame, x) within the tile; invalid rows (t >= Wt*Nt, x >= W, frame >= n) are dropped
-        const int per_group = cv.tiles_x * cv.H;
-        const int fg = m_blk / per_group;
-        const int rem = m_blk - fg * per_group;
-        const int y = rem / cv.tiles_x;
-        const int x0 = (rem - y * cv.tiles_x) * cv.Wt;
-        const int fi = t / cv.Wt;
-        const int x = x0 + (t - fi * cv.Wt);
-        const int f = fg * cv.Nt + fi;
-        row = (fi < cv.Nt && x < cv.W && f < cv.n_frames) ? (f * cv.H + y) * cv.W + x : M;
-      }
-      if (row > M) row = M;
-      int sample = 0;
-      const long long orow = epi_out_row(ep, row, sample);
+      int row, sample;
+      long long orow;
+      epilogue_row(ep, cv, m_blk, quarter, lane, M, row, orow, sample);
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                              static_cast<uint32_t>(acc * BN + half * (BN / 2));
-      if (kind == K_QKV) {
-        // this warp owns one 128-column head of the tile: pass 1 = sum of squares per row (q/k heads), pass 2 =
-        // normalise + rotate + store.  TMEM is read twice; the accumulator never leaves the SM in fp32.
-        const int head0 = n_blk * BN + half * (BN / 2);
-        const bool is_qk = head0 < ep.qk_cols;
-        const float* nw = (head0 < ep.qk_cols / 2) ? ep.qk_wq : ep.qk_wk;
-        float rstd = 1.f;
-        if (is_qk && head0 < N) {
-          float ss = 0.f;
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t r[32];
-            ptx::tmem_ld32(t_addr + c * 32, r);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float t2 = __uint_as_float(r[j]) + (ep.bias != nullptr ? __ldg(ep.bias + head0 + c * 32 + j) : 0.f);
-              ss = fmaf(t2, t2, ss);
-            }
-          }
-          rstd = rsqrtf(ss * (1.0f / 128.0f) + ep.qk_eps);
-        }
-        const int tok = row % ep.rows_per_sample;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld32(t_addr + c * 32, r);
-          ptx::tmem_ld_wait();
-          const int n0 = head0 + c * 32;
-          if (n0 < N) epilogue_qkv_block(ep, r, tbuf, lane, row, orow, tok, rstd, n0, c * 32, is_qk, nw, M);
-        }
-      } else
-#pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld32(t_addr + c * 32, r);
-        ptx::tmem_ld_wait();
-        const int n0 = n_blk * BN + half * (BN / 2) + c * 32;
-        if (n0 < N) {
-          switch (kind) {
-            case K_STORE_BF16: epilogue_act_dispatch<K_STORE_BF16>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
-            case K_STORE_F32: epilogue_act_dispatch<K_STORE_F32>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
-            case K_GATED: epilogue_block<K_GATED, ACT_NONE>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
-            case K_RESID: epilogue_act_dispatch<K_RESID>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
-            default: epilogue_act_dispatch<K_UNPATCH>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
-          }
-        }
-      }
+      epilogue_drain<BN>(ep, kind, n_blk, quarter, half, lane, tbuf, tmem_base, acc, row, orow, sample, M, N);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
