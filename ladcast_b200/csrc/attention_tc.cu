@@ -2,15 +2,17 @@
 // LaDCast_3D_model.py:199-201).  Q/K/V are read by TMA straight out of the token-major [B*S, 3d] projection
 // buffer (q | k | v), so no head-major transposes exist anywhere.
 //
-//   CTA = one (sample, head, 128-query tile), KV tiles of 64 keys; 192 threads, TWO CTAs per SM (96 KB smem and
-//   256 TMEM columns each) so that one CTA's softmax overlaps the other's tensor-core work:
-//     warp 0 : TMA producer (Q once; K_j / V_j double buffered)
-//     warp 1 : TMEM allocator + single-thread tcgen05.mma issuer:  S_j = Q K_j^T  (TMEM, double buffered),
-//              O += P_j V_j  (V consumed MN-major, i.e. exactly as it lies in memory)
-//     warps 2-5 : softmax; one thread per query row reads its S row from TMEM (no shuffles), online softmax in the
-//              log2 domain with lazy rescaling of O (only when the row max grows by > 2^8), writes P_j (bf16) into a
-//              128B-swizzled smem tile that is the A operand of the PV product (the tile re-uses K_j's buffer, which is
-//              dead once S_j exists); final O / l epilogue.
+//   CTA = one (sample, head, 256-query block) = two 128-query tiles A and B that share every K/V tile; 320 threads:
+//     warp 0    : TMA producer — Q (both tiles) once, K_j / V_j tiles of 64 keys through a 4-stage ring, so loads run
+//                 ~3 tiles ahead of the tensor pipe (L2->smem latency under load is ~2 us, longer than one tile)
+//     warp 1    : TMEM allocator + single-thread tcgen05.mma issuer.  Per KV tile: S_A = Q_A K^T, S_B = Q_B K^T
+//                 (double-buffered in TMEM, issued one tile ahead), O_A += P_A V, O_B += P_B V (V consumed MN-major,
+//                 i.e. exactly as it lies in memory)
+//     warps 2-5 : softmax of tile A, warps 6-9: softmax of tile B.  One thread per query row reads its S row from
+//                 TMEM (no shuffles), online softmax in the log2 domain (one FFMA + one MUFU.EX2 per element), lazy
+//                 rescale of O (only when the row max grows by more than 2^8), P (bf16) into a 128B-swizzled smem tile
+//                 that is the A operand of the PV product.  While one tile's softmax runs, the tensor pipe works on
+//                 the other tile.  Final O / l epilogue per tile.
 #include "kernels.h"
 #include "ptx.cuh"
 #include "tmap.h"
@@ -19,41 +21,45 @@ namespace lc {
 namespace {
 
 constexpr int HD = 128;
-constexpr int BQ = 128;
+constexpr int BQ = 128;                    // rows per query tile; two tiles per CTA
 constexpr int BKV = 64;
-constexpr int Q_BYTES = 128 * 128 * 2;     // 32 KB: two [128 rows][64 dims] swizzled boxes
+constexpr int STAGES = 4;
+constexpr int Q_BYTES = 128 * 128 * 2;     // 32 KB per query tile: two [128 rows][64 dims] swizzled boxes
 constexpr int QSUB_BYTES = 128 * 64 * 2;   // 16 KB
 constexpr int KV_BYTES = BKV * 128 * 2;    // 16 KB: two [64 keys][64 dims] swizzled boxes
 constexpr int KVSUB_BYTES = BKV * 64 * 2;  // 8 KB
-constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_BYTES /*K (+P alias)*/ + 2 * KV_BYTES /*V*/ + 1024 + 256;
-constexpr int NUM_THREADS = 192;
-constexpr uint32_t TMEM_COLS = 256;
-constexpr uint32_t COL_S0 = 0, COL_O = 128;
+constexpr int P_BYTES = 128 * BKV * 2;     // 16 KB: [128 rows][64 keys]
+constexpr int SMEM_BYTES = 2 * Q_BYTES + 2 * P_BYTES + 2 * STAGES * KV_BYTES + 1024 + 256;
+constexpr int NUM_THREADS = 320;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t COL_S = 0;    // S[tile][buf] at COL_S + tile*128 + buf*64
+constexpr uint32_t COL_O = 256;  // O[tile] at COL_O + tile*128
 constexpr float RESCALE_THRESHOLD = 8.0f;
 
-__global__ void __launch_bounds__(NUM_THREADS, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmkv, int S, int heads, bf16* __restrict__ out_p, int Np,
-                    bf16* __restrict__ out_c) {
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmkv, int S, int heads,
+                    bf16* __restrict__ out_p, int Np, bf16* __restrict__ out_c) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Q_BYTES;
-  uint8_t* sV = sK + 2 * KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * KV_BYTES);
-  uint64_t* q_full = bars;           // 1
-  uint64_t* k_full = bars + 1;       // 2
-  uint64_t* v_full = bars + 3;       // 2
-  uint64_t* kv_empty = bars + 5;     // 2
-  uint64_t* s_full = bars + 7;       // 2
-  uint64_t* p_full = bars + 9;       // 2 (4 arrivals each: one per softmax warp); P_j sits in K stage j&1
-  uint64_t* p_empty = bars + 11;     // 1 (PV_j complete; only waited on when O has to be rescaled)
-  uint64_t* o_full = bars + 12;      // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint8_t* sQ = smem;                       // [2][Q_BYTES]
+  uint8_t* sP = sQ + 2 * Q_BYTES;           // [2][P_BYTES]
+  uint8_t* sK = sP + 2 * P_BYTES;           // [STAGES][KV_BYTES]
+  uint8_t* sV = sK + STAGES * KV_BYTES;     // [STAGES][KV_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + STAGES * KV_BYTES);
+  uint64_t* q_full = bars;                  // 1
+  uint64_t* k_full = bars + 1;              // STAGES
+  uint64_t* v_full = k_full + STAGES;       // STAGES
+  uint64_t* kv_empty = v_full + STAGES;     // STAGES
+  uint64_t* s_full = kv_empty + STAGES;     // [tile][buf] = 4
+  uint64_t* p_full = s_full + 4;            // [tile] (4 arrivals: one per softmax warp)
+  uint64_t* p_empty = p_full + 2;           // [tile] (PV of the tile's previous KV tile complete)
+  uint64_t* o_full = p_empty + 2;           // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = heads * HD;
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * (2 * BQ);
   const int n_tiles = (S + BKV - 1) / BKV;
   const int row_base = b * S;
 
@@ -61,15 +67,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     ptx::prefetch_tmap(&tmq);
     ptx::prefetch_tmap(&tmkv);
     ptx::mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < STAGES; ++i) {
       ptx::mbar_init(&k_full[i], 1);
       ptx::mbar_init(&v_full[i], 1);
       ptx::mbar_init(&kv_empty[i], 1);
-      ptx::mbar_init(&s_full[i], 1);
     }
-    ptx::mbar_init(&p_full[0], 4);
-    ptx::mbar_init(&p_full[1], 4);
-    ptx::mbar_init(p_empty, 1);
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(&s_full[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&p_full[i], 4);
+      ptx::mbar_init(&p_empty[i], 1);
+    }
     ptx::mbar_init(o_full, 1);
     ptx::fence_barrier_init();
   }
@@ -81,12 +88,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
-    ptx::mbar_expect_tx(q_full, Q_BYTES);
-    ptx::tma_load_2d(sQ, &tmq, q_full, h * HD, row_base + q0);
-    ptx::tma_load_2d(sQ + QSUB_BYTES, &tmq, q_full, h * HD + 64, row_base + q0);
+    ptx::mbar_expect_tx(q_full, 2 * Q_BYTES);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      ptx::tma_load_2d(sQ + t * Q_BYTES, &tmq, q_full, h * HD, row_base + q0 + t * BQ);
+      ptx::tma_load_2d(sQ + t * Q_BYTES + QSUB_BYTES, &tmq, q_full, h * HD + 64, row_base + q0 + t * BQ);
+    }
+    int st = 0;
+    uint32_t ph = 0;
     for (int j = 0; j < n_tiles; ++j) {
-      const int st = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
       ptx::mbar_wait(&kv_empty[st], ph ^ 1);
       const int kr = row_base + j * BKV;
       ptx::mbar_expect_tx(&k_full[st], KV_BYTES);
@@ -95,60 +105,68 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       ptx::mbar_expect_tx(&v_full[st], KV_BYTES);
       ptx::tma_load_2d(sV + st * KV_BYTES, &tmkv, &v_full[st], 2 * d + h * HD, kr);
       ptx::tma_load_2d(sV + st * KV_BYTES + KVSUB_BYTES, &tmkv, &v_full[st], 2 * d + h * HD + 64, kr);
+      if (++st == STAGES) { st = 0; ph ^= 1; }
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(128, BKV, 0, 0);  // A = Q (K-major), B = K (K-major)
     constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(128, 128, 0, 1);  // A = P (K-major), B = V (MN-major)
-    const uint32_t q_addr = ptx::smem_u32(sQ);
-    auto issue_qk = [&](int j) {
-      const int st = j & 1;
-      ptx::mbar_wait(&k_full[st], (j >> 1) & 1);
+    const uint32_t q_addr = ptx::smem_u32(sQ), p_addr = ptx::smem_u32(sP);
+    auto issue_qk = [&](int j) {  // both query tiles against K_j
+      const int st = j % STAGES;
+      ptx::mbar_wait(&k_full[st], (j / STAGES) & 1);
       ptx::tc_fence_after();
       const uint32_t k_addr = ptx::smem_u32(sK + st * KV_BYTES);
-      const uint32_t d_tmem = tmem_base + COL_S0 + static_cast<uint32_t>(st * BKV);
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {  // 128 head dims = 2 sub-tiles x 4 K-steps of 16
-        const uint32_t qoff = (kk >> 2) * QSUB_BYTES + (kk & 3) * 32;
-        const uint32_t koff = (kk >> 2) * KVSUB_BYTES + (kk & 3) * 32;
-        ptx::umma_f16(d_tmem, ptx::make_smem_desc(q_addr + qoff, 16, 1024), ptx::make_smem_desc(k_addr + koff, 16, 1024),
-                      idesc_qk, kk != 0 ? 1u : 0u);
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t d_tmem = tmem_base + COL_S + static_cast<uint32_t>(t * 128 + (j & 1) * BKV);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {  // 128 head dims = 2 sub-tiles x 4 K-steps of 16
+          const uint32_t qoff = t * Q_BYTES + (kk >> 2) * QSUB_BYTES + (kk & 3) * 32;
+          const uint32_t koff = (kk >> 2) * KVSUB_BYTES + (kk & 3) * 32;
+          ptx::umma_f16(d_tmem, ptx::make_smem_desc(q_addr + qoff, 16, 1024),
+                        ptx::make_smem_desc(k_addr + koff, 16, 1024), idesc_qk, kk != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&s_full[t * 2 + (j & 1)]);
       }
-      ptx::umma_commit(&s_full[st]);
     };
     ptx::mbar_wait(q_full, 0);
     issue_qk(0);
     for (int j = 0; j < n_tiles; ++j) {
-      const int st = j & 1;
+      const int st = j % STAGES;
       if (j + 1 < n_tiles) issue_qk(j + 1);
-      ptx::mbar_wait(&v_full[st], (j >> 1) & 1);
-      ptx::mbar_wait(&p_full[st], (j >> 1) & 1);
-      ptx::tc_fence_after();
+      ptx::mbar_wait(&v_full[st], (j / STAGES) & 1);
       const uint32_t v_addr = ptx::smem_u32(sV + st * KV_BYTES);
-      const uint32_t p_addr = ptx::smem_u32(sK + st * KV_BYTES);  // P_j lives in K_j's (dead) buffer
 #pragma unroll
-      for (int kk = 0; kk < BKV / 16; ++kk) {  // 64 keys = 4 K-steps of 16
-        const uint64_t da = ptx::make_smem_desc(p_addr + kk * 32, 16, 1024);
-        const uint64_t db = ptx::make_smem_desc(v_addr + kk * 2048, KVSUB_BYTES, 1024);
-        ptx::umma_f16(tmem_base + COL_O, da, db, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+      for (int t = 0; t < 2; ++t) {
+        ptx::mbar_wait(&p_full[t], j & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk) {  // 64 keys = 4 K-steps of 16
+          const uint64_t da = ptx::make_smem_desc(p_addr + t * P_BYTES + kk * 32, 16, 1024);
+          const uint64_t db = ptx::make_smem_desc(v_addr + kk * 2048, KVSUB_BYTES, 1024);
+          ptx::umma_f16(tmem_base + COL_O + static_cast<uint32_t>(t * 128), da, db, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&p_empty[t]);
       }
-      ptx::umma_commit(&kv_empty[st]);
-      ptx::umma_commit(p_empty);
+      ptx::umma_commit(&kv_empty[st]);  // K_j and V_j are dead once both tiles' PV products have completed
     }
     ptx::umma_commit(o_full);
   } else if (warp >= 2) {
-    // ===================== softmax + epilogue (thread = query row) =====================
-    const int quarter = warp & 3;
+    // ===================== softmax + epilogue (thread = query row of tile t) =====================
+    const int t = (warp - 2) >> 2;  // 0: tile A (warps 2-5), 1: tile B (warps 6-9)
+    const int quarter = warp & 3;   // TMEM lane quarter this warp may access (= warp id % 4)
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const float scale_log2 = 0.08838834764831845f * 1.4426950408889634f;
+    const uint32_t o_addr = tmem_base + lane_addr + COL_O + static_cast<uint32_t>(t * 128);
+    uint8_t* prow = sP + t * P_BYTES + r * 128;
     float m_used = -INFINITY, l = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
-      const int st = j & 1;
-      ptx::mbar_wait(&s_full[st], (j >> 1) & 1);
+      ptx::mbar_wait(&s_full[t * 2 + (j & 1)], (j >> 1) & 1);
       ptx::tc_fence_after();
       uint32_t sreg[BKV / 32][32];
-      const uint32_t s_addr = tmem_base + lane_addr + COL_S0 + static_cast<uint32_t>(st * BKV);
+      const uint32_t s_addr = tmem_base + lane_addr + COL_S + static_cast<uint32_t>(t * 128 + (j & 1) * BKV);
 #pragma unroll
       for (int c = 0; c < BKV / 32; ++c) ptx::tmem_ld32(s_addr + c * 32, sreg[c]);
       ptx::tmem_ld_wait();
@@ -175,7 +193,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       }
       // p = 2^(s*scale - m): one FFMA + one MUFU per element; arguments are <= 8 by construction
       const float neg_m = -m_used;
-      float ps[4] = {0.f, 0.f, 0.f, 0.f};  // independent partial sums: no 64-long dependent FADD chain
+      float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < BKV / 32; ++c)
 #pragma unroll
@@ -185,13 +203,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
           sreg[c][i] = __float_as_uint(p);
         }
       l = l * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
-      // P_j goes to K stage j&1, which nothing else touches until PV_j: no wait needed to write it.  Only a
-      // rescale of O has to wait for PV_{j-1} (rare after the first tiles thanks to the 2^8 lazy threshold).
-      if (j > 0 && need) {
-        ptx::mbar_wait(p_empty, (j - 1) & 1);
+      if (j > 0) {
+        // PV of this tile's previous KV tile must be complete: the P buffer is free and O is quiescent
+        ptx::mbar_wait(&p_empty[t], (j - 1) & 1);
         ptx::tc_fence_after();
-        {
-          const uint32_t o_addr = tmem_base + lane_addr + COL_O;
+        if (need) {
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
             uint32_t o[32];
@@ -204,8 +220,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
           ptx::tmem_st_wait();
         }
       }
-      // P (bf16) -> smem (K_j's buffer), K-major [128 rows][64 keys], 128-byte swizzle: 16-B chunk index ^= row & 7
-      uint8_t* prow = sK + st * KV_BYTES + r * 128;
+      // P (bf16) -> smem, K-major [128 rows][64 keys], 128-byte swizzle: 16-B chunk index ^= row & 7
 #pragma unroll
       for (int g = 0; g < BKV / 8; ++g) {
         const int c = g >> 2, i0 = (g & 3) * 8;
@@ -223,17 +238,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&p_full[st]);
+      if (lane == 0) ptx::mbar_arrive(&p_full[t]);
     }
     ptx::mbar_wait(o_full, 0);
     ptx::tc_fence_after();
-    const int tok = q0 + r;
+    const int tok = q0 + t * BQ + r;
     const float inv = 1.0f / l;
     bf16* dst = nullptr;
     if (tok < S)
       dst = (tok < Np) ? out_p + (static_cast<long long>(b) * Np + tok) * d + h * HD
                        : out_c + (static_cast<long long>(b) * (S - Np) + (tok - Np)) * d + h * HD;
-    const uint32_t o_addr = tmem_base + lane_addr + COL_O;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t o[32];
@@ -278,7 +292,7 @@ int attention_bf16(const bf16* qkv, int B, int S, int heads, int head_dim, bf16*
                            static_cast<uint64_t>(3) * d * 2, 64, 128));
   LC_TRY(make_tmap_2d_bf16(&tmkv, qkv, static_cast<uint64_t>(3) * d, static_cast<uint64_t>(B) * S,
                            static_cast<uint64_t>(3) * d * 2, 64, BKV));
-  dim3 grid(ceil_div(S, BQ), heads, B);
+  dim3 grid(ceil_div(S, 2 * BQ), heads, B);
   prof_begin(PROF_ATTN, s);
   attention_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(tmq, tmkv, S, heads, out_p, Np, out_c);
   prof_end(PROF_ATTN, 4.0 * B * heads * static_cast<double>(S) * S * HD, s);

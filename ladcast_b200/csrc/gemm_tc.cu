@@ -10,6 +10,8 @@
 // [attention | mlp] without a concat (reference: LaDCast_3D_model.py:460-461).
 // The same kernel serves as an implicit-GEMM 3x3 sphere convolution (A tiles fetched from a padded NHWC tensor
 // with a 4-D tensor map at tap-shifted coordinates; reference: models/sphere_conv.py:138-192).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gemm_tc.h"
 #include "ptx.cuh"
@@ -89,6 +91,39 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& ep, const uint32
         if (has_scale) o = o * __ldg(ep.ch_scale + n0 + j) + __ldg(ep.ch_shift + n0 + j);
         op[static_cast<long long>(j) * ep.rows_per_sample] = o;
       }
+    }
+    return;
+  }
+  if (KIND == K_STORE_BF16 && n0 + 32 <= N && (ep.ldo & 7) == 0) {
+    // bf16 output, full chunk: each thread owns 32 consecutive columns of its row = 64 contiguous bytes.  Four
+    // 16-byte stores per thread need ~4x fewer instructions than the transposed path and the epilogue of the
+    // K=1536 projections is instruction-bound; L2 merges the half-sector writes before they reach HBM.
+    if (row_mine >= M) return;
+    float v[32];
+    if (ep.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
+        v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+        v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    }
+    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + orow_mine * ep.ldo + n0);
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      __nv_bfloat162 t0 = __floats2bfloat162_rn(act_fast<ACT>(v[j]), act_fast<ACT>(v[j + 1]));
+      __nv_bfloat162 t1 = __floats2bfloat162_rn(act_fast<ACT>(v[j + 2]), act_fast<ACT>(v[j + 3]));
+      __nv_bfloat162 t2 = __floats2bfloat162_rn(act_fast<ACT>(v[j + 4]), act_fast<ACT>(v[j + 5]));
+      __nv_bfloat162 t3 = __floats2bfloat162_rn(act_fast<ACT>(v[j + 6]), act_fast<ACT>(v[j + 7]));
+      uint4 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&t0);
+      pk.y = *reinterpret_cast<uint32_t*>(&t1);
+      pk.z = *reinterpret_cast<uint32_t*>(&t2);
+      pk.w = *reinterpret_cast<uint32_t*>(&t3);
+      op[j >> 3] = pk;
     }
     return;
   }
@@ -200,23 +235,29 @@ __device__ __forceinline__ void epilogue_qkv_block(const EpiParams& ep, const ui
   __syncwarp();
 }
 
-template <int KIND>
-__device__ __forceinline__ void epilogue_act_dispatch(const EpiParams& ep, const uint32_t (&r)[32], float* tbuf, int lane,
-                                                      int row, long long orow, int sample, int n0, int M, int N) {
-  switch (ep.act) {
-    case ACT_GELU_TANH: epilogue_block<KIND, ACT_GELU_TANH>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
-    case ACT_SILU: epilogue_block<KIND, ACT_SILU>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
-    case ACT_RELU: epilogue_block<KIND, ACT_RELU>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
-    default: epilogue_block<KIND, ACT_NONE>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
-  }
-}
-
 __device__ __forceinline__ int epi_kind(const EpiParams& ep) {
   if (ep.qk_cols > 0) return K_QKV;
   if (ep.mode == EPI_GATED_RESID) return K_GATED;
   if (ep.mode == EPI_UNPATCHIFY) return K_UNPATCH;
   if (ep.mode == EPI_RESID_STORE) return K_RESID;  // f32 output only on the tensor-core path
   return ep.out_f32 ? K_STORE_F32 : K_STORE_BF16;
+}
+
+// Chunk loop of one accumulator stage with the TMEM load of chunk c+1 in flight while chunk c is processed; kind and
+// activation are compile-time so the loop body is straight-line code.
+template <int BN, int KIND, int ACT>
+__device__ __forceinline__ void drain_loop(const EpiParams& ep, uint32_t t_addr, int n_base, float* tbuf, int lane, int row,
+                                           long long orow, int sample, int M, int N) {
+  constexpr int NC = BN / 64;
+  uint32_t r[2][32];
+  ptx::tmem_ld32(t_addr, r[0]);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    ptx::tmem_ld_wait();
+    if (c + 1 < NC) ptx::tmem_ld32(t_addr + (c + 1) * 32, r[(c + 1) & 1]);
+    const int n0 = n_base + c * 32;
+    if (n0 < N) epilogue_block<KIND, ACT>(ep, r[c & 1], tbuf, lane, row, orow, sample, n0, M, N);
+  }
 }
 
 // Row bookkeeping of one epilogue thread for tile (m_blk, .): global row (or M when the tile row is padding), remapped
@@ -280,22 +321,25 @@ __device__ __forceinline__ void epilogue_drain(const EpiParams& ep, int kind, in
       const int n0 = head0 + c * 32;
       if (n0 < N) epilogue_qkv_block(ep, r, tbuf, lane, row, orow, tok, rstd, n0, c * 32, is_qk, nw, M);
     }
-  } else
-#pragma unroll 1
-  for (int c = 0; c < BN / 64; ++c) {
-    uint32_t r[32];
-    ptx::tmem_ld32(t_addr + c * 32, r);
-    ptx::tmem_ld_wait();
-    const int n0 = n_blk * BN + half * (BN / 2) + c * 32;
-    if (n0 < N) {
-      switch (kind) {
-        case K_STORE_BF16: epilogue_act_dispatch<K_STORE_BF16>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
-        case K_STORE_F32: epilogue_act_dispatch<K_STORE_F32>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
-        case K_GATED: epilogue_block<K_GATED, ACT_NONE>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
-        case K_RESID: epilogue_act_dispatch<K_RESID>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
-        default: epilogue_act_dispatch<K_UNPATCH>(ep, r, tbuf, lane, row, orow, sample, n0, M, N); break;
-      }
+  } else {
+    const int n_base = n_blk * BN + half * (BN / 2);
+#define LC_DRAIN(KIND, ACT) drain_loop<BN, KIND, ACT>(ep, t_addr, n_base, tbuf, lane, row, orow, sample, M, N)
+#define LC_DRAIN_ACT(KIND)                                   \
+  switch (ep.act) {                                          \
+    case ACT_GELU_TANH: LC_DRAIN(KIND, ACT_GELU_TANH); break; \
+    case ACT_SILU: LC_DRAIN(KIND, ACT_SILU); break;           \
+    case ACT_RELU: LC_DRAIN(KIND, ACT_RELU); break;           \
+    default: LC_DRAIN(KIND, ACT_NONE); break;                 \
+  }
+    switch (kind) {
+      case K_STORE_BF16: LC_DRAIN_ACT(K_STORE_BF16) break;
+      case K_STORE_F32: LC_DRAIN_ACT(K_STORE_F32) break;
+      case K_GATED: LC_DRAIN(K_GATED, ACT_NONE); break;
+      case K_RESID: LC_DRAIN_ACT(K_RESID) break;
+      default: LC_DRAIN_ACT(K_UNPATCH) break;
     }
+#undef LC_DRAIN_ACT
+#undef LC_DRAIN
   }
 }
 
@@ -446,6 +490,202 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 2) ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair variant
+// cta_group::2: a cluster of two CTAs computes a 256 x 256 tile.  Each CTA loads ITS 128 rows of A and HALF of the W
+// tile (128 of the 256 N rows) — 32 KB per k-block instead of 48 KB, which takes the shared-memory port below the
+// rate the tensor pipe consumes operands at — the leader CTA issues one M = 256 tcgen05.mma per K-step, and each
+// CTA's TMEM receives the accumulators of its own 128 rows.  Barriers: TMA bytes of both CTAs are signalled on the
+// leader's `full` barrier; tcgen05.commit multicasts to the `empty` / `tmem_full` barriers of both CTAs; the
+// epilogue warps of both CTAs arrive on the leader's `tmem_empty`.
+struct Cfg2 {
+  static constexpr int BN = 256;
+  static constexpr int STAGE_A = BM * BK * 2;        // 16 KB: this CTA's 128 rows of A
+  static constexpr int STAGE_B = (BN / 2) * BK * 2;  // 16 KB: this CTA's half of the W tile
+  static constexpr int STAGE = STAGE_A + STAGE_B;
+  static constexpr int STAGES = 6;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM = STAGES * STAGE + EPI_SMEM + 1024 + 256;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                const __grid_constant__ CUtensorMap tmW, int M, int N, int K, int K0, EpiParams ep, TileSched sched,
+                ConvLoad cv) {
+  using C = Cfg2;
+  constexpr int BN = C::BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::STAGES * C::STAGE_A;
+  float* epi_smem = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE + EPI_SMEM);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::STAGES;
+  uint64_t* tmem_full = bars + 2 * C::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = ptx::cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int num_pairs = static_cast<int>(gridDim.x >> 1);
+  const int pair_id = static_cast<int>(blockIdx.x >> 1);
+  const int num_tiles = sched.num_m * sched.num_n;  // sched.num_m counts 256-row pair tiles
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA0);
+    ptx::prefetch_tmap(&tmA1);
+    ptx::prefetch_tmap(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 2 * NUM_EPI_WARPS);  // epilogue warps of BOTH CTAs
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc_pair<C::TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();  // peer's barriers are initialised and its TMEM is allocated
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      int mp, n_blk;
+      sched.decode(tile, mp, n_blk);
+      const int m_blk = mp * 2 + static_cast<int>(cta_rank);
+      int cn0 = 0, cy = 0, cx0 = 0;
+      if (cv.enabled) {
+        const int per_group = cv.tiles_x * cv.H;
+        const int fg = m_blk / per_group;
+        const int rem = m_blk - fg * per_group;
+        cy = rem / cv.tiles_x;
+        cx0 = (rem - cy * cv.tiles_x) * cv.Wt;
+        cn0 = fg * cv.Nt;
+      }
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        const uint32_t full_leader = ptx::map_to_cta(&full_bar[stage], 0);
+        if (leader) {
+          // bytes of both CTAs; in conv mode the partner's A box may be a different (but equally sized) tile
+          ptx::mbar_expect_tx(&full_bar[stage], 2u * (cv.enabled ? (cv.a_bytes + C::STAGE_B) : C::STAGE));
+        }
+        void* a_dst = smem_a + stage * C::STAGE_A;
+        void* b_dst = smem_b + stage * C::STAGE_B;
+        const int k = kb * BK;
+        if (!cv.enabled) {
+          if (k < K0)
+            ptx::tma_load_2d_pair(a_dst, &tmA0, full_leader, k, m_blk * BM);
+          else
+            ptx::tma_load_2d_pair(a_dst, &tmA1, full_leader, k - K0, m_blk * BM);
+        } else {
+          const int tap = kb / cv.kb_per_tap;
+          const int c0 = (kb - tap * cv.kb_per_tap) * BK;
+          const int ky = tap / 3;
+          int kx = tap - ky * 3;
+          if ((cy == 0 && ky == 0) || (cy == cv.H - 1 && ky == 2)) kx = 2 - kx;
+          ptx::tma_load_4d_pair(a_dst, &tmA0, full_leader, c0, cx0 + kx, cy + ky, cn0);
+        }
+        ptx::tma_load_2d_pair(b_dst, &tmW, full_leader, k, n_blk * BN + static_cast<int>(cta_rank) * (BN / 2));
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(2 * BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t a_base = ptx::smem_u32(smem_a + stage * C::STAGE_A);
+        const uint32_t b_base = ptx::smem_u32(smem_b + stage * C::STAGE_B);
+#pragma unroll
+        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+          const uint64_t da = ptx::make_smem_desc(a_base + kk * UMMA_K * 2, 16, 1024);
+          const uint64_t db = ptx::make_smem_desc(b_base + kk * UMMA_K * 2, 16, 1024);
+          ptx::umma_f16_pair(d_tmem, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit_pair(&empty_bar[stage]);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+      ptx::umma_commit_pair(&tmem_full[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===================== epilogue (8 warps per CTA, own 128 rows) =====================
+    const int ew = warp - EPI_WARP0;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    float* tbuf = epi_smem + ew * (32 * 33);
+    const int kind = epi_kind(ep);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      int mp, n_blk;
+      sched.decode(tile, mp, n_blk);
+      const int m_blk = mp * 2 + static_cast<int>(cta_rank);
+      int row, sample;
+      long long orow;
+      epilogue_row(ep, cv, m_blk, quarter, lane, M, row, orow, sample);
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      epilogue_drain<BN>(ep, kind, n_blk, quarter, half, lane, tbuf, tmem_base, acc, row, orow, sample, M, N);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::map_to_cta(&tmem_empty[acc], 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();  // nobody may exit (or free TMEM) while the partner still reads its smem / signals its barriers
+  if (warp == 2) ptx::tmem_dealloc_pair<C::TMEM_COLS>(tmem_base);
+}
+
+int launch_pair(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, int M_tiles, int M, int N, int K,
+                int K0, const EpiParams& ep, const ConvLoad& cv, cudaStream_t stream) {
+  using C = Cfg2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set = true;
+  }
+  TileSched sched;
+  sched.num_m = ceil_div(M_tiles, 2);  // 256-row pair tiles
+  sched.num_n = ceil_div(N, C::BN);
+  sched.group_m = 4;
+  const int tiles = sched.num_m * sched.num_n;
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  const int cls = cv.enabled ? PROF_CONV : PROF_GEMM;
+  const double flops = 2.0 * M * N * (cv.enabled ? 9.0 * cv.c_real : static_cast<double>(K));
+  prof_begin(cls, stream);
+  gemm_tc2_kernel<<<grid, NUM_THREADS, C::SMEM, stream>>>(a0, a1, w, M, N, K, K0, ep, sched, cv);
+  prof_end(cls, flops, stream);
+  LC_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int BN>
 int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, int M_tiles, int M, int N, int K, int K0,
            const EpiParams& ep, const ConvLoad& cv, cudaStream_t stream) {
@@ -484,6 +724,16 @@ int num_sms() {
 
 static int pick_bn(int N) { return (N > 128) ? 256 : 128; }
 
+// CTA pairs pay off once there are enough 256 x 256 tiles to fill the 74 pairs; LADCAST_B200_GEMM_PAIR=0 disables.
+static bool use_pair(int m_tiles, int N) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("LADCAST_B200_GEMM_PAIR");
+    mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return mode == 1 && m_tiles >= 2 && static_cast<long long>(ceil_div(m_tiles, 2)) * ceil_div(N, 256) >= 37;
+}
+
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   LC_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "empty GEMM");
   LC_REQUIRE(g.epi.qk_cols == 0 || (g.N > 128 && g.N % 128 == 0 && g.epi.qk_cols % 256 == 0 && !g.epi.out_f32),
@@ -503,6 +753,12 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
                            static_cast<uint64_t>(g.ldw) * 2, BK, static_cast<uint32_t>(bn)));
   ConvLoad cv;
   const int m_tiles = ceil_div(g.M, BM);
+  if (bn == 256 && use_pair(m_tiles, g.N)) {
+    // pair kernel: each CTA loads half of the W tile -> its tensor map has a 128-row box
+    LC_TRY(make_tmap_2d_bf16(&tw, g.W, static_cast<uint64_t>(g.K), static_cast<uint64_t>(g.N),
+                             static_cast<uint64_t>(g.ldw) * 2, BK, 128));
+    return launch_pair(ta0, ta1, tw, m_tiles, g.M, g.N, g.K, K0, g.epi, cv, stream);
+  }
   if (bn == 256) return launch<256>(ta0, ta1, tw, m_tiles, g.M, g.N, g.K, K0, g.epi, cv, stream);
   return launch<128>(ta0, ta1, tw, m_tiles, g.M, g.N, g.K, K0, g.epi, cv, stream);
 }
@@ -539,6 +795,11 @@ int conv3x3_bf16(const void* xpad, int n_frames, int H, int W, int Cp, const voi
   LC_TRY(make_tmap_bf16(&ta, xpad, 4, dims, strides, box));
   LC_TRY(make_tmap_2d_bf16(&tw, wmat, static_cast<uint64_t>(K), static_cast<uint64_t>(C_out),
                            static_cast<uint64_t>(K) * 2, BK, static_cast<uint32_t>(bn)));
+  if (bn == 256 && use_pair(m_tiles, C_out)) {
+    LC_TRY(make_tmap_2d_bf16(&tw, wmat, static_cast<uint64_t>(K), static_cast<uint64_t>(C_out),
+                             static_cast<uint64_t>(K) * 2, BK, 128));
+    return launch_pair(ta, ta, tw, m_tiles, M, C_out, K, K, epi, cv, stream);
+  }
   if (bn == 256) return launch<256>(ta, ta, tw, m_tiles, M, C_out, K, K, epi, cv, stream);
   return launch<128>(ta, ta, tw, m_tiles, M, C_out, K, K, epi, cv, stream);
 }
