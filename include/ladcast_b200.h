@@ -144,6 +144,10 @@ LC_API int lc_dcae_decode(lc_dcae* h, const float* z, int n, int height, int wid
  * sum/(H*W) with NaN propagation is formed by the caller.  Zeroes the outputs itself. */
 LC_API int lc_metrics_accumulate(const float* fields, const float* truth, const double* lat_weights, int members,
                                  long long planes, int height, int width, double* sums, double* counts, void* stream);
+/* anomaly-correlation terms of get_acc (evaluate/utils.py:122-149): sums/counts [3, planes] fp64 of the NaN-skipping
+ * (optionally latitude-weighted) spatial sums of fa*ta, fa^2, ta^2 with fa = forecast - climate, ta = truth - climate */
+LC_API int lc_metrics_acc(const float* forecast, const float* truth, const float* climate, const double* lat_weights,
+                          long long planes, int height, int width, double* sums, double* counts, void* stream);
 /* per-pixel outputs [planes, H*W] fp32 (any may be NULL): CRPS skill, CRPS spread, ensemble mean */
 LC_API int lc_metrics_pointwise(const float* fields, const float* truth, int members, long long planes, int height,
                                 int width, float* out_skill, float* out_spread, float* out_mean, void* stream);

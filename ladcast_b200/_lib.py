@@ -66,6 +66,7 @@ _OPTIONAL = {
     "lc_dcae_debug_read": ([_vp, _cp, _vp, _i64, _vp], _i),
     "lc_sphere_conv3x3": ([_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "lc_metrics_accumulate": ([_vp, _vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, _vp, _vp], _i),
+    "lc_metrics_acc": ([_vp, _vp, _vp, _vp, ctypes.c_longlong, _i, _i, _vp, _vp, _vp], _i),
     "lc_metrics_pointwise": ([_vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, _vp, _vp, _vp], _i),
 }
 

@@ -91,6 +91,45 @@ __global__ void __launch_bounds__(THREADS) metrics_kernel(const float* __restric
   }
 }
 
+// Anomaly correlation coefficient terms (evaluate/utils.py:122-149): per plane, NaN-skipping weighted sums of
+// fa*ta, fa^2, ta^2 (fa = forecast - climate, ta = truth - climate) and their non-NaN counts.
+__global__ void __launch_bounds__(THREADS) acc_kernel(const float* __restrict__ fc, const float* __restrict__ tr,
+                                                      const float* __restrict__ cl, const double* __restrict__ latw,
+                                                      long long N, int H, int W, double* __restrict__ sums,
+                                                      double* __restrict__ counts) {
+  const int HW = H * W;
+  const long long n = blockIdx.y;
+  const int p = blockIdx.x * THREADS + threadIdx.x;
+  double v[6] = {0, 0, 0, 0, 0, 0};
+  if (p < HW) {
+    const double w = latw != nullptr ? latw[p / W] : 1.0;
+    const float c = cl[n * HW + p];
+    const float fa = fc[n * HW + p] - c, ta = tr[n * HW + p] - c;
+    const double vals[3] = {static_cast<double>(fa * ta) * w, static_cast<double>(fa * fa) * w,
+                            static_cast<double>(ta * ta) * w};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const bool ok = !isnan(vals[k]);
+      v[k] = ok ? vals[k] : 0.0;
+      v[3 + k] = ok ? 1.0 : 0.0;
+    }
+  }
+  __shared__ double red[6][THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double s = warp_sum_d(v[k]);
+    if (lane == 0) red[k][wid] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double s = 0.0;
+    for (int i = 0; i < THREADS / 32; ++i) s += red[threadIdx.x][i];
+    if (threadIdx.x < 3) atomicAdd(&sums[threadIdx.x * N + n], s);
+    else atomicAdd(&counts[(threadIdx.x - 3) * N + n], s);
+  }
+}
+
 }  // namespace
 }  // namespace lc
 
@@ -137,6 +176,20 @@ int lc_metrics_pointwise(const float* fields, const float* truth, int members, l
   LC_PREFER_SMEM(metrics_kernel<false>);
   metrics_kernel<false><<<grid, THREADS, smem, st>>>(fields, truth, nullptr, members, planes, height, width, nullptr,
                                                      nullptr, out_skill, out_spread, out_mean);
+  LC_LAUNCH_CHECK();
+  return 0;
+}
+
+int lc_metrics_acc(const float* forecast, const float* truth, const float* climate, const double* lat_weights,
+                   long long planes, int height, int width, double* sums, double* counts, void* stream) {
+  LC_REQUIRE(forecast && truth && climate && sums && counts, "null argument");
+  LC_REQUIRE(planes > 0 && planes <= 65535, "number of planes must be in [1, 65535] per call");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LC_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 3 * planes, st));
+  LC_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(double) * 3 * planes, st));
+  dim3 grid(ceil_div(height * width, THREADS), static_cast<unsigned>(planes));
+  LC_PREFER_SMEM(acc_kernel);
+  acc_kernel<<<grid, THREADS, 0, st>>>(forecast, truth, climate, lat_weights, planes, height, width, sums, counts);
   LC_LAUNCH_CHECK();
   return 0;
 }

@@ -73,6 +73,36 @@ def get_crps(forecast: torch.Tensor, truth: torch.Tensor, ensemble_dim: int = 0)
     return r["skill"] - 0.5 * r["spread"]
 
 
+@torch.no_grad()
+def get_acc(forecast: torch.Tensor, truth: torch.Tensor, climate: torch.Tensor,
+            lat_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Anomaly correlation coefficient over the last two (spatial) dims with nanmean semantics (reference
+    evaluate/utils.py:122-149); forecast / truth / climate [..., H, W] broadcastable, lat_weight broadcastable [H, 1]."""
+    shape = torch.broadcast_shapes(forecast.shape, truth.shape, climate.shape)
+    H, W = shape[-2], shape[-1]
+    dev = forecast.device
+    f, t, c = [torch.broadcast_to(x.to(dev, torch.float32), shape).reshape(-1, H * W).contiguous() for x in (forecast, truth, climate)]
+    N = f.shape[0]
+    lw = None
+    if lat_weight is not None:
+        lw = torch.broadcast_to(torch.as_tensor(lat_weight).to(dev, torch.float64).reshape(-1, 1) if torch.as_tensor(lat_weight).numel() == H
+                                else torch.as_tensor(lat_weight).to(dev, torch.float64), (H, 1)).reshape(H).contiguous()
+    lib = _lib.load()
+    out = torch.empty(N, device=dev, dtype=torch.float64)
+    done = 0
+    while done < N:
+        n = min(N - done, 65535)
+        s = torch.empty((3, n), device=dev, dtype=torch.float64)
+        k = torch.empty((3, n), device=dev, dtype=torch.float64)
+        _lib.check(lib.lc_metrics_acc(_lib.ptr(f[done : done + n]), _lib.ptr(t[done : done + n]), _lib.ptr(c[done : done + n]),
+                                      _lib.ptr(lw), n, H, W, _lib.ptr(s), _lib.ptr(k), _lib.stream()), "lc_metrics_acc")
+        m = s / k
+        out[done : done + n] = m[0] / torch.sqrt(m[1] * m[2])
+        done += n
+    res = out.reshape(shape[:-2])
+    return res if lat_weight is not None and torch.as_tensor(lat_weight).dtype == torch.float64 else res.to(torch.float32)
+
+
 def _tables_from_sums(sums, counts, n_pix, channels, leads, sst_channel):
     """sums/counts [4, C*T] fp64 -> dict of [C, T] fp64 tables: mean over pixels, nanmean for the SST channel, NaN
     propagation elsewhere (torch.mean semantics)."""

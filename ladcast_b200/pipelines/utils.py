@@ -161,6 +161,24 @@ def roll_out_latent(pipeline, encdec_model, known_latents: torch.Tensor, init_ti
     return out
 
 
+def save_latents_npy(path_dir: str, init_timestamp: int, initial_latent: torch.Tensor, rollout: torch.Tensor) -> str:
+    """Writes `latent_YYYYMMDDHH.npy` in the reference's on-disk format (evaluate/pred_rollout.py:421-430): float32
+    array (ensemble, C, T+1, h, w) whose t=0 slot holds the encoded initial condition (de-normalised latent
+    (C, h, w), same for every member) and t>=1 the predicted latents.  `rollout` is roll_out_latent(...,
+    return_latent=True) output, either lead-major (ens, C, T, h, w) or AR-blocked (n_ar, ens, C, T_out, h, w)."""
+    import os
+
+    lat = rollout_as_lead_major(rollout) if rollout.dim() == 6 else rollout
+    ens, C, T, h, w = lat.shape
+    arr = np.empty((ens, C, T + 1, h, w), dtype=np.float32)
+    arr[:, :, 0] = initial_latent.detach().to("cpu", torch.float32).numpy()[None]
+    arr[:, :, 1:] = lat.detach().to("cpu", torch.float32).numpy()
+    os.makedirs(path_dir, exist_ok=True)
+    out = os.path.join(path_dir, f"latent_{int(init_timestamp):010d}.npy")
+    np.save(out, arr)
+    return out
+
+
 def rollout_as_lead_major(out: torch.Tensor, n_lead: Optional[int] = None) -> torch.Tensor:
     """(n_ar, ens, C, T_out, H, W) -> the reference's (ens, C, n_ar*T_out, H, W) ordering (a copy), optionally cut to
     the first n_lead lead steps (roll_out_serial's `pred_selection` when T_out does not divide the lead count)."""

@@ -99,3 +99,21 @@ def test_dcae_full_bf16_vs_oracle():
     print("dcae full bf16 rel-L2", r)
     assert r < 2e-2
     assert _rel(fused, want * std[None, :, None, None] + mean[None, :, None, None]) < 2e-2
+
+
+def test_dcae_decode_160_latents_batch_consistency():
+    """BASELINE config 3: decoder-only batch decode of 160 ensemble latents -> 84x120x240 fields (V0.1.X
+    architecture).  Size-independent property: a frame decoded inside the batch (any chunk / tile grouping) is
+    bit-identical to the same frame decoded alone, and de-normalisation commutes with the fused epilogue."""
+    cfg, sd, ae = _ae("V0.1.X", 23, "bf16")
+    z = _seeded((160, 84, 15, 30), 700).cuda()
+    out = ae.decode(z).sample
+    torch.cuda.synchronize()
+    assert out.shape == (160, 84, 120, 240) and torch.isfinite(out).all()
+    for i in (0, 79, 80, 159):
+        one = ae.decode(z[i : i + 1].contiguous()).sample
+        assert torch.equal(one[0], out[i]), i
+    mean, std = _seeded((84,), 105), _seeded((84,), 106).abs() + 0.5
+    fused = ae.decode_fused(z[:4].contiguous(), mean, std)
+    ref = out[:4] * std.cuda()[None, :, None, None] + mean.cuda()[None, :, None, None]
+    assert torch.allclose(fused, ref, rtol=1e-5, atol=1e-5)

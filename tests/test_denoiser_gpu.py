@@ -109,3 +109,45 @@ def test_denoiser_375M_bf16_vs_oracle():
     out = m(x, t.cuda(), cond, time_elapsed=ts).sample
     torch.cuda.synchronize()
     assert _rel(out, want) < 1e-2
+
+
+def test_denoiser_1p6B_bf16_vs_oracle():
+    """ladcast_1.6B geometry (d=2048, 16 heads, 5+10+3 blocks), one member, production sequence."""
+    cfg, sd, m = _model("1.6B", 14, "bf16")
+    x = _seeded((1, 84, 4, 15, 30), 410).cuda()
+    cond = _seeded((1, 84, 1, 15, 30), 411, 0.5).cuda()
+    t = torch.tensor([0.2306])
+    ts = torch.tensor([2018070112])
+    want = O.denoiser_forward(sd, cfg, x.cpu(), t, cond.cpu(), ts)
+    out = m(x, t.cuda(), cond, time_elapsed=ts).sample
+    torch.cuda.synchronize()
+    r = _rel(out, want)
+    print("1.6B bf16 rel-L2", r)
+    assert r < 1e-2
+
+
+def test_rollout_two_ar_steps_vs_oracle():
+    """roll_out_latent (sampler -> feed back -> de-normalise -> decode, two AR steps, T_out=2) vs the oracle rollout,
+    in the FP32 validation mode so that the AR feedback does not amplify bf16 noise."""
+    from ladcast_b200.models import AutoencoderDC
+    from ladcast_b200.pipelines import AutoRegressive2DPipeline, EDMDPMSolverMultistepScheduler
+    from ladcast_b200.pipelines.utils import roll_out_latent, rollout_as_lead_major
+
+    cfg, sd, m = _model("tiny", 11, "fp32")
+    acfg = O.dcae_config("tiny")
+    asd = O.make_state_dict(O.dcae_decoder_param_shapes(acfg), 21)
+    ae = AutoencoderDC(**acfg)
+    ae.load_state_dict(asd)
+    ae.to("cuda").set_precision("fp32")
+    pipe = AutoRegressive2DPipeline(m, EDMDPMSolverMultistepScheduler())
+    known = _seeded((1, 84, 1, 15, 30), 102, 0.5)
+    lat_mean, lat_std = _seeded((84,), 31) * 0.1, _seeded((84,), 32).abs() + 0.5
+    f_mean, f_std = _seeded((84,), 33), _seeded((84,), 34).abs() + 0.5
+    members = [3, 4]  # global member ids (a shard of a larger ensemble)
+    out = roll_out_latent(pipe, ae, known, 2018123118, 2, lat_mean, lat_std, f_mean, f_std, num_inference_steps=4,
+                          return_seq_len=2, total_lead_time_hour=24, member_indices=members)
+    got = rollout_as_lead_major(out)
+    lat_want, fld_want = O.rollout(sd, cfg, asd, acfg, known, members, 2018123118, 4, 2, 4, lat_mean, lat_std, f_mean,
+                                   f_std, sampler="pipeline")
+    assert got.shape == fld_want.shape == (2, 84, 4, 120, 240)
+    assert _rel(got, fld_want) < 2e-3

@@ -178,3 +178,19 @@ def test_member_sharded_metrics_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_latent_npy_writer_matches_reference_layout(tmp_path):
+    """evaluate/pred_rollout.py:421-430: latent_YYYYMMDDHH.npy, (ens, 84, T+1, 15, 30) float32, t=0 = encoded IC."""
+    from ladcast_b200.pipelines.utils import rollout_as_lead_major, save_latents_npy
+
+    g = torch.Generator("cpu").manual_seed(1)
+    blocks = torch.randn((2, 3, 84, 4, 15, 30), generator=g)  # 2 AR steps, 3 members, T_out=4
+    ic = torch.randn((84, 15, 30), generator=g)
+    path = save_latents_npy(str(tmp_path), 2018010100, ic, blocks)
+    assert os.path.basename(path) == "latent_2018010100.npy"
+    arr = np.load(path)
+    assert arr.shape == (3, 84, 9, 15, 30) and arr.dtype == np.float32
+    assert np.array_equal(arr[1, :, 0], ic.numpy())
+    lead = rollout_as_lead_major(blocks)
+    assert np.array_equal(arr[:, :, 1:], lead.numpy()) and np.array_equal(arr[2, :, 5], blocks[1, 2, :, 0].numpy())

@@ -63,3 +63,21 @@ def test_metrics_full_size_properties():
     same = t.unsqueeze(0).expand(20, -1, -1, -1, -1).contiguous()
     z = ensemble_metrics(same, t)
     assert float(z["crps_spread"].abs().max()) == 0.0 and float(z["crps_skill"].abs().max()) == 0.0
+
+
+def test_get_acc_vs_reference_formula():
+    """get_acc (evaluate/utils.py:122-149): lat-weighted and unweighted, with NaNs in truth (nanmean semantics)."""
+    from ladcast_b200.evaluate.utils import get_acc
+
+    f = _seeded((84, 120, 24), 21)
+    t = _seeded((84, 120, 24), 22)
+    c = _seeded((84, 120, 24), 23, 0.3)
+    t[82, :4] = float("nan")
+    w = torch.from_numpy(O.lat_weights(120)).view(-1, 1)
+    fa, ta = f - c, t - c
+    want_w = (fa * ta * w).nanmean(dim=(-2, -1)) / torch.sqrt((fa**2 * w).nanmean(dim=(-2, -1)) * (ta**2 * w).nanmean(dim=(-2, -1)))
+    want_u = (fa * ta).nanmean(dim=(-2, -1)) / torch.sqrt((fa**2).nanmean(dim=(-2, -1)) * (ta**2).nanmean(dim=(-2, -1)))
+    got_w = get_acc(f.cuda(), t.cuda(), c.cuda(), w.cuda())
+    got_u = get_acc(f.cuda(), t.cuda(), c.cuda())
+    assert torch.allclose(got_w.cpu(), want_w, rtol=1e-6, atol=1e-9)
+    assert torch.allclose(got_u.cpu(), want_u, rtol=1e-5, atol=1e-6)
