@@ -168,7 +168,8 @@ struct Run {
   lc_dcae* D;
   cudaStream_t st;
   int n;
-  bool xb_valid = false;  // xb == T(x)?
+  bool xb_valid = false;    // xb == T(x)?
+  bool padA_valid = false;  // interior of padA == T(x) in the padded layout of the current (H, W, C)?
 
   int conv(const T* xpad, int H, int W, const ConvW& cw, const EpiParams& ep) const {
     if (sizeof(T) == 2) return conv3x3_bf16(xpad, n, H, W, cw.cp, cw.w, cw.cout, ep, st, cw.cin);
@@ -195,7 +196,9 @@ struct Run {
     T* padA = D->padA.as<T>();
     T* padB = D->padB.as<T>();
     float* x = D->x.as<float>();
-    LC_TRY(pad_from_nhwc<T>(x, padA, n, C, H, W, w.c1.cp, st));
+    if (padA_valid) LC_TRY(halo_fill<T>(padA, n, H, W, w.c1.cp, st));  // the producer wrote the interior already
+    else LC_TRY(pad_from_nhwc<T>(x, padA, n, C, H, W, w.c1.cp, st));
+    padA_valid = false;
     // conv1 + bias + SiLU written straight into the interior of padB (conv2's padded input)
     EpiParams e;
     e.mode = EPI_STORE; e.act = ACT_SILU; e.bias = w.c1.bias; e.out = padB; e.ldo = w.c2.cp; e.out_f32 = sizeof(T) == 4;
@@ -204,10 +207,14 @@ struct Run {
     LC_TRY(conv(padA, H, W, w.c1, e));
     LC_TRY(halo_fill<T>(padB, n, H, W, w.c2.cp, st));
     LC_TRY(conv(padB, H, W, w.c2, store_f32(D->y.as<float>(), C, nullptr)));
-    return rmsnorm_rows<T>(D->y.as<float>(), w.n_w, w.n_b, 1e-5f, x, nullptr, static_cast<T*>(nullptr), P, C, 0, st);
+    // x += norm(y); the new x is also written (as T) into padA's interior: the next 3x3 conv's padded input
+    LC_TRY(rmsnorm_rows<T>(D->y.as<float>(), w.n_w, w.n_b, 1e-5f, x, nullptr, padA, P, C, 0, st, H, W, w.c1.cp));
+    padA_valid = true;
+    return 0;
   }
 
   int evit_block(const Block& b, int H, int W) {
+    padA_valid = false;
     const EvitW& w = b.ev;
     const int C = b.cin, HW = H * W;
     const long long P = static_cast<long long>(n) * HW;
@@ -229,14 +236,24 @@ struct Run {
     return rmsnorm_rows<T>(y, w.n_w, w.n_b, 1e-7f, x, nullptr, xb, P, C, 0, st);
   }
 
-  int up_block(const Block& b, int& H, int& W) {
-    xb_valid = true;
+  int up_block(const Block& b, int& H, int& W, bool next_is_res) {
     const long long P = static_cast<long long>(n) * H * W;
     (void)P;
-    LC_TRY(pad_from_nhwc<T>(D->x.as<float>(), D->padA.as<T>(), n, b.cin, H, W, b.up.cp, st));
+    if (padA_valid) LC_TRY(halo_fill<T>(D->padA.as<T>(), n, H, W, b.up.cp, st));
+    else LC_TRY(pad_from_nhwc<T>(D->x.as<float>(), D->padA.as<T>(), n, b.cin, H, W, b.up.cp, st));
+    padA_valid = false;
     LC_TRY(conv(D->padA.as<T>(), H, W, b.up, store_f32(D->y.as<float>(), 4 * b.cout, b.up.bias)));
-    LC_TRY(pixel_shuffle_shortcut<T>(D->y.as<float>(), D->x.as<float>(), D->x2.as<float>(), D->xb.as<T>(), n, H, W, b.cin,
-                                     b.cout, st));
+    // the shuffled result is also written as T: into padA's interior when a 3x3 conv follows, else as xb rows
+    if (next_is_res) {
+      LC_TRY(pixel_shuffle_shortcut<T>(D->y.as<float>(), D->x.as<float>(), D->x2.as<float>(), D->padA.as<T>(), n, H, W,
+                                       b.cin, b.cout, st, r64(b.cout)));
+      padA_valid = true;
+      xb_valid = false;
+    } else {
+      LC_TRY(pixel_shuffle_shortcut<T>(D->y.as<float>(), D->x.as<float>(), D->x2.as<float>(), D->xb.as<T>(), n, H, W,
+                                       b.cin, b.cout, st));
+      xb_valid = true;
+    }
     std::swap(D->x, D->x2);
     H *= 2; W *= 2;
     return 0;
@@ -249,15 +266,19 @@ struct Run {
     LC_TRY(conv(D->padA.as<T>(), H, W, D->conv_in, store_f32(D->x.as<float>(), C0, D->conv_in.bias)));
     LC_TRY(in_shortcut<T>(D->x.as<float>(), D->xb.as<T>(), z, n, H * W, C0, D->cfg.latent_channels, st));
     xb_valid = true;
-    for (const Block& b : D->blocks) {
-      if (b.kind == 0) LC_TRY(up_block(b, H, W));
+    for (size_t bi = 0; bi < D->blocks.size(); ++bi) {
+      const Block& b = D->blocks[bi];
+      const bool next_is_res = bi + 1 < D->blocks.size() && D->blocks[bi + 1].kind == 1;
+      if (b.kind == 0) LC_TRY(up_block(b, H, W, next_is_res));
       else if (b.kind == 1) LC_TRY(res_block(b, H, W));
       else LC_TRY(evit_block(b, H, W));
     }
     const int C = D->conv_out.cin;
     const long long P = static_cast<long long>(n) * H * W;
-    LC_TRY(rmsnorm_rows<T>(D->x.as<float>(), D->no_w, D->no_b, 1e-7f, nullptr, D->y.as<float>(), static_cast<T*>(nullptr), P, C, 1, st));
-    LC_TRY(pad_from_nhwc<T>(D->y.as<float>(), D->padA.as<T>(), n, C, H, W, D->conv_out.cp, st));
+    // norm_out + ReLU written straight into the padded input of conv_out
+    LC_TRY(rmsnorm_rows<T>(D->x.as<float>(), D->no_w, D->no_b, 1e-7f, nullptr, nullptr, D->padA.as<T>(), P, C, 1, st, H, W,
+                           D->conv_out.cp));
+    LC_TRY(halo_fill<T>(D->padA.as<T>(), n, H, W, D->conv_out.cp, st));
     EpiParams e;
     e.mode = EPI_UNPATCHIFY; e.bias = D->conv_out.bias; e.out = out; e.rows_per_sample = H * W;
     e.n_valid = keep; e.ch_scale = stdv; e.ch_shift = mean;
@@ -417,6 +438,7 @@ int lc_dcae_reserve(lc_dcae* D, int max_frames, int h, int w, void* stream) {
   LC_TRY(D->glu.alloc(n * std::max<size_t>(mx_glu, 1) * e));
   // padB's channel padding is never written by a conv epilogue: keep it zero
   LC_CHECK_CUDA(cudaMemsetAsync(D->padB.p, 0, D->padB.bytes, static_cast<cudaStream_t>(stream)));
+  LC_CHECK_CUDA(cudaMemsetAsync(D->padA.p, 0, D->padA.bytes, static_cast<cudaStream_t>(stream)));
   D->max_frames = max_frames; D->h0 = h; D->w0 = w;
   return 0;
 }

@@ -249,62 +249,82 @@ __global__ void __launch_bounds__(256) grouped1x1_kernel(const float* __restrict
 template <typename TO>
 __global__ void __launch_bounds__(256) linear_attn_kernel(const float* __restrict__ qkv, const float* __restrict__ ms,
                                                           TO* __restrict__ out, int HW, int heads, float eps) {
-  __shared__ float S[33][33];
-  __shared__ float kt[64][33];
-  __shared__ float vt[64][33];
+  constexpr int TP = 128;                   // pixels per staged tile
+  __shared__ __align__(16) float ka[TP][32];  // relu(K) tile, later relu(Q) tile
+  __shared__ __align__(16) float va[TP][32];  // V tile
+  __shared__ __align__(16) float S[33][32];
   const int g = blockIdx.x % (2 * heads);
   const int f = blockIdx.x / (2 * heads);
   const int scale = g / heads, hg = g % heads;
   const int C3 = heads * 96;
   const float* src = (scale ? ms : qkv) + static_cast<long long>(f) * HW * C3 + hg * 96;
-  // phase 1: S[c][c'] = sum_p v1[p][c] * relu(k[p][c'])
-  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // entries e = tid + 256*j of the 33x32 matrix
-  for (int p0 = 0; p0 < HW; p0 += 64) {
-    for (int i = threadIdx.x; i < 64 * 32; i += 256) {
-      const int pp = i >> 5, c = i & 31;
-      const bool ok = p0 + pp < HW;
-      const float* row = src + static_cast<long long>(p0 + pp) * C3;
-      kt[pp][c] = ok ? fmaxf(row[32 + c], 0.f) : 0.f;
-      vt[pp][c] = ok ? row[64 + c] : 0.f;
-    }
-    for (int i = threadIdx.x; i < 64; i += 256) vt[i][32] = (p0 + i < HW) ? 1.f : 0.f;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- phase 1: S[c][c'] = sum_p v1[p][c] * relu(k[p][c']).  Thread (c = tid/8, 4 consecutive c' = 4*(tid%8)..)
+  const int c = tid >> 3, c4 = (tid & 7) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), ksum = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p0 = 0; p0 < HW; p0 += TP) {
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const int e = threadIdx.x + 256 * j;
-      if (e < 33 * 32) {
-        const int c = e >> 5, cp = e & 31;
-        float a = acc[j];
-        for (int pp = 0; pp < 64; ++pp) a = fmaf(vt[pp][c], kt[pp][cp], a);
-        acc[j] = a;
+    for (int i = tid; i < TP * 8; i += 256) {  // 8 float4 per pixel row for K and for V
+      const int pp = i >> 3, q4 = (i & 7) * 4;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (p0 + pp < HW) {
+        const float* row = src + static_cast<long long>(p0 + pp) * C3;
+        kv = *reinterpret_cast<const float4*>(row + 32 + q4);
+        vv = *reinterpret_cast<const float4*>(row + 64 + q4);
+        kv.x = fmaxf(kv.x, 0.f); kv.y = fmaxf(kv.y, 0.f); kv.z = fmaxf(kv.z, 0.f); kv.w = fmaxf(kv.w, 0.f);
       }
+      *reinterpret_cast<float4*>(&ka[pp][q4]) = kv;
+      *reinterpret_cast<float4*>(&va[pp][q4]) = vv;
     }
     __syncthreads();
-  }
-#pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    const int e = threadIdx.x + 256 * j;
-    if (e < 33 * 32) S[e >> 5][e & 31] = acc[j];
-  }
-  __syncthreads();
-  // phase 2: per pixel, out[c] = (S[c] . relu(q)) / (S[32] . relu(q) + eps)
-  const int Co = 2 * heads * 32;
-  for (int p = threadIdx.x; p < HW; p += 256) {
-    const float* row = src + static_cast<long long>(p) * C3;
-    float q[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) q[c] = fmaxf(row[c], 0.f);
-    float den = 0.f;
-#pragma unroll
-    for (int c = 0; c < 32; ++c) den = fmaf(S[32][c], q[c], den);
-    const float inv = 1.0f / (den + eps);
-    TO* o = out + (static_cast<long long>(f) * HW + p) * Co + g * 32;
+    const int np = min(TP, HW - p0);
 #pragma unroll 4
-    for (int c = 0; c < 32; ++c) {
+    for (int pp = 0; pp < np; ++pp) {
+      const float v = va[pp][c];
+      const float4 k4 = *reinterpret_cast<const float4*>(&ka[pp][c4]);
+      acc.x = fmaf(v, k4.x, acc.x); acc.y = fmaf(v, k4.y, acc.y); acc.z = fmaf(v, k4.z, acc.z); acc.w = fmaf(v, k4.w, acc.w);
+      if (c == 0) { ksum.x += k4.x; ksum.y += k4.y; ksum.z += k4.z; ksum.w += k4.w; }
+    }
+  }
+  *reinterpret_cast<float4*>(&S[c][c4]) = acc;
+  if (c == 0) *reinterpret_cast<float4*>(&S[32][c4]) = ksum;  // the padded row of ones of V
+  __syncthreads();
+
+  // ---- phase 2: out[p][c] = (S[c] . relu(q[p])) / (S[32] . relu(q[p]) + eps).  Lane = output channel with its row of S
+  // in registers; each warp walks over pixels, q[p][:] is a broadcast read.
+  float sr[32];
+#pragma unroll
+  for (int k = 0; k < 32; k += 4) {
+    const float4 t4 = *reinterpret_cast<const float4*>(&S[lane][k]);
+    sr[k] = t4.x; sr[k + 1] = t4.y; sr[k + 2] = t4.z; sr[k + 3] = t4.w;
+  }
+  const float s32 = S[32][lane];
+  const int Co = 2 * heads * 32;
+  for (int p0 = 0; p0 < HW; p0 += TP) {
+    __syncthreads();
+    for (int i = tid; i < TP * 8; i += 256) {
+      const int pp = i >> 3, q4 = (i & 7) * 4;
+      float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p0 + pp < HW) {
+        qv = *reinterpret_cast<const float4*>(src + static_cast<long long>(p0 + pp) * C3 + q4);
+        qv.x = fmaxf(qv.x, 0.f); qv.y = fmaxf(qv.y, 0.f); qv.z = fmaxf(qv.z, 0.f); qv.w = fmaxf(qv.w, 0.f);
+      }
+      *reinterpret_cast<float4*>(&ka[pp][q4]) = qv;
+    }
+    __syncthreads();
+    const int np = min(TP, HW - p0);
+    for (int pp = warp; pp < np; pp += 8) {
       float a = 0.f;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) a = fmaf(S[c][k], q[k], a);
-      o[c] = from_f32<TO>(a * inv);
+      for (int k = 0; k < 32; k += 4) {
+        const float4 q4v = *reinterpret_cast<const float4*>(&ka[pp][k]);
+        a = fmaf(sr[k], q4v.x, a); a = fmaf(sr[k + 1], q4v.y, a); a = fmaf(sr[k + 2], q4v.z, a); a = fmaf(sr[k + 3], q4v.w, a);
+      }
+      float den = s32 * ka[pp][lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+      out[(static_cast<long long>(f) * HW + p0 + pp) * Co + g * 32 + lane] = from_f32<TO>(a / (den + eps));
     }
   }
 }
@@ -315,7 +335,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) rmsnorm_rows_kernel(const float* __restrict__ y, const float* __restrict__ w,
                                                            const float* __restrict__ b, float eps, float* __restrict__ resid,
                                                            float* __restrict__ out_f32, T* __restrict__ out_t, long long P,
-                                                           int C, int relu) {
+                                                           int C, int relu, int pH, int pW, int pCp) {
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= P) return;
@@ -343,7 +363,16 @@ __global__ void __launch_bounds__(256) rmsnorm_rows_kernel(const float* __restri
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + row * C + c) = o;
     if (out_t != nullptr) {
-      T* ot = out_t + row * C + c;
+      // plain [P, C] rows, or (pCp > 0) the interior of a sphere-padded [n, pH+2, pW+2, pCp] conv input
+      long long obase = row * C;
+      if (pCp > 0) {
+        const long long fy = row / pW;
+        const int xx = static_cast<int>(row - fy * pW);
+        const long long ff = fy / pH;
+        const int yy = static_cast<int>(fy - ff * pH);
+        obase = ((ff * (pH + 2) + yy + 1) * (pW + 2) + xx + 1) * pCp;
+      }
+      T* ot = out_t + obase + c;
       ot[0] = from_f32<T>(o.x); ot[1] = from_f32<T>(o.y); ot[2] = from_f32<T>(o.z); ot[3] = from_f32<T>(o.w);
     }
   }
@@ -354,7 +383,7 @@ __global__ void __launch_bounds__(256) rmsnorm_rows_kernel(const float* __restri
 template <typename T>
 __global__ void __launch_bounds__(256) pixel_shuffle_kernel(const float* __restrict__ conv, const float* __restrict__ xin,
                                                             float* __restrict__ out, T* __restrict__ out_t, int n, int H,
-                                                            int W, int Cin, int Cout, int rep) {
+                                                            int W, int Cin, int Cout, int rep, int pCp) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(n) * 2 * H * 2 * W * Cout;
   if (i >= total) return;
@@ -369,7 +398,11 @@ __global__ void __launch_bounds__(256) pixel_shuffle_kernel(const float* __restr
   const long long pin = (static_cast<long long>(f) * H + y) * W + x;
   const float v = conv[pin * (4 * Cout) + ch] + xin[pin * Cin + ch / rep];
   out[i] = v;
-  if (out_t != nullptr) out_t[i] = from_f32<T>(v);
+  if (out_t != nullptr) {
+    // plain rows, or (pCp > 0) the interior of the sphere-padded [n, 2H+2, 2W+2, pCp] input of the next 3x3 conv
+    const long long o = pCp > 0 ? ((static_cast<long long>(f) * (2 * H + 2) + Y + 1) * (2 * W + 2) + X + 1) * pCp + c : i;
+    out_t[o] = from_f32<T>(v);
+  }
 }
 
 // ---------------------------------------------------------------- conv_in shortcut: x[p, c] += z[f, c / rep, y, x]
@@ -452,19 +485,19 @@ int linear_attention(const float* qkv, const float* ms, T* out, int n, int HW, i
 }
 template <typename T>
 int rmsnorm_rows(const float* y, const float* w, const float* b, float eps, float* resid, float* out_f32, T* out_t,
-                 long long P, int C, int relu, cudaStream_t s) {
+                 long long P, int C, int relu, cudaStream_t s, int pH, int pW, int pCp) {
   LC_REQUIRE(C % 4 == 0, "rmsnorm: C must be a multiple of 4");
   LC_PREFER_SMEM(rmsnorm_rows_kernel<T>);
-  rmsnorm_rows_kernel<T><<<blocks(P, 8), 256, 0, s>>>(y, w, b, eps, resid, out_f32, out_t, P, C, relu);
+  rmsnorm_rows_kernel<T><<<blocks(P, 8), 256, 0, s>>>(y, w, b, eps, resid, out_f32, out_t, P, C, relu, pH, pW, pCp);
   LC_LAUNCH_CHECK();
   return 0;
 }
 template <typename T>
 int pixel_shuffle_shortcut(const float* conv, const float* xin, float* out, T* out_t, int n, int H, int W, int Cin,
-                           int Cout, cudaStream_t s) {
+                           int Cout, cudaStream_t s, int pCp) {
   const long long total = static_cast<long long>(n) * 4 * H * W * Cout;
   LC_PREFER_SMEM(pixel_shuffle_kernel<T>);
-  pixel_shuffle_kernel<T><<<blocks(total), 256, 0, s>>>(conv, xin, out, out_t, n, H, W, Cin, Cout, 4 * Cout / Cin);
+  pixel_shuffle_kernel<T><<<blocks(total), 256, 0, s>>>(conv, xin, out, out_t, n, H, W, Cin, Cout, 4 * Cout / Cin, pCp);
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -484,9 +517,9 @@ int in_shortcut(float* x, T* x_t, const float* z, int n, int HW, int C, int Cz, 
   template int dwconv3_glu<T>(const T*, const float*, const float*, T*, int, int, int, int, cudaStream_t);           \
   template int linear_attention<T>(const float*, const float*, T*, int, int, int, float, cudaStream_t);              \
   template int rmsnorm_rows<T>(const float*, const float*, const float*, float, float*, float*, T*, long long, int,  \
-                               int, cudaStream_t);                                                                   \
+                               int, cudaStream_t, int, int, int);                                                                   \
   template int pixel_shuffle_shortcut<T>(const float*, const float*, float*, T*, int, int, int, int, int,            \
-                                         cudaStream_t);                                                              \
+                                         cudaStream_t, int);                                                              \
   template int in_shortcut<T>(float*, T*, const float*, int, int, int, int, cudaStream_t);
 LC_INST(float)
 LC_INST(bf16)

@@ -17,10 +17,10 @@ template <typename T>
 int linear_attention(const float* qkv, const float* ms, T* out, int n, int HW, int heads, float eps, cudaStream_t s);
 template <typename T>
 int rmsnorm_rows(const float* y, const float* w, const float* b, float eps, float* resid, float* out_f32, T* out_t,
-                 long long P, int C, int relu, cudaStream_t s);
+                 long long P, int C, int relu, cudaStream_t s, int pH = 0, int pW = 0, int pCp = 0);
 template <typename T>
 int pixel_shuffle_shortcut(const float* conv, const float* xin, float* out, T* out_t, int n, int H, int W, int Cin,
-                           int Cout, cudaStream_t s);
+                           int Cout, cudaStream_t s, int pCp = 0);
 template <typename T>
 int in_shortcut(float* x, T* x_t, const float* z, int n, int HW, int C, int Cz, cudaStream_t s);
 
