@@ -112,7 +112,6 @@ int attention_f32(const float* qkv, int B, int S, int heads, int head_dim, float
                   cudaStream_t s) {
   LC_REQUIRE(head_dim == HD, "attention: head_dim must be 128");
   dim3 grid(ceil_div(S, BQ), heads, B);
-  LC_PREFER_SMEM(attention_f32_kernel);
   attention_f32_kernel<<<grid, 128, 0, s>>>(qkv, S, heads, out_p, Np, out_c);
   LC_LAUNCH_CHECK();
   return 0;

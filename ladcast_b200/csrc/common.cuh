@@ -40,17 +40,6 @@ void count_launch();
     LC_CHECK_CUDA(cudaGetLastError()); \
   } while (0)
 
-// All kernels ask for the maximum shared-memory carveout: the tensor-core kernels need ~225 KB, and alternating
-// between carveouts forces the SMs to drain and reconfigure between consecutive launches of a stream.
-#define LC_PREFER_SMEM(...)                                                                                        \
-  do {                                                                                                             \
-    static bool _lc_done = false;                                                                                  \
-    if (!_lc_done) {                                                                                               \
-      cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
-      _lc_done = true;                                                                                             \
-    }                                                                                                              \
-  } while (0)
-
 #define LC_TRY(expr)          \
   do {                        \
     int _r = (expr);          \

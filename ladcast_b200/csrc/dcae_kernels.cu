@@ -111,45 +111,60 @@ __device__ __forceinline__ void sphere_row(int py, int p, int H, int& sy, bool& 
   else if (py >= H + p) { sy = H - 1 - (py - (H + p)); rolled = true; }
   else { sy = py - p; rolled = false; }
 }
-__device__ __forceinline__ int sphere_col(int px, int p, int W, bool rolled) {
-  int cx = px - p;
-  if (cx < 0) cx += W;
-  if (cx >= W) cx -= W;
-  if (rolled) { cx += W / 2; if (cx >= W) cx -= W; }
-  return cx;
+// Depthwise kernels: lane = channel quad (a warp reads 128 consecutive channels of one pixel: whole 128-B lines),
+// each thread slides along XT consecutive x so every loaded input vector feeds up to K outputs and the K taps of a
+// kernel row are loaded once per XT outputs.  The kernels are L1-wavefront bound, not DRAM bound (profiles/): this
+// cuts the wavefronts per output ~3x against one-output-per-thread.
+__device__ __forceinline__ int sphere_col0(int x0, int p, int W, bool rolled) {
+  int cx = (x0 - p + (rolled ? W / 2 : 0)) % W;
+  return cx < 0 ? cx + W : cx;
 }
 
-// 5x5, fp32 in/out, 4 channels per thread (multiscale projection, DCAE.py:76-85)
+// 5x5, fp32 in/out (multiscale projection, DCAE.py:76-85)
+template <int XT>
 __global__ void __launch_bounds__(256) dwconv5_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                       float* __restrict__ out, int n, int H, int W, int C) {
-  // block = 32 consecutive x of one image row x 8 channel quads: the K taps along x re-use L1 lines within the block
-  const int c = (blockIdx.x * 8 + (threadIdx.x & 7)) * 4;
-  const int x = blockIdx.y * 32 + (threadIdx.x >> 3);
+  const int c = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
+  const int x0 = (blockIdx.y * 8 + (threadIdx.x >> 5)) * XT;
   const int y = blockIdx.z % H, f = blockIdx.z / H;
-  if (c >= C || x >= W) return;
-  const long long i = ((static_cast<long long>(f) * H + y) * W + x) * (C / 4) + c / 4;
+  if (c >= C || x0 >= W) return;
   const float* base = in + static_cast<long long>(f) * H * W * C + c;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc[XT];
+#pragma unroll
+  for (int o = 0; o < XT; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int ky = 0; ky < 5; ++ky) {
     int sy;
     bool rolled;
     sphere_row(y + ky, 2, H, sy, rolled);
     const bool flip = (y == 0 && ky < 2) || (y == H - 1 && ky >= 3);
-    const float* rowp = base + static_cast<long long>(sy) * W * C;
+    float4 wr[5];
 #pragma unroll
-    for (int kx = 0; kx < 5; ++kx) {
-      const int sx = sphere_col(x + kx, 2, W, rolled);
-      const float4 v = *reinterpret_cast<const float4*>(rowp + static_cast<long long>(sx) * C);
-      const float4 ww = __ldg(reinterpret_cast<const float4*>(w + (ky * 5 + (flip ? 4 - kx : kx)) * C + c));
-      acc.x = fmaf(ww.x, v.x, acc.x); acc.y = fmaf(ww.y, v.y, acc.y);
-      acc.z = fmaf(ww.z, v.z, acc.z); acc.w = fmaf(ww.w, v.w, acc.w);
+    for (int kx = 0; kx < 5; ++kx)
+      wr[kx] = __ldg(reinterpret_cast<const float4*>(w + (ky * 5 + (flip ? 4 - kx : kx)) * C + c));
+    const float* rowp = base + static_cast<long long>(sy) * W * C;
+    int cx = sphere_col0(x0, 2, W, rolled);
+#pragma unroll
+    for (int j = 0; j < XT + 4; ++j) {
+      const float4 v = *reinterpret_cast<const float4*>(rowp + static_cast<long long>(cx) * C);
+      if (++cx == W) cx = 0;
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx) {
+        const int o = j - kx;
+        if (o >= 0 && o < XT) {
+          acc[o].x = fmaf(wr[kx].x, v.x, acc[o].x); acc[o].y = fmaf(wr[kx].y, v.y, acc[o].y);
+          acc[o].z = fmaf(wr[kx].z, v.z, acc[o].z); acc[o].w = fmaf(wr[kx].w, v.w, acc[o].w);
+        }
+      }
     }
   }
-  *reinterpret_cast<float4*>(out + i * 4) = acc;
+  float* op = out + ((static_cast<long long>(f) * H + y) * W + x0) * C + c;
+#pragma unroll
+  for (int o = 0; o < XT; ++o)
+    if (x0 + o < W) *reinterpret_cast<float4*>(op + static_cast<long long>(o) * C) = acc[o];
 }
 
-// 3x3 + bias + GLU: channels [value | gate] halves -> value * silu(gate); T in/out, 4 channels per thread
+// 3x3 + bias + GLU: channels [value | gate] halves -> value * silu(gate); T in/out
 // (GLUMBConv.conv_depth + chunk + nonlinearity, DCAE.py:312-315)
 template <typename T>
 __device__ __forceinline__ float4 ld4(const T* p);
@@ -174,52 +189,79 @@ __device__ __forceinline__ void st4<bf16>(bf16* p, float4 v) {
   u.y = *reinterpret_cast<uint32_t*>(&hi);
   *reinterpret_cast<uint2*>(p) = u;
 }
+__device__ __forceinline__ void fma4(float4& a, const float4& w, const float4& v) {
+  a.x = fmaf(w.x, v.x, a.x); a.y = fmaf(w.y, v.y, a.y); a.z = fmaf(w.z, v.z, a.z); a.w = fmaf(w.w, v.w, a.w);
+}
 
-template <typename T>
-__global__ void __launch_bounds__(256) dwconv3_glu_kernel(const T* __restrict__ in, const float* __restrict__ w,
+template <typename T, int XT>
+__global__ void __launch_bounds__(256, 3) dwconv3_glu_kernel(const T* __restrict__ in, const float* __restrict__ w,
                                                           const float* __restrict__ bias, T* __restrict__ out, int n,
                                                           int H, int W, int C) {
   const int Co = C / 2;
-  const int c = (blockIdx.x * 8 + (threadIdx.x & 7)) * 4;
-  const int x = blockIdx.y * 32 + (threadIdx.x >> 3);
+  const int c = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
+  const int x0 = (blockIdx.y * 8 + (threadIdx.x >> 5)) * XT;
   const int y = blockIdx.z % H, f = blockIdx.z / H;
-  if (c >= Co || x >= W) return;
-  const long long i = ((static_cast<long long>(f) * H + y) * W + x) * (Co / 4) + c / 4;
+  if (c >= Co || x0 >= W) return;
   const T* base = in + static_cast<long long>(f) * H * W * C + c;
-  float4 a0 = __ldg(reinterpret_cast<const float4*>(bias + c));
-  float4 a1 = __ldg(reinterpret_cast<const float4*>(bias + Co + c));
+  float4 a0[XT], a1[XT];
+  {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + Co + c));
+#pragma unroll
+    for (int o = 0; o < XT; ++o) { a0[o] = b0; a1[o] = b1; }
+  }
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     int sy;
     bool rolled;
     sphere_row(y + ky, 1, H, sy, rolled);
     const bool flip = (y == 0 && ky == 0) || (y == H - 1 && ky == 2);
-    const T* rowp = base + static_cast<long long>(sy) * W * C;
+    float4 wv[3], wg[3];
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
-      const int sx = sphere_col(x + kx, 1, W, rolled);
-      const T* px = rowp + static_cast<long long>(sx) * C;
-      const float4 v = ld4<T>(px), g = ld4<T>(px + Co);
       const float* wt = w + (ky * 3 + (flip ? 2 - kx : kx)) * C + c;
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(wt));
-      const float4 wg = __ldg(reinterpret_cast<const float4*>(wt + Co));
-      a0.x = fmaf(wv.x, v.x, a0.x); a0.y = fmaf(wv.y, v.y, a0.y); a0.z = fmaf(wv.z, v.z, a0.z); a0.w = fmaf(wv.w, v.w, a0.w);
-      a1.x = fmaf(wg.x, g.x, a1.x); a1.y = fmaf(wg.y, g.y, a1.y); a1.z = fmaf(wg.z, g.z, a1.z); a1.w = fmaf(wg.w, g.w, a1.w);
+      wv[kx] = __ldg(reinterpret_cast<const float4*>(wt));
+      wg[kx] = __ldg(reinterpret_cast<const float4*>(wt + Co));
+    }
+    const T* rowp = base + static_cast<long long>(sy) * W * C;
+    int cx = sphere_col0(x0, 1, W, rolled);
+#pragma unroll
+    for (int j = 0; j < XT + 2; ++j) {
+      const T* px = rowp + static_cast<long long>(cx) * C;
+      const float4 v = ld4<T>(px), g = ld4<T>(px + Co);
+      if (++cx == W) cx = 0;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int o = j - kx;
+        if (o >= 0 && o < XT) { fma4(a0[o], wv[kx], v); fma4(a1[o], wg[kx], g); }
+      }
     }
   }
-  st4<T>(out + i * 4, make_float4(a0.x * silu(a1.x), a0.y * silu(a1.y), a0.z * silu(a1.z), a0.w * silu(a1.w)));
+  T* op = out + ((static_cast<long long>(f) * H + y) * W + x0) * Co + c;
+#pragma unroll
+  for (int o = 0; o < XT; ++o)
+    if (x0 + o < W)
+      st4<T>(op + static_cast<long long>(o) * Co, make_float4(a0[o].x * silu(a1[o].x), a0[o].y * silu(a1[o].y),
+                                                             a0[o].z * silu(a1[o].z), a0[o].w * silu(a1[o].w)));
 }
 
 // ---------------------------------------------------------------- grouped 1x1 conv, 32 -> 32 per group (DCAE.py:86-88)
-// One warp per (4-pixel strip, group): lane = output channel, its 32 weights live in registers, inputs are
-// broadcast with shuffles.  All global accesses are 128 B row segments.
+// Block = (64-pixel strip, group).  The strip's 64x32 inputs are staged in shared memory; lane = output channel
+// with its 32 weights in registers; each warp walks over pixels reading the input row as broadcast float4s
+// (8 LDS.128 per 32 FFMA: FMA-bound, no shuffles).  All global accesses are 128 B row segments.
 __global__ void __launch_bounds__(256) grouped1x1_kernel(const float* __restrict__ in, const float* __restrict__ w,
-                                                         float* __restrict__ out, long long P, int C, int pix_per_warp) {
-  const int lane = threadIdx.x & 31;
-  const int g = blockIdx.y;
-  const long long wid = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  const long long p0 = wid * pix_per_warp;
-  if (p0 >= P) return;
+                                                         float* __restrict__ out, long long P, int C) {
+  constexpr int TP = 64;
+  __shared__ __align__(16) float xs[TP][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = blockIdx.x;  // groups vary fastest: concurrently resident blocks read whole NHWC rows together
+  const long long p0 = static_cast<long long>(blockIdx.y) * TP;
+  for (int i = threadIdx.x; i < TP * 8; i += 256) {
+    const int pp = i >> 3, q4 = (i & 7) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p0 + pp < P) v = *reinterpret_cast<const float4*>(in + (p0 + pp) * C + g * 32 + q4);
+    *reinterpret_cast<float4*>(&xs[pp][q4]) = v;
+  }
   float wr[32];
   const float* wp = w + (static_cast<long long>(g) * 32 + lane) * 32;
 #pragma unroll
@@ -227,19 +269,17 @@ __global__ void __launch_bounds__(256) grouped1x1_kernel(const float* __restrict
     const float4 t = __ldg(reinterpret_cast<const float4*>(wp + k));
     wr[k] = t.x; wr[k + 1] = t.y; wr[k + 2] = t.z; wr[k + 3] = t.w;
   }
-  const long long pend = (p0 + pix_per_warp < P) ? p0 + pix_per_warp : P;
-  for (long long p = p0; p < pend; p += 4) {
-    float xv[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+  __syncthreads();
+#pragma unroll 2
+  for (int pp = warp; pp < TP; pp += 8) {
+    if (p0 + pp >= P) break;
+    float a = 0.f;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) xv[q] = (p + q < pend) ? in[(p + q) * C + g * 32 + lane] : 0.f;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q] = fmaf(wr[k], __shfl_sync(0xffffffffu, xv[q], k), acc[q]);
+    for (int k = 0; k < 32; k += 4) {
+      const float4 x4 = *reinterpret_cast<const float4*>(&xs[pp][k]);
+      a = fmaf(wr[k], x4.x, a); a = fmaf(wr[k + 1], x4.y, a); a = fmaf(wr[k + 2], x4.z, a); a = fmaf(wr[k + 3], x4.w, a);
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (p + q < pend) out[(p + q) * C + g * 32 + lane] = acc[q];
+    out[(p0 + pp) * C + g * 32 + lane] = a;
   }
 }
 
@@ -384,24 +424,40 @@ template <typename T>
 __global__ void __launch_bounds__(256) pixel_shuffle_kernel(const float* __restrict__ conv, const float* __restrict__ xin,
                                                             float* __restrict__ out, T* __restrict__ out_t, int n, int H,
                                                             int W, int Cin, int Cout, int rep, int pCp) {
+  // one thread = (input pixel, 4 consecutive output channels): 4 float4 of the conv output -> 4 float4 stores, one
+  // per sub-pixel (i, j)
+  const int c4n = Cout / 4;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(n) * 2 * H * 2 * W * Cout;
+  const long long total = static_cast<long long>(n) * H * W * c4n;
   if (i >= total) return;
-  const int c = static_cast<int>(i % Cout);
-  long long r = i / Cout;
-  const int X = static_cast<int>(r % (2 * W));
-  r /= (2 * W);
-  const int Y = static_cast<int>(r % (2 * H));
-  const int f = static_cast<int>(r / (2 * H));
-  const int y = Y >> 1, ii = Y & 1, x = X >> 1, jj = X & 1;
-  const int ch = 4 * c + 2 * ii + jj;
-  const long long pin = (static_cast<long long>(f) * H + y) * W + x;
-  const float v = conv[pin * (4 * Cout) + ch] + xin[pin * Cin + ch / rep];
-  out[i] = v;
-  if (out_t != nullptr) {
-    // plain rows, or (pCp > 0) the interior of the sphere-padded [n, 2H+2, 2W+2, pCp] input of the next 3x3 conv
-    const long long o = pCp > 0 ? ((static_cast<long long>(f) * (2 * H + 2) + Y + 1) * (2 * W + 2) + X + 1) * pCp + c : i;
-    out_t[o] = from_f32<T>(v);
+  const int c = static_cast<int>(i % c4n) * 4;
+  const long long pin = i / c4n;
+  const int x = static_cast<int>(pin % W);
+  const long long fy = pin / W;
+  const int y = static_cast<int>(fy % H);
+  const long long f = fy / H;
+  const float* cp = conv + pin * (4LL * Cout) + 4 * c;
+  const float* xp = xin + pin * Cin;
+  float v[4][4];  // [channel k][sub-pixel 2i+j]
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4 t = *reinterpret_cast<const float4*>(cp + 4 * k);
+    const int ch = 4 * (c + k);
+    v[k][0] = t.x + __ldg(xp + (ch + 0) / rep);
+    v[k][1] = t.y + __ldg(xp + (ch + 1) / rep);
+    v[k][2] = t.z + __ldg(xp + (ch + 2) / rep);
+    v[k][3] = t.w + __ldg(xp + (ch + 3) / rep);
+  }
+#pragma unroll
+  for (int sp = 0; sp < 4; ++sp) {
+    const int Y = 2 * y + (sp >> 1), X = 2 * x + (sp & 1);
+    const long long opix = (f * (2 * H) + Y) * (2 * W) + X;
+    *reinterpret_cast<float4*>(out + opix * Cout + c) = make_float4(v[0][sp], v[1][sp], v[2][sp], v[3][sp]);
+    if (out_t != nullptr) {
+      // plain rows, or (pCp > 0) the interior of the sphere-padded [n, 2H+2, 2W+2, pCp] input of the next 3x3 conv
+      const long long o = pCp > 0 ? ((f * (2 * H + 2) + Y + 1) * (2 * W + 2) + X + 1) * pCp + c : opix * Cout + c;
+      st4<T>(out_t + o, make_float4(v[0][sp], v[1][sp], v[2][sp], v[3][sp]));
+    }
   }
 }
 
@@ -427,7 +483,6 @@ inline unsigned blocks(long long n, int t = 256) { return static_cast<unsigned>(
 template <typename T>
 int pad_from_nchw(const float* z, T* out, int n, int C, int H, int W, int Cp, cudaStream_t s) {
   const long long total = static_cast<long long>(n) * (H + 2) * (W + 2) * Cp;
-  LC_PREFER_SMEM(pad_from_nchw_kernel<T>);
   pad_from_nchw_kernel<T><<<blocks(total), 256, 0, s>>>(z, out, n, C, H, W, Cp);
   LC_LAUNCH_CHECK();
   return 0;
@@ -436,7 +491,6 @@ template <typename T>
 int pad_from_nhwc(const float* x, T* out, int n, int C, int H, int W, int Cp, cudaStream_t s) {
   LC_REQUIRE(C % 4 == 0 && Cp % 4 == 0, "pad: channels must be multiples of 4");
   const long long total = static_cast<long long>(n) * (H + 2) * (W + 2) * (Cp / 4);
-  LC_PREFER_SMEM(pad_from_nhwc_kernel<T>);
   pad_from_nhwc_kernel<T><<<blocks(total), 256, 0, s>>>(x, out, n, C, H, W, Cp);
   LC_LAUNCH_CHECK();
   return 0;
@@ -445,40 +499,37 @@ template <typename T>
 int halo_fill(T* buf, int n, int H, int W, int Cp, cudaStream_t s) {
   LC_REQUIRE(Cp % 8 == 0, "halo_fill: Cp must be a multiple of 8");
   const long long total = static_cast<long long>(n) * (2 * (W + 2) + 2 * H) * (Cp / 8);
-  LC_PREFER_SMEM(halo_fill_kernel<T>);
   halo_fill_kernel<T><<<blocks(total), 256, 0, s>>>(buf, n, H, W, Cp);
   LC_LAUNCH_CHECK();
   return 0;
 }
 int dwconv5(const float* in, const float* w, float* out, int n, int H, int W, int C, cudaStream_t s) {
   LC_REQUIRE(C % 4 == 0, "dwconv5: channels must be a multiple of 4");
-  dim3 grid((C / 4 + 7) / 8, (W + 31) / 32, n * H);
-  LC_PREFER_SMEM(dwconv5_kernel);
-  dwconv5_kernel<<<grid, 256, 0, s>>>(in, w, out, n, H, W, C);
+  constexpr int XT = 4;
+  dim3 grid((C / 4 + 31) / 32, (W + 8 * XT - 1) / (8 * XT), n * H);
+  dwconv5_kernel<XT><<<grid, 256, 0, s>>>(in, w, out, n, H, W, C);
   LC_LAUNCH_CHECK();
   return 0;
 }
 template <typename T>
 int dwconv3_glu(const T* in, const float* w, const float* bias, T* out, int n, int H, int W, int C, cudaStream_t s) {
   LC_REQUIRE(C % 8 == 0, "dwconv3_glu: channels must be a multiple of 8");
-  dim3 grid((C / 8 + 7) / 8, (W + 31) / 32, n * H);
-  LC_PREFER_SMEM(dwconv3_glu_kernel<T>);
-  dwconv3_glu_kernel<T><<<grid, 256, 0, s>>>(in, w, bias, out, n, H, W, C);
+  constexpr int XT = 4;
+  dim3 grid((C / 8 + 31) / 32, (W + 8 * XT - 1) / (8 * XT), n * H);
+  dwconv3_glu_kernel<T, XT><<<grid, 256, 0, s>>>(in, w, bias, out, n, H, W, C);
   LC_LAUNCH_CHECK();
   return 0;
 }
 int grouped1x1(const float* in, const float* w, float* out, long long P, int C, cudaStream_t s) {
   LC_REQUIRE(C % 32 == 0, "grouped 1x1: channels must be a multiple of 32");
-  const int ppw = 32;
-  dim3 grid(static_cast<unsigned>((P + ppw * 8 - 1) / (ppw * 8)), C / 32);
-  LC_PREFER_SMEM(grouped1x1_kernel);
-  grouped1x1_kernel<<<grid, 256, 0, s>>>(in, w, out, P, C, ppw);
+  LC_REQUIRE((P + 63) / 64 <= 65535, "grouped 1x1: too many pixels per call");
+  dim3 grid(C / 32, static_cast<unsigned>((P + 63) / 64));
+  grouped1x1_kernel<<<grid, 256, 0, s>>>(in, w, out, P, C);
   LC_LAUNCH_CHECK();
   return 0;
 }
 template <typename T>
 int linear_attention(const float* qkv, const float* ms, T* out, int n, int HW, int heads, float eps, cudaStream_t s) {
-  LC_PREFER_SMEM(linear_attn_kernel<T>);
   linear_attn_kernel<T><<<n * 2 * heads, 256, 0, s>>>(qkv, ms, out, HW, heads, eps);
   LC_LAUNCH_CHECK();
   return 0;
@@ -487,7 +538,6 @@ template <typename T>
 int rmsnorm_rows(const float* y, const float* w, const float* b, float eps, float* resid, float* out_f32, T* out_t,
                  long long P, int C, int relu, cudaStream_t s, int pH, int pW, int pCp) {
   LC_REQUIRE(C % 4 == 0, "rmsnorm: C must be a multiple of 4");
-  LC_PREFER_SMEM(rmsnorm_rows_kernel<T>);
   rmsnorm_rows_kernel<T><<<blocks(P, 8), 256, 0, s>>>(y, w, b, eps, resid, out_f32, out_t, P, C, relu, pH, pW, pCp);
   LC_LAUNCH_CHECK();
   return 0;
@@ -495,8 +545,8 @@ int rmsnorm_rows(const float* y, const float* w, const float* b, float eps, floa
 template <typename T>
 int pixel_shuffle_shortcut(const float* conv, const float* xin, float* out, T* out_t, int n, int H, int W, int Cin,
                            int Cout, cudaStream_t s, int pCp) {
-  const long long total = static_cast<long long>(n) * 4 * H * W * Cout;
-  LC_PREFER_SMEM(pixel_shuffle_kernel<T>);
+  LC_REQUIRE(Cout % 4 == 0, "pixel_shuffle: C_out must be a multiple of 4");
+  const long long total = static_cast<long long>(n) * H * W * (Cout / 4);
   pixel_shuffle_kernel<T><<<blocks(total), 256, 0, s>>>(conv, xin, out, out_t, n, H, W, Cin, Cout, 4 * Cout / Cin, pCp);
   LC_LAUNCH_CHECK();
   return 0;
@@ -504,7 +554,6 @@ int pixel_shuffle_shortcut(const float* conv, const float* xin, float* out, T* o
 template <typename T>
 int in_shortcut(float* x, T* x_t, const float* z, int n, int HW, int C, int Cz, cudaStream_t s) {
   const long long total = static_cast<long long>(n) * HW * C;
-  LC_PREFER_SMEM(in_shortcut_kernel<T>);
   in_shortcut_kernel<T><<<blocks(total), 256, 0, s>>>(x, x_t, z, n, HW, C, Cz, C / Cz);
   LC_LAUNCH_CHECK();
   return 0;

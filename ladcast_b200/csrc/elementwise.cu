@@ -334,8 +334,6 @@ int layernorm_modulate(const float* x, T* out, int M, int d, float eps, int rows
   dim3 grid(ceil_div(M, 8));
 #define LC_LN_CASE(NV)                                                                                            \
   case NV:                                                                                                        \
-    cudaFuncSetAttribute(layernorm_kernel<T, NV>, cudaFuncAttributePreferredSharedMemoryCarveout,                   \
-                         cudaSharedmemCarveoutMaxShared);                                                            \
     layernorm_kernel<T, NV><<<grid, 256, 0, s>>>(x, out, M, d, eps, rows_per_sample, scale, shift, mod_stride, w, b); \
     break;
   switch (nv) {
@@ -356,13 +354,11 @@ int qk_norm_rope(T* qkv, long long ld, int B, int S, int heads, int head_dim, fl
   const long long total = static_cast<long long>(B) * S * 2 * heads;
   RopeSeg s1 = nseg > 1 ? segs[1] : segs[0];
   if (sizeof(T) == 2) {
-    LC_PREFER_SMEM(qk_norm_rope_bf16_kernel);
     qk_norm_rope_bf16_kernel<<<static_cast<unsigned>(ceil_div_ll(total * 16, 256)), 256, 0, s>>>(
         reinterpret_cast<bf16*>(qkv), ld, B, S, heads, eps, segs[0], s1, nseg);
     LC_LAUNCH_CHECK();
     return 0;
   }
-  LC_PREFER_SMEM(qk_norm_rope_kernel<T>);
   qk_norm_rope_kernel<T><<<static_cast<unsigned>(ceil_div_ll(total, 8)), 256, 0, s>>>(qkv, ld, B, S, heads, eps, segs[0],
                                                                                      s1, nseg);
   LC_LAUNCH_CHECK();
@@ -372,7 +368,6 @@ int qk_norm_rope(T* qkv, long long ld, int B, int S, int heads, int head_dim, fl
 template <typename T>
 int patchify(const float* x, T* out, int B, int C, int THW, int Kp, cudaStream_t s) {
   dim3 grid(ceil_div(THW, 32), ceil_div(Kp, 32), B);
-  LC_PREFER_SMEM(patchify_kernel<T>);
   patchify_kernel<T><<<grid, 256, 0, s>>>(x, out, C, THW, Kp);
   LC_LAUNCH_CHECK();
   return 0;
@@ -380,7 +375,6 @@ int patchify(const float* x, T* out, int B, int C, int THW, int Kp, cudaStream_t
 
 template <typename T>
 int timestep_embed(const float* t, int n_t, int B, T* out, cudaStream_t s) {
-  LC_PREFER_SMEM(timestep_embed_kernel<T>);
   timestep_embed_kernel<T><<<ceil_div(B * 128, 128), 128, 0, s>>>(t, n_t, B, out);
   LC_LAUNCH_CHECK();
   return 0;
@@ -389,7 +383,6 @@ int timestep_embed(const float* t, int n_t, int B, T* out, cudaStream_t s) {
 template <typename T>
 int token_mean(const float* x, int B, int N, int d, T* out, cudaStream_t s) {
   dim3 grid(ceil_div(d, 128), B);
-  LC_PREFER_SMEM(token_mean_kernel<T>);
   token_mean_kernel<T><<<grid, 256, 0, s>>>(x, N, d, out);
   LC_LAUNCH_CHECK();
   return 0;
@@ -399,7 +392,6 @@ template <typename T>
 int gated_add(float* h, const T* a, const float* gate, long long gate_stride, int M, int d, int rows_per_sample,
               cudaStream_t s) {
   const long long n4 = static_cast<long long>(M) * d / 4;
-  LC_PREFER_SMEM(gated_add_kernel<T>);
   gated_add_kernel<T><<<static_cast<unsigned>(ceil_div_ll(n4, 256)), 256, 0, s>>>(h, a, gate, gate_stride, n4, d,
                                                                                 rows_per_sample);
   LC_LAUNCH_CHECK();
@@ -409,7 +401,6 @@ int gated_add(float* h, const T* a, const float* gate, long long gate_stride, in
 template <typename T>
 int temb_combine(const float* a, const float* b, const float* sc, const float* sh, long long sc_stride, int B, int d,
                  float* out_f32, T* out_silu, cudaStream_t s) {
-  LC_PREFER_SMEM(temb_combine_kernel<T>);
   temb_combine_kernel<T><<<ceil_div(B * d, 256), 256, 0, s>>>(a, b, sc, sh, sc_stride, B, d, out_f32, out_silu);
   LC_LAUNCH_CHECK();
   return 0;
@@ -417,7 +408,6 @@ int temb_combine(const float* a, const float* b, const float* sc, const float* s
 
 template <typename T>
 int cast_rows(const float* x, T* out, long long n, cudaStream_t s) {
-  LC_PREFER_SMEM(cast_kernel<T>);
   cast_kernel<T><<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s>>>(x, out, n);
   LC_LAUNCH_CHECK();
   return 0;
@@ -427,7 +417,6 @@ int sched_dpmpp2m_step(const float* f, float* x, float* x0_prev, float* x_in_nex
                        cudaStream_t s) {
   LC_REQUIRE(n % 4 == 0, "scheduler: element count must be a multiple of 4");
   const long long n4 = n / 4;
-  LC_PREFER_SMEM(dpmpp2m_kernel);
   dpmpp2m_kernel<<<static_cast<unsigned>(ceil_div_ll(n4, 256)), 256, 0, s>>>(f, x, x0_prev, x_in_next, n4, c);
   LC_LAUNCH_CHECK();
   return 0;
@@ -435,7 +424,6 @@ int sched_dpmpp2m_step(const float* f, float* x, float* x0_prev, float* x_in_nex
 
 int sched_heun_step(const float* f, double* x, double* x_hat, double* d_cur, float* x_in_next, long long n, int phase,
                     double t_cur, double t_next, double c_skip, double c_out, double c_in_next, cudaStream_t s) {
-  LC_PREFER_SMEM(heun_kernel);
   heun_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s>>>(f, x, x_hat, d_cur, x_in_next, n, phase, t_cur,
                                                                        t_next, c_skip, c_out, c_in_next);
   LC_LAUNCH_CHECK();

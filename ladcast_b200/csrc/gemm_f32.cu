@@ -107,7 +107,6 @@ int gemm_f32(const GemmArgs& g, cudaStream_t stream) {
   LC_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "empty GEMM");
   const int K0 = (g.A1 != nullptr) ? g.K0 : g.K;
   dim3 grid(ceil_div(g.N, TN), ceil_div(g.M, TM));
-  LC_PREFER_SMEM(gemm_f32_kernel);
   gemm_f32_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(g.A0), g.lda0, K0,
                                             reinterpret_cast<const float*>(g.A1), g.lda1,
                                             reinterpret_cast<const float*>(g.W), g.ldw, g.M, g.N, g.K, g.epi,
@@ -122,7 +121,6 @@ int conv3x3_f32(const float* xpad, int n_frames, int H, int W, int Cp, const flo
   cv.enabled = 1; cv.H = H; cv.W = W; cv.Cp = Cp;
   const int M = n_frames * H * W, K = 9 * Cp;
   dim3 grid(ceil_div(C_out, TN), ceil_div(M, TM));
-  LC_PREFER_SMEM(gemm_f32_kernel);
   gemm_f32_kernel<<<grid, 256, 0, stream>>>(xpad, 0, K, nullptr, 0, wmat, K, M, C_out, K, epi, cv);
   LC_LAUNCH_CHECK();
   return 0;

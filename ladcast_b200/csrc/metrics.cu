@@ -152,7 +152,6 @@ int lc_metrics_accumulate(const float* fields, const float* truth, const double*
   LC_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * planes, st));
   LC_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(double) * 4 * planes, st));
   dim3 grid(ceil_div(height * width, THREADS), static_cast<unsigned>(planes));
-  LC_PREFER_SMEM(metrics_kernel<true>);
   metrics_kernel<true><<<grid, THREADS, smem, st>>>(fields, truth, latw, members, planes, height, width, sums, counts,
                                                     nullptr, nullptr, nullptr);
   LC_LAUNCH_CHECK();
@@ -173,7 +172,6 @@ int lc_metrics_pointwise(const float* fields, const float* truth, int members, l
     attr = smem;
   }
   dim3 grid(ceil_div(height * width, THREADS), static_cast<unsigned>(planes));
-  LC_PREFER_SMEM(metrics_kernel<false>);
   metrics_kernel<false><<<grid, THREADS, smem, st>>>(fields, truth, nullptr, members, planes, height, width, nullptr,
                                                      nullptr, out_skill, out_spread, out_mean);
   LC_LAUNCH_CHECK();
@@ -188,7 +186,6 @@ int lc_metrics_acc(const float* forecast, const float* truth, const float* clima
   LC_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 3 * planes, st));
   LC_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(double) * 3 * planes, st));
   dim3 grid(ceil_div(height * width, THREADS), static_cast<unsigned>(planes));
-  LC_PREFER_SMEM(acc_kernel);
   acc_kernel<<<grid, THREADS, 0, st>>>(forecast, truth, climate, lat_weights, planes, height, width, sums, counts);
   LC_LAUNCH_CHECK();
   return 0;
