@@ -91,7 +91,7 @@ struct lc_dcae {
   float *no_w = nullptr, *no_b = nullptr;
   std::vector<Block> blocks;
   int max_frames = 0, h0 = 0, w0 = 0;
-  Buf x, x2, y, padA, padB, xb, qkv, ms1, ms, att, hid, glu;
+  Buf x, x2, y, padA, padB, xb, qkv, ms, att, hid, glu;
 };
 
 namespace lc {
@@ -225,8 +225,7 @@ struct Run {
     if (!xb_valid) LC_TRY(cast_rows<T>(x, xb, P * C, st));
     xb_valid = true;
     LC_TRY(gemm(xb, C, P, w.qkv, D->qkv.p, true, ACT_NONE));
-    LC_TRY(dwconv5(D->qkv.as<float>(), w.dw5, D->ms1.as<float>(), n, H, W, 3 * w.inner, st));
-    LC_TRY(grouped1x1(D->ms1.as<float>(), w.g1, D->ms.as<float>(), P, 3 * w.inner, st));
+    LC_TRY(multiscale_fused(D->qkv.as<float>(), w.dw5, w.g1, D->ms.as<float>(), n, H, W, 3 * w.inner, st));
     LC_TRY(linear_attention<T>(D->qkv.as<float>(), D->ms.as<float>(), D->att.as<T>(), n, HW, w.heads, 1e-15f, st));
     LC_TRY(gemm(D->att.p, 2 * w.inner, P, w.to_out, y, true, ACT_NONE));
     LC_TRY(rmsnorm_rows<T>(y, w.no_w, w.no_b, 1e-5f, x, nullptr, xb, P, C, 0, st));
@@ -373,7 +372,7 @@ void lc_dcae_destroy(lc_dcae* D) {
   if (!D) return;
   for (void* p : D->owned) cudaFree(p);
   for (auto& kv : D->staged) cudaFree(kv.second.p);
-  Buf* bufs[] = {&D->x, &D->x2, &D->y, &D->padA, &D->padB, &D->xb, &D->qkv, &D->ms1, &D->ms, &D->att, &D->hid, &D->glu};
+  Buf* bufs[] = {&D->x, &D->x2, &D->y, &D->padA, &D->padB, &D->xb, &D->qkv, &D->ms, &D->att, &D->hid, &D->glu};
   for (Buf* b : bufs) b->release();
   delete D;
 }
@@ -432,7 +431,7 @@ int lc_dcae_reserve(lc_dcae* D, int max_frames, int h, int w, void* stream) {
   LC_TRY(D->x.alloc(n * mx_x * 4)); LC_TRY(D->x2.alloc(n * mx_x * 4)); LC_TRY(D->y.alloc(n * mx_y * 4));
   LC_TRY(D->padA.alloc(n * mx_pad * e)); LC_TRY(D->padB.alloc(n * mx_pad * e));
   LC_TRY(D->xb.alloc(n * mx_xb * e));
-  LC_TRY(D->qkv.alloc(n * std::max<size_t>(mx_qkv, 1) * 4)); LC_TRY(D->ms1.alloc(n * std::max<size_t>(mx_qkv, 1) * 4));
+  LC_TRY(D->qkv.alloc(n * std::max<size_t>(mx_qkv, 1) * 4));
   LC_TRY(D->ms.alloc(n * std::max<size_t>(mx_qkv, 1) * 4));
   LC_TRY(D->att.alloc(n * std::max<size_t>(mx_att, 1) * e)); LC_TRY(D->hid.alloc(n * std::max<size_t>(mx_hid, 1) * e));
   LC_TRY(D->glu.alloc(n * std::max<size_t>(mx_glu, 1) * e));

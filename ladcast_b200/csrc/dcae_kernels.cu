@@ -120,6 +120,24 @@ __device__ __forceinline__ int sphere_col0(int x0, int p, int W, bool rolled) {
   return cx < 0 ? cx + W : cx;
 }
 
+// a += w * v on the packed fp32 pipe (FFMA2: two lanes per issue slot; these kernels are issue-bound)
+__device__ __forceinline__ void fma4(float4& a, const float4& w, const float4& v) {
+  const float2 lo = __ffma2_rn(make_float2(w.x, w.y), make_float2(v.x, v.y), make_float2(a.x, a.y));
+  const float2 hi = __ffma2_rn(make_float2(w.z, w.w), make_float2(v.z, v.w), make_float2(a.z, a.w));
+  a = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+// element offsets of the NJ source columns a thread slides over (x0-p .. x0-p+NJ-1, wrapped; +W/2 on pole rows)
+template <int NJ>
+__device__ __forceinline__ void col_offsets(int (&co)[NJ], int x0, int p, int W, int C, bool rolled) {
+  int cx = sphere_col0(x0, p, W, rolled);
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    co[j] = cx * C;
+    if (++cx == W) cx = 0;
+  }
+}
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
 // 5x5, fp32 in/out (multiscale projection, DCAE.py:76-85)
 template <int XT>
 __global__ void __launch_bounds__(256) dwconv5_kernel(const float* __restrict__ in, const float* __restrict__ w,
@@ -132,6 +150,8 @@ __global__ void __launch_bounds__(256) dwconv5_kernel(const float* __restrict__ 
   float4 acc[XT];
 #pragma unroll
   for (int o = 0; o < XT; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int con[XT + 4];
+  col_offsets<XT + 4>(con, x0, 2, W, C, false);
 #pragma unroll
   for (int ky = 0; ky < 5; ++ky) {
     int sy;
@@ -143,18 +163,17 @@ __global__ void __launch_bounds__(256) dwconv5_kernel(const float* __restrict__ 
     for (int kx = 0; kx < 5; ++kx)
       wr[kx] = __ldg(reinterpret_cast<const float4*>(w + (ky * 5 + (flip ? 4 - kx : kx)) * C + c));
     const float* rowp = base + static_cast<long long>(sy) * W * C;
-    int cx = sphere_col0(x0, 2, W, rolled);
+    int co[XT + 4];
+#pragma unroll
+    for (int j = 0; j < XT + 4; ++j) co[j] = con[j];
+    if (rolled) col_offsets<XT + 4>(co, x0, 2, W, C, true);
 #pragma unroll
     for (int j = 0; j < XT + 4; ++j) {
-      const float4 v = *reinterpret_cast<const float4*>(rowp + static_cast<long long>(cx) * C);
-      if (++cx == W) cx = 0;
+      const float4 v = *reinterpret_cast<const float4*>(rowp + co[j]);
 #pragma unroll
       for (int kx = 0; kx < 5; ++kx) {
         const int o = j - kx;
-        if (o >= 0 && o < XT) {
-          acc[o].x = fmaf(wr[kx].x, v.x, acc[o].x); acc[o].y = fmaf(wr[kx].y, v.y, acc[o].y);
-          acc[o].z = fmaf(wr[kx].z, v.z, acc[o].z); acc[o].w = fmaf(wr[kx].w, v.w, acc[o].w);
-        }
+        if (o >= 0 && o < XT) fma4(acc[o], wr[kx], v);
       }
     }
   }
@@ -189,9 +208,6 @@ __device__ __forceinline__ void st4<bf16>(bf16* p, float4 v) {
   u.y = *reinterpret_cast<uint32_t*>(&hi);
   *reinterpret_cast<uint2*>(p) = u;
 }
-__device__ __forceinline__ void fma4(float4& a, const float4& w, const float4& v) {
-  a.x = fmaf(w.x, v.x, a.x); a.y = fmaf(w.y, v.y, a.y); a.z = fmaf(w.z, v.z, a.z); a.w = fmaf(w.w, v.w, a.w);
-}
 
 template <typename T, int XT>
 __global__ void __launch_bounds__(256, 3) dwconv3_glu_kernel(const T* __restrict__ in, const float* __restrict__ w,
@@ -210,6 +226,8 @@ __global__ void __launch_bounds__(256, 3) dwconv3_glu_kernel(const T* __restrict
 #pragma unroll
     for (int o = 0; o < XT; ++o) { a0[o] = b0; a1[o] = b1; }
   }
+  int con[XT + 2];
+  col_offsets<XT + 2>(con, x0, 1, W, C, false);
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     int sy;
@@ -224,12 +242,14 @@ __global__ void __launch_bounds__(256, 3) dwconv3_glu_kernel(const T* __restrict
       wg[kx] = __ldg(reinterpret_cast<const float4*>(wt + Co));
     }
     const T* rowp = base + static_cast<long long>(sy) * W * C;
-    int cx = sphere_col0(x0, 1, W, rolled);
+    int co[XT + 2];
+#pragma unroll
+    for (int j = 0; j < XT + 2; ++j) co[j] = con[j];
+    if (rolled) col_offsets<XT + 2>(co, x0, 1, W, C, true);
 #pragma unroll
     for (int j = 0; j < XT + 2; ++j) {
-      const T* px = rowp + static_cast<long long>(cx) * C;
+      const T* px = rowp + co[j];
       const float4 v = ld4<T>(px), g = ld4<T>(px + Co);
-      if (++cx == W) cx = 0;
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const int o = j - kx;
@@ -241,8 +261,8 @@ __global__ void __launch_bounds__(256, 3) dwconv3_glu_kernel(const T* __restrict
 #pragma unroll
   for (int o = 0; o < XT; ++o)
     if (x0 + o < W)
-      st4<T>(op + static_cast<long long>(o) * Co, make_float4(a0[o].x * silu(a1[o].x), a0[o].y * silu(a1[o].y),
-                                                             a0[o].z * silu(a1[o].z), a0[o].w * silu(a1[o].w)));
+      st4<T>(op + static_cast<long long>(o) * Co, make_float4(a0[o].x * silu_fast(a1[o].x), a0[o].y * silu_fast(a1[o].y),
+                                                             a0[o].z * silu_fast(a1[o].z), a0[o].w * silu_fast(a1[o].w)));
 }
 
 // ---------------------------------------------------------------- grouped 1x1 conv, 32 -> 32 per group (DCAE.py:86-88)
@@ -280,6 +300,115 @@ __global__ void __launch_bounds__(256) grouped1x1_kernel(const float* __restrict
       a = fmaf(wr[k], x4.x, a); a = fmaf(wr[k + 1], x4.y, a); a = fmaf(wr[k + 2], x4.z, a); a = fmaf(wr[k + 3], x4.w, a);
     }
     out[(p0 + pp) * C + g * 32 + lane] = a;
+  }
+}
+
+// ---------------------------------------------------------------- fused multiscale projection (DCAE.py:76-88)
+// depthwise 5x5 sphere conv -> grouped 32->32 1x1 conv in one pass; the intermediate never leaves the SM.
+// Block = 128 channels (4 groups) x one image row, walked in 64-pixel segments:
+//   phase A: the sliding-window 5x5 above, results stored channel-major into ds[ch][px] (XOR-swizzled 16-B chunks so
+//            both the transposing stores and the phase-B reads are bank-conflict free);
+//   phase B: warp = (group, 32-pixel half); thread tile 8 px x 4 outputs, outer product over the 32 inputs of the
+//            group: 3 LDS.128 per 32 FFMA (the stand-alone kernel's broadcast reads cost 8 per 32).
+__global__ void __launch_bounds__(256, 3) multiscale_fused_kernel(const float* __restrict__ in, const float* __restrict__ w5,
+                                                               const float* __restrict__ wg, float* __restrict__ out,
+                                                               int n, int H, int W, int C) {
+  __shared__ __align__(16) float ds[128][64];
+  __shared__ __align__(16) float ws[4][32][32];  // [group][k][o ^ swizzle(k)]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ncb = (C + 127) / 128;
+  const int cb = (blockIdx.x % ncb) * 128;
+  const int fy = blockIdx.x / ncb;
+  const int y = fy % H, f = fy / H;
+  // group weights, transposed to k-major
+  for (int i = tid; i < 4096; i += 256) {
+    const int g = i >> 10, o = (i >> 5) & 31, k = i & 31;
+    float v = 0.f;
+    if (cb + g * 32 < C) v = wg[(static_cast<long long>(cb) + g * 32 + o) * 32 + k];
+    ws[g][k][o ^ ((k & 7) * 4)] = v;
+  }
+  const int c = cb + lane * 4;
+  const bool c_ok = c < C;
+  const float* base = in + static_cast<long long>(f) * H * W * C + c;
+  const int g = warp & 3, half = warp >> 2;
+  const int nl = lane & 7, ml = lane >> 3;
+  const bool g_ok = cb + g * 32 < C;
+  for (int seg = 0; seg < W; seg += 64) {
+    __syncthreads();  // ws ready / previous segment's phase B done
+    // ---- phase A
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {
+      const int xl = (it * 8 + warp) * 4;
+      const int x0 = seg + xl;
+      if (!c_ok || x0 >= W) continue;
+      float4 acc[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+      int con[8];
+      col_offsets<8>(con, x0, 2, W, C, false);
+#pragma unroll
+      for (int ky = 0; ky < 5; ++ky) {
+        int sy;
+        bool rolled;
+        sphere_row(y + ky, 2, H, sy, rolled);
+        const bool flip = (y == 0 && ky < 2) || (y == H - 1 && ky >= 3);
+        float4 wr[5];
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx)
+          wr[kx] = __ldg(reinterpret_cast<const float4*>(w5 + (ky * 5 + (flip ? 4 - kx : kx)) * C + c));
+        const float* rowp = base + static_cast<long long>(sy) * W * C;
+        int co[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) co[j] = con[j];
+        if (rolled) col_offsets<8>(co, x0, 2, W, C, true);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(rowp + co[j]);
+#pragma unroll
+          for (int kx = 0; kx < 5; ++kx) {
+            const int o = j - kx;
+            if (o >= 0 && o < 4) fma4(acc[o], wr[kx], v);
+          }
+        }
+      }
+      const int sw = (lane & 7) * 4;  // swizzle of rows 4*lane .. 4*lane+3
+      *reinterpret_cast<float4*>(&ds[lane * 4 + 0][xl ^ sw]) = make_float4(acc[0].x, acc[1].x, acc[2].x, acc[3].x);
+      *reinterpret_cast<float4*>(&ds[lane * 4 + 1][xl ^ sw]) = make_float4(acc[0].y, acc[1].y, acc[2].y, acc[3].y);
+      *reinterpret_cast<float4*>(&ds[lane * 4 + 2][xl ^ sw]) = make_float4(acc[0].z, acc[1].z, acc[2].z, acc[3].z);
+      *reinterpret_cast<float4*>(&ds[lane * 4 + 3][xl ^ sw]) = make_float4(acc[0].w, acc[1].w, acc[2].w, acc[3].w);
+    }
+    __syncthreads();
+    // ---- phase B
+    const int px0 = half * 32 + ml * 8;
+    if (!g_ok || seg + half * 32 >= W) continue;
+    float2 a[4][4];  // [pixel pair][output]: packed FMA lanes = two adjacent pixels
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[i][j] = make_float2(0.f, 0.f);
+#pragma unroll 4
+    for (int k = 0; k < 32; ++k) {
+      const int row = g * 32 + k;
+      const int sw = ((row >> 2) & 7) * 4;
+      const float4 xa = *reinterpret_cast<const float4*>(&ds[row][px0 ^ sw]);
+      const float4 xb = *reinterpret_cast<const float4*>(&ds[row][(px0 + 4) ^ sw]);
+      const float4 wv = *reinterpret_cast<const float4*>(&ws[g][k][(nl * 4) ^ ((k & 7) * 4)]);
+      const float2 xs[4] = {make_float2(xa.x, xa.y), make_float2(xa.z, xa.w), make_float2(xb.x, xb.y),
+                            make_float2(xb.z, xb.w)};
+      const float2 w2[4] = {make_float2(wv.x, wv.x), make_float2(wv.y, wv.y), make_float2(wv.z, wv.z),
+                            make_float2(wv.w, wv.w)};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[i][j] = __ffma2_rn(xs[i], w2[j], a[i][j]);
+    }
+    float* op = out + ((static_cast<long long>(f) * H + y) * W + seg + px0) * C + cb + g * 32 + nl * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (seg + px0 + i < W)
+        *reinterpret_cast<float4*>(op + static_cast<long long>(i) * C) =
+            (i & 1) ? make_float4(a[i >> 1][0].y, a[i >> 1][1].y, a[i >> 1][2].y, a[i >> 1][3].y)
+                    : make_float4(a[i >> 1][0].x, a[i >> 1][1].x, a[i >> 1][2].x, a[i >> 1][3].x);
   }
 }
 
@@ -525,6 +654,15 @@ int grouped1x1(const float* in, const float* w, float* out, long long P, int C, 
   LC_REQUIRE((P + 63) / 64 <= 65535, "grouped 1x1: too many pixels per call");
   dim3 grid(C / 32, static_cast<unsigned>((P + 63) / 64));
   grouped1x1_kernel<<<grid, 256, 0, s>>>(in, w, out, P, C);
+  LC_LAUNCH_CHECK();
+  return 0;
+}
+int multiscale_fused(const float* in, const float* w5, const float* wg, float* out, int n, int H, int W, int C,
+                     cudaStream_t s) {
+  LC_REQUIRE(C % 32 == 0, "multiscale projection: channels must be a multiple of 32");
+  const long long nblk = static_cast<long long>(n) * H * ((C + 127) / 128);
+  LC_REQUIRE(nblk < (1ll << 31), "multiscale projection: too many image rows per call");
+  multiscale_fused_kernel<<<static_cast<unsigned>(nblk), 256, 0, s>>>(in, w5, wg, out, n, H, W, C);
   LC_LAUNCH_CHECK();
   return 0;
 }

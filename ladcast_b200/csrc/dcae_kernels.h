@@ -13,6 +13,8 @@ int dwconv5(const float* in, const float* w, float* out, int n, int H, int W, in
 template <typename T>
 int dwconv3_glu(const T* in, const float* w, const float* bias, T* out, int n, int H, int W, int C, cudaStream_t s);
 int grouped1x1(const float* in, const float* w, float* out, long long P, int C, cudaStream_t s);
+int multiscale_fused(const float* in, const float* w5, const float* wg, float* out, int n, int H, int W, int C,
+                     cudaStream_t s);
 template <typename T>
 int linear_attention(const float* qkv, const float* ms, T* out, int n, int HW, int heads, float eps, cudaStream_t s);
 template <typename T>
