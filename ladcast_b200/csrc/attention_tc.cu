@@ -2,17 +2,22 @@
 // LaDCast_3D_model.py:199-201).  Q/K/V are read by TMA straight out of the token-major [B*S, 3d] projection
 // buffer (q | k | v), so no head-major transposes exist anywhere.
 //
+// Shape of the kernel follows from the measured tcgen05.mma issue rate (tools/ubench/mma_rate.cu): an M=128 MMA costs
+// ~75-80 cycles whether N is 64 or 128, so S tiles are 128 keys wide, and reading the A operand from tensor memory
+// is the fastest form, so P never goes through shared memory:
+//
 //   CTA = one (sample, head, 256-query block) = two 128-query tiles A and B that share every K/V tile; 320 threads:
-//     warp 0    : TMA producer — Q (both tiles) once, K_j / V_j tiles of 64 keys through a 4-stage ring, so loads run
-//                 ~3 tiles ahead of the tensor pipe (L2->smem latency under load is ~2 us, longer than one tile)
-//     warp 1    : TMEM allocator + single-thread tcgen05.mma issuer.  Per KV tile: S_A = Q_A K^T, S_B = Q_B K^T
-//                 (double-buffered in TMEM, issued one tile ahead), O_A += P_A V, O_B += P_B V (V consumed MN-major,
-//                 i.e. exactly as it lies in memory)
+//     warp 0    : TMA producer — Q (both tiles) once, then K_0 V_0 K_1 V_1 ... (128 keys x 128 dims = 32 KB each)
+//                 through a 5-slot ring, ~2.5 KV steps ahead of the tensor pipe
+//     warp 1    : TMEM allocator + single-thread tcgen05.mma issuer.  Per tile and KV step: O_t += P_t V_j with P_t
+//                 read from TMEM, then S_t = Q_t K_{j+1}^T into the same TMEM columns (S and the bf16 P alias; the
+//                 tensor pipe executes in issue order, so the overwrite is safe).  The two tiles ping-pong: while
+//                 one tile's softmax runs, the tensor pipe works for the other.
 //     warps 2-5 : softmax of tile A, warps 6-9: softmax of tile B.  One thread per query row reads its S row from
 //                 TMEM (no shuffles), online softmax in the log2 domain (one FFMA + one MUFU.EX2 per element), lazy
-//                 rescale of O (only when the row max grows by more than 2^8), P (bf16) into a 128B-swizzled smem tile
-//                 that is the A operand of the PV product.  While one tile's softmax runs, the tensor pipe works on
-//                 the other tile.  Final O / l epilogue per tile.
+//                 rescale of O (only when the row max grows by more than 2^8), P (bf16) stored back to TMEM over S.
+//                 Final O / l epilogue per tile.
+//   TMEM columns: S_A/P_A 0..127, S_B/P_B 128..255, O_A 256..383, O_B 384..511.
 #include "kernels.h"
 #include "ptx.cuh"
 #include "tmap.h"
@@ -21,40 +26,33 @@ namespace lc {
 namespace {
 
 constexpr int HD = 128;
-constexpr int BQ = 128;                    // rows per query tile; two tiles per CTA
-constexpr int BKV = 64;
-constexpr int STAGES = 4;
-constexpr int Q_BYTES = 128 * 128 * 2;     // 32 KB per query tile: two [128 rows][64 dims] swizzled boxes
-constexpr int QSUB_BYTES = 128 * 64 * 2;   // 16 KB
-constexpr int KV_BYTES = BKV * 128 * 2;    // 16 KB: two [64 keys][64 dims] swizzled boxes
-constexpr int KVSUB_BYTES = BKV * 64 * 2;  // 8 KB
-constexpr int P_BYTES = 128 * BKV * 2;     // 16 KB: [128 rows][64 keys]
-constexpr int SMEM_BYTES = 2 * Q_BYTES + 2 * P_BYTES + 2 * STAGES * KV_BYTES + 1024 + 256;
+constexpr int BQ = 128;                     // rows per query tile; two tiles per CTA
+constexpr int BKV = 128;
+constexpr int RING = 5;
+constexpr int TILE_BYTES = 128 * 128 * 2;   // 32 KB: two [128 rows][64 dims] swizzled boxes
+constexpr int SUB_BYTES = 128 * 64 * 2;     // 16 KB
+constexpr int SMEM_BYTES = 2 * TILE_BYTES + RING * TILE_BYTES + 1024 + 256;
 constexpr int NUM_THREADS = 320;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t COL_S = 0;    // S[tile][buf] at COL_S + tile*128 + buf*64
+constexpr uint32_t COL_S = 0;    // S[tile] (fp32, 128 cols) / P[tile] (bf16 pairs, first 64 cols) at COL_S + tile*128
 constexpr uint32_t COL_O = 256;  // O[tile] at COL_O + tile*128
 constexpr float RESCALE_THRESHOLD = 8.0f;
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmkv, int S, int heads,
-                    bf16* __restrict__ out_p, int Np, bf16* __restrict__ out_c) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf16* __restrict__ out_p, int Np,
+                    bf16* __restrict__ out_c) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-  uint8_t* sQ = smem;                       // [2][Q_BYTES]
-  uint8_t* sP = sQ + 2 * Q_BYTES;           // [2][P_BYTES]
-  uint8_t* sK = sP + 2 * P_BYTES;           // [STAGES][KV_BYTES]
-  uint8_t* sV = sK + STAGES * KV_BYTES;     // [STAGES][KV_BYTES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + STAGES * KV_BYTES);
-  uint64_t* q_full = bars;                  // 1
-  uint64_t* k_full = bars + 1;              // STAGES
-  uint64_t* v_full = k_full + STAGES;       // STAGES
-  uint64_t* kv_empty = v_full + STAGES;     // STAGES
-  uint64_t* s_full = kv_empty + STAGES;     // [tile][buf] = 4
-  uint64_t* p_full = s_full + 4;            // [tile] (4 arrivals: one per softmax warp)
-  uint64_t* p_empty = p_full + 2;           // [tile] (PV of the tile's previous KV tile complete)
-  uint64_t* o_full = p_empty + 2;           // 1
+  uint8_t* sQ = smem;                        // [2][TILE_BYTES]
+  uint8_t* sR = sQ + 2 * TILE_BYTES;         // [RING][TILE_BYTES]: K_0 V_0 K_1 V_1 ...
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sR + RING * TILE_BYTES);
+  uint64_t* q_full = bars;                   // 1
+  uint64_t* r_full = bars + 1;               // RING
+  uint64_t* r_empty = r_full + RING;         // RING
+  uint64_t* s_full = r_empty + RING;         // [tile]: S_t(j) complete (and with it every earlier MMA)
+  uint64_t* p_full = s_full + 2;             // [tile] (4 arrivals: one per softmax warp)
+  uint64_t* o_full = p_full + 2;             // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -64,18 +62,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   const int row_base = b * S;
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmq);
-    ptx::prefetch_tmap(&tmkv);
+    ptx::prefetch_tmap(&tm);
     ptx::mbar_init(q_full, 1);
-    for (int i = 0; i < STAGES; ++i) {
-      ptx::mbar_init(&k_full[i], 1);
-      ptx::mbar_init(&v_full[i], 1);
-      ptx::mbar_init(&kv_empty[i], 1);
+    for (int i = 0; i < RING; ++i) {
+      ptx::mbar_init(&r_full[i], 1);
+      ptx::mbar_init(&r_empty[i], 1);
     }
-    for (int i = 0; i < 4; ++i) ptx::mbar_init(&s_full[i], 1);
     for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&s_full[i], 1);
       ptx::mbar_init(&p_full[i], 4);
-      ptx::mbar_init(&p_empty[i], 1);
     }
     ptx::mbar_init(o_full, 1);
     ptx::fence_barrier_init();
@@ -88,68 +83,85 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
-    ptx::mbar_expect_tx(q_full, 2 * Q_BYTES);
+    ptx::mbar_expect_tx(q_full, 2 * TILE_BYTES);
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
-      ptx::tma_load_2d(sQ + t * Q_BYTES, &tmq, q_full, h * HD, row_base + q0 + t * BQ);
-      ptx::tma_load_2d(sQ + t * Q_BYTES + QSUB_BYTES, &tmq, q_full, h * HD + 64, row_base + q0 + t * BQ);
+      ptx::tma_load_2d(sQ + t * TILE_BYTES, &tm, q_full, h * HD, row_base + q0 + t * BQ);
+      ptx::tma_load_2d(sQ + t * TILE_BYTES + SUB_BYTES, &tm, q_full, h * HD + 64, row_base + q0 + t * BQ);
     }
     int st = 0;
     uint32_t ph = 0;
     for (int j = 0; j < n_tiles; ++j) {
-      ptx::mbar_wait(&kv_empty[st], ph ^ 1);
       const int kr = row_base + j * BKV;
-      ptx::mbar_expect_tx(&k_full[st], KV_BYTES);
-      ptx::tma_load_2d(sK + st * KV_BYTES, &tmkv, &k_full[st], d + h * HD, kr);
-      ptx::tma_load_2d(sK + st * KV_BYTES + KVSUB_BYTES, &tmkv, &k_full[st], d + h * HD + 64, kr);
-      ptx::mbar_expect_tx(&v_full[st], KV_BYTES);
-      ptx::tma_load_2d(sV + st * KV_BYTES, &tmkv, &v_full[st], 2 * d + h * HD, kr);
-      ptx::tma_load_2d(sV + st * KV_BYTES + KVSUB_BYTES, &tmkv, &v_full[st], 2 * d + h * HD + 64, kr);
-      if (++st == STAGES) { st = 0; ph ^= 1; }
+#pragma unroll
+      for (int kv = 0; kv < 2; ++kv) {  // 0: K_j, 1: V_j
+        ptx::mbar_wait_spin(&r_empty[st], ph ^ 1);
+        const int col = (kv + 1) * d + h * HD;
+        uint8_t* dst = sR + st * TILE_BYTES;
+        ptx::mbar_expect_tx(&r_full[st], TILE_BYTES);
+        ptx::tma_load_2d(dst, &tm, &r_full[st], col, kr);
+        ptx::tma_load_2d(dst + SUB_BYTES, &tm, &r_full[st], col + 64, kr);
+        if (++st == RING) { st = 0; ph ^= 1; }
+      }
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(128, BKV, 0, 0);  // A = Q (K-major), B = K (K-major)
-    constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(128, 128, 0, 1);  // A = P (K-major), B = V (MN-major)
-    const uint32_t q_addr = ptx::smem_u32(sQ), p_addr = ptx::smem_u32(sP);
-    auto issue_qk = [&](int j) {  // both query tiles against K_j
-      const int st = j % STAGES;
-      ptx::mbar_wait(&k_full[st], (j / STAGES) & 1);
-      ptx::tc_fence_after();
-      const uint32_t k_addr = ptx::smem_u32(sK + st * KV_BYTES);
+    constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(128, HD, 0, 1);   // A = P (TMEM), B = V (MN-major)
+    const uint32_t q_addr = ptx::smem_u32(sQ), r_addr = ptx::smem_u32(sR);
+    auto issue_qk = [&](int t, int slot) {
+      const uint32_t k_addr = r_addr + slot * TILE_BYTES;
+      const uint32_t d_tmem = tmem_base + COL_S + static_cast<uint32_t>(t * 128);
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const uint32_t d_tmem = tmem_base + COL_S + static_cast<uint32_t>(t * 128 + (j & 1) * BKV);
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {  // 128 head dims = 2 sub-tiles x 4 K-steps of 16
-          const uint32_t qoff = t * Q_BYTES + (kk >> 2) * QSUB_BYTES + (kk & 3) * 32;
-          const uint32_t koff = (kk >> 2) * KVSUB_BYTES + (kk & 3) * 32;
-          ptx::umma_f16(d_tmem, ptx::make_smem_desc(q_addr + qoff, 16, 1024),
-                        ptx::make_smem_desc(k_addr + koff, 16, 1024), idesc_qk, kk != 0 ? 1u : 0u);
-        }
-        ptx::umma_commit(&s_full[t * 2 + (j & 1)]);
+      for (int kk = 0; kk < 8; ++kk) {  // 128 head dims = 2 sub-tiles x 4 K-steps of 16
+        const uint32_t off = (kk >> 2) * SUB_BYTES + (kk & 3) * 32;
+        ptx::umma_f16(d_tmem, ptx::make_smem_desc(q_addr + t * TILE_BYTES + off, 16, 1024),
+                      ptx::make_smem_desc(k_addr + off, 16, 1024), idesc_qk, kk != 0 ? 1u : 0u);
       }
+      ptx::umma_commit(&s_full[t]);
     };
-    ptx::mbar_wait(q_full, 0);
-    issue_qk(0);
+    auto issue_pv = [&](int t, int slot, bool first) {
+      const uint32_t v_addr = r_addr + slot * TILE_BYTES;
+      const uint32_t d_tmem = tmem_base + COL_O + static_cast<uint32_t>(t * 128);
+      const uint32_t a_tmem = tmem_base + COL_S + static_cast<uint32_t>(t * 128);
+#pragma unroll
+      for (int kk = 0; kk < BKV / 16; ++kk)  // 128 keys = 8 K-steps of 16 (16 key rows x 128 B = 2 KB per sub-tile)
+        ptx::umma_f16_ts(d_tmem, a_tmem + kk * 8, ptx::make_smem_desc(v_addr + kk * 2048, SUB_BYTES, 1024), idesc_pv,
+                         (first && kk == 0) ? 0u : 1u);
+    };
+    int st = 0;        // ring slot of the next tile to consume (K_0 first)
+    uint32_t ph = 0;
+    auto advance = [&]() { if (++st == RING) { st = 0; ph ^= 1; } };
+    ptx::mbar_wait_spin(q_full, 0);
+    ptx::mbar_wait_spin(&r_full[st], ph);
+    ptx::tc_fence_after();
+    issue_qk(0, st);
+    issue_qk(1, st);
+    ptx::umma_commit(&r_empty[st]);
+    advance();
     for (int j = 0; j < n_tiles; ++j) {
-      const int st = j % STAGES;
-      if (j + 1 < n_tiles) issue_qk(j + 1);
-      ptx::mbar_wait(&v_full[st], (j / STAGES) & 1);
-      const uint32_t v_addr = ptx::smem_u32(sV + st * KV_BYTES);
+      const int v_slot = st;
+      ptx::mbar_wait_spin(&r_full[v_slot], ph);
+      advance();
+      const int k_slot = st;  // K_{j+1}
+      const uint32_t k_ph = ph;
+      const bool more = j + 1 < n_tiles;
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        ptx::mbar_wait(&p_full[t], j & 1);
+        ptx::mbar_wait_spin(&p_full[t], j & 1);
         ptx::tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < BKV / 16; ++kk) {  // 64 keys = 4 K-steps of 16
-          const uint64_t da = ptx::make_smem_desc(p_addr + t * P_BYTES + kk * 32, 16, 1024);
-          const uint64_t db = ptx::make_smem_desc(v_addr + kk * 2048, KVSUB_BYTES, 1024);
-          ptx::umma_f16(tmem_base + COL_O + static_cast<uint32_t>(t * 128), da, db, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+        issue_pv(t, v_slot, j == 0);
+        if (t == 1) ptx::umma_commit(&r_empty[v_slot]);
+        if (more) {
+          if (t == 0) {
+            ptx::mbar_wait_spin(&r_full[k_slot], k_ph);
+            ptx::tc_fence_after();
+          }
+          issue_qk(t, k_slot);
+          if (t == 1) ptx::umma_commit(&r_empty[k_slot]);
         }
-        ptx::umma_commit(&p_empty[t]);
       }
-      ptx::umma_commit(&kv_empty[st]);  // K_j and V_j are dead once both tiles' PV products have completed
+      if (more) advance();
     }
     ptx::umma_commit(o_full);
   } else if (warp >= 2) {
@@ -159,14 +171,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const float scale_log2 = 0.08838834764831845f * 1.4426950408889634f;
+    const uint32_t s_addr = tmem_base + lane_addr + COL_S + static_cast<uint32_t>(t * 128);
     const uint32_t o_addr = tmem_base + lane_addr + COL_O + static_cast<uint32_t>(t * 128);
-    uint8_t* prow = sP + t * P_BYTES + r * 128;
     float m_used = -INFINITY, l = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
-      ptx::mbar_wait(&s_full[t * 2 + (j & 1)], (j >> 1) & 1);
+      // S_t(j) complete; the commit also covers PV_t(j-1), so O_t is quiescent until this thread hands over P_t(j)
+      ptx::mbar_wait_spin(&s_full[t], j & 1);
       ptx::tc_fence_after();
       uint32_t sreg[BKV / 32][32];
-      const uint32_t s_addr = tmem_base + lane_addr + COL_S + static_cast<uint32_t>(t * 128 + (j & 1) * BKV);
 #pragma unroll
       for (int c = 0; c < BKV / 32; ++c) ptx::tmem_ld32(s_addr + c * 32, sreg[c]);
       ptx::tmem_ld_wait();
@@ -190,24 +202,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       if (need) {
         alpha = (m_used == -INFINITY) ? 0.f : exp2f(m_used - m_new);
         m_used = m_new;
-      }
-      // p = 2^(s*scale - m): one FFMA + one MUFU per element; arguments are <= 8 by construction
-      const float neg_m = -m_used;
-      float ps[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c = 0; c < BKV / 32; ++c)
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float p = ptx::ex2_approx(fmaf(__uint_as_float(sreg[c][i]), scale_log2, neg_m));
-          ps[i & 3] += p;
-          sreg[c][i] = __float_as_uint(p);
-        }
-      l = l * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
-      if (j > 0) {
-        // PV of this tile's previous KV tile must be complete: the P buffer is free and O is quiescent
-        ptx::mbar_wait(&p_empty[t], (j - 1) & 1);
-        ptx::tc_fence_after();
-        if (need) {
+        if (j > 0) {
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
             uint32_t o[32];
@@ -217,30 +212,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
             ptx::tmem_st32(o_addr + c * 32, o);
           }
-          ptx::tmem_st_wait();
         }
       }
-      // P (bf16) -> smem, K-major [128 rows][64 keys], 128-byte swizzle: 16-B chunk index ^= row & 7
+      // p = 2^(s*scale - m): one FFMA + one MUFU per element; arguments are <= 8 by construction.
+      // P (bf16 pairs) goes back to TMEM over the S columns already consumed: A operand of the PV product.
+      const float neg_m = -m_used;
+      float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int g = 0; g < BKV / 8; ++g) {
-        const int c = g >> 2, i0 = (g & 3) * 8;
-        uint4 pk;
-        __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(sreg[c][i0]), __uint_as_float(sreg[c][i0 + 1]));
-        __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(sreg[c][i0 + 2]), __uint_as_float(sreg[c][i0 + 3]));
-        __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(sreg[c][i0 + 4]), __uint_as_float(sreg[c][i0 + 5]));
-        __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(sreg[c][i0 + 6]), __uint_as_float(sreg[c][i0 + 7]));
-        pk.x = *reinterpret_cast<uint32_t*>(&t0);
-        pk.y = *reinterpret_cast<uint32_t*>(&t1);
-        pk.z = *reinterpret_cast<uint32_t*>(&t2);
-        pk.w = *reinterpret_cast<uint32_t*>(&t3);
-        *reinterpret_cast<uint4*>(prow + ((g ^ (r & 7)) << 4)) = pk;
+      for (int c2 = 0; c2 < BKV / 64; ++c2) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 64; i += 2) {
+          const int c = c2 * 2 + (i >> 5), ii = i & 31;
+          const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(sreg[c][ii]), scale_log2, neg_m));
+          const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(sreg[c][ii + 1]), scale_log2, neg_m));
+          ps[(i >> 1) & 3] += p0 + p1;
+          __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&pb);
+        }
+        ptx::tmem_st32(s_addr + c2 * 32, pk);
       }
-      ptx::fence_proxy_async();
+      l = l * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
+      ptx::tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&p_full[t]);
     }
-    ptx::mbar_wait(o_full, 0);
+    ptx::mbar_wait_spin(o_full, 0);
     ptx::tc_fence_after();
     const int tok = q0 + t * BQ + r;
     const float inv = 1.0f / l;
@@ -287,14 +285,12 @@ int attention_bf16(const bf16* qkv, int B, int S, int heads, int head_dim, bf16*
     attr_set = true;
   }
   const int d = heads * HD;
-  CUtensorMap tmq, tmkv;
-  LC_TRY(make_tmap_2d_bf16(&tmq, qkv, static_cast<uint64_t>(3) * d, static_cast<uint64_t>(B) * S,
+  CUtensorMap tm;
+  LC_TRY(make_tmap_2d_bf16(&tm, qkv, static_cast<uint64_t>(3) * d, static_cast<uint64_t>(B) * S,
                            static_cast<uint64_t>(3) * d * 2, 64, 128));
-  LC_TRY(make_tmap_2d_bf16(&tmkv, qkv, static_cast<uint64_t>(3) * d, static_cast<uint64_t>(B) * S,
-                           static_cast<uint64_t>(3) * d * 2, 64, BKV));
   dim3 grid(ceil_div(S, 2 * BQ), heads, B);
   prof_begin(PROF_ATTN, s);
-  attention_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(tmq, tmkv, S, heads, out_p, Np, out_c);
+  attention_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(tm, S, heads, out_p, Np, out_c);
   prof_end(PROF_ATTN, 4.0 * B * heads * static_cast<double>(S) * S * HD, s);
   LC_LAUNCH_CHECK();
   return 0;
