@@ -38,6 +38,13 @@ constexpr uint32_t COL_S = 0;    // S[tile] (fp32, 128 cols) / P[tile] (bf16 pai
 constexpr uint32_t COL_O = 256;  // O[tile] at COL_O + tile*128
 constexpr float RESCALE_THRESHOLD = 8.0f;
 
+// Optional in-kernel timeline of CTA (0,0,0) for tuning (tools/attn_trace.py): clock64 stamps, [role][step][4].
+__device__ long long* g_trace = nullptr;
+#define LC_TRACE(role, j, k)                                           \
+  do {                                                                 \
+    if (trace != nullptr) trace[((role) * 64 + (j)) * 4 + (k)] = clock64(); \
+  } while (0)
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf16* __restrict__ out_p, int Np,
                     bf16* __restrict__ out_c) {
@@ -60,6 +67,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * (2 * BQ);
   const int n_tiles = (S + BKV - 1) / BKV;
   const int row_base = b * S;
+  long long* trace = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0 ? g_trace : nullptr;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm);
@@ -150,6 +158,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
       for (int t = 0; t < 2; ++t) {
         ptx::mbar_wait_spin(&p_full[t], j & 1);
         ptx::tc_fence_after();
+        LC_TRACE(0, j, 2 * t);
         issue_pv(t, v_slot, j == 0);
         if (t == 1) ptx::umma_commit(&r_empty[v_slot]);
         if (more) {
@@ -160,6 +169,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
           issue_qk(t, k_slot);
           if (t == 1) ptx::umma_commit(&r_empty[k_slot]);
         }
+        LC_TRACE(0, j, 2 * t + 1);
       }
       if (more) advance();
     }
@@ -168,6 +178,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
     // ===================== softmax + epilogue (thread = query row of tile t) =====================
     const int t = (warp - 2) >> 2;  // 0: tile A (warps 2-5), 1: tile B (warps 6-9)
     const int quarter = warp & 3;   // TMEM lane quarter this warp may access (= warp id % 4)
+    if ((warp - 2) & 3) trace = nullptr;  // one traced warp per tile
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const float scale_log2 = 0.08838834764831845f * 1.4426950408889634f;
@@ -176,12 +187,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
     float m_used = -INFINITY, l = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
       // S_t(j) complete; the commit also covers PV_t(j-1), so O_t is quiescent until this thread hands over P_t(j)
+      LC_TRACE(1 + t, j, 0);
       ptx::mbar_wait_spin(&s_full[t], j & 1);
       ptx::tc_fence_after();
+      LC_TRACE(1 + t, j, 1);
       uint32_t sreg[BKV / 32][32];
 #pragma unroll
       for (int c = 0; c < BKV / 32; ++c) ptx::tmem_ld32(s_addr + c * 32, sreg[c]);
       ptx::tmem_ld_wait();
+      LC_TRACE(1 + t, j, 2);
       const int n_valid = S - j * BKV;  // keys >= n_valid are padding (only ever true for the last tile)
       if (n_valid < BKV) {
 #pragma unroll
@@ -237,6 +251,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&p_full[t]);
+      LC_TRACE(1 + t, j, 3);
     }
     ptx::mbar_wait_spin(o_full, 0);
     ptx::tc_fence_after();
@@ -275,6 +290,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
 }
 
 }  // namespace
+
+int attention_set_trace(long long* buf) {
+  LC_CHECK_CUDA(cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)));
+  return 0;
+}
 
 int attention_bf16(const bf16* qkv, int B, int S, int heads, int head_dim, bf16* out_p, int Np, bf16* out_c,
                    cudaStream_t s) {

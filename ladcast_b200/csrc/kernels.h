@@ -39,6 +39,7 @@ int cast_rows(const float* x, T* out, long long n, cudaStream_t s);
 // token-major and split: tokens [0, Np) -> out_p [B*Np, d], tokens [Np, S) -> out_c [B*(S-Np), d].
 int attention_f32(const float* qkv, int B, int S, int heads, int head_dim, float* out_p, int Np, float* out_c,
                   cudaStream_t s);
+int attention_set_trace(long long* buf);  // tuning aid: timeline of CTA 0 (nullptr = off)
 int attention_bf16(const bf16* qkv, int B, int S, int heads, int head_dim, bf16* out_p, int Np, bf16* out_c,
                    cudaStream_t s);
 

@@ -1,0 +1,29 @@
+"""Timeline of attention CTA (0,0,0): where the tensor-pipe issuer and the two softmax tiles spend their cycles."""
+import sys, os, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from ladcast_b200 import _lib
+lib = _lib.load()
+b, s, h = 20, 2250, 12
+d = h * 128
+qkv = torch.randn(b, s, 3 * d, device="cuda").bfloat16()
+out = torch.empty(b, s, d, device="cuda", dtype=torch.bfloat16)
+for _ in range(2):
+    _lib.check(lib.lc_attention(0, _lib.ptr(qkv), _lib.ptr(out), b, s, h, _lib.stream()))
+tr = torch.zeros(3, 64, 4, dtype=torch.int64, device="cuda")
+lib.lc_debug_attention_trace.argtypes = [ctypes.c_void_p]
+lib.lc_debug_attention_trace(_lib.ptr(tr))
+_lib.check(lib.lc_attention(0, _lib.ptr(qkv), _lib.ptr(out), b, s, h, _lib.stream()))
+torch.cuda.synchronize()
+lib.lc_debug_attention_trace(None)
+t = tr.cpu()
+n = (s + 127) // 128
+t0 = int(t[1, 0, 0])
+print("step | MMA: pfullA issuedA pfullB issuedB | smA: enter sfull ld done | smB: enter sfull ld done   (cycles from start)")
+for j in range(n):
+    m = [int(x) - t0 for x in t[0, j]]
+    a = [int(x) - t0 for x in t[1, j]]
+    bb = [int(x) - t0 for x in t[2, j]]
+    print(f"{j:3d} | {m[0]:7d} {m[1]:7d} {m[2]:7d} {m[3]:7d} | {a[0]:7d} {a[1]:7d} {a[2]:7d} {a[3]:7d} | {bb[0]:7d} {bb[1]:7d} {bb[2]:7d} {bb[3]:7d}")
+print("softmax A: wait-for-S / load / compute per step:",
+      [(int(t[1, j, 1] - t[1, j, 0]), int(t[1, j, 2] - t[1, j, 1]), int(t[1, j, 3] - t[1, j, 2])) for j in range(4, 10)])
