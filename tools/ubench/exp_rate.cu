@@ -1,0 +1,70 @@
+// Micro-benchmark: cycles per 128-key softmax row-chunk for different instruction mixes and warps per SM sub-partition.
+#include <cstdio>
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// exp2 on the FMA pipe: round-to-nearest split + degree-3 polynomial on [-0.5, 0.5] + exponent insert
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -120.f);
+  const float t = x + 12582912.f;             // 1.5 * 2^23: integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);       // [-0.5, 0.5]
+  float p = fmaf(f, 0.0555041f, 0.2402265f);
+  p = fmaf(p, f, 0.6931472f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(1024, 1) k(float* out, long long* cyc, int iters, float scale, float negm) {
+  float s[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) s[i] = -(float)((threadIdx.x * 7 + i * 13) % 97) * 0.05f;
+  float acc[4] = {0, 0, 0, 0};
+  uint32_t pk = 0;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 64; i += 2) {
+      float p0, p1;
+      const float a0 = fmaf(s[i], scale, negm), a1 = fmaf(s[i + 1], scale, negm);
+      if (MODE == 3 && (i & 6) == 0) { p0 = ex2_poly(a0); p1 = ex2_poly(a1); }   // 25 % on the FMA pipe
+      else if (MODE == 4 && (i & 2) == 0) { p0 = ex2_poly(a0); p1 = ex2_poly(a1); }  // 50 %
+      else { p0 = ex2(a0); p1 = ex2(a1); }
+      if (MODE >= 1) acc[(i >> 1) & 3] += p0 + p1; else { acc[0] = p0; acc[1] = p1; }
+      if (MODE >= 2) { __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1); pk ^= *reinterpret_cast<uint32_t*>(&b); }
+      s[i] += 1e-7f * p0; s[i + 1] += 1e-7f * p1;   // keep the chain live (2 extra FFMA per pair)
+    }
+  }
+  long long t1 = clock64();
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc[0] + acc[1] + acc[2] + acc[3] + __uint_as_float(pk) + s[5];
+}
+
+template <int MODE>
+void run(const char* name) {
+  float* out; long long* cyc;
+  cudaMalloc(&out, 148 * 1024 * 4); cudaMalloc(&cyc, 148 * 8);
+  for (int threads : {128, 256, 512, 1024}) {
+    const int iters = 200;
+    k<MODE><<<148, threads>>>(out, cyc, iters, 0.1275f, -0.3f);
+    cudaDeviceSynchronize();
+    long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    const double per_iter = double(h) / iters;               // cycles for 64 elements per thread
+    const double el_per_clk_sm = 64.0 * threads / per_iter;
+    printf("%-46s warps/SMSP %d: %7.1f cycles per 64-element pass, %5.2f exp/clk/SM\n", name, threads / 128, per_iter, el_per_clk_sm);
+  }
+  cudaFree(out); cudaFree(cyc);
+}
+
+int main() {
+  run<0>("FFMA + MUFU (+2 FFMA keepalive)");
+  run<1>("+ FADD row sum");
+  run<2>("+ F2FP bf16 pack");
+  run<3>("+ 25% of the exps as FMA-pipe polynomial");
+  run<4>("+ 50% of the exps as FMA-pipe polynomial");
+  return 0;
+}
