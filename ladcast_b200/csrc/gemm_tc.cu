@@ -151,6 +151,53 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& ep, const uint32
         else if (one_ok) outp[orow * ldo] = __float2bfloat16_rn(v0);
       }
     }
+  } else if (n0 + 32 <= N && (ep.ldo & 3) == 0 && (KIND != K_GATED || (ep.gate_stride & 3) == 0) &&
+             (KIND != K_RESID || (ep.ldr & 3) == 0)) {
+    // fp32 output, full chunk: 8 lanes x float4 cover one 128-B row segment, a warp instruction covers 4 rows, and
+    // all 8 row groups' residual / gate loads are issued before the first use: 4 KB of residual in flight per warp.
+    // (With one 4-B column per lane the read-modify-write epilogue of the K=1536 out-projections was bound by
+    // DRAM latency x 1 KB in flight per warp: 1.6 TB/s.)
+    const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+    const int col = n0 + c4;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ep.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+    float* outp = reinterpret_cast<float*>(ep.out) + col;
+    const long long ldo = ep.ldo;
+    float4 prev[8], gq[8];
+    long long orows[8];
+    bool ok[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const int rr = g * 4 + rsub;
+      ok[g] = __shfl_sync(0xffffffffu, row_mine, rr) < M;
+      orows[g] = __shfl_sync(0xffffffffu, orow_mine, rr);
+      prev[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+      gq[g] = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (KIND == K_GATED) {
+        const int smp = __shfl_sync(0xffffffffu, sample_mine, rr);
+        if (ok[g]) {
+          prev[g] = *reinterpret_cast<const float4*>(outp + orows[g] * ldo);
+          if (ep.gate != nullptr)
+            gq[g] = __ldg(reinterpret_cast<const float4*>(ep.gate + static_cast<long long>(smp) * ep.gate_stride + col));
+        }
+      } else if (KIND == K_RESID) {
+        if (ok[g]) prev[g] = *reinterpret_cast<const float4*>(ep.resid + orows[g] * ep.ldr + col);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float* tb = tbuf + (g * 4 + rsub) * 33 + c4;
+      const float t0 = tb[0] + bias4.x, t1 = tb[1] + bias4.y, t2 = tb[2] + bias4.z, t3 = tb[3] + bias4.w;
+      float4 o;
+      if (KIND == K_GATED) {
+        o = make_float4(fmaf(gq[g].x, t0, prev[g].x), fmaf(gq[g].y, t1, prev[g].y), fmaf(gq[g].z, t2, prev[g].z),
+                        fmaf(gq[g].w, t3, prev[g].w));
+      } else {
+        o = make_float4(act_fast<ACT>(t0) + prev[g].x, act_fast<ACT>(t1) + prev[g].y, act_fast<ACT>(t2) + prev[g].z,
+                        act_fast<ACT>(t3) + prev[g].w);
+      }
+      if (ok[g]) *reinterpret_cast<float4*>(outp + orows[g] * ldo) = o;
+    }
   } else {
     const int col = n0 + lane;
     const bool col_ok = col < N;
