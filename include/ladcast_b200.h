@@ -117,11 +117,17 @@ typedef struct {
   int stage_channels[8]; /* decoder_block_out_channels, index 0 = highest resolution: 252, 504, 504, 1008 */
   int stage_layers[8];   /* decoder_layers_per_block */
   int stage_is_evit[8];  /* 1 where decoder_block_types[i] == "EfficientViTBlock" */
+  /* encoder (optional: leave in_channels = 0 for a decode-only handle); same number of stages as the decoder */
+  int in_channels;           /* encoder conv_in channels = fields + static, 89 */
+  int enc_stage_channels[8]; /* encoder_block_out_channels, index 0 = highest resolution */
+  int enc_stage_layers[8];   /* encoder_layers_per_block (layers[0] must be > 0) */
+  int enc_stage_is_evit[8];  /* 1 where encoder_block_types[i] == "EfficientViTBlock" */
 } lc_dcae_cfg;
 
 LC_API int lc_dcae_create(const lc_dcae_cfg* cfg, lc_dcae** out);
 LC_API void lc_dcae_destroy(lc_dcae* h);
-/* state-dict entries with prefix "decoder." (reference key names); encoder.* are ignored */
+/* state-dict entries with prefix "decoder." and/or "encoder." (reference key names); the
+ * decoder / encoder is built at finalize when its conv_in.weight was loaded */
 LC_API int lc_dcae_load(lc_dcae* h, const char* key, const float* data, const int64_t* shape, int ndim, void* stream);
 LC_API int lc_dcae_finalize(lc_dcae* h, void* stream);
 /* allocates the workspace for up to max_frames latents of size h x w (the only allocating call after finalize) */
@@ -132,6 +138,13 @@ LC_API int lc_dcae_reserve(lc_dcae* h, int max_frames, int height, int width, vo
  * dataloader/utils.py:233-240). */
 LC_API int lc_dcae_decode(lc_dcae* h, const float* z, int n, int height, int width, float* out, int keep_channels,
                           const float* mean, const float* std, void* stream);
+
+/* x: [n, in_channels, 8h, 8w] fp32 NCHW (fields already concatenated with the static channels, DCAE.py:985-986)
+ * -> out: [n, latent_channels, h, w] fp32 — replaces AutoencoderDC.encode / Encoder.forward (models/DCAE.py:964-1000,
+ * 617-631), used once per forecast init time (pipelines/utils.py:471).  If mean/std ([latent_channels] fp32) are
+ * given the output is (z - mean) / std * target_std (normalize_transform_3D, dataloader/utils.py:223-231). */
+LC_API int lc_dcae_encode(lc_dcae* h, const float* x, int n, int height, int width, float* out, const float* mean,
+                          const float* std, float target_std, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Ensemble metrics — replaces pointwise_crps_skill / pointwise_crps_spread / get_crps (evaluate/utils.py:52-118)

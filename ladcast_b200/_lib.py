@@ -27,7 +27,9 @@ class DenoiserCfg(ctypes.Structure):
 class DcaeCfg(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in (
         "latent_channels", "out_channels", "head_dim", "n_stages", "precision")] + [
-        ("stage_channels", ctypes.c_int * 8), ("stage_layers", ctypes.c_int * 8), ("stage_is_evit", ctypes.c_int * 8)]
+        ("stage_channels", ctypes.c_int * 8), ("stage_layers", ctypes.c_int * 8), ("stage_is_evit", ctypes.c_int * 8),
+        ("in_channels", ctypes.c_int), ("enc_stage_channels", ctypes.c_int * 8), ("enc_stage_layers", ctypes.c_int * 8),
+        ("enc_stage_is_evit", ctypes.c_int * 8)]
 
 
 _lib = None
@@ -63,6 +65,7 @@ _OPTIONAL = {
     "lc_dcae_finalize": ([_vp, _vp], _i),
     "lc_dcae_reserve": ([_vp, _i, _i, _i, _vp], _i),
     "lc_dcae_decode": ([_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp], _i),
+    "lc_dcae_encode": ([_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _f, _vp], _i),
     "lc_dcae_debug_read": ([_vp, _cp, _vp, _i64, _vp], _i),
     "lc_sphere_conv3x3": ([_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "lc_metrics_accumulate": ([_vp, _vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, _vp, _vp], _i),

@@ -43,7 +43,7 @@ struct EvitW {
   int heads = 0, inner = 0;
 };
 struct ResW { ConvW c1, c2; float *n_w = nullptr, *n_b = nullptr; };
-struct Block { int kind = 0; /*0 up, 1 res, 2 evit*/ int cin = 0, cout = 0; ConvW up; ResW res; EvitW ev; };
+struct Block { int kind = 0; /*0 up, 1 res, 2 evit, 3 down*/ int cin = 0, cout = 0; ConvW up; ResW res; EvitW ev; };
 
 inline int r64(int c) { return (c + 63) / 64 * 64; }
 
@@ -90,6 +90,9 @@ struct lc_dcae {
   ConvW conv_in, conv_out;
   float *no_w = nullptr, *no_b = nullptr;
   std::vector<Block> blocks;
+  bool has_decoder = false, has_encoder = false;
+  ConvW enc_conv_in, enc_conv_out;
+  std::vector<Block> enc_blocks;
   int max_frames = 0, h0 = 0, w0 = 0;
   Buf x, x2, y, padA, padB, xb, qkv, ms, att, hid, glu;
 };
@@ -258,6 +261,54 @@ struct Run {
     return 0;
   }
 
+  // DCDownBlock2d (DCAE.py:447-490): 3x3 conv C_in -> C_out/4 at the fine resolution, pixel_unshuffle(2), plus the
+  // channel-averaged unshuffled input
+  int down_block(const Block& b, int& H, int& W, bool next_is_res) {
+    if (padA_valid) LC_TRY(halo_fill<T>(D->padA.as<T>(), n, H, W, b.up.cp, st));
+    else LC_TRY(pad_from_nhwc<T>(D->x.as<float>(), D->padA.as<T>(), n, b.cin, H, W, b.up.cp, st));
+    padA_valid = false;
+    LC_TRY(conv(D->padA.as<T>(), H, W, b.up, store_f32(D->y.as<float>(), b.cout / 4, b.up.bias)));
+    if (next_is_res) {
+      LC_TRY(pixel_unshuffle_shortcut<T>(D->y.as<float>(), D->x.as<float>(), D->x2.as<float>(), D->padA.as<T>(), n, H, W,
+                                         b.cin, b.cout, st, r64(b.cout)));
+      padA_valid = true;
+      xb_valid = false;
+    } else {
+      LC_TRY(pixel_unshuffle_shortcut<T>(D->y.as<float>(), D->x.as<float>(), D->x2.as<float>(), D->xb.as<T>(), n, H, W,
+                                         b.cin, b.cout, st));
+      xb_valid = true;
+    }
+    std::swap(D->x, D->x2);
+    H /= 2; W /= 2;
+    return 0;
+  }
+
+  // Encoder.forward (DCAE.py:617-631): x [n, in_channels, H, W] f32 NCHW -> out [n, latent, H/2^(ns-1), W/2^(ns-1)]
+  int encode(const float* xin, int H, int W, float* out, const float* mean, const float* stdv, float target) {
+    const lc_dcae_cfg& c = D->cfg;
+    LC_TRY(pad_from_nchw<T>(xin, D->padA.as<T>(), n, c.in_channels, H, W, D->enc_conv_in.cp, st));
+    LC_TRY(conv(D->padA.as<T>(), H, W, D->enc_conv_in,
+                store_f32(D->x.as<float>(), D->enc_conv_in.cout, D->enc_conv_in.bias)));
+    xb_valid = false;
+    padA_valid = false;
+    for (size_t bi = 0; bi < D->enc_blocks.size(); ++bi) {
+      const Block& b = D->enc_blocks[bi];
+      const bool next_is_res = bi + 1 < D->enc_blocks.size() && D->enc_blocks[bi + 1].kind == 1;
+      if (b.kind == 3) LC_TRY(down_block(b, H, W, next_is_res));
+      else if (b.kind == 1) LC_TRY(res_block(b, H, W));
+      else LC_TRY(evit_block(b, H, W));
+    }
+    const int C = D->enc_conv_out.cin;
+    if (padA_valid) LC_TRY(halo_fill<T>(D->padA.as<T>(), n, H, W, D->enc_conv_out.cp, st));
+    else LC_TRY(pad_from_nhwc<T>(D->x.as<float>(), D->padA.as<T>(), n, C, H, W, D->enc_conv_out.cp, st));
+    padA_valid = false;
+    EpiParams e;
+    e.mode = EPI_UNPATCHIFY; e.bias = D->enc_conv_out.bias; e.out = out; e.rows_per_sample = H * W;
+    e.n_valid = c.latent_channels;
+    LC_TRY(conv(D->padA.as<T>(), H, W, D->enc_conv_out, e));
+    return enc_out_shortcut(out, D->x.as<float>(), n, H * W, C, c.latent_channels, mean, stdv, target, st);
+  }
+
   int decode(const float* z, int h, int w, float* out, int keep, const float* mean, const float* stdv) {
     int H = h, W = w;
     const int C0 = D->conv_in.cout;
@@ -285,7 +336,39 @@ struct Run {
   }
 };
 
-int finalize_impl(lc_dcae* D, cudaStream_t st) {
+// ResBlock / EfficientViTBlock weights under key prefix p (same module classes in encoder and decoder, DCAE.py:417-444)
+int build_block(lc_dcae* D, const std::string& p, bool evit, int C, Block* b, cudaStream_t st) {
+  const lc_dcae_cfg& c = D->cfg;
+  b->cin = b->cout = C;
+  if (!evit) {
+    b->kind = 1;
+    LC_TRY(make_conv(D, p + ".conv1", C, C, true, &b->res.c1, st));
+    LC_TRY(make_conv(D, p + ".conv2", C, C, false, &b->res.c2, st));
+    LC_TRY(fvec(D, p + ".norm.weight", C, &b->res.n_w, st));
+    LC_TRY(fvec(D, p + ".norm.bias", C, &b->res.n_b, st));
+    return 0;
+  }
+  b->kind = 2;
+  EvitW& e = b->ev;
+  e.heads = C / c.head_dim;
+  e.inner = e.heads * c.head_dim;
+  LC_REQUIRE(c.head_dim == 32, "EfficientViT attention_head_dim must be 32");
+  LC_TRY(make_mat(D, {p + ".attn.to_q", p + ".attn.to_k", p + ".attn.to_v"}, C, false, &e.qkv, st));
+  LC_TRY(fvec_taps(D, p + ".attn.to_qkv_multiscale.0.proj_in.weight", 3 * e.inner, 25, &e.dw5, st));
+  LC_TRY(fvec(D, p + ".attn.to_qkv_multiscale.0.proj_out.weight", 3LL * e.inner * 32, &e.g1, st));
+  LC_TRY(make_mat(D, {p + ".attn.to_out"}, 2 * e.inner, false, &e.to_out, st));
+  LC_TRY(fvec(D, p + ".attn.norm_out.weight", C, &e.no_w, st));
+  LC_TRY(fvec(D, p + ".attn.norm_out.bias", C, &e.no_b, st));
+  LC_TRY(make_mat(D, {p + ".conv_out.conv_inverted"}, C, true, &e.inv, st));
+  LC_TRY(fvec_taps(D, p + ".conv_out.conv_depth.weight", 8 * C, 9, &e.dw3, st));
+  LC_TRY(fvec(D, p + ".conv_out.conv_depth.bias", 8LL * C, &e.dw3_b, st));
+  LC_TRY(make_mat(D, {p + ".conv_out.conv_point"}, 4 * C, false, &e.point, st));
+  LC_TRY(fvec(D, p + ".conv_out.norm.weight", C, &e.n_w, st));
+  LC_TRY(fvec(D, p + ".conv_out.norm.bias", C, &e.n_b, st));
+  return 0;
+}
+
+int finalize_decoder(lc_dcae* D, cudaStream_t st) {
   const lc_dcae_cfg& c = D->cfg;
   const int ns = c.n_stages;
   const int Ctop = c.stage_channels[ns - 1];
@@ -302,34 +385,8 @@ int finalize_impl(lc_dcae* D, cudaStream_t st) {
       ++j;
     }
     for (int l = 0; l < c.stage_layers[i]; ++l) {
-      const std::string p = "decoder.up_blocks." + std::to_string(j);
       Block b;
-      b.cin = b.cout = C;
-      if (!c.stage_is_evit[i]) {
-        b.kind = 1;
-        LC_TRY(make_conv(D, p + ".conv1", C, C, true, &b.res.c1, st));
-        LC_TRY(make_conv(D, p + ".conv2", C, C, false, &b.res.c2, st));
-        LC_TRY(fvec(D, p + ".norm.weight", C, &b.res.n_w, st));
-        LC_TRY(fvec(D, p + ".norm.bias", C, &b.res.n_b, st));
-      } else {
-        b.kind = 2;
-        EvitW& e = b.ev;
-        e.heads = C / c.head_dim;
-        e.inner = e.heads * c.head_dim;
-        LC_REQUIRE(c.head_dim == 32, "EfficientViT attention_head_dim must be 32");
-        LC_TRY(make_mat(D, {p + ".attn.to_q", p + ".attn.to_k", p + ".attn.to_v"}, C, false, &e.qkv, st));
-        LC_TRY(fvec_taps(D, p + ".attn.to_qkv_multiscale.0.proj_in.weight", 3 * e.inner, 25, &e.dw5, st));
-        LC_TRY(fvec(D, p + ".attn.to_qkv_multiscale.0.proj_out.weight", 3LL * e.inner * 32, &e.g1, st));
-        LC_TRY(make_mat(D, {p + ".attn.to_out"}, 2 * e.inner, false, &e.to_out, st));
-        LC_TRY(fvec(D, p + ".attn.norm_out.weight", C, &e.no_w, st));
-        LC_TRY(fvec(D, p + ".attn.norm_out.bias", C, &e.no_b, st));
-        LC_TRY(make_mat(D, {p + ".conv_out.conv_inverted"}, C, true, &e.inv, st));
-        LC_TRY(fvec_taps(D, p + ".conv_out.conv_depth.weight", 8 * C, 9, &e.dw3, st));
-        LC_TRY(fvec(D, p + ".conv_out.conv_depth.bias", 8LL * C, &e.dw3_b, st));
-        LC_TRY(make_mat(D, {p + ".conv_out.conv_point"}, 4 * C, false, &e.point, st));
-        LC_TRY(fvec(D, p + ".conv_out.norm.weight", C, &e.n_w, st));
-        LC_TRY(fvec(D, p + ".conv_out.norm.bias", C, &e.n_b, st));
-      }
+      LC_TRY(build_block(D, "decoder.up_blocks." + std::to_string(j), c.stage_is_evit[i] != 0, C, &b, st));
       D->blocks.push_back(b);
       ++j;
     }
@@ -338,6 +395,46 @@ int finalize_impl(lc_dcae* D, cudaStream_t st) {
   LC_TRY(fvec(D, "decoder.norm_out.weight", C0, &D->no_w, st));
   LC_TRY(fvec(D, "decoder.norm_out.bias", C0, &D->no_b, st));
   LC_TRY(make_conv(D, "decoder.conv_out", c.out_channels, C0, true, &D->conv_out, st));
+  D->has_decoder = true;
+  return 0;
+}
+
+// Encoder (DCAE.py:539-615), layers_per_block[0] > 0 variant: conv_in is a plain SphereConv2d
+int finalize_encoder(lc_dcae* D, cudaStream_t st) {
+  const lc_dcae_cfg& c = D->cfg;
+  const int ns = c.n_stages;
+  LC_REQUIRE(c.in_channels > 0, "encoder weights given but lc_dcae_cfg.in_channels is not set");
+  LC_REQUIRE(c.enc_stage_layers[0] > 0, "encoder with layers_per_block[0] == 0 (down-sampling conv_in) is not implemented");
+  LC_REQUIRE(c.enc_stage_channels[ns - 1] % c.latent_channels == 0, "encoder out shortcut needs C_top divisible by latent_channels");
+  LC_TRY(make_conv(D, "encoder.conv_in", c.enc_stage_channels[0], c.in_channels, true, &D->enc_conv_in, st));
+  int j = 0;
+  for (int i = 0; i < ns; ++i) {
+    const int C = c.enc_stage_channels[i];
+    for (int l = 0; l < c.enc_stage_layers[i]; ++l) {
+      Block b;
+      LC_TRY(build_block(D, "encoder.down_blocks." + std::to_string(j), c.enc_stage_is_evit[i] != 0, C, &b, st));
+      D->enc_blocks.push_back(b);
+      ++j;
+    }
+    if (i < ns - 1 && c.enc_stage_layers[i] > 0) {
+      Block b;
+      b.kind = 3; b.cin = C; b.cout = c.enc_stage_channels[i + 1];
+      LC_REQUIRE(b.cout % 4 == 0 && (4 * b.cin) % b.cout == 0, "down-block needs C_out % 4 == 0 and 4*C_in divisible by C_out");
+      LC_TRY(make_conv(D, "encoder.down_blocks." + std::to_string(j) + ".conv", b.cout / 4, b.cin, true, &b.up, st));
+      D->enc_blocks.push_back(b);
+      ++j;
+    }
+  }
+  LC_TRY(make_conv(D, "encoder.conv_out", c.latent_channels, c.enc_stage_channels[ns - 1], true, &D->enc_conv_out, st));
+  D->has_encoder = true;
+  return 0;
+}
+
+int finalize_impl(lc_dcae* D, cudaStream_t st) {
+  const bool dec = D->staged.count("decoder.conv_in.weight") != 0, enc = D->staged.count("encoder.conv_in.weight") != 0;
+  LC_REQUIRE(dec || enc, "no decoder.* or encoder.* tensors were loaded");
+  if (dec) LC_TRY(finalize_decoder(D, st));
+  if (enc) LC_TRY(finalize_encoder(D, st));
   LC_CHECK_CUDA(cudaStreamSynchronize(st));
   for (auto& kv : D->staged) cudaFree(kv.second.p);
   D->staged.clear();
@@ -359,6 +456,13 @@ int lc_dcae_create(const lc_dcae_cfg* cfg, lc_dcae** out) {
       LC_REQUIRE(!cfg->stage_is_evit[i] || cfg->stage_layers[i] == 0 || cfg->stage_channels[i] % 8 == 0,
                  "bf16 decoder needs EfficientViT stage channels divisible by 8 (TMA 16-byte row pitch)");
   for (int i = 0; i < cfg->n_stages; ++i) LC_REQUIRE(cfg->stage_channels[i] % 4 == 0, "stage channels must be multiples of 4");
+  if (cfg->in_channels > 0)
+    for (int i = 0; i < cfg->n_stages; ++i) {
+      LC_REQUIRE(cfg->enc_stage_channels[i] > 0 && cfg->enc_stage_channels[i] % 4 == 0, "encoder stage channels must be multiples of 4");
+      LC_REQUIRE(cfg->precision != LC_PRECISION_BF16 || !cfg->enc_stage_is_evit[i] || cfg->enc_stage_layers[i] == 0 ||
+                     cfg->enc_stage_channels[i] % 8 == 0,
+                 "bf16 encoder needs EfficientViT stage channels divisible by 8 (TMA 16-byte row pitch)");
+    }
   LC_REQUIRE(cfg->stage_channels[cfg->n_stages - 1] % cfg->latent_channels == 0, "in_shortcut needs C_top divisible by latent_channels");
   lc_dcae* D = new lc_dcae();
   D->cfg = *cfg;
@@ -427,6 +531,25 @@ int lc_dcae_reserve(lc_dcae* D, int max_frames, int h, int w, void* stream) {
     const size_t H = h, W = w;
     mx_pad = std::max(mx_pad, (H + 2) * (W + 2) * static_cast<size_t>(r64(c.latent_channels)));
   }
+  if (c.in_channels > 0) {  // encoder stages (same resolutions, possibly other widths) + its 89-channel input
+    for (int i = ns - 1; i >= 0; --i) {
+      const size_t H = static_cast<size_t>(h) << (ns - 1 - i), W = static_cast<size_t>(w) << (ns - 1 - i);
+      const size_t C = c.enc_stage_channels[i], P = H * W;
+      mx_x = std::max(mx_x, P * C);
+      mx_y = std::max(mx_y, P * C);
+      mx_xb = std::max(mx_xb, P * C);
+      mx_pad = std::max(mx_pad, (H + 2) * (W + 2) * static_cast<size_t>(r64(static_cast<int>(C))));
+      if (c.enc_stage_is_evit[i] && c.enc_stage_layers[i] > 0) {
+        const size_t inner = (C / c.head_dim) * c.head_dim;
+        mx_qkv = std::max(mx_qkv, P * 3 * inner);
+        mx_att = std::max(mx_att, P * 2 * inner);
+        mx_hid = std::max(mx_hid, P * 8 * C);
+        mx_glu = std::max(mx_glu, P * 4 * C);
+      }
+    }
+    const size_t H = static_cast<size_t>(h) << (ns - 1), W = static_cast<size_t>(w) << (ns - 1);
+    mx_pad = std::max(mx_pad, (H + 2) * (W + 2) * static_cast<size_t>(r64(c.in_channels)));
+  }
   const size_t n = max_frames, e = D->esz;
   LC_TRY(D->x.alloc(n * mx_x * 4)); LC_TRY(D->x2.alloc(n * mx_x * 4)); LC_TRY(D->y.alloc(n * mx_y * 4));
   LC_TRY(D->padA.alloc(n * mx_pad * e)); LC_TRY(D->padB.alloc(n * mx_pad * e));
@@ -445,6 +568,7 @@ int lc_dcae_reserve(lc_dcae* D, int max_frames, int h, int w, void* stream) {
 int lc_dcae_decode(lc_dcae* D, const float* z, int n, int h, int w, float* out, int keep_channels, const float* mean,
                    const float* stdv, void* stream) {
   LC_REQUIRE(D && D->max_frames > 0, "decode before reserve");
+  LC_REQUIRE(D->has_decoder, "no decoder.* weights were loaded into this handle");
   LC_REQUIRE(n > 0 && n <= D->max_frames && h == D->h0 && w == D->w0, "decode geometry differs from lc_dcae_reserve");
   LC_REQUIRE(z && out, "null argument");
   LC_REQUIRE(keep_channels > 0 && keep_channels <= D->cfg.out_channels, "keep_channels out of range");
@@ -460,6 +584,26 @@ int lc_dcae_decode(lc_dcae* D, const float* z, int n, int h, int w, float* out, 
   Run<bf16> r;
   r.D = D; r.st = st; r.n = n;
   return r.decode(z, h, w, out, keep_channels, mean, stdv);
+}
+
+int lc_dcae_encode(lc_dcae* D, const float* x, int n, int height, int width, float* out, const float* mean,
+                   const float* stdv, float target_std, void* stream) {
+  LC_REQUIRE(D && D->max_frames > 0, "encode before reserve");
+  LC_REQUIRE(D->has_encoder, "no encoder.* weights were loaded into this handle");
+  const int r = 1 << (D->cfg.n_stages - 1);
+  LC_REQUIRE(n > 0 && n <= D->max_frames && height == D->h0 * r && width == D->w0 * r,
+             "encode geometry differs from lc_dcae_reserve (fields must be 2^(n_stages-1) x the reserved latent size)");
+  LC_REQUIRE(x && out, "null argument");
+  LC_REQUIRE((mean == nullptr) == (stdv == nullptr), "mean and std must be given together");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (D->f32) {
+    Run<float> rr;
+    rr.D = D; rr.st = st; rr.n = n;
+    return rr.encode(x, height, width, out, mean, stdv, target_std);
+  }
+  Run<bf16> rr;
+  rr.D = D; rr.st = st; rr.n = n;
+  return rr.encode(x, height, width, out, mean, stdv, target_std);
 }
 
 // Test export: one 3x3 sphere convolution (+bias, act) NCHW f32 -> NCHW f32 through the implicit-GEMM path.

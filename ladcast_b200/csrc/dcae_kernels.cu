@@ -605,6 +605,61 @@ __global__ void in_shortcut_kernel(float* __restrict__ x, T* __restrict__ x_t, c
   if (x_t != nullptr) x_t[i] = from_f32<T>(v);
 }
 
+// ---------------------------------------------------------------- pixel_unshuffle(2) of conv output + shortcut
+// DCDownBlock2d (DCAE.py:476-490), H x W = the FINE resolution, Cq = Cout / 4 conv channels, g = 4 Cin / Cout:
+//   out[f, y, x, k] = conv[f, 2y + (k&3)/2, 2x + (k&1), k / 4] + mean_{j<g} xu[k g + j],
+//   xu[u] = x_in[f, 2y + (u&3)/2, 2x + (u&1), u / 4]                (pixel_unshuffle, then unflatten(1, (-1, g)).mean(2))
+template <typename T>
+__global__ void __launch_bounds__(256) pixel_unshuffle_kernel(const float* __restrict__ conv, const float* __restrict__ xin,
+                                                              float* __restrict__ out, T* __restrict__ out_t, int n, int H,
+                                                              int W, int Cin, int Cout, int g, int pCp) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int Ho = H / 2, Wo = W / 2, Cq = Cout / 4;
+  const long long total = static_cast<long long>(n) * Ho * Wo * Cout;
+  if (i >= total) return;
+  const int k = static_cast<int>(i % Cout);
+  const long long opix = i / Cout;
+  const int x = static_cast<int>(opix % Wo);
+  const long long fy = opix / Wo;
+  const int y = static_cast<int>(fy % Ho);
+  const long long f = fy / Ho;
+  auto fine = [&](int sub) { return (f * H + 2 * y + (sub >> 1)) * W + 2 * x + (sub & 1); };
+  float v = conv[fine(k & 3) * Cq + (k >> 2)];
+  float sc = 0.f;
+  for (int j = 0; j < g; ++j) {
+    const int u = k * g + j;
+    sc += xin[fine(u & 3) * Cin + (u >> 2)];
+  }
+  v += sc / static_cast<float>(g);
+  out[i] = v;
+  if (out_t != nullptr) {
+    // plain rows, or (pCp > 0) the interior of the sphere-padded [n, Ho+2, Wo+2, pCp] input of the next 3x3 conv
+    const long long o = pCp > 0 ? ((f * (Ho + 2) + y + 1) * (Wo + 2) + x + 1) * pCp + k : i;
+    out_t[o] = from_f32<T>(v);
+  }
+}
+
+// ---------------------------------------------------------------- encoder output shortcut (+ latent normalisation)
+// out[f, l, p] (NCHW, conv_out already stored there) += mean_{j<g} x[f, p, l g + j]   (Encoder.forward, DCAE.py:624-627)
+// then optionally (v - mean[l]) / std[l] * target  (normalize_transform_3D, dataloader/utils.py:223-231)
+__global__ void __launch_bounds__(256) enc_out_shortcut_kernel(float* __restrict__ out, const float* __restrict__ x, int n,
+                                                               int HW, int C, int L, int g, const float* __restrict__ mean,
+                                                               const float* __restrict__ stdv, float target) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n) * L * HW;
+  if (i >= total) return;
+  const int p = static_cast<int>(i % HW);
+  const long long fl = i / HW;
+  const int l = static_cast<int>(fl % L);
+  const long long f = fl / L;
+  const float* xp = x + (f * HW + p) * C + l * g;
+  float sc = 0.f;
+  for (int j = 0; j < g; ++j) sc += xp[j];
+  float v = out[i] + sc / static_cast<float>(g);
+  if (mean != nullptr) v = (v - mean[l]) / stdv[l] * target;
+  out[i] = v;
+}
+
 inline unsigned blocks(long long n, int t = 256) { return static_cast<unsigned>((n + t - 1) / t); }
 
 }  // namespace
@@ -690,6 +745,23 @@ int pixel_shuffle_shortcut(const float* conv, const float* xin, float* out, T* o
   return 0;
 }
 template <typename T>
+int pixel_unshuffle_shortcut(const float* conv, const float* xin, float* out, T* out_t, int n, int H, int W, int Cin,
+                             int Cout, cudaStream_t s, int pCp) {
+  LC_REQUIRE(Cout % 4 == 0 && (4 * Cin) % Cout == 0 && H % 2 == 0 && W % 2 == 0, "pixel_unshuffle: bad geometry");
+  const long long total = static_cast<long long>(n) * (H / 2) * (W / 2) * Cout;
+  pixel_unshuffle_kernel<T><<<blocks(total), 256, 0, s>>>(conv, xin, out, out_t, n, H, W, Cin, Cout, 4 * Cin / Cout, pCp);
+  LC_LAUNCH_CHECK();
+  return 0;
+}
+int enc_out_shortcut(float* out, const float* x, int n, int HW, int C, int L, const float* mean, const float* stdv,
+                     float target, cudaStream_t s) {
+  LC_REQUIRE(C % L == 0, "encoder out shortcut needs C divisible by latent_channels");
+  const long long total = static_cast<long long>(n) * L * HW;
+  enc_out_shortcut_kernel<<<blocks(total), 256, 0, s>>>(out, x, n, HW, C, L, C / L, mean, stdv, target);
+  LC_LAUNCH_CHECK();
+  return 0;
+}
+template <typename T>
 int in_shortcut(float* x, T* x_t, const float* z, int n, int HW, int C, int Cz, cudaStream_t s) {
   const long long total = static_cast<long long>(n) * HW * C;
   in_shortcut_kernel<T><<<blocks(total), 256, 0, s>>>(x, x_t, z, n, HW, C, Cz, C / Cz);
@@ -707,6 +779,8 @@ int in_shortcut(float* x, T* x_t, const float* z, int n, int HW, int C, int Cz, 
                                int, cudaStream_t, int, int, int);                                                                   \
   template int pixel_shuffle_shortcut<T>(const float*, const float*, float*, T*, int, int, int, int, int,            \
                                          cudaStream_t, int);                                                              \
+  template int pixel_unshuffle_shortcut<T>(const float*, const float*, float*, T*, int, int, int, int, int,          \
+                                           cudaStream_t, int);                                                       \
   template int in_shortcut<T>(float*, T*, const float*, int, int, int, int, cudaStream_t);
 LC_INST(float)
 LC_INST(bf16)

@@ -23,6 +23,12 @@ int rmsnorm_rows(const float* y, const float* w, const float* b, float eps, floa
 template <typename T>
 int pixel_shuffle_shortcut(const float* conv, const float* xin, float* out, T* out_t, int n, int H, int W, int Cin,
                            int Cout, cudaStream_t s, int pCp = 0);
+// encoder: DCDownBlock2d tail (H x W = fine resolution) and the Encoder.forward output shortcut (+ normalisation)
+template <typename T>
+int pixel_unshuffle_shortcut(const float* conv, const float* xin, float* out, T* out_t, int n, int H, int W, int Cin,
+                             int Cout, cudaStream_t s, int pCp = 0);
+int enc_out_shortcut(float* out, const float* x, int n, int HW, int C, int L, const float* mean, const float* stdv,
+                     float target, cudaStream_t s);
 template <typename T>
 int in_shortcut(float* x, T* x_t, const float* z, int n, int HW, int C, int Cz, cudaStream_t s);
 

@@ -118,62 +118,83 @@ __global__ void __launch_bounds__(256) qk_norm_rope_kernel(T* __restrict__ qkv, 
   store4<T>(p, v.x, v.y, v.z, v.w);
 }
 
-// bf16 production variant: 16 lanes per head, 8 features (16 B) per lane -> 128-bit loads/stores, half the
-// instructions per byte of the generic kernel above.
-__global__ void __launch_bounds__(256) qk_norm_rope_bf16_kernel(bf16* __restrict__ qkv, long long ld, int B, int S,
-                                                                int heads, float eps, RopeSeg s0, RopeSeg s1, int nseg) {
-  const long long gt = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  const long long unit = gt >> 4;  // (row, q|k, head)
-  const int sub = static_cast<int>(gt & 15);
-  const long long total = static_cast<long long>(B) * S * 2 * heads;
-  const bool live = unit < total;  // no early return: every lane takes part in the shuffles below
-  const long long u = live ? unit : total - 1;
-  const int head = static_cast<int>(u % heads);
-  const int which = static_cast<int>((u / heads) % 2);
-  const long long row = u / (2 * heads);
-  const int tok = static_cast<int>(row % S);
-  const RopeSeg& sg = (nseg > 1 && tok >= s1.start) ? s1 : s0;
-  bf16* p = qkv + row * ld + static_cast<long long>(which) * heads * 128 + head * 128 + sub * 8;
-  const uint4 raw = *reinterpret_cast<const uint4*>(p);
-  float v[8];
-  {
-    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+// bf16 production variant: 16 lanes per (token, head), 8 features (16 B) per lane -> 128-bit loads/stores.  A thread
+// normalises and rotates q AND k of its (token, head, 8-feature slice): both loads are issued up front and the cos /
+// sin rows are fetched once for the pair; all index arithmetic is 32-bit.
+__device__ __forceinline__ void unpack8(const uint4& raw, float (&v)[8]) {
+  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __bfloat1622float2(h2[i]);
-      v[2 * i] = f.x;
-      v[2 * i + 1] = f.y;
-    }
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h2[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
   }
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) ss = fmaf(v[i], v[i], ss);
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  const float r = rsqrtf(ss * (1.0f / 128.0f) + eps);
-  const float* wp = (which ? sg.wk : sg.wq) + sub * 8;
-  const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp)), w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
-  const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] *= r * w[i];
-  if (sg.cos != nullptr) {
-    const long long t = static_cast<long long>(tok - sg.start) * 128 + sub * 8;
-    const float4 c0 = __ldg(reinterpret_cast<const float4*>(sg.cos + t)), c1 = __ldg(reinterpret_cast<const float4*>(sg.cos + t + 4));
-    const float4 n0 = __ldg(reinterpret_cast<const float4*>(sg.sin + t)), n1 = __ldg(reinterpret_cast<const float4*>(sg.sin + t + 4));
-    const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-    const float sn[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
-#pragma unroll
-    for (int i = 0; i < 8; i += 2) {
-      const float a = v[i], b = v[i + 1];
-      v[i] = a * cs[i] - b * sn[i];
-      v[i + 1] = b * cs[i + 1] + a * sn[i + 1];
-    }
-  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
   uint4 o;
   __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
   for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-  if (live) *reinterpret_cast<uint4*>(p) = o;
+  return o;
+}
+__global__ void __launch_bounds__(256) qk_norm_rope_bf16_kernel(bf16* __restrict__ qkv, long long ld, int B, int S,
+                                                                int heads, float eps, RopeSeg s0, RopeSeg s1, int nseg) {
+  const unsigned total = static_cast<unsigned>(B) * S * heads;  // (token row, head) units
+  const unsigned unit = blockIdx.x * 16u + (threadIdx.x >> 4);
+  const int sub = threadIdx.x & 15;
+  const bool live = unit < total;  // no early return: every lane takes part in the shuffles below
+  const unsigned u = live ? unit : total - 1;
+  const unsigned row = u / heads;
+  const int head = static_cast<int>(u - row * heads);
+  const int tok = static_cast<int>(row % S);
+  const RopeSeg& sg = (nseg > 1 && tok >= s1.start) ? s1 : s0;
+  bf16* pq = qkv + static_cast<long long>(row) * ld + head * 128 + sub * 8;
+  bf16* pk = pq + heads * 128;
+  const uint4 raw_q = *reinterpret_cast<const uint4*>(pq);
+  const uint4 raw_k = *reinterpret_cast<const uint4*>(pk);
+  float cs[8], sn[8];
+  const bool rope = sg.cos != nullptr;
+  if (rope) {
+    const int t = (tok - sg.start) * 128 + sub * 8;
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(sg.cos + t)), c1 = __ldg(reinterpret_cast<const float4*>(sg.cos + t + 4));
+    const float4 n0 = __ldg(reinterpret_cast<const float4*>(sg.sin + t)), n1 = __ldg(reinterpret_cast<const float4*>(sg.sin + t + 4));
+    cs[0] = c0.x; cs[1] = c0.y; cs[2] = c0.z; cs[3] = c0.w; cs[4] = c1.x; cs[5] = c1.y; cs[6] = c1.z; cs[7] = c1.w;
+    sn[0] = n0.x; sn[1] = n0.y; sn[2] = n0.z; sn[3] = n0.w; sn[4] = n1.x; sn[5] = n1.y; sn[6] = n1.z; sn[7] = n1.w;
+  }
+  float q[8], k[8];
+  unpack8(raw_q, q);
+  unpack8(raw_k, k);
+  float sq = 0.f, sk = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sq = fmaf(q[i], q[i], sq); sk = fmaf(k[i], k[i], sk); }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    sk += __shfl_xor_sync(0xffffffffu, sk, o);
+  }
+  const float rq = rsqrtf(sq * (1.0f / 128.0f) + eps), rk = rsqrtf(sk * (1.0f / 128.0f) + eps);
+  {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(sg.wq + sub * 8)), a1 = __ldg(reinterpret_cast<const float4*>(sg.wq + sub * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(sg.wk + sub * 8)), b1 = __ldg(reinterpret_cast<const float4*>(sg.wk + sub * 8 + 4));
+    const float wq[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float wk[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { q[i] *= rq * wq[i]; k[i] *= rk * wk[i]; }
+  }
+  if (rope) {
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      const float a = q[i], b = q[i + 1], c = k[i], d = k[i + 1];
+      q[i] = a * cs[i] - b * sn[i];
+      q[i + 1] = b * cs[i + 1] + a * sn[i + 1];
+      k[i] = c * cs[i] - d * sn[i];
+      k[i + 1] = d * cs[i + 1] + c * sn[i + 1];
+    }
+  }
+  if (live) {
+    *reinterpret_cast<uint4*>(pq) = pack8(q);
+    *reinterpret_cast<uint4*>(pk) = pack8(k);
+  }
 }
 
 // ---------------------------------------------------------------- patchify: [B,C,THW] f32 -> [B*THW, Kp] T (zero pad)
@@ -354,7 +375,7 @@ int qk_norm_rope(T* qkv, long long ld, int B, int S, int heads, int head_dim, fl
   const long long total = static_cast<long long>(B) * S * 2 * heads;
   RopeSeg s1 = nseg > 1 ? segs[1] : segs[0];
   if (sizeof(T) == 2) {
-    qk_norm_rope_bf16_kernel<<<static_cast<unsigned>(ceil_div_ll(total * 16, 256)), 256, 0, s>>>(
+    qk_norm_rope_bf16_kernel<<<static_cast<unsigned>(ceil_div_ll(total / 2, 16)), 256, 0, s>>>(
         reinterpret_cast<bf16*>(qkv), ld, B, S, heads, eps, segs[0], s1, nseg);
     LC_LAUNCH_CHECK();
     return 0;

@@ -1,6 +1,6 @@
 """Drop-in for `ladcast.models.DCAE.AutoencoderDC` (reference models/DCAE.py:735-1087): same constructor keywords,
-`.config`, checkpoint layout / key names, `decode(...)` signature.  `decode` runs the sm_100a decoder
-(`lc_dcae_*`); `encode` (used once per forecast init time) is not on the rollout hot path yet."""
+`.config`, checkpoint layout / key names, `encode(...)` / `decode(...)` signatures.  Both run the sm_100a kernels
+behind `lc_dcae_*` (decoder: every AR step; encoder: once per forecast init time)."""
 import ctypes
 import os
 from dataclasses import dataclass
@@ -51,6 +51,20 @@ class AutoencoderDC(CheckpointMixin):
         if upsample_block_type != "pixel_shuffle" or decoder_norm_types != "rms_norm" or decoder_act_fns != "silu":
             raise NotImplementedError("only the V0.1.X decoder variant (pixel_shuffle / rms_norm / silu) is implemented")
         n = len(decoder_block_out_channels)
+        etypes = (encoder_block_types,) * n if isinstance(encoder_block_types, str) else tuple(encoder_block_types)
+        # the encoder is optional: configurations the CUDA encoder does not cover only disable encode()
+        self._enc_error = None
+        if len(encoder_block_out_channels) != n:
+            self._enc_error = "encoder and decoder must have the same number of stages"
+        elif downsample_block_type != "pixel_unshuffle":
+            self._enc_error = "only the pixel_unshuffle down-sampling variant is implemented"
+        elif encoder_layers_per_block[0] <= 0:
+            self._enc_error = "encoder_layers_per_block[0] == 0 (down-sampling conv_in) is not implemented"
+        else:
+            for i, t in enumerate(etypes):
+                if t == "EfficientViTBlock" and tuple(encoder_qkv_multiscales[i]) != (5,) and encoder_layers_per_block[i] > 0:
+                    self._enc_error = "EfficientViT stages must use qkv_multiscales == (5,)"
+        self._etypes = etypes
         types = (decoder_block_types,) * n if isinstance(decoder_block_types, str) else tuple(decoder_block_types)
         for i, t in enumerate(types):
             if t == "EfficientViTBlock" and tuple(decoder_qkv_multiscales[i]) != (5,) and decoder_layers_per_block[i] > 0:
@@ -68,6 +82,44 @@ class AutoencoderDC(CheckpointMixin):
         self._sd: Dict[str, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ parameters
+    def encoder_param_shapes(self) -> Dict[str, Tuple[int, ...]]:
+        """encoder.* keys / shapes (models/DCAE.py:539-615)."""
+        if self._enc_error is not None:
+            return {}
+        c = self.config
+        ch, layers, hd = list(c.encoder_block_out_channels), list(c.encoder_layers_per_block), c.attention_head_dim
+        s: Dict[str, Tuple[int, ...]] = {"encoder.conv_in.weight": (ch[0], c.in_channels, 3, 3), "encoder.conv_in.bias": (ch[0],)}
+        j, n = 0, len(ch)
+        for i in range(n):
+            for _ in range(layers[i]):
+                p, C = f"encoder.down_blocks.{j}", ch[i]
+                if self._etypes[i] == "ResBlock":
+                    s.update({f"{p}.conv1.weight": (C, C, 3, 3), f"{p}.conv1.bias": (C,), f"{p}.conv2.weight": (C, C, 3, 3),
+                              f"{p}.norm.weight": (C,), f"{p}.norm.bias": (C,)})
+                else:
+                    inner = (C // hd) * hd
+                    for nm in ("to_q", "to_k", "to_v"):
+                        s[f"{p}.attn.{nm}.weight"] = (inner, C)
+                    s.update({f"{p}.attn.to_qkv_multiscale.0.proj_in.weight": (3 * inner, 1, 5, 5),
+                              f"{p}.attn.to_qkv_multiscale.0.proj_out.weight": (3 * inner, hd, 1, 1),
+                              f"{p}.attn.to_out.weight": (C, 2 * inner), f"{p}.attn.norm_out.weight": (C,),
+                              f"{p}.attn.norm_out.bias": (C,), f"{p}.conv_out.conv_inverted.weight": (8 * C, C, 1, 1),
+                              f"{p}.conv_out.conv_inverted.bias": (8 * C,), f"{p}.conv_out.conv_depth.weight": (8 * C, 1, 3, 3),
+                              f"{p}.conv_out.conv_depth.bias": (8 * C,), f"{p}.conv_out.conv_point.weight": (C, 4 * C, 1, 1),
+                              f"{p}.conv_out.norm.weight": (C,), f"{p}.conv_out.norm.bias": (C,)})
+                j += 1
+            if i < n - 1 and layers[i] > 0:
+                s[f"encoder.down_blocks.{j}.conv.weight"] = (ch[i + 1] // 4, ch[i], 3, 3)
+                s[f"encoder.down_blocks.{j}.conv.bias"] = (ch[i + 1] // 4,)
+                j += 1
+        s["encoder.conv_out.weight"], s["encoder.conv_out.bias"] = (c.latent_channels, ch[-1], 3, 3), (c.latent_channels,)
+        return s
+
+    def param_shapes(self) -> Dict[str, Tuple[int, ...]]:
+        s = dict(self.encoder_param_shapes())
+        s.update(self.decoder_param_shapes())
+        return s
+
     def decoder_param_shapes(self) -> Dict[str, Tuple[int, ...]]:
         c = self.config
         ch, layers, hd = list(c.decoder_block_out_channels), list(c.decoder_layers_per_block), c.attention_head_dim
@@ -102,7 +154,7 @@ class AutoencoderDC(CheckpointMixin):
         return s
 
     def _materialize(self):
-        for k, shp in self.decoder_param_shapes().items():
+        for k, shp in self.param_shapes().items():
             if k not in self._sd:
                 if k.endswith(".weight") and len(shp) > 1:
                     fan = 1
@@ -119,11 +171,20 @@ class AutoencoderDC(CheckpointMixin):
         return dict(self._sd)
 
     def load_state_dict(self, state_dict, strict: bool = True):
-        """Decoder tensors are consumed by the CUDA decoder; `encoder.*` tensors are kept as-is for save_pretrained."""
-        shapes = self.decoder_param_shapes()
+        """`decoder.*` / `encoder.*` tensors (reference key names) are re-packed by lc_dcae_load at first use."""
+        shapes = self.param_shapes()
         missing = [k for k in shapes if k not in state_dict]
-        if strict and missing:
-            raise RuntimeError(f"Error(s) in loading state_dict: missing {missing[:5]}")
+        if strict:
+            # strict = every sub-module (decoder / encoder) that appears in the state dict must be complete, and at
+            # least one must appear; a decoder-only (rollout) or encoder-only (compression) checkpoint is legal
+            seen = False
+            for grp in (self.decoder_param_shapes(), self.encoder_param_shapes()):
+                present = [k for k in grp if k in state_dict]
+                seen = seen or bool(present)
+                if present and len(present) != len(grp):
+                    raise RuntimeError(f"Error(s) in loading state_dict: missing {[k for k in grp if k not in state_dict][:5]}")
+            if not seen:
+                raise RuntimeError(f"Error(s) in loading state_dict: missing {missing[:5]}")
         for k, t in state_dict.items():
             if k in shapes and tuple(t.shape) != tuple(shapes[k]):
                 raise RuntimeError(f"size mismatch for {k}: {tuple(t.shape)} vs {tuple(shapes[k])}")
@@ -185,7 +246,7 @@ class AutoencoderDC(CheckpointMixin):
         if self._handle is not None:
             return
         if self._device.type != "cuda":
-            raise _lib.LadcastB200Error("AutoencoderDC.decode runs on CUDA only (sm_100a); call .to('cuda') first")
+            raise _lib.LadcastB200Error("AutoencoderDC runs on CUDA only (sm_100a); call .to('cuda') first")
         lib = _lib.load()
         c = self.config
         ch, layers = list(c.decoder_block_out_channels), list(c.decoder_layers_per_block)
@@ -198,12 +259,18 @@ class AutoencoderDC(CheckpointMixin):
         for i in range(len(ch)):
             cfg.stage_channels[i], cfg.stage_layers[i] = ch[i], layers[i]
             cfg.stage_is_evit[i] = int(self._types[i] == "EfficientViTBlock")
+        if self._enc_error is None:
+            cfg.in_channels = c.in_channels
+            for i in range(len(ch)):
+                cfg.enc_stage_channels[i] = c.encoder_block_out_channels[i]
+                cfg.enc_stage_layers[i] = c.encoder_layers_per_block[i]
+                cfg.enc_stage_is_evit[i] = int(self._etypes[i] == "EfficientViTBlock")
         h = ctypes.c_void_p()
         self._materialize()
         _lib.check(lib.lc_dcae_create(ctypes.byref(cfg), ctypes.byref(h)), "lc_dcae_create")
         with torch.cuda.device(self._device):
             st = _lib.stream()
-            for k in self.decoder_param_shapes():
+            for k in self.param_shapes():
                 dv = self._sd[k].to(self._device, torch.float32).contiguous()
                 shp = (ctypes.c_int64 * dv.dim())(*dv.shape)
                 _lib.check(lib.lc_dcae_load(h, k.encode(), _lib.ptr(dv), shp, dv.dim(), st), f"lc_dcae_load({k})")
@@ -220,9 +287,7 @@ class AutoencoderDC(CheckpointMixin):
         out = torch.empty(n, keep, h * r, w * r, device=self._device, dtype=torch.float32)
         with torch.cuda.device(self._device):
             chunk = min(n, self.MAX_FRAMES_PER_CALL)
-            if self._reserved is None or self._reserved[0] < chunk or self._reserved[1:] != (h, w):
-                _lib.check(lib.lc_dcae_reserve(self._handle, chunk, h, w, _lib.stream()), "lc_dcae_reserve")
-                self._reserved = (chunk, h, w)
+            self._reserve(lib, chunk, h, w)
             mean_d = mean.to(self._device, torch.float32).contiguous() if mean is not None else None
             std_d = std.to(self._device, torch.float32).contiguous() if std is not None else None
             for i in range(0, n, chunk):
@@ -249,10 +314,55 @@ class AutoencoderDC(CheckpointMixin):
         keep = oc - self.static_channels if self.static_channels else oc
         return self._decode_native(z, keep, mean, std)
 
-    def encode(self, x, return_dict: bool = True, temb=None, embedded_t: bool = False, static_conditioning_tensor=None):
-        raise NotImplementedError(
-            "AutoencoderDC.encode (once per forecast init time) is outside the B200 rollout hot path in this release; "
-            "encode with the reference implementation and pass the latents (SURVEY.md §8 row f-3)")
+    def _reserve(self, lib, chunk, h, w):
+        if self._reserved is None or self._reserved[0] < chunk or self._reserved[1:] != (h, w):
+            _lib.check(lib.lc_dcae_reserve(self._handle, chunk, h, w, _lib.stream()), "lc_dcae_reserve")
+            self._reserved = (chunk, h, w)
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("AutoencoderDC.forward (encode + decode) needs the encoder; see encode()")
+    def _encode_native(self, x, mean=None, std=None, target_std=0.5):
+        if self._enc_error is not None:
+            raise NotImplementedError(f"AutoencoderDC.encode: {self._enc_error}")
+        self._ensure_handle()
+        lib = _lib.load()
+        x = x.to(self._device, torch.float32).contiguous()
+        n, cin, H, W = x.shape
+        r = self.spatial_compression_ratio
+        if cin != self.config.in_channels:
+            raise ValueError(f"encode expects {self.config.in_channels} channels (fields + static), got {cin}")
+        if H % r or W % r:
+            raise ValueError(f"field size {H}x{W} is not a multiple of the compression ratio {r}")
+        h, w = H // r, W // r
+        out = torch.empty(n, self.config.latent_channels, h, w, device=self._device, dtype=torch.float32)
+        with torch.cuda.device(self._device):
+            chunk = min(n, self.MAX_FRAMES_PER_CALL)
+            self._reserve(lib, chunk, h, w)
+            mean_d = mean.to(self._device, torch.float32).contiguous() if mean is not None else None
+            std_d = std.to(self._device, torch.float32).contiguous() if std is not None else None
+            for i in range(0, n, chunk):
+                m = min(chunk, n - i)
+                _lib.check(lib.lc_dcae_encode(self._handle, _lib.ptr(x[i : i + m]), m, H, W, _lib.ptr(out[i : i + m]),
+                                              _lib.ptr(mean_d), _lib.ptr(std_d), float(target_std), _lib.stream()),
+                           "lc_dcae_encode")
+        return out
+
+    def encode(self, x, return_dict: bool = True, temb=None, embedded_t: bool = False, static_conditioning_tensor=None):
+        """AutoencoderDC.encode (DCAE.py:964-1000): x [n, C, H, W] (+ static_conditioning_tensor [n, C_s, H, W])."""
+        if temb is not None:
+            raise NotImplementedError("temb-conditioned encoding is not part of the V0.1.X checkpoint")
+        if static_conditioning_tensor is not None:
+            x = torch.cat((x.to(self._device), static_conditioning_tensor.to(self._device)), dim=1)
+        encoded = self._encode_native(x)
+        if not return_dict:
+            return (encoded,)
+        return EncoderOutput(latent=encoded)
+
+    def encode_fused(self, x, mean, std, target_std: float = 0.5, static_conditioning_tensor=None):
+        """encode + normalize_transform_3D ((z - mean) / std * target_std) in the last kernel."""
+        if static_conditioning_tensor is not None:
+            x = torch.cat((x.to(self._device), static_conditioning_tensor.to(self._device)), dim=1)
+        return self._encode_native(x, mean, std, target_std)
+
+    def forward(self, sample: torch.Tensor, return_dict: bool = True, static_conditioning_tensor=None):
+        """encode -> decode (DCAE.py:1058-1087)."""
+        z = self.encode(sample, return_dict=False, static_conditioning_tensor=static_conditioning_tensor)[0]
+        return self.decode(z, return_dict=return_dict)

@@ -55,6 +55,9 @@ def dcae_config(name: str = "V0.1.X", **over) -> dict:
         cfg.update(decoder_block_out_channels=[84, 168, 168, 336], decoder_layers_per_block=[1, 1, 1, 1])
     elif name != "V0.1.X":
         raise ValueError(name)
+    # the shipped config mirrors the decoder in the encoder (configs/DC_AE_84_ft.yaml)
+    for k in ("block_types", "block_out_channels", "layers_per_block", "qkv_multiscales"):
+        cfg["encoder_" + k] = list(cfg["decoder_" + k])
     cfg.update(over)
     return cfg
 
@@ -205,6 +208,68 @@ def dcae_decoder_param_shapes(cfg: dict) -> Dict[str, Tuple[int, ...]]:
     s["decoder.norm_out.bias"] = (chans[0],)
     s["decoder.conv_out.weight"] = (cfg["out_channels"], chans[0], 3, 3)
     s["decoder.conv_out.bias"] = (cfg["out_channels"],)
+    return s
+
+
+def dcae_encoder_layout(cfg: dict) -> List[Tuple[str, str, int, int]]:
+    """Ordered encoder.down_blocks: (kind, key-prefix, C_in, C_out).  models/DCAE.py:582-606."""
+    chans = cfg["encoder_block_out_channels"]
+    layers = cfg["encoder_layers_per_block"]
+    types = cfg["encoder_block_types"]
+    out: List[Tuple[str, str, int, int]] = []
+    j = 0
+    n = len(chans)
+    for i in range(n):
+        for _ in range(layers[i]):
+            kind = "res" if types[i] == "ResBlock" else "evit"
+            out.append((kind, f"encoder.down_blocks.{j}", chans[i], chans[i]))
+            j += 1
+        if i < n - 1 and layers[i] > 0:
+            out.append(("down", f"encoder.down_blocks.{j}", chans[i], chans[i + 1]))
+            j += 1
+    return out
+
+
+def _block_param_shapes(s: Dict[str, Tuple[int, ...]], kind: str, p: str, ci: int, co: int, hd: int) -> None:
+    if kind == "res":
+        s[f"{p}.conv1.weight"] = (ci, ci, 3, 3)
+        s[f"{p}.conv1.bias"] = (ci,)
+        s[f"{p}.conv2.weight"] = (co, ci, 3, 3)
+        s[f"{p}.norm.weight"] = (co,)
+        s[f"{p}.norm.bias"] = (co,)
+    else:
+        inner = int(ci // hd) * hd
+        for nme in ("to_q", "to_k", "to_v"):
+            s[f"{p}.attn.{nme}.weight"] = (inner, ci)
+        s[f"{p}.attn.to_qkv_multiscale.0.proj_in.weight"] = (3 * inner, 1, 5, 5)
+        s[f"{p}.attn.to_qkv_multiscale.0.proj_out.weight"] = (3 * inner, hd, 1, 1)
+        s[f"{p}.attn.to_out.weight"] = (ci, 2 * inner)
+        s[f"{p}.attn.norm_out.weight"] = (ci,)
+        s[f"{p}.attn.norm_out.bias"] = (ci,)
+        s[f"{p}.conv_out.conv_inverted.weight"] = (8 * ci, ci, 1, 1)
+        s[f"{p}.conv_out.conv_inverted.bias"] = (8 * ci,)
+        s[f"{p}.conv_out.conv_depth.weight"] = (8 * ci, 1, 3, 3)
+        s[f"{p}.conv_out.conv_depth.bias"] = (8 * ci,)
+        s[f"{p}.conv_out.conv_point.weight"] = (co, 4 * ci, 1, 1)
+        s[f"{p}.conv_out.norm.weight"] = (co,)
+        s[f"{p}.conv_out.norm.bias"] = (co,)
+
+
+def dcae_encoder_param_shapes(cfg: dict) -> Dict[str, Tuple[int, ...]]:
+    """State-dict keys/shapes of AutoencoderDC.encoder (models/DCAE.py:539-615), layers_per_block[0] > 0 variant."""
+    s: Dict[str, Tuple[int, ...]] = {}
+    chans = cfg["encoder_block_out_channels"]
+    assert cfg["encoder_layers_per_block"][0] > 0, "conv_in as DCDownBlock2d (layers_per_block[0] == 0) is not covered"
+    s["encoder.conv_in.weight"] = (chans[0], cfg["in_channels"], 3, 3)
+    s["encoder.conv_in.bias"] = (chans[0],)
+    for kind, p, ci, co in dcae_encoder_layout(cfg):
+        if kind == "down":
+            s[f"{p}.conv.weight"] = (co // 4, ci, 3, 3)
+            s[f"{p}.conv.bias"] = (co // 4,)
+        else:
+            _block_param_shapes(s, kind, p, ci, co, cfg["attention_head_dim"])
+    s["encoder.conv_out.weight"] = (cfg["latent_channels"], chans[-1], 3, 3)
+    s["encoder.conv_out.bias"] = (cfg["latent_channels"],)
     return s
 
 
@@ -511,6 +576,34 @@ def up_block(sd: SD, p: str, x: torch.Tensor, c_out: int) -> torch.Tensor:
     y = F.pixel_shuffle(sphere_conv(x, sd[p + ".conv.weight"], sd[p + ".conv.bias"]), 2)
     rep = c_out * 4 // x.shape[1]
     return y + F.pixel_shuffle(x.repeat_interleave(rep, dim=1), 2)
+
+
+def down_block(sd: SD, p: str, x: torch.Tensor, c_out: int) -> torch.Tensor:
+    """DCDownBlock2d.forward, pixel-unshuffle variant with the channel-averaging shortcut (DCAE.py:476-490)."""
+    y = F.pixel_unshuffle(sphere_conv(x, sd[p + ".conv.weight"], sd[p + ".conv.bias"]), 2)
+    g = x.shape[1] * 4 // c_out
+    return y + F.pixel_unshuffle(x, 2).unflatten(1, (-1, g)).mean(dim=2)
+
+
+def dcae_encode(sd: SD, cfg: dict, x: torch.Tensor, static: Optional[torch.Tensor] = None,
+                taps: Optional[dict] = None) -> torch.Tensor:
+    """AutoencoderDC.encode -> Encoder.forward (DCAE.py:964-1000, 617-631).  x [n,84(+5),H,W] -> [n,84,H/8,W/8]."""
+    if static is not None:
+        x = torch.cat((x, static), dim=1)
+    h = sphere_conv(x, sd["encoder.conv_in.weight"], sd["encoder.conv_in.bias"])
+    if taps is not None:
+        taps["conv_in"] = h.clone()
+    for kind, p, ci, co in dcae_encoder_layout(cfg):
+        if kind == "down":
+            h = down_block(sd, p, h, co)
+        elif kind == "res":
+            h = res_block(sd, p, h)
+        else:
+            h = evit_block(sd, p, h, cfg["attention_head_dim"])
+        if taps is not None:
+            taps[p] = h.clone()
+    g = cfg["encoder_block_out_channels"][-1] // cfg["latent_channels"]
+    return sphere_conv(h, sd["encoder.conv_out.weight"], sd["encoder.conv_out.bias"]) + h.unflatten(1, (-1, g)).mean(dim=2)
 
 
 def dcae_decode(sd: SD, cfg: dict, z: torch.Tensor, return_static: bool = False,

@@ -106,6 +106,22 @@ def golden_dcae():
     print("dcae", out.shape, float(out.abs().mean()))
 
 
+def golden_dcae_encode():
+    cfg = O.dcae_config("tiny")
+    full = dict(cfg, upsample_block_type="pixel_shuffle", downsample_block_type="pixel_unshuffle")
+    ae = AutoencoderDC.from_config(full).eval()
+    sd = O.make_state_dict(O.dcae_encoder_param_shapes(cfg), 23)
+    missing = ae.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and all(k.startswith("decoder.") for k in missing.missing_keys)
+    x = seeded((2, 84, 40, 64), 107)
+    static = seeded((2, 5, 40, 64), 108)
+    lat = ae.encode(x, static_conditioning_tensor=static).latent
+    lat_cat = ae.encode(torch.cat((x, static), dim=1)).latent
+    assert torch.equal(lat, lat_cat)
+    np.savez(os.path.join(OUT, "dcae_encode_tiny.npz"), salt=23, latent=lat.numpy().astype(np.float32))
+    print("dcae encode", lat.shape, float(lat.abs().mean()))
+
+
 def golden_sphere():
     conv = SphereConv2d(6, 8, 3, 1, 1)
     conv.weight.data = O.det_tensor("sphere3.weight", (8, 6, 3, 3), 31)
@@ -162,6 +178,7 @@ if __name__ == "__main__":
     golden_embeddings()
     golden_metrics()
     golden_dcae()
+    golden_dcae_encode()
     golden_samplers()
     golden_denoiser()
     print("golden vectors written to", OUT)

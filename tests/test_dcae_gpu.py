@@ -117,3 +117,73 @@ def test_dcae_decode_160_latents_batch_consistency():
     fused = ae.decode_fused(z[:4].contiguous(), mean, std)
     ref = out[:4] * std.cuda()[None, :, None, None] + mean.cuda()[None, :, None, None]
     assert torch.allclose(fused, ref, rtol=1e-5, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# encoder (AutoencoderDC.encode, DCAE.py:964-1000 / Encoder.forward :617-631)
+# ---------------------------------------------------------------------------------------------------------------
+def _ae_enc(name, salt, precision):
+    from ladcast_b200.models import AutoencoderDC
+
+    cfg = O.dcae_config(name) if isinstance(name, str) else name
+    sd = O.make_state_dict(O.dcae_encoder_param_shapes(cfg), salt)
+    ae = AutoencoderDC(**cfg)
+    ae.load_state_dict(sd, strict=True)
+    return cfg, sd, ae.to("cuda").set_precision(precision)
+
+
+def test_dcae_encode_tiny_vs_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "dcae_encode_tiny.npz"))
+    cfg, sd, ae = _ae_enc("tiny", int(g["salt"]), "fp32")
+    x, static = _seeded((2, 84, 40, 64), 107).cuda(), _seeded((2, 5, 40, 64), 108).cuda()
+    lat = ae.encode(x, static_conditioning_tensor=static).latent
+    torch.cuda.synchronize()
+    assert lat.shape == (2, 84, 5, 8)
+    assert _rel(lat, g["latent"]) < 1e-4
+    lat2 = ae.encode(torch.cat((x, static), dim=1), return_dict=False)[0]
+    assert torch.equal(lat, lat2)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_dcae_encode_small_vs_oracle(precision, tol):
+    """Different geometry / batch than the golden, plus the fused latent normalisation."""
+    cfg, sd, ae = _ae_enc("tiny", 31, precision)
+    x = _seeded((3, 89, 48, 80), 211)
+    want = O.dcae_encode(sd, cfg, x)
+    got = ae.encode(x.cuda()).latent
+    assert got.shape == (3, 84, 6, 10)
+    assert _rel(got, want) < tol
+    mean, std = _seeded((84,), 212), _seeded((84,), 213).abs() + 0.5
+    want_n = O.normalize_latent(want.unsqueeze(2), mean, std, 0.5).squeeze(2)
+    got_n = ae.encode_fused(x.cuda(), mean, std, 0.5)
+    assert _rel(got_n, want_n) < tol
+
+
+def test_dcae_encode_full_config_bf16():
+    """V0.1.X encoder (4x4 layers, 252/504/504/1008) on one 120x240 frame against the CPU oracle."""
+    cfg, sd, ae = _ae_enc("V0.1.X", 33, "bf16")
+    x = _seeded((1, 89, 120, 240), 214)
+    want = O.dcae_encode(sd, cfg, x)
+    got = ae.encode(x.cuda()).latent
+    assert got.shape == (1, 84, 15, 30)
+    assert _rel(got, want) < 2e-2
+
+
+def test_dcae_roundtrip_shapes_and_determinism():
+    """encode -> decode through one handle holding both halves; repeated calls are bit-identical."""
+    from ladcast_b200.models import AutoencoderDC
+
+    cfg = O.dcae_config("tiny")
+    sd = O.make_state_dict(O.dcae_encoder_param_shapes(cfg), 35)
+    sd.update(O.make_state_dict(O.dcae_decoder_param_shapes(cfg), 36))
+    ae = AutoencoderDC(**cfg)
+    ae.load_state_dict(sd, strict=True)
+    ae.to("cuda").set_precision("bf16")
+    x = _seeded((2, 89, 40, 64), 215).cuda()
+    z1 = ae.encode(x).latent
+    y1 = ae.decode(z1).sample
+    z2 = ae.encode(x).latent
+    assert torch.equal(z1, z2)
+    assert y1.shape == (2, 84, 40, 64) and torch.isfinite(y1).all()
+    want = O.dcae_decode(sd, cfg, O.dcae_encode(sd, cfg, x.cpu()))
+    assert _rel(y1, want) < 3e-2
