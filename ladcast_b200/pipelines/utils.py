@@ -161,6 +161,34 @@ def roll_out_latent(pipeline, encdec_model, known_latents: torch.Tensor, init_ti
     return out
 
 
+def encode_initial_condition(encdec_model, input_fields: torch.Tensor, static_fields: Optional[torch.Tensor],
+                             latent_mean: torch.Tensor, latent_std: torch.Tensor, target_std: float = 0.5) -> torch.Tensor:
+    """The encode + normalise front of `roll_out_serial` (reference pipelines/utils.py:457-481 and
+    normalize_transform_3D, dataloader/utils.py:223-231): standardised fields (C, T_in, H, W) + static channels
+    (C_s, H, W) -> normalised known latents (1, C_lat, T_in, h, w) on the autoencoder's device."""
+    if input_fields.dim() != 4:
+        raise ValueError("input_fields must be (C, T_in, H, W)")
+    x = input_fields.permute(1, 0, 2, 3)  # (T_in, C, H, W): frames are the encoder's batch
+    st = None
+    if static_fields is not None:
+        st = static_fields.unsqueeze(0).expand(x.shape[0], -1, -1, -1)
+    z = encdec_model.encode_fused(x, latent_mean, latent_std, target_std, static_conditioning_tensor=st)
+    return z.permute(1, 0, 2, 3).unsqueeze(0).contiguous()
+
+
+def roll_out_serial(pipeline, encdec_model, input_fields: torch.Tensor, static_fields: Optional[torch.Tensor],
+                    init_timestamp: int, ensemble_size: int, latent_mean: torch.Tensor, latent_std: torch.Tensor,
+                    field_mean: Optional[torch.Tensor] = None, field_std: Optional[torch.Tensor] = None, **kw):
+    """Tensor-in / tensor-out `roll_out_serial` (reference pipelines/utils.py:250-661 without the xarray layer):
+    encode the initial condition, normalise it, then run `roll_out_latent`.  `input_fields` (C, T_in, H, W) are the
+    standardised fields of the T_in input times; returns (rollout, known_latents)."""
+    known = encode_initial_condition(encdec_model, input_fields, static_fields, latent_mean, latent_std,
+                                     kw.get("target_std", 0.5))
+    out = roll_out_latent(pipeline, encdec_model, known, init_timestamp, ensemble_size, latent_mean, latent_std,
+                          field_mean, field_std, **kw)
+    return out, known
+
+
 def save_latents_npy(path_dir: str, init_timestamp: int, initial_latent: torch.Tensor, rollout: torch.Tensor) -> str:
     """Writes `latent_YYYYMMDDHH.npy` in the reference's on-disk format (evaluate/pred_rollout.py:421-430): float32
     array (ensemble, C, T+1, h, w) whose t=0 slot holds the encoded initial condition (de-normalised latent

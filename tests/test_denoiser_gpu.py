@@ -151,3 +151,35 @@ def test_rollout_two_ar_steps_vs_oracle():
                                    f_std, sampler="pipeline")
     assert got.shape == fld_want.shape == (2, 84, 4, 120, 240)
     assert _rel(got, fld_want) < 2e-3
+
+
+def test_roll_out_serial_from_fields_vs_oracle():
+    """Full a1 path from standardised fields: encode (+static) -> normalise -> one AR step (T_out=2) -> decode, FP32
+    validation mode, against oracle encode + normalise + rollout."""
+    from ladcast_b200.models import AutoencoderDC
+    from ladcast_b200.pipelines import AutoRegressive2DPipeline, EDMDPMSolverMultistepScheduler
+    from ladcast_b200.pipelines.utils import roll_out_serial, rollout_as_lead_major
+
+    cfg, sd, m = _model("tiny", 11, "fp32")
+    acfg = O.dcae_config("tiny")
+    asd = O.make_state_dict(O.dcae_decoder_param_shapes(acfg), 21)
+    asd.update(O.make_state_dict(O.dcae_encoder_param_shapes(acfg), 23))
+    ae = AutoencoderDC(**acfg)
+    ae.load_state_dict(asd)
+    ae.to("cuda").set_precision("fp32")
+    pipe = AutoRegressive2DPipeline(m, EDMDPMSolverMultistepScheduler())
+    fields = _seeded((84, 1, 120, 240), 501)  # (C, T_in, H, W), standardised units
+    static = _seeded((5, 120, 240), 502)
+    lat_mean, lat_std = _seeded((84,), 31) * 0.1, _seeded((84,), 32).abs() + 0.5
+    f_mean, f_std = _seeded((84,), 33), _seeded((84,), 34).abs() + 0.5
+    out, known = roll_out_serial(pipe, ae, fields.cuda(), static.cuda(), 2018010100, 2, lat_mean, lat_std, f_mean, f_std,
+                                 num_inference_steps=4, return_seq_len=2, total_lead_time_hour=12)
+    z = O.dcae_encode(asd, acfg, fields.permute(1, 0, 2, 3), static.unsqueeze(0))
+    known_want = O.normalize_latent(z.permute(1, 0, 2, 3).unsqueeze(0), lat_mean, lat_std, 0.5)
+    assert known.shape == known_want.shape == (1, 84, 1, 15, 30)
+    assert _rel(known, known_want) < 1e-4
+    _, fld_want = O.rollout(sd, cfg, asd, acfg, known_want, [0, 1], 2018010100, 2, 2, 4, lat_mean, lat_std, f_mean, f_std,
+                            sampler="pipeline")
+    got = rollout_as_lead_major(out)
+    assert got.shape == fld_want.shape == (2, 84, 2, 120, 240)
+    assert _rel(got, fld_want) < 2e-3
