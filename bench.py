@@ -271,9 +271,13 @@ def main():
             classes[nme] = {"launches": int(pln[i]), "ms": round(pms[i], 3), "tflops": round(pfl[i] / (pms[i] * 1e-3) / 1e12, 1)}
     gemm_ach = pfl[0] / (pms[0] * 1e-3) / 1e12 if pms[0] > 0 else 0.0
     step_ms = ms / args.steps
-    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, denoiser linears + decoder 1x1)",
+    roofline = {"bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05 bf16 GEMM, CTA-pair; denoiser linears + decoder 1x1)",
                 "achieved": round(gemm_ach, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(gemm_ach / peak_tf, 4),
-                "peak_source": peak_src, "traffic": None,
+                "peak_source": peak_src,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over 36 consecutive launches of this
+                # kernel in a 375M B=20 denoiser call (profiles/r01_gemm_ncu_final.md); only valid for that workload
+                "traffic": 383.1e6 if (args.model == "375M" and args.ens == 20 and args.t_out == 4) else None,
+                "traffic_source": "profiles/r01_gemm_ncu_final.md (ncu, per-launch average, bytes)",
                 "avg_launch_ms": round(pms[0] / max(1, pln[0]), 4), "share_of_step": round(pms[0] / step_ms, 3),
                 "classes": classes,
                 "step_algorithmic_tflops": round(flops_per_member_step(args.model, args.t_out, args.denoise_steps) * args.ens
