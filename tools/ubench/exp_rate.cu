@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -15,6 +16,14 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, f, 0.6931472f);
   p = fmaf(p, f, 1.0f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// two exps per MUFU instruction: fp32 args -> f16x2 -> ex2.approx.f16x2
+__device__ __forceinline__ uint32_t ex2_h2(float a0, float a1) {
+  __half2 h = __floats2half2_rn(a0, a1);
+  uint32_t x = *reinterpret_cast<uint32_t*>(&h), y;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
 }
 
 template <int MODE>
@@ -31,6 +40,15 @@ __global__ void __launch_bounds__(1024, 1) k(float* out, long long* cyc, int ite
     for (int i = 0; i < 64; i += 2) {
       float p0, p1;
       const float a0 = fmaf(s[i], scale, negm), a1 = fmaf(s[i + 1], scale, negm);
+      if (MODE == 5) {
+        const uint32_t y = ex2_h2(a0, a1);
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&y));
+        p0 = f.x; p1 = f.y;
+        acc[(i >> 1) & 3] += p0 + p1;
+        pk ^= y;
+        s[i] += 1e-7f * p0; s[i + 1] += 1e-7f * p1;
+        continue;
+      }
       if (MODE == 3 && (i & 6) == 0) { p0 = ex2_poly(a0); p1 = ex2_poly(a1); }   // 25 % on the FMA pipe
       else if (MODE == 4 && (i & 2) == 0) { p0 = ex2_poly(a0); p1 = ex2_poly(a1); }  // 50 %
       else { p0 = ex2(a0); p1 = ex2(a1); }
@@ -66,5 +84,6 @@ int main() {
   run<2>("+ F2FP bf16 pack");
   run<3>("+ 25% of the exps as FMA-pipe polynomial");
   run<4>("+ 50% of the exps as FMA-pipe polynomial");
+  run<5>("f16x2 exp (2 per MUFU) + fp32 row sum, P stays f16x2");
   return 0;
 }
