@@ -103,7 +103,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
       const int kr = row_base + j * BKV;
 #pragma unroll
       for (int kv = 0; kv < 2; ++kv) {  // 0: K_j, 1: V_j
-        ptx::mbar_wait_spin(&r_empty[st], ph ^ 1);
+        ptx::mbar_wait(&r_empty[st], ph ^ 1);
         const int col = (kv + 1) * d + h * HD;
         uint8_t* dst = sR + st * TILE_BYTES;
         ptx::mbar_expect_tx(&r_full[st], TILE_BYTES);
@@ -140,8 +140,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
     int st = 0;        // ring slot of the next tile to consume (K_0 first)
     uint32_t ph = 0;
     auto advance = [&]() { if (++st == RING) { st = 0; ph ^= 1; } };
-    ptx::mbar_wait_spin(q_full, 0);
-    ptx::mbar_wait_spin(&r_full[st], ph);
+    ptx::mbar_wait(q_full, 0);
+    ptx::mbar_wait(&r_full[st], ph);
     ptx::tc_fence_after();
     issue_qk(0, st);
     issue_qk(1, st);
@@ -149,21 +149,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
     advance();
     for (int j = 0; j < n_tiles; ++j) {
       const int v_slot = st;
-      ptx::mbar_wait_spin(&r_full[v_slot], ph);
+      ptx::mbar_wait(&r_full[v_slot], ph);
       advance();
       const int k_slot = st;  // K_{j+1}
       const uint32_t k_ph = ph;
       const bool more = j + 1 < n_tiles;
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        ptx::mbar_wait_spin(&p_full[t], j & 1);
+        ptx::mbar_wait(&p_full[t], j & 1);
         ptx::tc_fence_after();
         LC_TRACE(0, j, 2 * t);
         issue_pv(t, v_slot, j == 0);
         if (t == 1) ptx::umma_commit(&r_empty[v_slot]);
         if (more) {
           if (t == 0) {
-            ptx::mbar_wait_spin(&r_full[k_slot], k_ph);
+            ptx::mbar_wait(&r_full[k_slot], k_ph);
             ptx::tc_fence_after();
           }
           issue_qk(t, k_slot);
@@ -188,7 +188,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
     for (int j = 0; j < n_tiles; ++j) {
       // S_t(j) complete; the commit also covers PV_t(j-1), so O_t is quiescent until this thread hands over P_t(j)
       LC_TRACE(1 + t, j, 0);
-      ptx::mbar_wait_spin(&s_full[t], j & 1);
+      ptx::mbar_wait(&s_full[t], j & 1);
       ptx::tc_fence_after();
       LC_TRACE(1 + t, j, 1);
       uint32_t sreg[BKV / 32][32];
@@ -253,7 +253,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
       if (lane == 0) ptx::mbar_arrive(&p_full[t]);
       LC_TRACE(1 + t, j, 3);
     }
-    ptx::mbar_wait_spin(o_full, 0);
+    ptx::mbar_wait(o_full, 0);
     ptx::tc_fence_after();
     const int tok = q0 + t * BQ + r;
     const float inv = 1.0f / l;
