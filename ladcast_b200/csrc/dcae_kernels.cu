@@ -415,12 +415,18 @@ __global__ void __launch_bounds__(256, 3) multiscale_fused_kernel(const float* _
 // ---------------------------------------------------------------- ReLU linear attention (DCAE.py:155-175, 226-262)
 // One CTA per (frame, head).  Head g of scale s reads channels [g*96, g*96+96) of qkv (s=0) or of the multiscale
 // branch (s=1): 32 q | 32 k | 32 v.  S = [V;1] relu(K)^T (33x32, fp32), out = S relu(Q), out[:32] / (out[32] + eps).
+// Both phases are register-tiled (the kernel used to be bound by shared-memory wavefronts):
+//   phase 1: each warp owns every 8th pixel and a private 33x32 partial of S; lane = (4 v-channels) x (8 k-channels),
+//            operands straight from global memory as 128-B row segments, 4 pixels in flight, packed FFMA2;
+//   phase 2: lane = (4 output channels) x (8-wide slice of the q dot product); 4 pixels per step, the partial dot
+//            products are combined with a transposing butterfly (15 shuffles per 4 pixels) that leaves lane kl with
+//            the finished sums of pixel kl.
+__device__ __forceinline__ float2 relu2(float a, float b) { return make_float2(fmaxf(a, 0.f), fmaxf(b, 0.f)); }
+
 template <typename TO>
-__global__ void __launch_bounds__(256) linear_attn_kernel(const float* __restrict__ qkv, const float* __restrict__ ms,
-                                                          TO* __restrict__ out, int HW, int heads, float eps) {
-  constexpr int TP = 128;                   // pixels per staged tile
-  __shared__ __align__(16) float ka[TP][32];  // relu(K) tile, later relu(Q) tile
-  __shared__ __align__(16) float va[TP][32];  // V tile
+__global__ void __launch_bounds__(256, 2) linear_attn_kernel(const float* __restrict__ qkv, const float* __restrict__ ms,
+                                                             TO* __restrict__ out, int HW, int heads, float eps) {
+  __shared__ __align__(16) float red[8][33][32];  // per-warp partials of S
   __shared__ __align__(16) float S[33][32];
   const int g = blockIdx.x % (2 * heads);
   const int f = blockIdx.x / (2 * heads);
@@ -428,72 +434,120 @@ __global__ void __launch_bounds__(256) linear_attn_kernel(const float* __restric
   const int C3 = heads * 96;
   const float* src = (scale ? ms : qkv) + static_cast<long long>(f) * HW * C3 + hg * 96;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cl = lane >> 2, kl = lane & 3;
 
-  // ---- phase 1: S[c][c'] = sum_p v1[p][c] * relu(k[p][c']).  Thread (c = tid/8, 4 consecutive c' = 4*(tid%8)..)
-  const int c = tid >> 3, c4 = (tid & 7) * 4;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), ksum = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int p0 = 0; p0 < HW; p0 += TP) {
-    __syncthreads();
-    for (int i = tid; i < TP * 8; i += 256) {  // 8 float4 per pixel row for K and for V
-      const int pp = i >> 3, q4 = (i & 7) * 4;
-      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-      if (p0 + pp < HW) {
-        const float* row = src + static_cast<long long>(p0 + pp) * C3;
-        kv = *reinterpret_cast<const float4*>(row + 32 + q4);
-        vv = *reinterpret_cast<const float4*>(row + 64 + q4);
-        kv.x = fmaxf(kv.x, 0.f); kv.y = fmaxf(kv.y, 0.f); kv.z = fmaxf(kv.z, 0.f); kv.w = fmaxf(kv.w, 0.f);
-      }
-      *reinterpret_cast<float4*>(&ka[pp][q4]) = kv;
-      *reinterpret_cast<float4*>(&va[pp][q4]) = vv;
+  // ---- phase 1: S[c][c'] += v[p][c] * relu(k[p][c']),  S[32][c'] += relu(k[p][c'])
+  {
+    float2 acc[4][4];  // [v channel 4cl+i][k channel pair 8kl+2j, +1]
+    float2 ks[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ks[i] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
     }
-    __syncthreads();
-    const int np = min(TP, HW - p0);
-#pragma unroll 4
-    for (int pp = 0; pp < np; ++pp) {
-      const float v = va[pp][c];
-      const float4 k4 = *reinterpret_cast<const float4*>(&ka[pp][c4]);
-      acc.x = fmaf(v, k4.x, acc.x); acc.y = fmaf(v, k4.y, acc.y); acc.z = fmaf(v, k4.z, acc.z); acc.w = fmaf(v, k4.w, acc.w);
-      if (c == 0) { ksum.x += k4.x; ksum.y += k4.y; ksum.z += k4.z; ksum.w += k4.w; }
+    constexpr int U = 4;
+    for (int p0 = warp * U; p0 < HW; p0 += 8 * U) {
+      float4 v4[U], ka[U], kb[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        v4[u] = ka[u] = kb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p0 + u < HW) {
+          const float* row = src + static_cast<long long>(p0 + u) * C3;
+          v4[u] = *reinterpret_cast<const float4*>(row + 64 + cl * 4);
+          ka[u] = *reinterpret_cast<const float4*>(row + 32 + kl * 8);
+          kb[u] = *reinterpret_cast<const float4*>(row + 32 + kl * 8 + 4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float2 k2[4] = {relu2(ka[u].x, ka[u].y), relu2(ka[u].z, ka[u].w), relu2(kb[u].x, kb[u].y),
+                              relu2(kb[u].z, kb[u].w)};
+        const float vv[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 vd = make_float2(vv[i], vv[i]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(vd, k2[j], acc[i][j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ks[j] = __fadd2_rn(ks[j], k2[j]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<float2*>(&red[warp][cl * 4 + i][kl * 8 + 2 * j]) = acc[i][j];
+    if (cl == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<float2*>(&red[warp][32][kl * 8 + 2 * j]) = ks[j];
     }
   }
-  *reinterpret_cast<float4*>(&S[c][c4]) = acc;
-  if (c == 0) *reinterpret_cast<float4*>(&S[32][c4]) = ksum;  // the padded row of ones of V
+  __syncthreads();
+  for (int i = tid; i < 33 * 32; i += 256) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += (&red[w][0][0])[i];
+    (&S[0][0])[i] = a;
+  }
   __syncthreads();
 
-  // ---- phase 2: out[p][c] = (S[c] . relu(q[p])) / (S[32] . relu(q[p]) + eps).  Lane = output channel with its row of S
-  // in registers; each warp walks over pixels, q[p][:] is a broadcast read.
-  float sr[32];
+  // ---- phase 2: out[p][c] = (S[c] . relu(q[p])) / (S[32] . relu(q[p]) + eps)
+  float2 sr[5][4];  // rows 4cl..4cl+3 of S and the row of ones (index 4), k slice 8kl..8kl+7 as pairs
 #pragma unroll
-  for (int k = 0; k < 32; k += 4) {
-    const float4 t4 = *reinterpret_cast<const float4*>(&S[lane][k]);
-    sr[k] = t4.x; sr[k + 1] = t4.y; sr[k + 2] = t4.z; sr[k + 3] = t4.w;
+  for (int i = 0; i < 5; ++i) {
+    const float* srow = i < 4 ? &S[cl * 4 + i][kl * 8] : &S[32][kl * 8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sr[i][j] = *reinterpret_cast<const float2*>(srow + 2 * j);
   }
-  const float s32 = S[32][lane];
   const int Co = 2 * heads * 32;
-  for (int p0 = 0; p0 < HW; p0 += TP) {
-    __syncthreads();
-    for (int i = tid; i < TP * 8; i += 256) {
-      const int pp = i >> 3, q4 = (i & 7) * 4;
-      float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p0 + pp < HW) {
-        qv = *reinterpret_cast<const float4*>(src + static_cast<long long>(p0 + pp) * C3 + q4);
-        qv.x = fmaxf(qv.x, 0.f); qv.y = fmaxf(qv.y, 0.f); qv.z = fmaxf(qv.z, 0.f); qv.w = fmaxf(qv.w, 0.f);
+  const int my_px = (kl & 1) * 2 + (kl >> 1);  // pixel of the group of 4 this lane finishes
+  for (int p0 = warp * 4; p0 < HW; p0 += 32) {
+    float4 qa[4], qb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      qa[u] = qb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p0 + u < HW) {
+        const float* row = src + static_cast<long long>(p0 + u) * C3 + kl * 8;
+        qa[u] = *reinterpret_cast<const float4*>(row);
+        qb[u] = *reinterpret_cast<const float4*>(row + 4);
       }
-      *reinterpret_cast<float4*>(&ka[pp][q4]) = qv;
     }
-    __syncthreads();
-    const int np = min(TP, HW - p0);
-    for (int pp = warp; pp < np; pp += 8) {
-      float a = 0.f;
+    float val[4][5];
 #pragma unroll
-      for (int k = 0; k < 32; k += 4) {
-        const float4 q4v = *reinterpret_cast<const float4*>(&ka[pp][k]);
-        a = fmaf(sr[k], q4v.x, a); a = fmaf(sr[k + 1], q4v.y, a); a = fmaf(sr[k + 2], q4v.z, a); a = fmaf(sr[k + 3], q4v.w, a);
+    for (int u = 0; u < 4; ++u) {
+      const float2 q2[4] = {relu2(qa[u].x, qa[u].y), relu2(qa[u].z, qa[u].w), relu2(qb[u].x, qb[u].y),
+                            relu2(qb[u].z, qb[u].w)};
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a = __ffma2_rn(sr[i][j], q2[j], a);
+        val[u][i] = a.x + a.y;
       }
-      float den = s32 * ka[pp][lane];
+    }
+    // transposing butterfly over the 4 k-slices: after it, this lane holds the full sums of pixel p0 + my_px
+    float keep[2][5], fin[5];
+    const bool odd1 = kl & 1, odd2 = kl & 2;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
-      out[(static_cast<long long>(f) * HW + p0 + pp) * Co + g * 32 + lane] = from_f32<TO>(a / (den + eps));
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const float send = odd1 ? val[i][j] : val[i + 2][j];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+        keep[i][j] = (odd1 ? val[i + 2][j] : val[i][j]) + recv;
+      }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const float send = odd2 ? keep[0][j] : keep[1][j];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+      fin[j] = (odd2 ? keep[1][j] : keep[0][j]) + recv;
+    }
+    const int p = p0 + my_px;
+    if (p < HW) {
+      const float inv = 1.0f / (fin[4] + eps);
+      st4<TO>(out + (static_cast<long long>(f) * HW + p) * Co + g * 32 + cl * 4,
+              make_float4(fin[0] * inv, fin[1] * inv, fin[2] * inv, fin[3] * inv));
     }
   }
 }
