@@ -286,7 +286,7 @@ def main():
     # ---- end to end through the public API with host buffers (H2D of inputs, D2H of decoded fields, each step)
     e2e = None
     if not args.no_e2e:
-        k_e2e = min(args.steps, 3)
+        k_e2e = min(args.steps, 5)
         host_known = known0.clone().pin_memory()
         host_out = torch.empty((k_e2e, args.ens, 84, args.t_out, 120, 240), dtype=torch.float32, pin_memory=True)
         barrier()
