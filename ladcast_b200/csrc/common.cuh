@@ -122,6 +122,7 @@ struct EpiParams {
   const float* qk_wk = nullptr;
   const float* rope_cos = nullptr;
   const float* rope_sin = nullptr;
+  const uint32_t* rope_cs = nullptr;  // [tokens, 64] half2 (cos, sin) per rotation pair; null = no rotation
 };
 
 __device__ __forceinline__ long long epi_out_row(const EpiParams& ep, int row, int& sample) {

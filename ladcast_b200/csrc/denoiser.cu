@@ -89,7 +89,7 @@ struct lc_denoiser {
   // geometry
   int maxB = 0, T_in = 0, T_out = 0, H = 0, W = 0, Np = 0, Nc = 0, S = 0;
   int curB = 0, n_ts = 0;
-  DevBuf cos_p, sin_p, cos_c, sin_c;
+  DevBuf cos_p, sin_p, cos_c, sin_c, cs_p, cs_c;  // cs_*: [tokens, 64] half2 (cos, sin) for the fused qkv epilogue
   // workspace
   DevBuf tok_x, tok_c, h, e, e0, e0T, e_proj, n_p, n_c, qkv, att_p, att_c, mlp_p, mlp_c;
   DevBuf sincos, tmpA, tmpB, r_te, r_pe, r_tembS, gates, t_te, pooled, pe, temb, tembS, modv, te_out, yearT;
@@ -206,6 +206,8 @@ struct Ctx {
     if (!D->f32 && seg != nullptr && D->fuse_qk) {
       g.epi.qk_cols = 2 * D->d; g.epi.qk_eps = 1e-7f; g.epi.qk_wq = seg->wq; g.epi.qk_wk = seg->wk;
       g.epi.rope_cos = seg->cos; g.epi.rope_sin = seg->sin;
+      g.epi.rope_cs = seg->cos == nullptr ? nullptr
+                      : (seg->cos == D->cos_p.as<float>() ? D->cs_p.as<uint32_t>() : D->cs_c.as<uint32_t>());
     }
     return run(g);
   }
@@ -480,7 +482,7 @@ void lc_denoiser_destroy(lc_denoiser* D) {
   if (!D) return;
   for (void* p : D->owned) cudaFree(p);
   for (auto& kv : D->staged) cudaFree(kv.second.p);
-  DevBuf* bufs[] = {&D->cos_p, &D->sin_p, &D->cos_c, &D->sin_c, &D->tok_x, &D->tok_c, &D->h, &D->e, &D->e0, &D->e0T,
+  DevBuf* bufs[] = {&D->cos_p, &D->sin_p, &D->cos_c, &D->sin_c, &D->cs_p, &D->cs_c, &D->tok_x, &D->tok_c, &D->h, &D->e, &D->e0, &D->e0T,
                     &D->e_proj, &D->n_p, &D->n_c, &D->qkv, &D->att_p, &D->att_c, &D->mlp_p, &D->mlp_c, &D->sincos,
                     &D->tmpA, &D->tmpB, &D->r_te, &D->r_pe, &D->r_tembS, &D->gates, &D->t_te, &D->pooled, &D->pe,
                     &D->temb, &D->tembS, &D->modv, &D->te_out, &D->yearT};
@@ -526,6 +528,9 @@ int lc_denoiser_set_geometry(lc_denoiser* D, int max_batch, int t_in, int t_out,
   LC_CHECK_CUDA(cudaMemcpyAsync(D->sin_p.p, sin_pred, Np * 128 * 4, cudaMemcpyDeviceToDevice, st));
   LC_CHECK_CUDA(cudaMemcpyAsync(D->cos_c.p, cos_cond, Nc * 128 * 4, cudaMemcpyDeviceToDevice, st));
   LC_CHECK_CUDA(cudaMemcpyAsync(D->sin_c.p, sin_cond, Nc * 128 * 4, cudaMemcpyDeviceToDevice, st));
+  LC_TRY(D->cs_p.alloc(Np * 64 * 4)); LC_TRY(D->cs_c.alloc(Nc * 64 * 4));
+  LC_TRY(pack_rope_pairs(D->cos_p.as<float>(), D->sin_p.as<float>(), D->cs_p.as<uint32_t>(), static_cast<int>(Np), st));
+  LC_TRY(pack_rope_pairs(D->cos_c.as<float>(), D->sin_c.as<float>(), D->cs_c.as<uint32_t>(), static_cast<int>(Nc), st));
   LC_TRY(D->tok_x.alloc(B * Np * D->kp_in * e)); LC_TRY(D->tok_c.alloc(B * Nc * D->kp_in * e));
   LC_TRY(D->h.alloc(B * Np * d * 4)); LC_TRY(D->e.alloc(B * Nc * d * 4));
   LC_TRY(D->e0.alloc(B * Nc * d * 4)); LC_TRY(D->e0T.alloc(B * Nc * d * e)); LC_TRY(D->e_proj.alloc(B * Nc * d * 4));

@@ -1,6 +1,7 @@
 // HBM-bound kernels of the denoiser: LayerNorm + modulation, QK RMSNorm + RoPE, patchify, timestep embedding,
 // token pooling, gated residual, temb combine; and the fused scheduler steps.  All vectorised (128-bit) with
 // warp-shuffle reductions; fp32 statistics regardless of the storage type.
+#include <cuda_fp16.h>
 #include "kernels.h"
 
 namespace lc {
@@ -407,6 +408,21 @@ int qk_norm_rope(T* qkv, long long ld, int B, int S, int heads, int head_dim, fl
   }
   qk_norm_rope_kernel<T><<<static_cast<unsigned>(ceil_div_ll(total, 8)), 256, 0, s>>>(qkv, ld, B, S, heads, eps, segs[0],
                                                                                      s1, nseg);
+  LC_LAUNCH_CHECK();
+  return 0;
+}
+
+// [tokens, 128] fp32 cos / sin (each frequency repeated twice, interleaved: embeddings.py:315-327) -> [tokens, 64]
+// half2 (cos, sin) per rotation pair for the fused qkv epilogue
+__global__ void pack_rope_pairs_kernel(const float* __restrict__ cs, const float* __restrict__ sn, uint32_t* __restrict__ out,
+                                       int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 64) return;
+  const __half2 h = __floats2half2_rn(cs[2 * i], sn[2 * i]);
+  out[i] = *reinterpret_cast<const uint32_t*>(&h);
+}
+int pack_rope_pairs(const float* cos, const float* sin, uint32_t* out, int n_tokens, cudaStream_t s) {
+  pack_rope_pairs_kernel<<<ceil_div(n_tokens * 64, 256), 256, 0, s>>>(cos, sin, out, n_tokens);
   LC_LAUNCH_CHECK();
   return 0;
 }

@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "gemm_tc.h"
+#include <cuda_fp16.h>
 #include "ptx.cuh"
 #include "tmap.h"
 
@@ -239,47 +240,57 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& ep, const uint32
   __syncwarp();
 }
 
-// qkv projection block: bias, then (q/k heads only) per-head RMSNorm with the row's precomputed rstd and RoPE on
-// interleaved pairs, bf16 store.  Lanes own adjacent column pairs == rotation pairs; cos/sin rows load coalesced.
+// qkv projection chunk (32 columns of one head, thread = row): bias, then (q/k heads only) per-head RMSNorm with the
+// row's rstd and RoPE on interleaved pairs, bf16, four 16-byte stores.  The rotation factors come from a packed
+// [tokens, 64] half2 (cos, sin) table: 64 B per thread and chunk instead of 256 B of fp32 cos + sin.
 // Reference: LaDCast_3D_model.py:92-169 (to_q/k/v, norm_q/k, apply_rotary_emb).
-__device__ __forceinline__ void epilogue_qkv_block(const EpiParams& ep, const uint32_t (&r)[32], float* tbuf, int lane,
-                                                   int row_mine, long long orow_mine, int tok_mine, float rstd_mine,
-                                                   int n0, int col_in_head0, bool is_qk, const float* nw, int M) {
+__device__ __forceinline__ void epilogue_qkv_chunk(const EpiParams& ep, const uint32_t (&r)[32], bool row_ok,
+                                                   long long orow, int tok, float rstd, int n0, int colh0, bool is_qk,
+                                                   const float* nw) {
+  float v[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
-  __syncwarp();
-  const int cc = (lane & 15) * 2;
-  const int col = n0 + cc;
-  const int colh = col_in_head0 + cc;
-  const float2 b2 = ep.bias != nullptr ? __ldg(reinterpret_cast<const float2*>(ep.bias + col)) : make_float2(0.f, 0.f);
-  const float2 w2 = is_qk ? __ldg(reinterpret_cast<const float2*>(nw + colh)) : make_float2(1.f, 1.f);
-  const bool rope = is_qk && ep.rope_cos != nullptr;
-  bf16* outp = reinterpret_cast<bf16*>(ep.out) + col;
-  const long long ldo = ep.ldo;
+  for (int j = 0; j < 32; j += 4) {
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
+    v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+    v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+  }
+  if (is_qk) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int rr = 2 * i + (lane >> 4);
-    const int row = __shfl_sync(0xffffffffu, row_mine, rr);
-    const long long orow = __shfl_sync(0xffffffffu, orow_mine, rr);
-    const float rs = __shfl_sync(0xffffffffu, rstd_mine, rr);
-    const int tok = __shfl_sync(0xffffffffu, tok_mine, rr);
-    float v0 = tbuf[rr * 33 + cc] + b2.x, v1 = tbuf[rr * 33 + cc + 1] + b2.y;
-    if (is_qk) {
-      v0 *= rs * w2.x;
-      v1 *= rs * w2.y;
+    for (int j = 0; j < 32; j += 4) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(nw + colh0 + j));
+      v[j] *= rstd * w4.x; v[j + 1] *= rstd * w4.y; v[j + 2] *= rstd * w4.z; v[j + 3] *= rstd * w4.w;
     }
-    if (row < M) {
-      if (rope) {
-        const float2 c2 = __ldg(reinterpret_cast<const float2*>(ep.rope_cos + static_cast<long long>(tok) * 128 + colh));
-        const float2 s2 = __ldg(reinterpret_cast<const float2*>(ep.rope_sin + static_cast<long long>(tok) * 128 + colh));
-        const float o0 = v0 * c2.x - v1 * s2.x, o1 = v1 * c2.y + v0 * s2.y;
-        v0 = o0;
-        v1 = o1;
+    if (ep.rope_cs != nullptr && row_ok) {
+      const uint4* cs = reinterpret_cast<const uint4*>(ep.rope_cs + static_cast<long long>(tok) * 64 + (colh0 >> 1));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 c4 = __ldg(cs + q);
+        const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&cw[k]));  // (cos, sin)
+          const int j = (q * 4 + k) * 2;
+          const float a = v[j], b = v[j + 1];
+          v[j] = a * f.x - b * f.y;
+          v[j + 1] = b * f.x + a * f.y;
+        }
       }
-      *reinterpret_cast<__nv_bfloat162*>(outp + orow * ldo) = __floats2bfloat162_rn(v0, v1);
     }
   }
-  __syncwarp();
+  if (!row_ok) return;
+  uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + orow * ep.ldo + n0);
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]), t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+    __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+    uint4 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&t0);
+    pk.y = *reinterpret_cast<uint32_t*>(&t1);
+    pk.z = *reinterpret_cast<uint32_t*>(&t2);
+    pk.w = *reinterpret_cast<uint32_t*>(&t3);
+    op[j >> 3] = pk;
+  }
 }
 
 __device__ __forceinline__ int epi_kind(const EpiParams& ep) {
@@ -344,29 +355,36 @@ __device__ __forceinline__ void epilogue_drain(const EpiParams& ep, int kind, in
     const bool is_qk = head0 < ep.qk_cols;
     const float* nw = (head0 < ep.qk_cols / 2) ? ep.qk_wq : ep.qk_wk;
     float rstd = 1.f;
+    uint32_t r[2][32];
     if (is_qk && head0 < N) {
-      float ss = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld32(t_addr + c * 32, r);
-        ptx::tmem_ld_wait();
+      // pass 1, software-pipelined: the TMEM load of chunk c+1 is in flight while chunk c is squared
+      float ss[4] = {0.f, 0.f, 0.f, 0.f};
+      ptx::tmem_ld32(t_addr, r[0]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float t2 = __uint_as_float(r[j]) + (ep.bias != nullptr ? __ldg(ep.bias + head0 + c * 32 + j) : 0.f);
-          ss = fmaf(t2, t2, ss);
+      for (int c = 0; c < 4; ++c) {
+        ptx::tmem_ld_wait();
+        if (c + 1 < 4) ptx::tmem_ld32(t_addr + (c + 1) * 32, r[(c + 1) & 1]);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + head0 + c * 32 + j));
+          const float t0 = __uint_as_float(r[c & 1][j]) + b4.x, t1 = __uint_as_float(r[c & 1][j + 1]) + b4.y;
+          const float t2 = __uint_as_float(r[c & 1][j + 2]) + b4.z, t3 = __uint_as_float(r[c & 1][j + 3]) + b4.w;
+          ss[0] = fmaf(t0, t0, ss[0]); ss[1] = fmaf(t1, t1, ss[1]); ss[2] = fmaf(t2, t2, ss[2]); ss[3] = fmaf(t3, t3, ss[3]);
         }
       }
-      rstd = rsqrtf(ss * (1.0f / 128.0f) + ep.qk_eps);
+      rstd = rsqrtf(((ss[0] + ss[1]) + (ss[2] + ss[3])) * (1.0f / 128.0f) + ep.qk_eps);
     }
     const int tok = row % ep.rows_per_sample;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      ptx::tmem_ld32(t_addr + c * 32, r);
-      ptx::tmem_ld_wait();
-      const int n0 = head0 + c * 32;
-      if (n0 < N) epilogue_qkv_block(ep, r, tbuf, lane, row, orow, tok, rstd, n0, c * 32, is_qk, nw, M);
+    const bool row_ok = row < M;
+    if (head0 < N) {
+      ptx::tmem_ld32(t_addr, r[0]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        ptx::tmem_ld_wait();
+        if (c + 1 < 4) ptx::tmem_ld32(t_addr + (c + 1) * 32, r[(c + 1) & 1]);
+        epilogue_qkv_chunk(ep, r[c & 1], row_ok, orow, tok, rstd, head0 + c * 32, c * 32, is_qk, nw);
+      }
     }
   } else {
     const int n_base = n_blk * BN + half * (BN / 2);

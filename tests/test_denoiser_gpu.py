@@ -183,3 +183,21 @@ def test_roll_out_serial_from_fields_vs_oracle():
     got = rollout_as_lead_major(out)
     assert got.shape == fld_want.shape == (2, 84, 2, 120, 240)
     assert _rel(got, fld_want) < 2e-3
+
+
+def test_fused_qk_epilogue_variant(golden_dir, monkeypatch):
+    """LADCAST_B200_FUSE_QK=1 moves RMSNorm(q,k) + RoPE into the qkv GEMM epilogue (packed half2 cos/sin table):
+    same golden, same tolerance, and within bf16 noise of the separate-kernel path."""
+    g = np.load(os.path.join(golden_dir, "denoiser_tiny.npz"))
+    B, T_out = int(g["B"]), int(g["T_out"])
+    x = _seeded((B, 84, T_out, 15, 30), 100).cuda()
+    cond = _seeded((B, 84, 1, 15, 30), 101, 0.5).cuda()
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("LADCAST_B200_FUSE_QK", flag)
+        cfg, sd, m = _model("tiny", int(g["salt"]), "bf16")
+        outs[flag] = m(x, torch.from_numpy(g["t"]).cuda(), cond, time_elapsed=torch.from_numpy(g["ts"]),
+                       return_dict=False)[0].clone()
+        torch.cuda.synchronize()
+        assert _rel(outs[flag], g["out"]) < TOL["bf16"]
+    assert _rel(outs["1"], outs["0"]) < 5e-3
