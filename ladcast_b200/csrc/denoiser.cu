@@ -81,9 +81,11 @@ struct lc_denoiser {
   std::vector<DualW> dual;
   std::vector<SingleW> single;
   int mod_dim = 0, kp_in = 96;
-  // RMSNorm(q,k)+RoPE fused into the qkv GEMM epilogue (gemm_tc.cu K_QKV).  Measured slower than the separate
-  // HBM-bound kernel on the K=1536 projections (their epilogue is already the critical path), so off by default;
-  // LADCAST_B200_FUSE_QK=1 turns it on.
+  // RMSNorm(q,k)+RoPE fused into the qkv GEMM epilogue (gemm_tc.cu K_QKV, thread-per-row, packed half2 rotation
+  // table).  Measured in-step A/B on B200 (375M, B=20): 505.0 vs 508.3 ms per AR step, i.e. +0.6 % — the K=1536
+  // projections' epilogue becomes their critical path (GEMM class 1157 vs 1217 TFLOP/s) and eats most of the
+  // 19 ms of the removed HBM-bound kernel.  Within box-to-box noise, so off by default; LADCAST_B200_FUSE_QK=1
+  // turns it on.
   bool fuse_qk = false;
 
   // geometry
