@@ -101,6 +101,7 @@ int lc_gemm_bf16out(const void* a, const void* w, const float* bias, void* c, in
   return gemm_bf16(g, static_cast<cudaStream_t>(stream));
 }
 
+LC_API int lc_debug_gemm_trace(void* buf) { return lc::gemm_set_trace(reinterpret_cast<long long*>(buf)); }
 LC_API int lc_debug_attention_trace(void* buf) { return lc::attention_set_trace(reinterpret_cast<long long*>(buf)); }
 int lc_attention(int precision, const void* qkv, void* out, int batch, int seq, int heads, void* stream) {
   LC_REQUIRE(qkv && out, "null argument");

@@ -147,7 +147,8 @@ struct GemmArgs {
 };
 
 int gemm_f32(const GemmArgs& g, cudaStream_t stream);   // SIMT fp32 validation path
-int gemm_bf16(const GemmArgs& g, cudaStream_t stream);  // tcgen05 / TMEM / TMA path
+int gemm_bf16(const GemmArgs& g, cudaStream_t stream);
+int gemm_set_trace(long long* buf);  // tuning aid: timeline of CTA pair 0 of gemm_tc2_kernel (nullptr = off)  // tcgen05 / TMEM / TMA path
 int gemm_bf16_selftest_smem_bytes();
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -68,6 +68,9 @@ __device__ __forceinline__ float act_fast(float v) {
   return v;
 }
 
+// Optional in-kernel timeline of pair 0 for tuning (tools/gemm_trace.py): clock64 stamps, [role][tile][4].
+__device__ long long* g_gemm_trace = nullptr;
+
 enum EpiKind { K_STORE_BF16 = 0, K_STORE_F32 = 1, K_GATED = 2, K_RESID = 3, K_UNPATCH = 4, K_QKV = 5 };
 
 // One 32x32 accumulator block (lane = row, r[j] = column n0+j).  K_UNPATCH keeps this layout (consecutive rows are
@@ -674,13 +677,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+    long long* trace = pair_id == 0 ? g_gemm_trace : nullptr;
+    int tix = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tix) {
+      if (trace != nullptr && tix < 64) trace[tix * 4 + 0] = clock64();
       ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
+      if (trace != nullptr && tix < 64) trace[tix * 4 + 1] = clock64();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
+        if (trace != nullptr && tix < 64 && kb == 0) trace[tix * 4 + 2] = clock64();
         const uint32_t a_base = ptx::smem_u32(smem_a + stage * C::STAGE_A);
         const uint32_t b_base = ptx::smem_u32(smem_b + stage * C::STAGE_B);
 #pragma unroll
@@ -693,6 +701,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
       ptx::umma_commit_pair(&tmem_full[acc]);
+      if (trace != nullptr && tix < 64) trace[tix * 4 + 3] = clock64();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= EPI_WARP0) {
@@ -704,18 +713,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const int kind = epi_kind(ep);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+    long long* trace = (pair_id == 0 && leader && ew == 0 && lane == 0) ? g_gemm_trace : nullptr;
+    int tix = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tix) {
       int mp, n_blk;
       sched.decode(tile, mp, n_blk);
       const int m_blk = mp * 2 + static_cast<int>(cta_rank);
       int row, sample;
       long long orow;
       epilogue_row(ep, cv, m_blk, quarter, lane, M, row, orow, sample);
+      if (trace != nullptr && tix < 64) trace[256 + tix * 4 + 0] = clock64();
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
+      if (trace != nullptr && tix < 64) trace[256 + tix * 4 + 1] = clock64();
       epilogue_drain<BN>(ep, kind, n_blk, quarter, half, lane, tbuf, tmem_base, acc, row, orow, sample, M, N);
       ptx::tc_fence_before();
       __syncwarp();
+      if (trace != nullptr && tix < 64) trace[256 + tix * 4 + 2] = clock64();
       if (lane == 0) ptx::mbar_arrive_cluster(ptx::map_to_cta(&tmem_empty[acc], 0));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -738,7 +752,8 @@ int launch_pair(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   TileSched sched;
   sched.num_m = ceil_div(M_tiles, 2);  // 256-row pair tiles
   sched.num_n = ceil_div(N, C::BN);
-  sched.group_m = 4;
+  static const int group_m_env = [] { const char* e = getenv("LADCAST_B200_GROUP_M"); return e ? atoi(e) : 0; }();
+  sched.group_m = group_m_env > 0 ? group_m_env : 4;
   const int tiles = sched.num_m * sched.num_n;
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
@@ -797,6 +812,11 @@ static bool use_pair(int m_tiles, int N) {
     mode = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
   return mode == 1 && m_tiles >= 2 && static_cast<long long>(ceil_div(m_tiles, 2)) * ceil_div(N, 256) >= 37;
+}
+
+int gemm_set_trace(long long* buf) {
+  LC_CHECK_CUDA(cudaMemcpyToSymbol(g_gemm_trace, &buf, sizeof(buf)));
+  return 0;
 }
 
 int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
