@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--t-out", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the extra event-profiled step (for ncu launch lists)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -253,7 +254,8 @@ def main():
     import ctypes
 
     lib.lc_prof_enable(1)
-    ar_step()
+    if not args.no_roofline:
+        ar_step()
     torch.cuda.synchronize()
     pms, pfl, pln = (ctypes.c_double * 3)(), (ctypes.c_double * 3)(), (ctypes.c_longlong * 3)()
     _lib.check(lib.lc_prof_collect(pms, pfl, pln), "lc_prof_collect")
