@@ -194,3 +194,43 @@ def test_latent_npy_writer_matches_reference_layout(tmp_path):
     assert np.array_equal(arr[1, :, 0], ic.numpy())
     lead = rollout_as_lead_major(blocks)
     assert np.array_equal(arr[:, :, 1:], lead.numpy()) and np.array_equal(arr[2, :, 5], blocks[1, 2, :, 0].numpy())
+
+
+def test_autoencoder_encoder_contract():
+    """Encoder half of the AutoencoderDC drop-in: reference key names / shapes (256.4 M parameters in total for the
+    V0.1.X config), per-sub-module strict loading, loud failure without CUDA, unsupported variants."""
+    from ladcast_b200 import _lib
+    from ladcast_b200.models import AutoencoderDC
+
+    cfg = O.dcae_config()
+    ae = AutoencoderDC(**cfg)
+    assert ae.encoder_param_shapes() == O.dcae_encoder_param_shapes(cfg)
+    n_params = sum(int(np.prod(s)) for s in ae.param_shapes().values())
+    assert n_params == 256_411_145  # SURVEY: exact parameter count of the reference AutoencoderDC(V0.1.X)
+
+    tiny = O.dcae_config("tiny")
+    ae = AutoencoderDC(**tiny)
+    dec = O.make_state_dict(O.dcae_decoder_param_shapes(tiny), 1)
+    enc = O.make_state_dict(O.dcae_encoder_param_shapes(tiny), 2)
+    missing, _ = ae.load_state_dict(dec, strict=True)            # decoder-only checkpoint: legal, encoder reported
+    assert missing and all(k.startswith("encoder.") for k in missing)
+    assert ae.load_state_dict({**dec, **enc}, strict=True)[0] == []
+    partial = dict(enc)
+    partial.pop("encoder.conv_out.bias")
+    with pytest.raises(RuntimeError):
+        ae.load_state_dict({**dec, **partial}, strict=True)      # an incomplete sub-module is an error
+    with pytest.raises(RuntimeError):
+        ae.load_state_dict({"encoder.conv_in.weight": torch.zeros(3, 3, 3, 3)}, strict=False)  # wrong shape
+    with pytest.raises(_lib.LadcastB200Error):
+        ae.encode(torch.zeros(1, 89, 40, 64))                    # CPU-resident model: no fallback
+    no_enc = AutoencoderDC(**dict(tiny, encoder_layers_per_block=[0, 1, 1, 1]))
+    assert no_enc.encoder_param_shapes() == {}
+    with pytest.raises(NotImplementedError):
+        no_enc.to("cpu").encode(torch.zeros(1, 89, 40, 64))
+
+
+def test_encode_initial_condition_argument_checks():
+    from ladcast_b200.pipelines.utils import encode_initial_condition
+
+    with pytest.raises(ValueError):
+        encode_initial_condition(None, torch.zeros(84, 120, 240), None, torch.zeros(84), torch.ones(84))
