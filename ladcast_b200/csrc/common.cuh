@@ -102,6 +102,14 @@ struct EpiParams {
   int rows_per_sample = 1 << 30;
   int out_rows_per_sample = 1 << 30;
   int out_row_offset = 0;
+  // optional second row segment (rows >= seg_rows; the single-stream blocks run pred and cond tokens in ONE launch):
+  // r = row - seg_rows; orow = seg_out_base + (r / seg_rows_per_sample) * seg_out_rows_per_sample + seg_out_row_offset
+  //                            + r % seg_rows_per_sample;  sample = r / seg_rows_per_sample.  0 = disabled.
+  int seg_rows = 0;
+  int seg_rows_per_sample = 1;
+  int seg_out_rows_per_sample = 0;
+  int seg_out_row_offset = 0;
+  long long seg_out_base = 0;
   const float* gate = nullptr;  // [n_samples, gate_stride]
   long long gate_stride = 0;
   const float* resid = nullptr;  // EPI_RESID_STORE
@@ -126,6 +134,12 @@ struct EpiParams {
 };
 
 __device__ __forceinline__ long long epi_out_row(const EpiParams& ep, int row, int& sample) {
+  if (ep.seg_rows > 0 && row >= ep.seg_rows) {
+    const int r2 = row - ep.seg_rows;
+    sample = r2 / ep.seg_rows_per_sample;
+    return ep.seg_out_base + static_cast<long long>(sample) * ep.seg_out_rows_per_sample + ep.seg_out_row_offset +
+           (r2 - sample * ep.seg_rows_per_sample);
+  }
   sample = row / ep.rows_per_sample;
   int r = row - sample * ep.rows_per_sample;
   return static_cast<long long>(sample) * ep.out_rows_per_sample + ep.out_row_offset + r +

@@ -87,14 +87,18 @@ struct lc_denoiser {
   // 19 ms of the removed HBM-bound kernel.  Within box-to-box noise, so off by default; LADCAST_B200_FUSE_QK=1
   // turns it on.
   bool fuse_qk = false;
+  // single-stream blocks: pred and cond rows in one GEMM launch per projection (LADCAST_B200_MERGE_STREAMS=0: off)
+  bool merge_streams = true;
 
   // geometry
   int maxB = 0, T_in = 0, T_out = 0, H = 0, W = 0, Np = 0, Nc = 0, S = 0;
   int curB = 0, n_ts = 0;
   DevBuf cos_p, sin_p, cos_c, sin_c, cs_p, cs_c;  // cs_*: [tokens, 64] half2 (cos, sin) for the fused qkv epilogue
   // workspace
-  DevBuf tok_x, tok_c, h, e, e0, e0T, e_proj, n_p, n_c, qkv, att_p, att_c, mlp_p, mlp_c;
+  // h / n_p / att_p / mlp_p hold the pred-token rows followed by the cond-token rows of the current batch
+  DevBuf tok_x, tok_c, h, e0, e0T, e_proj, n_p, qkv, att_p, mlp_p;
   DevBuf sincos, tmpA, tmpB, r_te, r_pe, r_tembS, gates, t_te, pooled, pe, temb, tembS, modv, te_out, yearT;
+  float* e_ptr() const { return h.as<float>() + static_cast<size_t>(curB) * Np * d; }  // cond-token residual stream
 };
 
 namespace lc {
@@ -213,6 +217,29 @@ struct Ctx {
     }
     return run(g);
   }
+  // second row segment of a merged pred+cond launch: rows >= Mp are cond tokens (Nc per sample)
+  void cond_segment(EpiParams& ep, int Mp, int Nc, int out_rows_per_sample, int out_row_offset, long long out_base) const {
+    ep.seg_rows = Mp; ep.seg_rows_per_sample = Nc; ep.seg_out_rows_per_sample = out_rows_per_sample;
+    ep.seg_out_row_offset = out_row_offset; ep.seg_out_base = out_base;
+  }
+  // single-stream blocks: q|k|v of the pred rows [0, Mp) and the cond rows [Mp, Mp+Mc) of A into the joint qkv buffer
+  int lin_qkv_both(const void* A, int Mp, int Np, int Mc, int Nc, const Lin& L, void* qkv, int S) const {
+    GemmArgs g = base(A, D->d, Mp + Mc, L);
+    g.epi.mode = EPI_STORE; g.epi.out = qkv; g.epi.ldo = 3LL * D->d; g.epi.out_f32 = D->f32 ? 1 : 0;
+    g.epi.rows_per_sample = Np; g.epi.out_rows_per_sample = S; g.epi.out_row_offset = 0;
+    cond_segment(g.epi, Mp, Nc, S, Np, 0);
+    return run(g);
+  }
+  // single-stream blocks: gated residual update of both streams (rows are identity-mapped, gate per sample)
+  int lin_gated_both(const void* A0, long long lda0, int K0, const void* A1, long long lda1, int Mp, int Np, int Mc, int Nc,
+                     const Lin& L, float* resid, const float* gate, long long gate_stride) const {
+    GemmArgs g = base(A0, lda0, Mp + Mc, L);
+    if (A1 != nullptr) { g.A1 = A1; g.lda1 = lda1; g.K0 = K0; }
+    g.epi.mode = EPI_GATED_RESID; g.epi.out = resid; g.epi.ldo = D->d; g.epi.rows_per_sample = Np;
+    g.epi.out_rows_per_sample = Np; g.epi.gate = gate; g.epi.gate_stride = gate_stride;
+    cond_segment(g.epi, Mp, Nc, Nc, 0, Mp);
+    return run(g);
+  }
   // resid[row] += gate[sample] * (A W^T + b);  A may be two K-segments
   int lin_gated(const void* A0, long long lda0, int K0, const void* A1, long long lda1, int M, int rows_per_sample,
                 const Lin& L, float* resid, const float* gate, long long gate_stride) const {
@@ -228,11 +255,13 @@ template <typename T>
 int attention(lc_denoiser* D, int B, int S, int Np, cudaStream_t st);
 template <>
 int attention<float>(lc_denoiser* D, int B, int S, int Np, cudaStream_t st) {
-  return attention_f32(D->qkv.as<float>(), B, S, D->cfg.num_heads, 128, D->att_p.as<float>(), Np, D->att_c.as<float>(), st);
+  return attention_f32(D->qkv.as<float>(), B, S, D->cfg.num_heads, 128, D->att_p.as<float>(), Np,
+                       D->att_p.as<float>() + static_cast<size_t>(B) * D->Np * D->d, st);
 }
 template <>
 int attention<bf16>(lc_denoiser* D, int B, int S, int Np, cudaStream_t st) {
-  return attention_bf16(D->qkv.as<bf16>(), B, S, D->cfg.num_heads, 128, D->att_p.as<bf16>(), Np, D->att_c.as<bf16>(), st);
+  return attention_bf16(D->qkv.as<bf16>(), B, S, D->cfg.num_heads, 128, D->att_p.as<bf16>(), Np,
+                        D->att_p.as<bf16>() + static_cast<size_t>(B) * D->Np * D->d, st);
 }
 
 template <typename T>
@@ -268,10 +297,14 @@ int forward_impl(lc_denoiser* D, const float* x_in, const float* c_noise, int n_
   const int d = D->d, B = D->curB, Np = D->Np, Nc = D->Nc, S = D->S;
   const int Mp = B * Np, Mc = B * Nc;
   const int heads = D->cfg.num_heads;
+  // the cond-token stream lives directly behind the pred-token stream in every per-token buffer, so that the
+  // single-stream blocks (shared weights) can run both streams in one GEMM launch of M = Mp + Mc rows
   float* h = D->h.as<float>();
-  float* e = D->e.as<float>();
+  float* e = D->e_ptr();
   T* n_p = D->n_p.as<T>();
-  T* n_c = D->n_c.as<T>();
+  T* n_c = n_p + static_cast<size_t>(Mp) * d;
+  T* att_c = D->att_p.as<T>() + static_cast<size_t>(Mp) * d;
+  T* mlp_c = D->mlp_p.as<T>() + static_cast<size_t>(Mp) * D->cfg.mlp_dim;
   T* qkv = D->qkv.as<T>();
   const long long md = D->mod_dim;
   const float* mod = D->modv.as<float>();
@@ -300,10 +333,10 @@ int forward_impl(lc_denoiser* D, const float* x_in, const float* c_noise, int n_
     LC_TRY(c.lin_qkv(n_c, Mc, Nc, w.qkv, qkv, Nc, 0, &seg));
     if (!c.fused_qk()) LC_TRY(qk_norm_rope<T>(qkv, 3LL * d, B, Nc, heads, 128, 1e-7f, &seg, 1, st));
     LC_TRY(attention<T>(D, B, Nc, 0, st));  // all tokens -> att_c
-    LC_TRY(gated_add<T>(e, D->att_c.as<T>(), g_msa, gs, Mc, d, Nc, st));
+    LC_TRY(gated_add<T>(e, att_c, g_msa, gs, Mc, d, Nc, st));
     LC_TRY(layernorm_modulate<T>(e, n_c, Mc, d, 1e-7f, Nc, nullptr, nullptr, 0, w.n2w, w.n2b, st));
-    LC_TRY(c.lin_T(n_c, d, Mc, w.ff0, D->mlp_c.p, w.ff0.out, ACT_SILU));
-    LC_TRY(c.lin_gated(D->mlp_c.p, w.ff0.out, 0, nullptr, 0, Mc, Nc, w.ff2, e, g_mlp, gs));
+    LC_TRY(c.lin_T(n_c, d, Mc, w.ff0, mlp_c, w.ff0.out, ACT_SILU));
+    LC_TRY(c.lin_gated(mlp_c, w.ff0.out, 0, nullptr, 0, Mc, Nc, w.ff2, e, g_mlp, gs));
   }
 
   // ---- temb = time_text_embed(t, mean(e)) [* (1+scale_date) + shift_date]  (:953-969)
@@ -337,13 +370,13 @@ int forward_impl(lc_denoiser* D, const float* x_in, const float* c_noise, int n_
     if (!c.fused_qk()) LC_TRY(qk_norm_rope<T>(qkv, 3LL * d, B, S, heads, 128, 1e-7f, segs, 2, st));
     LC_TRY(attention<T>(D, B, S, Np, st));
     LC_TRY(c.lin_gated(D->att_p.p, d, 0, nullptr, 0, Mp, Np, w.to_out, h, mh + 2 * d, md));
-    LC_TRY(c.lin_gated(D->att_c.p, d, 0, nullptr, 0, Mc, Nc, w.to_add_out, e, mc + 2 * d, md));
+    LC_TRY(c.lin_gated(att_c, d, 0, nullptr, 0, Mc, Nc, w.to_add_out, e, mc + 2 * d, md));
     LC_TRY(layernorm_modulate<T>(h, n_p, Mp, d, 1e-7f, Np, mh + 4 * d, mh + 3 * d, md, nullptr, nullptr, st));
     LC_TRY(layernorm_modulate<T>(e, n_c, Mc, d, 1e-7f, Nc, mc + 4 * d, mc + 3 * d, md, nullptr, nullptr, st));
     LC_TRY(c.lin_T(n_p, d, Mp, w.ff0, D->mlp_p.p, w.ff0.out, ACT_GELU_TANH));
-    LC_TRY(c.lin_T(n_c, d, Mc, w.ffc0, D->mlp_c.p, w.ffc0.out, ACT_GELU_TANH));
+    LC_TRY(c.lin_T(n_c, d, Mc, w.ffc0, mlp_c, w.ffc0.out, ACT_GELU_TANH));
     LC_TRY(c.lin_gated(D->mlp_p.p, w.ff0.out, 0, nullptr, 0, Mp, Np, w.ff2, h, mh + 5 * d, md));
-    LC_TRY(c.lin_gated(D->mlp_c.p, w.ffc0.out, 0, nullptr, 0, Mc, Nc, w.ffc2, e, mc + 5 * d, md));
+    LC_TRY(c.lin_gated(mlp_c, w.ffc0.out, 0, nullptr, 0, Mc, Nc, w.ffc2, e, mc + 5 * d, md));
   }
 
   // ---- single-stream blocks (:426-468): both streams share weights and modulation
@@ -358,15 +391,29 @@ int forward_impl(lc_denoiser* D, const float* x_in, const float* c_noise, int n_
     segs[0].cos = D->cos_p.as<float>(); segs[0].sin = D->sin_p.as<float>();
     segs[1].start = Np; segs[1].len = Nc; segs[1].wq = w.nq; segs[1].wk = w.nk;
     segs[1].cos = D->cos_c.as<float>(); segs[1].sin = D->sin_c.as<float>();
-    LC_TRY(c.lin_qkv(n_p, Mp, Np, w.qkv, qkv, S, 0, &segs[0]));
-    LC_TRY(c.lin_qkv(n_c, Mc, Nc, w.qkv, qkv, S, Np, &segs[1]));
-    LC_TRY(c.lin_T(n_p, d, Mp, w.mlp, D->mlp_p.p, w.mlp.out, ACT_GELU_TANH));
-    LC_TRY(c.lin_T(n_c, d, Mc, w.mlp, D->mlp_c.p, w.mlp.out, ACT_GELU_TANH));
+    const bool merged = D->merge_streams;
+    if (c.fused_qk() || !merged) {  // (fused: per-stream rotation tables live in the epilogue)
+      LC_TRY(c.lin_qkv(n_p, Mp, Np, w.qkv, qkv, S, 0, &segs[0]));
+      LC_TRY(c.lin_qkv(n_c, Mc, Nc, w.qkv, qkv, S, Np, &segs[1]));
+    } else {
+      LC_TRY(c.lin_qkv_both(n_p, Mp, Np, Mc, Nc, w.qkv, qkv, S));
+    }
+    // both streams share the weights (:426-468): one launch over the Mp + Mc rows of n_p | n_c
+    if (merged) {
+      LC_TRY(c.lin_T(n_p, d, Mp + Mc, w.mlp, D->mlp_p.p, w.mlp.out, ACT_GELU_TANH));
+    } else {
+      LC_TRY(c.lin_T(n_p, d, Mp, w.mlp, D->mlp_p.p, w.mlp.out, ACT_GELU_TANH));
+      LC_TRY(c.lin_T(n_c, d, Mc, w.mlp, mlp_c, w.mlp.out, ACT_GELU_TANH));
+    }
     if (!c.fused_qk()) LC_TRY(qk_norm_rope<T>(qkv, 3LL * d, B, S, heads, 128, 1e-7f, segs, 2, st));
     LC_TRY(attention<T>(D, B, S, Np, st));
     // proj_out over [attn | mlp] (K = d + mlp_dim) read from two buffers, gate, + residual
-    LC_TRY(c.lin_gated(D->att_p.p, d, d, D->mlp_p.p, w.mlp.out, Mp, Np, w.proj_out, h, ms + 2 * d, md));
-    LC_TRY(c.lin_gated(D->att_c.p, d, d, D->mlp_c.p, w.mlp.out, Mc, Nc, w.proj_out, e, ms + 2 * d, md));
+    if (merged) {
+      LC_TRY(c.lin_gated_both(D->att_p.p, d, d, D->mlp_p.p, w.mlp.out, Mp, Np, Mc, Nc, w.proj_out, h, ms + 2 * d, md));
+    } else {
+      LC_TRY(c.lin_gated(D->att_p.p, d, d, D->mlp_p.p, w.mlp.out, Mp, Np, w.proj_out, h, ms + 2 * d, md));
+      LC_TRY(c.lin_gated(att_c, d, d, mlp_c, w.mlp.out, Mc, Nc, w.proj_out, e, ms + 2 * d, md));
+    }
   }
 
   // ---- norm_out (AdaLayerNormContinuous: chunk order scale, shift) + proj_out + unpatchify (:1044-1062)
@@ -476,6 +523,8 @@ int lc_denoiser_create(const lc_denoiser_cfg* cfg, lc_denoiser** out) {
   D->d = cfg->num_heads * cfg->head_dim;
   const char* fq = getenv("LADCAST_B200_FUSE_QK");
   D->fuse_qk = fq != nullptr && fq[0] == '1';
+  const char* mg = getenv("LADCAST_B200_MERGE_STREAMS");
+  D->merge_streams = !(mg != nullptr && mg[0] == '0');
   *out = D;
   return 0;
 }
@@ -484,8 +533,8 @@ void lc_denoiser_destroy(lc_denoiser* D) {
   if (!D) return;
   for (void* p : D->owned) cudaFree(p);
   for (auto& kv : D->staged) cudaFree(kv.second.p);
-  DevBuf* bufs[] = {&D->cos_p, &D->sin_p, &D->cos_c, &D->sin_c, &D->cs_p, &D->cs_c, &D->tok_x, &D->tok_c, &D->h, &D->e, &D->e0, &D->e0T,
-                    &D->e_proj, &D->n_p, &D->n_c, &D->qkv, &D->att_p, &D->att_c, &D->mlp_p, &D->mlp_c, &D->sincos,
+  DevBuf* bufs[] = {&D->cos_p, &D->sin_p, &D->cos_c, &D->sin_c, &D->cs_p, &D->cs_c, &D->tok_x, &D->tok_c, &D->h, &D->e0, &D->e0T,
+                    &D->e_proj, &D->n_p, &D->qkv, &D->att_p, &D->mlp_p, &D->sincos,
                     &D->tmpA, &D->tmpB, &D->r_te, &D->r_pe, &D->r_tembS, &D->gates, &D->t_te, &D->pooled, &D->pe,
                     &D->temb, &D->tembS, &D->modv, &D->te_out, &D->yearT};
   for (DevBuf* b : bufs) b->release();
@@ -534,12 +583,12 @@ int lc_denoiser_set_geometry(lc_denoiser* D, int max_batch, int t_in, int t_out,
   LC_TRY(pack_rope_pairs(D->cos_p.as<float>(), D->sin_p.as<float>(), D->cs_p.as<uint32_t>(), static_cast<int>(Np), st));
   LC_TRY(pack_rope_pairs(D->cos_c.as<float>(), D->sin_c.as<float>(), D->cs_c.as<uint32_t>(), static_cast<int>(Nc), st));
   LC_TRY(D->tok_x.alloc(B * Np * D->kp_in * e)); LC_TRY(D->tok_c.alloc(B * Nc * D->kp_in * e));
-  LC_TRY(D->h.alloc(B * Np * d * 4)); LC_TRY(D->e.alloc(B * Nc * d * 4));
+  LC_TRY(D->h.alloc(B * S * d * 4));
   LC_TRY(D->e0.alloc(B * Nc * d * 4)); LC_TRY(D->e0T.alloc(B * Nc * d * e)); LC_TRY(D->e_proj.alloc(B * Nc * d * 4));
-  LC_TRY(D->n_p.alloc(B * Np * d * e)); LC_TRY(D->n_c.alloc(B * Nc * d * e));
+  LC_TRY(D->n_p.alloc(B * S * d * e));
   LC_TRY(D->qkv.alloc(B * S * 3 * d * e));
-  LC_TRY(D->att_p.alloc(B * Np * d * e)); LC_TRY(D->att_c.alloc(B * Nc * d * e));
-  LC_TRY(D->mlp_p.alloc(B * Np * mlp * e)); LC_TRY(D->mlp_c.alloc(B * Nc * mlp * e));
+  LC_TRY(D->att_p.alloc(B * S * d * e));
+  LC_TRY(D->mlp_p.alloc(B * S * mlp * e));
   LC_TRY(D->sincos.alloc(B * 256 * e)); LC_TRY(D->tmpA.alloc(B * d * e)); LC_TRY(D->tmpB.alloc(B * 2 * d * e));
   LC_TRY(D->r_te.alloc(B * d * 4)); LC_TRY(D->r_pe.alloc(B * d * 4)); LC_TRY(D->r_tembS.alloc(B * d * e));
   LC_TRY(D->gates.alloc(B * 2 * d * (D->cfg.num_refiner_layers > 0 ? D->cfg.num_refiner_layers : 1) * 4));
@@ -574,7 +623,7 @@ int lc_denoiser_debug_read(lc_denoiser* D, const char* name, float* out, int64_t
   const float* src = nullptr;
   int64_t cnt = 0;
   if (n == "h") { src = D->h.as<float>(); cnt = static_cast<int64_t>(D->curB) * D->Np * D->d; }
-  else if (n == "e") { src = D->e.as<float>(); cnt = static_cast<int64_t>(D->curB) * D->Nc * D->d; }
+  else if (n == "e") { src = D->e_ptr(); cnt = static_cast<int64_t>(D->curB) * D->Nc * D->d; }
   else if (n == "temb") { src = D->temb.as<float>(); cnt = static_cast<int64_t>(D->curB) * D->d; }
   else if (n == "mod") { src = D->modv.as<float>(); cnt = static_cast<int64_t>(D->curB) * D->mod_dim; }
   LC_REQUIRE(src != nullptr, "unknown debug buffer '" + n + "'");
