@@ -384,14 +384,18 @@ int forward_impl(lc_denoiser* D, const float* x_in, const float* c_noise, int n_
   for (int i = 0; i < D->cfg.num_single_layers; ++i) {
     const SingleW& w = D->single[i];
     const float* ms = ms_base + 3LL * d * i;  // shift, scale, gate
-    LC_TRY(layernorm_modulate<T>(h, n_p, Mp, d, 1e-6f, Np, ms + d, ms, md, nullptr, nullptr, st));
-    LC_TRY(layernorm_modulate<T>(e, n_c, Mc, d, 1e-6f, Nc, ms + d, ms, md, nullptr, nullptr, st));
+    const bool merged = D->merge_streams;
+    if (merged) {  // same modulation for both streams: one pass over the Mp + Mc rows of h | e
+      LC_TRY(layernorm_modulate<T>(h, n_p, Mp + Mc, d, 1e-6f, Np, ms + d, ms, md, nullptr, nullptr, st, Mp, Nc));
+    } else {
+      LC_TRY(layernorm_modulate<T>(h, n_p, Mp, d, 1e-6f, Np, ms + d, ms, md, nullptr, nullptr, st));
+      LC_TRY(layernorm_modulate<T>(e, n_c, Mc, d, 1e-6f, Nc, ms + d, ms, md, nullptr, nullptr, st));
+    }
     RopeSeg segs[2];
     segs[0].start = 0; segs[0].len = Np; segs[0].wq = w.nq; segs[0].wk = w.nk;
     segs[0].cos = D->cos_p.as<float>(); segs[0].sin = D->sin_p.as<float>();
     segs[1].start = Np; segs[1].len = Nc; segs[1].wq = w.nq; segs[1].wk = w.nk;
     segs[1].cos = D->cos_c.as<float>(); segs[1].sin = D->sin_c.as<float>();
-    const bool merged = D->merge_streams;
     if (c.fused_qk() || !merged) {  // (fused: per-stream rotation tables live in the epilogue)
       LC_TRY(c.lin_qkv(n_p, Mp, Np, w.qkv, qkv, S, 0, &segs[0]));
       LC_TRY(c.lin_qkv(n_c, Mc, Nc, w.qkv, qkv, S, Np, &segs[1]));

@@ -47,7 +47,8 @@ __device__ __forceinline__ float4 load4<bf16>(const bf16* p) {
 // Reference: AdaLayerNormZero/ZeroSingle/Continuous (diffusers), LaDCast_3D_model.py:287-302, 524-552, 1044.
 template <typename T, int NV>
 __device__ __forceinline__ void ln_row(const float4 (&vin)[NV], int row, int lane, T* __restrict__ out, int d, float eps,
-                                       int rows_per_sample, const float* __restrict__ scale, const float* __restrict__ shift,
+                                       int rows_per_sample, int seg_rows, int seg_rows_per_sample,
+                                       const float* __restrict__ scale, const float* __restrict__ shift,
                                        long long mod_stride, const float* __restrict__ w, const float* __restrict__ b) {
   float4 v[NV];
   float s = 0.f;
@@ -64,7 +65,8 @@ __device__ __forceinline__ void ln_row(const float4 (&vin)[NV], int row, int lan
     q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
   }
   const float rstd = rsqrtf(warp_sum(q) / d + eps);
-  const int sample = row / rows_per_sample;
+  // rows >= seg_rows (> 0) are a second stream with seg_rows_per_sample rows per sample (pred | cond in one launch)
+  const int sample = (seg_rows > 0 && row >= seg_rows) ? (row - seg_rows) / seg_rows_per_sample : row / rows_per_sample;
   T* orow = out + static_cast<long long>(row) * d;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -88,7 +90,8 @@ constexpr int LN_RPW = 4;  // rows per warp (8 measured slower: too few blocks f
 
 template <typename T, int NV>
 __global__ void __launch_bounds__(256, 2) layernorm_kernel(const float* __restrict__ x, T* __restrict__ out, int M, int d,
-                                                           float eps, int rows_per_sample, const float* __restrict__ scale,
+                                                           float eps, int rows_per_sample, int seg_rows,
+                                                           int seg_rows_per_sample, const float* __restrict__ scale,
                                                            const float* __restrict__ shift, long long mod_stride,
                                                            const float* __restrict__ w, const float* __restrict__ b) {
   const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * LN_RPW;
@@ -107,7 +110,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_kernel(const float* __restri
         for (int i = 0; i < NV; ++i)
           buf[(r + 1) & 1][i] = *reinterpret_cast<const float4*>(xr + static_cast<long long>(r + 1) * d + i * 128);
       }
-      ln_row<T, NV>(buf[r & 1], row0 + r, lane, out, d, eps, rows_per_sample, scale, shift, mod_stride, w, b);
+      ln_row<T, NV>(buf[r & 1], row0 + r, lane, out, d, eps, rows_per_sample, seg_rows, seg_rows_per_sample, scale, shift,
+                    mod_stride, w, b);
     }
   }
 }
@@ -375,13 +379,15 @@ __global__ void __launch_bounds__(256) heun_kernel(const float* __restrict__ f, 
 
 template <typename T>
 int layernorm_modulate(const float* x, T* out, int M, int d, float eps, int rows_per_sample, const float* scale,
-                       const float* shift, long long mod_stride, const float* w, const float* b, cudaStream_t s) {
+                       const float* shift, long long mod_stride, const float* w, const float* b, cudaStream_t s,
+                       int seg_rows, int seg_rows_per_sample) {
   LC_REQUIRE(d % 128 == 0 && d <= 2048, "layernorm: d must be a multiple of 128, <= 2048");
   const int nv = d / 128;
   dim3 grid(ceil_div(M, 8 * LN_RPW));
 #define LC_LN_CASE(NV)                                                                                            \
   case NV:                                                                                                        \
-    layernorm_kernel<T, NV><<<grid, 256, 0, s>>>(x, out, M, d, eps, rows_per_sample, scale, shift, mod_stride, w, b); \
+    layernorm_kernel<T, NV><<<grid, 256, 0, s>>>(x, out, M, d, eps, rows_per_sample, seg_rows, seg_rows_per_sample,   \
+                                                 scale, shift, mod_stride, w, b);                                     \
     break;
   switch (nv) {
     LC_LN_CASE(1) LC_LN_CASE(2) LC_LN_CASE(3) LC_LN_CASE(4) LC_LN_CASE(5) LC_LN_CASE(6) LC_LN_CASE(7) LC_LN_CASE(8)
@@ -494,7 +500,7 @@ int sched_heun_step(const float* f, double* x, double* x_hat, double* d_cur, flo
 
 #define LC_INST(T)                                                                                                    \
   template int layernorm_modulate<T>(const float*, T*, int, int, float, int, const float*, const float*, long long,   \
-                                     const float*, const float*, cudaStream_t);                                       \
+                                     const float*, const float*, cudaStream_t, int, int);                             \
   template int qk_norm_rope<T>(T*, long long, int, int, int, int, float, const RopeSeg*, int, cudaStream_t);          \
   template int patchify<T>(const float*, T*, int, int, int, int, cudaStream_t);                                       \
   template int timestep_embed<T>(const float*, int, int, T*, cudaStream_t);                                           \

@@ -15,7 +15,8 @@ struct RopeSeg {
 
 template <typename T>
 int layernorm_modulate(const float* x, T* out, int M, int d, float eps, int rows_per_sample, const float* scale,
-                       const float* shift, long long mod_stride, const float* w, const float* b, cudaStream_t s);
+                       const float* shift, long long mod_stride, const float* w, const float* b, cudaStream_t s, int seg_rows = 0,
+                       int seg_rows_per_sample = 1);
 int pack_rope_pairs(const float* cos, const float* sin, uint32_t* out, int n_tokens, cudaStream_t s);
 template <typename T>
 int qk_norm_rope(T* qkv, long long ld, int B, int S, int heads, int head_dim, float eps, const RopeSeg* segs, int nseg,
