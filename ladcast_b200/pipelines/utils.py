@@ -17,15 +17,34 @@ class Fields2DPipelineOutput:
         return (self.fields,)[i]
 
 
+_NOISE_STAGING = {}  # (shape, dtype) -> [pinned host buffer, event of the last H2D copy out of it]
+
+
 def randn_tensor(shape, generator=None, device=None, dtype=None):
-    """Per-sample CPU generators -> one draw of (1, *shape[1:]) each, concatenated, then moved to `device`."""
+    """Per-sample CPU generators -> one draw of (1, *shape[1:]) each (diffusers randn_tensor semantics), then moved to
+    `device`.  For a CUDA target the draws are written into a reused pinned staging buffer and copied with an
+    asynchronous H2D, so the host is not blocked behind the previous AR step's kernels (a pageable multi-MB copy is)."""
     device = torch.device(device) if device is not None else torch.device("cpu")
     if isinstance(generator, list) and len(generator) == 1:
         generator = generator[0]
     if isinstance(generator, list):
         one = (1,) + tuple(shape[1:])
-        parts = [torch.randn(one, generator=g, device=g.device, dtype=dtype) for g in generator]
-        return torch.cat(parts, dim=0).to(device)
+        if device.type != "cuda":
+            parts = [torch.randn(one, generator=g, device=g.device, dtype=dtype) for g in generator]
+            return torch.cat(parts, dim=0).to(device)
+        key = ((len(generator),) + tuple(shape[1:]), dtype)
+        slot = _NOISE_STAGING.get(key)
+        if slot is None:
+            slot = [torch.empty(key[0], dtype=dtype, pin_memory=True), None]
+            _NOISE_STAGING[key] = slot
+        if slot[1] is not None:
+            slot[1].synchronize()  # the previous copy out of this buffer (issued one AR step ago) has long finished
+        for i, g in enumerate(generator):
+            torch.randn(one, generator=g, dtype=dtype, out=slot[0][i : i + 1])
+        dst = slot[0].to(device, non_blocking=True)
+        slot[1] = torch.cuda.Event()
+        slot[1].record(torch.cuda.current_stream(device))
+        return dst
     gdev = generator.device if generator is not None else device
     return torch.randn(tuple(shape), generator=generator, device=gdev, dtype=dtype).to(device)
 
