@@ -122,6 +122,31 @@ def golden_dcae_encode():
     print("dcae encode", lat.shape, float(lat.abs().mean()))
 
 
+def golden_transforms():
+    """Reference dataloader/utils.py transforms + precompute_mean_std on the shipped normalisation file."""
+    import json
+
+    from ladcast.dataloader.utils import get_inv_transform_3D, get_transform_3D, precompute_mean_std
+
+    var_list = ["geopotential", "specific_humidity", "temperature", "u_component_of_wind", "v_component_of_wind",
+                "vertical_velocity", "10m_u_component_of_wind", "10m_v_component_of_wind", "2m_temperature",
+                "mean_sea_level_pressure", "sea_surface_temperature", "total_precipitation_6hr"]
+    with open("/root/reference/ladcast/static/ERA5_normal_1979_2017.json") as f:
+        nd = json.load(f)
+    mean, std = precompute_mean_std(nd, var_list)
+    # a small synthetic dict with the same structure (what the CPU test rebuilds without the reference tree)
+    syn = {"a": {"mean": {"50": 1.0, "100": 2.0, "1000": -3.5}, "std": {"50": 0.5, "100": 4.0, "1000": 2.0}},
+           "b": {"mean": 7.25, "std": 0.125}}
+    sm, ss = precompute_mean_std(syn, ["b", "a"])
+    x = seeded((4, 3, 5, 6), 120)
+    args = {"mean": sm.tolist(), "std": ss.tolist(), "target_std": 0.5}
+    y = get_transform_3D("normalize", args)(x)
+    z = get_inv_transform_3D("normalize", args)(y)
+    np.savez(os.path.join(OUT, "transforms.npz"), era5_mean=mean.numpy(), era5_std=std.numpy(), syn_mean=sm.numpy(),
+             syn_std=ss.numpy(), y=y.numpy(), z=z.numpy())
+    print("transforms", mean.shape, float(mean[0]), float(std[82]))
+
+
 def golden_sphere():
     conv = SphereConv2d(6, 8, 3, 1, 1)
     conv.weight.data = O.det_tensor("sphere3.weight", (8, 6, 3, 3), 31)
@@ -179,6 +204,7 @@ if __name__ == "__main__":
     golden_metrics()
     golden_dcae()
     golden_dcae_encode()
+    golden_transforms()
     golden_samplers()
     golden_denoiser()
     print("golden vectors written to", OUT)

@@ -234,3 +234,34 @@ def test_encode_initial_condition_argument_checks():
 
     with pytest.raises(ValueError):
         encode_initial_condition(None, torch.zeros(84, 120, 240), None, torch.zeros(84), torch.ones(84))
+
+
+def test_dataloader_transforms_vs_reference_golden(golden_dir):
+    """normalize / inverse transforms and precompute_mean_std (reference dataloader/utils.py:223-306), pinned to the
+    outputs of the reference functions (oracle/make_golden.py::golden_transforms)."""
+    from ladcast_b200.dataloader.utils import (VAR_LIST, get_inv_transform_3D, get_transform_3D, precompute_mean_std,
+                                               prepare_static_conditioning)
+
+    g = np.load(os.path.join(golden_dir, "transforms.npz"))
+    syn = {"a": {"mean": {"50": 1.0, "100": 2.0, "1000": -3.5}, "std": {"50": 0.5, "100": 4.0, "1000": 2.0}},
+           "b": {"mean": 7.25, "std": 0.125}}
+    sm, ss = precompute_mean_std(syn, ["b", "a"])
+    assert np.array_equal(sm.numpy(), g["syn_mean"]) and np.array_equal(ss.numpy(), g["syn_std"])
+    with pytest.raises(ValueError):
+        precompute_mean_std(syn, ["c"])
+    x = torch.randn((4, 3, 5, 6), generator=torch.Generator("cpu").manual_seed(120))
+    args = {"mean": sm.tolist(), "std": ss.tolist(), "target_std": 0.5}
+    y = get_transform_3D("normalize", args)(x)
+    z = get_inv_transform_3D("normalize", args)(y)
+    assert np.array_equal(y.numpy(), g["y"]) and np.array_equal(z.numpy(), g["z"])
+    assert get_transform_3D(None, None)(x) is x
+    with pytest.raises(NotImplementedError):
+        get_transform_3D("minmax", {})
+    assert len(VAR_LIST) == 12 and g["era5_mean"].shape == (84,)  # 6 x 13 levels + 6 surface variables
+    lsm = torch.rand(121, 240, generator=torch.Generator("cpu").manual_seed(1))
+    oro = torch.rand(4, 121, 240, generator=torch.Generator("cpu").manual_seed(2))
+    st = prepare_static_conditioning(lsm, oro)
+    assert st.shape == (5, 120, 240)
+    assert torch.allclose(st.mean(dim=(1, 2)), torch.zeros(5), atol=1e-5)
+    assert torch.allclose(st.std(dim=(1, 2)), torch.ones(5), atol=1e-5)
+    assert prepare_static_conditioning(None, None) is None
