@@ -330,6 +330,7 @@ int forward_impl(lc_denoiser* D, const float* x_in, const float* c_noise, int n_
     LC_TRY(layernorm_modulate<T>(e, n_c, Mc, d, 1e-7f, Nc, nullptr, nullptr, 0, w.n1w, w.n1b, st));
     RopeSeg seg;
     seg.start = 0; seg.len = Nc; seg.wq = w.nq; seg.wk = w.nk; seg.cos = D->cos_c.as<float>(); seg.sin = D->sin_c.as<float>();
+    seg.cs = D->cs_c.as<uint32_t>();
     LC_TRY(c.lin_qkv(n_c, Mc, Nc, w.qkv, qkv, Nc, 0, &seg));
     if (!c.fused_qk()) LC_TRY(qk_norm_rope<T>(qkv, 3LL * d, B, Nc, heads, 128, 1e-7f, &seg, 1, st));
     LC_TRY(attention<T>(D, B, Nc, 0, st));  // all tokens -> att_c
@@ -363,7 +364,7 @@ int forward_impl(lc_denoiser* D, const float* x_in, const float* c_noise, int n_
     LC_TRY(layernorm_modulate<T>(e, n_c, Mc, d, 1e-6f, Nc, mc + d, mc, md, nullptr, nullptr, st));
     RopeSeg segs[2];
     segs[0].start = 0; segs[0].len = Np; segs[0].wq = w.nq; segs[0].wk = w.nk;
-    segs[0].cos = D->cos_p.as<float>(); segs[0].sin = D->sin_p.as<float>();
+    segs[0].cos = D->cos_p.as<float>(); segs[0].sin = D->sin_p.as<float>(); segs[0].cs = D->cs_p.as<uint32_t>();
     segs[1].start = Np; segs[1].len = Nc; segs[1].wq = w.naq; segs[1].wk = w.nak;  // no RoPE on cond (quirk C-3)
     LC_TRY(c.lin_qkv(n_p, Mp, Np, w.qkv, qkv, S, 0, &segs[0]));
     LC_TRY(c.lin_qkv(n_c, Mc, Nc, w.add_qkv, qkv, S, Np, &segs[1]));
@@ -393,9 +394,9 @@ int forward_impl(lc_denoiser* D, const float* x_in, const float* c_noise, int n_
     }
     RopeSeg segs[2];
     segs[0].start = 0; segs[0].len = Np; segs[0].wq = w.nq; segs[0].wk = w.nk;
-    segs[0].cos = D->cos_p.as<float>(); segs[0].sin = D->sin_p.as<float>();
+    segs[0].cos = D->cos_p.as<float>(); segs[0].sin = D->sin_p.as<float>(); segs[0].cs = D->cs_p.as<uint32_t>();
     segs[1].start = Np; segs[1].len = Nc; segs[1].wq = w.nq; segs[1].wk = w.nk;
-    segs[1].cos = D->cos_c.as<float>(); segs[1].sin = D->sin_c.as<float>();
+    segs[1].cos = D->cos_c.as<float>(); segs[1].sin = D->sin_c.as<float>(); segs[1].cs = D->cs_c.as<uint32_t>();
     if (c.fused_qk() || !merged) {  // (fused: per-stream rotation tables live in the epilogue)
       LC_TRY(c.lin_qkv(n_p, Mp, Np, w.qkv, qkv, S, 0, &segs[0]));
       LC_TRY(c.lin_qkv(n_c, Mc, Nc, w.qkv, qkv, S, Np, &segs[1]));

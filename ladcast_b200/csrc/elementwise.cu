@@ -184,7 +184,17 @@ __global__ void __launch_bounds__(256) qk_norm_rope_bf16_kernel(bf16* __restrict
   const uint4 raw_k = *reinterpret_cast<const uint4*>(pk);
   float cs[8], sn[8];
   const bool rope = sg.cos != nullptr;
-  if (rope) {
+  if (rope && sg.cs != nullptr) {
+    // packed table: 4 rotation pairs = one 16-byte load instead of 64 bytes of fp32 cos + sin
+    const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(sg.cs + (tok - sg.start) * 64 + sub * 4));
+    const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&cw[i]));
+      cs[2 * i] = cs[2 * i + 1] = f.x;
+      sn[2 * i] = sn[2 * i + 1] = f.y;
+    }
+  } else if (rope) {
     const int t = (tok - sg.start) * 128 + sub * 8;
     const float4 c0 = __ldg(reinterpret_cast<const float4*>(sg.cos + t)), c1 = __ldg(reinterpret_cast<const float4*>(sg.cos + t + 4));
     const float4 n0 = __ldg(reinterpret_cast<const float4*>(sg.sin + t)), n1 = __ldg(reinterpret_cast<const float4*>(sg.sin + t + 4));

@@ -11,6 +11,7 @@ struct RopeSeg {
   const float* wk = nullptr;
   const float* cos = nullptr;     // [len, head_dim] or null (no rotation: dual-stream cond tokens)
   const float* sin = nullptr;
+  const uint32_t* cs = nullptr;   // optional packed [len, 64] half2 (cos, sin) per rotation pair (bf16 kernel)
 };
 
 template <typename T>
