@@ -122,14 +122,12 @@ struct EpiParams {
   const float* ch_scale = nullptr;
   const float* ch_shift = nullptr;
   // fused per-head RMSNorm(q, k) + RoPE for qkv projections on the tensor-core path (head_dim 128): columns
-  // [0, qk_cols) are q|k heads, normalised with qk_wq / qk_wk ([128] each) and rotated with the [tokens, 128]
-  // cos/sin tables (token = row % rows_per_sample; tables may be null = no rotation).  0 = disabled.
+  // [0, qk_cols) are q|k heads, normalised with qk_wq / qk_wk ([128] each) and rotated with the packed rope_cs
+  // table (token = row % rows_per_sample; null = no rotation).  0 = disabled.
   int qk_cols = 0;
   float qk_eps = 0.f;
   const float* qk_wq = nullptr;
   const float* qk_wk = nullptr;
-  const float* rope_cos = nullptr;
-  const float* rope_sin = nullptr;
   const uint32_t* rope_cs = nullptr;  // [tokens, 64] half2 (cos, sin) per rotation pair; null = no rotation
 };
 

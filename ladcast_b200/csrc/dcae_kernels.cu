@@ -138,51 +138,6 @@ __device__ __forceinline__ void col_offsets(int (&co)[NJ], int x0, int p, int W,
 }
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
-// 5x5, fp32 in/out (multiscale projection, DCAE.py:76-85)
-template <int XT>
-__global__ void __launch_bounds__(256) dwconv5_kernel(const float* __restrict__ in, const float* __restrict__ w,
-                                                      float* __restrict__ out, int n, int H, int W, int C) {
-  const int c = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
-  const int x0 = (blockIdx.y * 8 + (threadIdx.x >> 5)) * XT;
-  const int y = blockIdx.z % H, f = blockIdx.z / H;
-  if (c >= C || x0 >= W) return;
-  const float* base = in + static_cast<long long>(f) * H * W * C + c;
-  float4 acc[XT];
-#pragma unroll
-  for (int o = 0; o < XT; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
-  int con[XT + 4];
-  col_offsets<XT + 4>(con, x0, 2, W, C, false);
-#pragma unroll
-  for (int ky = 0; ky < 5; ++ky) {
-    int sy;
-    bool rolled;
-    sphere_row(y + ky, 2, H, sy, rolled);
-    const bool flip = (y == 0 && ky < 2) || (y == H - 1 && ky >= 3);
-    float4 wr[5];
-#pragma unroll
-    for (int kx = 0; kx < 5; ++kx)
-      wr[kx] = __ldg(reinterpret_cast<const float4*>(w + (ky * 5 + (flip ? 4 - kx : kx)) * C + c));
-    const float* rowp = base + static_cast<long long>(sy) * W * C;
-    int co[XT + 4];
-#pragma unroll
-    for (int j = 0; j < XT + 4; ++j) co[j] = con[j];
-    if (rolled) col_offsets<XT + 4>(co, x0, 2, W, C, true);
-#pragma unroll
-    for (int j = 0; j < XT + 4; ++j) {
-      const float4 v = *reinterpret_cast<const float4*>(rowp + co[j]);
-#pragma unroll
-      for (int kx = 0; kx < 5; ++kx) {
-        const int o = j - kx;
-        if (o >= 0 && o < XT) fma4(acc[o], wr[kx], v);
-      }
-    }
-  }
-  float* op = out + ((static_cast<long long>(f) * H + y) * W + x0) * C + c;
-#pragma unroll
-  for (int o = 0; o < XT; ++o)
-    if (x0 + o < W) *reinterpret_cast<float4*>(op + static_cast<long long>(o) * C) = acc[o];
-}
-
 // 3x3 + bias + GLU: channels [value | gate] halves -> value * silu(gate); T in/out
 // (GLUMBConv.conv_depth + chunk + nonlinearity, DCAE.py:312-315)
 template <typename T>
@@ -265,48 +220,10 @@ __global__ void __launch_bounds__(256, 3) dwconv3_glu_kernel(const T* __restrict
                                                              a0[o].z * silu_fast(a1[o].z), a0[o].w * silu_fast(a1[o].w)));
 }
 
-// ---------------------------------------------------------------- grouped 1x1 conv, 32 -> 32 per group (DCAE.py:86-88)
-// Block = (64-pixel strip, group).  The strip's 64x32 inputs are staged in shared memory; lane = output channel
-// with its 32 weights in registers; each warp walks over pixels reading the input row as broadcast float4s
-// (8 LDS.128 per 32 FFMA: FMA-bound, no shuffles).  All global accesses are 128 B row segments.
-__global__ void __launch_bounds__(256) grouped1x1_kernel(const float* __restrict__ in, const float* __restrict__ w,
-                                                         float* __restrict__ out, long long P, int C) {
-  constexpr int TP = 64;
-  __shared__ __align__(16) float xs[TP][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = blockIdx.x;  // groups vary fastest: concurrently resident blocks read whole NHWC rows together
-  const long long p0 = static_cast<long long>(blockIdx.y) * TP;
-  for (int i = threadIdx.x; i < TP * 8; i += 256) {
-    const int pp = i >> 3, q4 = (i & 7) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p0 + pp < P) v = *reinterpret_cast<const float4*>(in + (p0 + pp) * C + g * 32 + q4);
-    *reinterpret_cast<float4*>(&xs[pp][q4]) = v;
-  }
-  float wr[32];
-  const float* wp = w + (static_cast<long long>(g) * 32 + lane) * 32;
-#pragma unroll
-  for (int k = 0; k < 32; k += 4) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(wp + k));
-    wr[k] = t.x; wr[k + 1] = t.y; wr[k + 2] = t.z; wr[k + 3] = t.w;
-  }
-  __syncthreads();
-#pragma unroll 2
-  for (int pp = warp; pp < TP; pp += 8) {
-    if (p0 + pp >= P) break;
-    float a = 0.f;
-#pragma unroll
-    for (int k = 0; k < 32; k += 4) {
-      const float4 x4 = *reinterpret_cast<const float4*>(&xs[pp][k]);
-      a = fmaf(wr[k], x4.x, a); a = fmaf(wr[k + 1], x4.y, a); a = fmaf(wr[k + 2], x4.z, a); a = fmaf(wr[k + 3], x4.w, a);
-    }
-    out[(p0 + pp) * C + g * 32 + lane] = a;
-  }
-}
-
 // ---------------------------------------------------------------- fused multiscale projection (DCAE.py:76-88)
 // depthwise 5x5 sphere conv -> grouped 32->32 1x1 conv in one pass; the intermediate never leaves the SM.
 // Block = 128 channels (4 groups) x one image row, walked in 64-pixel segments:
-//   phase A: the sliding-window 5x5 above, results stored channel-major into ds[ch][px] (XOR-swizzled 16-B chunks so
+//   phase A: sliding-window 5x5 (lane = channel quad, 4 outputs per thread), results stored channel-major into ds[ch][px] (XOR-swizzled 16-B chunks so
 //            both the transposing stores and the phase-B reads are bank-conflict free);
 //   phase B: warp = (group, 32-pixel half); thread tile 8 px x 4 outputs, outer product over the 32 inputs of the
 //            group: 3 LDS.128 per 32 FFMA (the stand-alone kernel's broadcast reads cost 8 per 32).
@@ -741,28 +658,12 @@ int halo_fill(T* buf, int n, int H, int W, int Cp, cudaStream_t s) {
   LC_LAUNCH_CHECK();
   return 0;
 }
-int dwconv5(const float* in, const float* w, float* out, int n, int H, int W, int C, cudaStream_t s) {
-  LC_REQUIRE(C % 4 == 0, "dwconv5: channels must be a multiple of 4");
-  constexpr int XT = 4;
-  dim3 grid((C / 4 + 31) / 32, (W + 8 * XT - 1) / (8 * XT), n * H);
-  dwconv5_kernel<XT><<<grid, 256, 0, s>>>(in, w, out, n, H, W, C);
-  LC_LAUNCH_CHECK();
-  return 0;
-}
 template <typename T>
 int dwconv3_glu(const T* in, const float* w, const float* bias, T* out, int n, int H, int W, int C, cudaStream_t s) {
   LC_REQUIRE(C % 8 == 0, "dwconv3_glu: channels must be a multiple of 8");
   constexpr int XT = 4;
   dim3 grid((C / 8 + 31) / 32, (W + 8 * XT - 1) / (8 * XT), n * H);
   dwconv3_glu_kernel<T, XT><<<grid, 256, 0, s>>>(in, w, bias, out, n, H, W, C);
-  LC_LAUNCH_CHECK();
-  return 0;
-}
-int grouped1x1(const float* in, const float* w, float* out, long long P, int C, cudaStream_t s) {
-  LC_REQUIRE(C % 32 == 0, "grouped 1x1: channels must be a multiple of 32");
-  LC_REQUIRE((P + 63) / 64 <= 65535, "grouped 1x1: too many pixels per call");
-  dim3 grid(C / 32, static_cast<unsigned>((P + 63) / 64));
-  grouped1x1_kernel<<<grid, 256, 0, s>>>(in, w, out, P, C);
   LC_LAUNCH_CHECK();
   return 0;
 }

@@ -9,10 +9,8 @@ template <typename T>
 int pad_from_nhwc(const float* x, T* out, int n, int C, int H, int W, int Cp, cudaStream_t s);
 template <typename T>
 int halo_fill(T* buf, int n, int H, int W, int Cp, cudaStream_t s);
-int dwconv5(const float* in, const float* w, float* out, int n, int H, int W, int C, cudaStream_t s);
 template <typename T>
 int dwconv3_glu(const T* in, const float* w, const float* bias, T* out, int n, int H, int W, int C, cudaStream_t s);
-int grouped1x1(const float* in, const float* w, float* out, long long P, int C, cudaStream_t s);
 int multiscale_fused(const float* in, const float* w5, const float* wg, float* out, int n, int H, int W, int C,
                      cudaStream_t s);
 template <typename T>

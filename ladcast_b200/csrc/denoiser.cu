@@ -211,7 +211,6 @@ struct Ctx {
     g.epi.rows_per_sample = rows_per_sample; g.epi.out_rows_per_sample = S; g.epi.out_row_offset = tok_off;
     if (!D->f32 && seg != nullptr && D->fuse_qk) {
       g.epi.qk_cols = 2 * D->d; g.epi.qk_eps = 1e-7f; g.epi.qk_wq = seg->wq; g.epi.qk_wk = seg->wk;
-      g.epi.rope_cos = seg->cos; g.epi.rope_sin = seg->sin;
       g.epi.rope_cs = seg->cos == nullptr ? nullptr
                       : (seg->cos == D->cos_p.as<float>() ? D->cs_p.as<uint32_t>() : D->cs_c.as<uint32_t>());
     }
