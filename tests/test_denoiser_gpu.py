@@ -201,3 +201,21 @@ def test_fused_qk_epilogue_variant(golden_dir, monkeypatch):
         torch.cuda.synchronize()
         assert _rel(outs[flag], g["out"]) < TOL["bf16"]
     assert _rel(outs["1"], outs["0"]) < 5e-3
+
+
+def test_merged_stream_launches_are_bit_identical(golden_dir, monkeypatch):
+    """Single-stream blocks run pred and cond tokens in one launch per projection (default) or in two
+    (LADCAST_B200_MERGE_STREAMS=0): every output element sees the same K-ordered accumulation, so the results agree
+    bit for bit."""
+    g = np.load(os.path.join(golden_dir, "denoiser_tiny.npz"))
+    B, T_out = int(g["B"]), int(g["T_out"])
+    x = _seeded((B, 84, T_out, 15, 30), 100).cuda()
+    cond = _seeded((B, 84, 1, 15, 30), 101, 0.5).cuda()
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("LADCAST_B200_MERGE_STREAMS", flag)
+        cfg, sd, m = _model("tiny", int(g["salt"]), "bf16")
+        outs[flag] = m(x, torch.from_numpy(g["t"]).cuda(), cond, time_elapsed=torch.from_numpy(g["ts"]),
+                       return_dict=False)[0].clone()
+        torch.cuda.synchronize()
+    assert torch.equal(outs["1"], outs["0"])

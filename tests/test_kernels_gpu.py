@@ -42,7 +42,7 @@ def test_gemm(lib, m, n, k, prec):
     assert _rel(c, ref) < tol
 
 
-@pytest.mark.parametrize("b,s,heads", [(1, 128, 1), (2, 450, 2), (1, 2250, 3), (3, 200, 1)])
+@pytest.mark.parametrize("b,s,heads", [(1, 128, 1), (2, 450, 2), (1, 2250, 3), (3, 200, 1), (1, 90, 2), (2, 129, 1), (1, 257, 1)])
 @pytest.mark.parametrize("prec", [_lib.PRECISION_F32, _lib.PRECISION_BF16], ids=["f32", "bf16"])
 def test_attention(lib, b, s, heads, prec):
     g = torch.Generator("cpu").manual_seed(b * 100 + s + heads)
