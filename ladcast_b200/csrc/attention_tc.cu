@@ -6,17 +6,18 @@
 // ~75-80 cycles whether N is 64 or 128, so S tiles are 128 keys wide, and reading the A operand from tensor memory
 // is the fastest form, so P never goes through shared memory:
 //
-//   CTA = one (sample, head, 256-query block) = two 128-query tiles A and B that share every K/V tile; 320 threads:
+//   CTA = one (sample, head, 256-query block) = two 128-query tiles A and B that share every K/V tile; 576 threads:
 //     warp 0    : TMA producer — Q (both tiles) once, then K_0 V_0 K_1 V_1 ... (128 keys x 128 dims = 32 KB each)
 //                 through a 5-slot ring, ~2.5 KV steps ahead of the tensor pipe
 //     warp 1    : TMEM allocator + single-thread tcgen05.mma issuer.  Per tile and KV step: O_t += P_t V_j with P_t
 //                 read from TMEM, then S_t = Q_t K_{j+1}^T into the same TMEM columns (S and the bf16 P alias; the
 //                 tensor pipe executes in issue order, so the overwrite is safe).  The two tiles ping-pong: while
 //                 one tile's softmax runs, the tensor pipe works for the other.
-//     warps 2-5 : softmax of tile A, warps 6-9: softmax of tile B.  One thread per query row reads its S row from
-//                 TMEM (no shuffles), online softmax in the log2 domain (one FFMA + one MUFU.EX2 per element), lazy
-//                 rescale of O (only when the row max grows by more than 2^8), P (bf16) stored back to TMEM over S.
-//                 Final O / l epilogue per tile.
+//     warps 2-9 : softmax of tile A, warps 10-17: softmax of tile B.  Two threads per query row (64 keys each, kept
+//                 in registers) read S from TMEM (no shuffles), complete the row max through a 2 KB shared-memory
+//                 exchange + a 64-thread named barrier, online softmax in the log2 domain (one FFMA + one MUFU.EX2
+//                 per element), lazy rescale of O (only when the row max grows by more than 2^8), P (bf16) stored
+//                 back to TMEM over S.  Final O / l epilogue per tile.  576 threads leave 96 registers per thread.
 //   TMEM columns: S_A/P_A 0..127, S_B/P_B 128..255, O_A 256..383, O_B 384..511.
 #include "kernels.h"
 #include "ptx.cuh"
@@ -31,8 +32,10 @@ constexpr int BKV = 128;
 constexpr int RING = 5;
 constexpr int TILE_BYTES = 128 * 128 * 2;   // 32 KB: two [128 rows][64 dims] swizzled boxes
 constexpr int SUB_BYTES = 128 * 64 * 2;     // 16 KB
-constexpr int SMEM_BYTES = 2 * TILE_BYTES + RING * TILE_BYTES + 1024 + 256;
-constexpr int NUM_THREADS = 320;
+constexpr int XCH_BYTES = 2 * 2 * 128 * 4;  // row-max exchange between the two threads of a row: [tile][half][row]
+// no alignment slack: the kernel has no static shared memory, so the dynamic window starts 1024-aligned (checked)
+constexpr int SMEM_BYTES = 2 * TILE_BYTES + RING * TILE_BYTES + 256 + XCH_BYTES;
+constexpr int NUM_THREADS = 576;  // TMA warp, MMA warp, 2 tiles x 8 softmax warps
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t COL_S = 0;    // S[tile] (fp32, 128 cols) / P[tile] (bf16 pairs, first 64 cols) at COL_S + tile*128
 constexpr uint32_t COL_O = 256;  // O[tile] at COL_O + tile*128
@@ -45,12 +48,12 @@ __device__ long long* g_trace = nullptr;
     if (trace != nullptr) trace[((role) * 64 + (j)) * 4 + (k)] = clock64(); \
   } while (0)
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __maxnreg__(96)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf16* __restrict__ out_p, int Np,
                     bf16* __restrict__ out_c) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = ptx::smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  if ((ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();  // swizzled TMA tiles need 1024-byte alignment
+  uint8_t* smem = smem_raw;
   uint8_t* sQ = smem;                        // [2][TILE_BYTES]
   uint8_t* sR = sQ + 2 * TILE_BYTES;         // [RING][TILE_BYTES]: K_0 V_0 K_1 V_1 ...
   uint64_t* bars = reinterpret_cast<uint64_t*>(sR + RING * TILE_BYTES);
@@ -58,9 +61,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
   uint64_t* r_full = bars + 1;               // RING
   uint64_t* r_empty = r_full + RING;         // RING
   uint64_t* s_full = r_empty + RING;         // [tile]: S_t(j) complete (and with it every earlier MMA)
-  uint64_t* p_full = s_full + 2;             // [tile] (4 arrivals: one per softmax warp)
+  uint64_t* p_full = s_full + 2;             // [tile] (8 arrivals: one per softmax warp)
   uint64_t* o_full = p_full + 2;             // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = heads * HD;
@@ -78,7 +82,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&s_full[i], 1);
-      ptx::mbar_init(&p_full[i], 4);
+      ptx::mbar_init(&p_full[i], 8);
     }
     ptx::mbar_init(o_full, 1);
     ptx::fence_barrier_init();
@@ -175,77 +179,85 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
     }
     ptx::umma_commit(o_full);
   } else if (warp >= 2) {
-    // ===================== softmax + epilogue (thread = query row of tile t) =====================
-    const int t = (warp - 2) >> 2;  // 0: tile A (warps 2-5), 1: tile B (warps 6-9)
-    const int quarter = warp & 3;   // TMEM lane quarter this warp may access (= warp id % 4)
-    if ((warp - 2) & 3) trace = nullptr;  // one traced warp per tile
+    // ===================== softmax + epilogue =====================
+    // Two threads per query row (warps with the same TMEM lane quarter): each owns 64 of the row's 128 keys, which
+    // shortens the per-step softmax latency (it sits in the serial softmax -> PV -> QK chain of a tile): a lone warp
+    // per sub-partition issues one MUFU.EX2 per ~14 cycles, two warps together one per ~11.5 (tools/ubench/exp_rate.cu).
+    const int idx = warp - 2;
+    const int t = idx >> 3;          // 0: tile A (warps 2-9), 1: tile B (warps 10-17)
+    const int hh = (idx >> 2) & 1;   // key half of the row this thread exponentiates
+    const int quarter = warp & 3;    // TMEM lane quarter this warp may access (= warp id % 4)
+    if (idx & 7) trace = nullptr;    // one traced warp per tile
     const int r = quarter * 32 + lane;
+    const uint32_t pair_bar = 1 + t * 4 + quarter;  // named barrier of the two warps sharing these 32 rows
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const float scale_log2 = 0.08838834764831845f * 1.4426950408889634f;
     const uint32_t s_addr = tmem_base + lane_addr + COL_S + static_cast<uint32_t>(t * 128);
-    const uint32_t o_addr = tmem_base + lane_addr + COL_O + static_cast<uint32_t>(t * 128);
+    const uint32_t o_addr = tmem_base + lane_addr + COL_O + static_cast<uint32_t>(t * 128 + hh * 64);
     float m_used = -INFINITY, l = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
-      // S_t(j) complete; the commit also covers PV_t(j-1), so O_t is quiescent until this thread hands over P_t(j)
+      // S_t(j) complete; the commit also covers PV_t(j-1), so O_t is quiescent until this tile hands over P_t(j)
       LC_TRACE(1 + t, j, 0);
       ptx::mbar_wait(&s_full[t], j & 1);
       ptx::tc_fence_after();
       LC_TRACE(1 + t, j, 1);
-      uint32_t sreg[BKV / 32][32];
-#pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) ptx::tmem_ld32(s_addr + c * 32, sreg[c]);
-      ptx::tmem_ld_wait();
-      LC_TRACE(1 + t, j, 2);
       const int n_valid = S - j * BKV;  // keys >= n_valid are padding (only ever true for the last tile)
+      // this thread's 64 keys of the row stay in registers; the row max is completed with the partner thread (the
+      // other warp on the same TMEM lanes) through shared memory.  The pair barrier doubles as "both halves of S
+      // have been read", after which P may overwrite the S columns.
+      uint32_t sreg[2][32];
+      ptx::tmem_ld32(s_addr + hh * 64, sreg[0]);
+      ptx::tmem_ld32(s_addr + hh * 64 + 32, sreg[1]);
+      ptx::tmem_ld_wait();
       if (n_valid < BKV) {
 #pragma unroll
-        for (int c = 0; c < BKV / 32; ++c)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= n_valid) sreg[c][i] = 0xff800000u;  // -inf
+            if (hh * 64 + c * 32 + i >= n_valid) sreg[c][i] = 0xff800000u;  // -inf
       }
       float mxs[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c)
+      for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int i = 0; i < 32; ++i) mxs[i & 3] = fmaxf(mxs[i & 3], __uint_as_float(sreg[c][i]));
-      const float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
+      float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
+      xch[(t * 2 + hh) * 128 + r] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      mx = fmaxf(mx, xch[(t * 2 + (1 - hh)) * 128 + r]);
+      LC_TRACE(1 + t, j, 2);
       const float m_new = fmaxf(m_used, mx * scale_log2);  // scale > 0: max commutes with the scaling
       const bool need = __any_sync(0xffffffffu, m_new > m_used + RESCALE_THRESHOLD);
       float alpha = 1.f;
       if (need) {
         alpha = (m_used == -INFINITY) ? 0.f : exp2f(m_used - m_new);
         m_used = m_new;
-        if (j > 0) {
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t o[32];
-            ptx::tmem_ld32(o_addr + c * 32, o);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            ptx::tmem_st32(o_addr + c * 32, o);
-          }
-        }
       }
       // p = 2^(s*scale - m): one FFMA + one MUFU per element; arguments are <= 8 by construction.
-      // P (bf16 pairs) goes back to TMEM over the S columns already consumed: A operand of the PV product.
+      // P (bf16 pairs) goes back to TMEM over S: columns [32*hh, 32*hh+32) hold keys [64*hh, 64*hh+64).
       const float neg_m = -m_used;
       float ps[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[32];
 #pragma unroll
-      for (int c2 = 0; c2 < BKV / 64; ++c2) {
-        uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 64; i += 2) {
-          const int c = c2 * 2 + (i >> 5), ii = i & 31;
-          const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(sreg[c][ii]), scale_log2, neg_m));
-          const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(sreg[c][ii + 1]), scale_log2, neg_m));
-          ps[(i >> 1) & 3] += p0 + p1;
-          __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&pb);
-        }
-        ptx::tmem_st32(s_addr + c2 * 32, pk);
+      for (int i = 0; i < 64; i += 2) {
+        const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(sreg[i >> 5][i & 31]), scale_log2, neg_m));
+        const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(sreg[i >> 5][(i & 31) + 1]), scale_log2, neg_m));
+        ps[(i >> 1) & 3] += p0 + p1;
+        __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&pb);
       }
+      if (need && j > 0) {  // rare: rescale this thread's 64 columns of O (quiescent: PV_t(j-1) has completed)
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t o[32];
+          ptx::tmem_ld32(o_addr + c * 32, o);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          ptx::tmem_st32(o_addr + c * 32, o);
+        }
+      }
+      ptx::tmem_st32(s_addr + hh * 32, pk);
       l = l * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
@@ -255,14 +267,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
     }
     ptx::mbar_wait(o_full, 0);
     ptx::tc_fence_after();
+    // row sum = the two halves' partial sums (same alpha sequence in both); Q's shared memory is dead by now
+    float* lx = reinterpret_cast<float*>(sQ);
+    lx[(t * 2 + hh) * 128 + r] = l;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    const float inv = 1.0f / (l + lx[(t * 2 + (1 - hh)) * 128 + r]);
     const int tok = q0 + t * BQ + r;
-    const float inv = 1.0f / l;
     bf16* dst = nullptr;
     if (tok < S)
-      dst = (tok < Np) ? out_p + (static_cast<long long>(b) * Np + tok) * d + h * HD
-                       : out_c + (static_cast<long long>(b) * (S - Np) + (tok - Np)) * d + h * HD;
+      dst = ((tok < Np) ? out_p + (static_cast<long long>(b) * Np + tok) * d
+                        : out_c + (static_cast<long long>(b) * (S - Np) + (tok - Np)) * d) + h * HD + hh * 64;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t o[32];
       ptx::tmem_ld32(o_addr + c * 32, o);
       ptx::tmem_ld_wait();
