@@ -41,6 +41,15 @@ LC_API long long lc_launch_count(void);
  * 3) and synchronises on the recorded events. */
 LC_API int lc_prof_enable(int on);
 LC_API int lc_prof_collect(double* ms, double* flops, long long* launches);
+/* the same for EVERY kernel class of the library (lc_prof_num_classes() entries per array; names from
+ * lc_prof_class_name): milliseconds, algorithmic FLOPs, algorithmic BYTES (HBM-bound kernels) and launch counts */
+LC_API int lc_prof_num_classes(void);
+LC_API const char* lc_prof_class_name(int cls);
+LC_API int lc_prof_collect_all(double* ms, double* flops, double* bytes, long long* launches);
+/* tuning aids (tools/gemm_trace.py, tools/attn_trace.py): device buffer of clock64 stamps written by CTA (pair) 0 of
+ * the tcgen05 GEMM / attention kernels; NULL switches the trace off.  Not part of the product path. */
+LC_API int lc_debug_gemm_trace(void* device_buf);
+LC_API int lc_debug_attention_trace(void* device_buf);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Denoiser — replaces LaDCastTransformer3DModel.__init__/forward (models/LaDCast_3D_model.py:624-650, 833-1071)
@@ -98,6 +107,16 @@ LC_API int lc_denoiser_debug_read(lc_denoiser* h, const char* name, float* out, 
  * x_in_next <- x*c_in_next (skipped when x_in_next is NULL).  n elements, n % 4 == 0. */
 LC_API int lc_sched_dpmpp2m_step(const float* f, float* x, float* x0_prev, float* x_in_next, int64_t n, float c_skip,
                           float c_out, float a_x, float a_x0, float a_d, float c_in_next, void* stream);
+/* x_in = x * c_in: scale_model_input of the FIRST step (pipeline_AR.py:90); later steps get it from the fused step */
+LC_API int lc_sched_scale_input(const float* x, float* x_in, int64_t n, float c_in, void* stream);
+/* Heun prologue (edm_sampler.py:44-58): x = float64(noise) * t_0 ; x_in = float32(x * c_in(t_0)) */
+LC_API int lc_sched_heun_init(const float* noise, double* x, float* x_in, int64_t n, double t0, double c_in, void* stream);
+/* AR feedback of roll_out_serial (pipelines/utils.py:560-585) on one sampler output samples[B, C, T_out, hw]
+ * (normalised latents): known_next[B, C, T_in, hw] = the last T_in frames (may be NULL); phys[B, C, T_out, hw] =
+ * (samples / target_std) * std[c] + mean[c] (inverse_normalize_transform_3D, dataloader/utils.py:233-240; may be
+ * NULL).  hw % 4 == 0. */
+LC_API int lc_latent_feedback(const float* samples, float* known_next, float* phys, const float* mean, const float* std,
+                              float target_std, int batch, int channels, int t_out, int t_in, int hw, void* stream);
 /* phase 0: Euler predictor from x (saved to x_hat) ; phase 1: trapezoid corrector.  State in fp64. */
 LC_API int lc_sched_heun_step(const float* f, double* x, double* x_hat, double* d_cur, float* x_in_next, int64_t n, int phase,
                        double t_cur, double t_next, double c_skip, double c_out, double c_in_next, void* stream);
@@ -138,6 +157,16 @@ LC_API int lc_dcae_reserve(lc_dcae* h, int max_frames, int height, int width, vo
  * dataloader/utils.py:233-240). */
 LC_API int lc_dcae_decode(lc_dcae* h, const float* z, int n, int height, int width, float* out, int keep_channels,
                           const float* mean, const float* std, void* stream);
+
+/* decode_latent_ens (pipelines/utils.py:52-80) without its permute / reshape copies: decodes frames
+ * [frame0, frame0 + n) of the (batch x t_take) block — frame f = b * t_take + t is latents[b, :, t] of the 5-D tensor
+ * latents [batch, latent_channels, t_total, h, w] read in place (t_take = extract_first <= t_total) — and writes it to
+ * out[b, :, t] of out [batch, keep_channels, t_take, 8h, 8w].  lat_mean/lat_std ([latent_channels]) optionally apply
+ * inverse_normalize_transform_3D to the latents first ((z / target_std) * std + mean, dataloader/utils.py:233-240, as
+ * roll_out_serial does at pipelines/utils.py:571-577); mean/std as in lc_dcae_decode.  n <= max_frames of reserve. */
+LC_API int lc_dcae_decode_ens(lc_dcae* h, const float* latents, int batch, int t_total, int t_take, int frame0, int n,
+                              int height, int width, float* out, int keep_channels, const float* mean, const float* std,
+                              const float* lat_mean, const float* lat_std, float target_std, void* stream);
 
 /* x: [n, in_channels, 8h, 8w] fp32 NCHW (fields already concatenated with the static channels, DCAE.py:985-986)
  * -> out: [n, latent_channels, h, w] fp32 — replaces AutoencoderDC.encode / Encoder.forward (models/DCAE.py:964-1000,

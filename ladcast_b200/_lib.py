@@ -43,6 +43,14 @@ _SIGNATURES = {
     "lc_launch_count": ([], ctypes.c_longlong),
     "lc_prof_enable": ([_i], _i),
     "lc_prof_collect": ([ctypes.POINTER(_d), ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_longlong)], _i),
+    "lc_prof_num_classes": ([], _i),
+    "lc_prof_class_name": ([_i], _cp),
+    "lc_prof_collect_all": ([ctypes.POINTER(_d), ctypes.POINTER(_d), ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_longlong)], _i),
+    "lc_debug_gemm_trace": ([_vp], _i),
+    "lc_debug_attention_trace": ([_vp], _i),
+    "lc_sched_scale_input": ([_vp, _vp, _i64, _f, _vp], _i),
+    "lc_sched_heun_init": ([_vp, _vp, _vp, _i64, _d, _d, _vp], _i),
+    "lc_latent_feedback": ([_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _vp], _i),
     "lc_denoiser_create": ([ctypes.POINTER(DenoiserCfg), ctypes.POINTER(_vp)], _i),
     "lc_denoiser_destroy": ([_vp], None),
     "lc_denoiser_load": ([_vp, _cp, _vp, ctypes.POINTER(_i64), _i, _vp], _i),
@@ -65,6 +73,7 @@ _OPTIONAL = {
     "lc_dcae_finalize": ([_vp, _vp], _i),
     "lc_dcae_reserve": ([_vp, _i, _i, _i, _vp], _i),
     "lc_dcae_decode": ([_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp], _i),
+    "lc_dcae_decode_ens": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _f, _vp], _i),
     "lc_dcae_encode": ([_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _f, _vp], _i),
     "lc_dcae_debug_read": ([_vp, _cp, _vp, _i64, _vp], _i),
     "lc_sphere_conv3x3": ([_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
@@ -95,6 +104,16 @@ def load():
             fn.restype = res
     _lib = lib
     return lib
+
+
+def prof_collect():
+    """{class name: {"launches", "ms", "flops", "bytes"}} of the launches recorded since lc_prof_enable(1)."""
+    lib = load()
+    n = lib.lc_prof_num_classes()
+    ms, fl, by, ln = (_d * n)(), (_d * n)(), (_d * n)(), (ctypes.c_longlong * n)()
+    check(lib.lc_prof_collect_all(ms, fl, by, ln), "lc_prof_collect_all")
+    return {lib.lc_prof_class_name(i).decode(): {"launches": int(ln[i]), "ms": float(ms[i]), "flops": float(fl[i]),
+                                                   "bytes": float(by[i])} for i in range(n) if ln[i]}
 
 
 def check(rc, what=""):

@@ -15,10 +15,15 @@ const char* last_error() { return g_err.c_str(); }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-struct ProfRec { cudaEvent_t a, b; int cls; double flops; };
+struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static cudaEvent_t g_pending[PROF_NUM];
+static const char* const g_prof_names[PROF_NUM] = {
+    "gemm_tc", "attention_tc", "sphere_conv_tc", "layernorm", "qk_norm_rope", "scheduler", "dec_rmsnorm",
+    "dec_multiscale", "dec_linear_attn", "dec_dwconv_glu", "dec_pixel_shuffle", "dec_pad", "metrics", "misc"};
+const char* prof_name(int cls) { return (cls >= 0 && cls < PROF_NUM) ? g_prof_names[cls] : "?"; }
+bool prof_on() { return g_prof_on; }
 void prof_begin(int cls, cudaStream_t s) {
   if (!g_prof_on) return;
   cudaEvent_t e;
@@ -26,7 +31,7 @@ void prof_begin(int cls, cudaStream_t s) {
   cudaEventRecord(e, s);
   g_pending[cls] = e;
 }
-void prof_end(int cls, double flops, cudaStream_t s) {
+void prof_end(int cls, double flops, cudaStream_t s, double bytes) {
   if (!g_prof_on) return;
   ProfRec r;
   r.a = g_pending[cls];
@@ -34,6 +39,7 @@ void prof_end(int cls, double flops, cudaStream_t s) {
   cudaEventRecord(r.b, s);
   r.cls = cls;
   r.flops = flops;
+  r.bytes = bytes;
   g_prof.push_back(r);
 }
 }  // namespace lc
@@ -55,13 +61,30 @@ int lc_prof_enable(int on) {
 
 int lc_prof_collect(double* ms, double* flops, long long* launches) {
   LC_REQUIRE(ms && flops && launches, "null argument");
-  for (int i = 0; i < PROF_NUM; ++i) { ms[i] = 0; flops[i] = 0; launches[i] = 0; }
+  for (int i = 0; i < 3; ++i) { ms[i] = 0; flops[i] = 0; launches[i] = 0; }
+  for (auto& r : lc::g_prof) {
+    if (r.cls >= 3) continue;
+    LC_CHECK_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    LC_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.cls] += t;
+    flops[r.cls] += r.flops;
+    launches[r.cls] += 1;
+  }
+  return 0;
+}
+int lc_prof_num_classes(void) { return PROF_NUM; }
+const char* lc_prof_class_name(int cls) { return lc::prof_name(cls); }
+int lc_prof_collect_all(double* ms, double* flops, double* bytes, long long* launches) {
+  LC_REQUIRE(ms && flops && bytes && launches, "null argument");
+  for (int i = 0; i < PROF_NUM; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; launches[i] = 0; }
   for (auto& r : lc::g_prof) {
     LC_CHECK_CUDA(cudaEventSynchronize(r.b));
     float t = 0.f;
     LC_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
     ms[r.cls] += t;
     flops[r.cls] += r.flops;
+    bytes[r.cls] += r.bytes;
     launches[r.cls] += 1;
   }
   return 0;
@@ -83,6 +106,24 @@ int lc_sched_heun_step(const float* f, double* x, double* x_hat, double* d_cur, 
                          static_cast<cudaStream_t>(stream));
 }
 
+int lc_sched_scale_input(const float* x, float* x_in, int64_t n, float c_in, void* stream) {
+  LC_REQUIRE(x && x_in, "null argument");
+  return sched_scale_input(x, x_in, n, c_in, static_cast<cudaStream_t>(stream));
+}
+
+int lc_sched_heun_init(const float* noise, double* x, float* x_in, int64_t n, double t0, double c_in, void* stream) {
+  LC_REQUIRE(noise && x && x_in, "null argument");
+  return sched_heun_init(noise, x, x_in, n, t0, c_in, static_cast<cudaStream_t>(stream));
+}
+
+int lc_latent_feedback(const float* samples, float* known_next, float* phys, const float* mean, const float* stdv,
+                       float target_std, int batch, int channels, int t_out, int t_in, int hw, void* stream) {
+  LC_REQUIRE(samples && (known_next || phys), "null argument");
+  LC_REQUIRE(batch > 0 && channels > 0 && t_out > 0 && hw > 0, "bad shape");
+  return latent_feedback(samples, known_next, phys, mean, stdv, target_std, batch, channels, t_out, t_in, hw,
+                         static_cast<cudaStream_t>(stream));
+}
+
 int lc_gemm(int precision, const void* a, const void* w, const float* bias, float* c, int m, int n, int k, int act,
             void* stream) {
   LC_REQUIRE(a && w && c, "null argument");
@@ -101,8 +142,8 @@ int lc_gemm_bf16out(const void* a, const void* w, const float* bias, void* c, in
   return gemm_bf16(g, static_cast<cudaStream_t>(stream));
 }
 
-LC_API int lc_debug_gemm_trace(void* buf) { return lc::gemm_set_trace(reinterpret_cast<long long*>(buf)); }
-LC_API int lc_debug_attention_trace(void* buf) { return lc::attention_set_trace(reinterpret_cast<long long*>(buf)); }
+int lc_debug_gemm_trace(void* buf) { return lc::gemm_set_trace(reinterpret_cast<long long*>(buf)); }
+int lc_debug_attention_trace(void* buf) { return lc::attention_set_trace(reinterpret_cast<long long*>(buf)); }
 int lc_attention(int precision, const void* qkv, void* out, int batch, int seq, int heads, void* stream) {
   LC_REQUIRE(qkv && out, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);

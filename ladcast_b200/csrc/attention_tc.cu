@@ -315,10 +315,10 @@ int attention_set_trace(long long* buf) {
 int attention_bf16(const bf16* qkv, int B, int S, int heads, int head_dim, bf16* out_p, int Np, bf16* out_c,
                    cudaStream_t s) {
   LC_REQUIRE(head_dim == HD, "attention: head_dim must be 128");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDevice<bool> attr_set;
+  if (!attr_set.here()) {
     LC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+    attr_set.here() = true;
   }
   const int d = heads * HD;
   CUtensorMap tm;
@@ -327,7 +327,7 @@ int attention_bf16(const bf16* qkv, int B, int S, int heads, int head_dim, bf16*
   dim3 grid(ceil_div(S, 2 * BQ), heads, B);
   prof_begin(PROF_ATTN, s);
   attention_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(tm, S, heads, out_p, Np, out_c);
-  prof_end(PROF_ATTN, 4.0 * B * heads * static_cast<double>(S) * S * HD, s);
+  prof_end(PROF_ATTN, 4.0 * B * heads * static_cast<double>(S) * S * HD, s, 8.0 * B * S * d);  // q, k, v in + o out (bf16)
   LC_LAUNCH_CHECK();
   return 0;
 }

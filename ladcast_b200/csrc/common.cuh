@@ -115,6 +115,10 @@ struct EpiParams {
   const float* resid = nullptr;  // EPI_RESID_STORE
   long long ldr = 0;
   int n_valid = 0;  // EPI_UNPATCHIFY: number of real output channels (<= N)
+  // EPI_UNPATCHIFY into a 5-D [B, n_valid, up_T, rows_per_sample] tensor: sample s of this launch is frame
+  // (up_frame0 + s) = b * up_T + t and lands in plane (b, n, t).  up_T = 1: plain [samples, n_valid, rows_per_sample].
+  int up_T = 1;
+  int up_frame0 = 0;
   // second-level remap (padded image buffers): orow += (row / rows_per_group) * group_extra_rows
   int rows_per_group = 1 << 30;
   int group_extra_rows = 0;
@@ -144,6 +148,14 @@ __device__ __forceinline__ long long epi_out_row(const EpiParams& ep, int row, i
          static_cast<long long>(row / ep.rows_per_group) * ep.group_extra_rows;
 }
 
+// element offset of (sample, channel 0, row-in-sample 0) and the channel stride of an EPI_UNPATCHIFY output
+__device__ __forceinline__ long long epi_unpatch_base(const EpiParams& ep, int sample, long long& ch_stride) {
+  const int fg = sample + ep.up_frame0;
+  const int b = fg / ep.up_T, t = fg - b * ep.up_T;
+  ch_stride = static_cast<long long>(ep.up_T) * ep.rows_per_sample;
+  return (static_cast<long long>(b) * ep.n_valid * ep.up_T + t) * ep.rows_per_sample;
+}
+
 // GEMM problem: A is [M, K] row-major split in up to two K-segments (A0: k < K0, A1: K0 <= k < K);
 // W is [N, K] row-major (nn.Linear layout).  bf16 path: A/W bf16, fp32 path: A/W float.
 struct GemmArgs {
@@ -166,13 +178,54 @@ int gemm_bf16_selftest_smem_bytes();
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 
-int num_sms();
+int num_sms();  // of the CURRENT device (cached per device)
+
+// Function attributes (cudaFuncSetAttribute) and device properties are per device, not per process: one-time guards
+// are indexed by the current device so that a process driving several GPUs opts every one of them in.
+constexpr int LC_MAX_DEVICES = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < LC_MAX_DEVICES) ? dev : 0;
+}
+template <typename V>
+struct PerDevice {
+  V v[LC_MAX_DEVICES] = {};
+  V& here() { return v[current_device()]; }
+};
 
 // ---------------------------------------------------------------- lightweight per-class kernel timing (bench only)
-// When enabled, tensor-core launches are bracketed with CUDA events on their stream; durations and algorithmic
-// FLOPs are accumulated per class at collect time.  Disabled by default (zero overhead: one branch per launch).
-enum ProfClass { PROF_GEMM = 0, PROF_ATTN = 1, PROF_CONV = 2, PROF_NUM = 3 };
+// When enabled, every launch of the library is bracketed with CUDA events on its stream; durations, algorithmic FLOPs
+// and algorithmic bytes are accumulated per class at collect time (bench.py: roofline + roofline.secondary).
+// Disabled by default (zero overhead: one branch per launch).
+enum ProfClass {
+  PROF_GEMM = 0,       // tcgen05 GEMM (denoiser linears, decoder 1x1)
+  PROF_ATTN = 1,       // tcgen05 flash attention
+  PROF_CONV = 2,       // implicit-GEMM 3x3 sphere convolution
+  PROF_LN = 3,         // LayerNorm + modulation
+  PROF_ROPE = 4,       // per-head RMSNorm(q, k) + RoPE
+  PROF_SCHED = 5,      // scheduler steps / latent feedback
+  PROF_DEC_NORM = 6,   // decoder channel RMSNorm (+ residual)
+  PROF_DEC_MS = 7,     // decoder fused multiscale projection
+  PROF_DEC_LINATTN = 8,// decoder ReLU linear attention
+  PROF_DEC_DWGLU = 9,  // decoder depthwise 3x3 + GLU
+  PROF_DEC_SHUFFLE = 10,  // pixel (un)shuffle + shortcut
+  PROF_DEC_PAD = 11,   // sphere padding / halo fill / shortcuts
+  PROF_METRICS = 12,   // ensemble metrics reduction
+  PROF_MISC = 13,      // patchify, embeddings, pooling, casts
+  PROF_NUM = 14
+};
+const char* prof_name(int cls);
+bool prof_on();
 void prof_begin(int cls, cudaStream_t s);
-void prof_end(int cls, double flops, cudaStream_t s);
+void prof_end(int cls, double flops, cudaStream_t s, double bytes = 0.0);
+// RAII bracket around one launch: ProfScope ps(PROF_LN, 0, bytes, stream); kernel<<<...>>>(...);
+struct ProfScope {
+  int cls;
+  double flops, bytes;
+  cudaStream_t s;
+  ProfScope(int c, double fl, double by, cudaStream_t st) : cls(c), flops(fl), bytes(by), s(st) { prof_begin(cls, s); }
+  ~ProfScope() { prof_end(cls, flops, s, bytes); }
+};
 
 }  // namespace lc

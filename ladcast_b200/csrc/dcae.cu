@@ -286,7 +286,8 @@ struct Run {
   // Encoder.forward (DCAE.py:617-631): x [n, in_channels, H, W] f32 NCHW -> out [n, latent, H/2^(ns-1), W/2^(ns-1)]
   int encode(const float* xin, int H, int W, float* out, const float* mean, const float* stdv, float target) {
     const lc_dcae_cfg& c = D->cfg;
-    LC_TRY(pad_from_nchw<T>(xin, D->padA.as<T>(), n, c.in_channels, H, W, D->enc_conv_in.cp, st));
+    LC_TRY(pad_from_nchw<T>(plane_src_4d(xin, c.in_channels, H * W), D->padA.as<T>(), n, c.in_channels, H, W,
+                            D->enc_conv_in.cp, st));
     LC_TRY(conv(D->padA.as<T>(), H, W, D->enc_conv_in,
                 store_f32(D->x.as<float>(), D->enc_conv_in.cout, D->enc_conv_in.bias)));
     xb_valid = false;
@@ -309,7 +310,9 @@ struct Run {
     return enc_out_shortcut(out, D->x.as<float>(), n, H * W, C, c.latent_channels, mean, stdv, target, st);
   }
 
-  int decode(const float* z, int h, int w, float* out, int keep, const float* mean, const float* stdv) {
+  // z: the n latent frames of this call (see PlaneSrc); out: [B, keep, out_T, 8h, 8w] with frame (z.frame0 + f) = b * out_T + t
+  // written to plane (b, c, t) — out_T = 1 is the plain [n, keep, 8h, 8w] batch of AutoencoderDC.decode
+  int decode(const PlaneSrc& z, int h, int w, float* out, int keep, const float* mean, const float* stdv, int out_T) {
     int H = h, W = w;
     const int C0 = D->conv_in.cout;
     LC_TRY(pad_from_nchw<T>(z, D->padA.as<T>(), n, D->cfg.latent_channels, H, W, D->conv_in.cp, st));
@@ -332,6 +335,7 @@ struct Run {
     EpiParams e;
     e.mode = EPI_UNPATCHIFY; e.bias = D->conv_out.bias; e.out = out; e.rows_per_sample = H * W;
     e.n_valid = keep; e.ch_scale = stdv; e.ch_shift = mean;
+    e.up_T = out_T; e.up_frame0 = out_T > 1 ? z.frame0 : 0;
     return conv(D->padA.as<T>(), H, W, D->conv_out, e);
   }
 };
@@ -576,14 +580,44 @@ int lc_dcae_decode(lc_dcae* D, const float* z, int n, int h, int w, float* out, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // the halo/channel padding of padB must be zero where conv epilogues do not write; re-zero is not needed between
   // calls because epilogues only ever write real channels and halo_fill rewrites the halo.
+  const PlaneSrc src = plane_src_4d(z, D->cfg.latent_channels, h * w);
   if (D->f32) {
     Run<float> r;
     r.D = D; r.st = st; r.n = n;
-    return r.decode(z, h, w, out, keep_channels, mean, stdv);
+    return r.decode(src, h, w, out, keep_channels, mean, stdv, 1);
   }
   Run<bf16> r;
   r.D = D; r.st = st; r.n = n;
-  return r.decode(z, h, w, out, keep_channels, mean, stdv);
+  return r.decode(src, h, w, out, keep_channels, mean, stdv, 1);
+}
+
+int lc_dcae_decode_ens(lc_dcae* D, const float* latents, int batch, int t_total, int t_take, int frame0, int n, int h, int w,
+                       float* out, int keep_channels, const float* mean, const float* stdv, const float* lat_mean,
+                       const float* lat_std, float target_std, void* stream) {
+  LC_REQUIRE(D && D->max_frames > 0, "decode before reserve");
+  LC_REQUIRE(D->has_decoder, "no decoder.* weights were loaded into this handle");
+  LC_REQUIRE(latents && out, "null argument");
+  LC_REQUIRE(batch > 0 && t_total > 0 && t_take > 0 && t_take <= t_total, "bad (batch, T, extract_first)");
+  LC_REQUIRE(frame0 >= 0 && n > 0 && frame0 + n <= batch * t_take, "frame range outside the [batch, extract_first] block");
+  LC_REQUIRE(n <= D->max_frames && h == D->h0 && w == D->w0, "decode geometry differs from lc_dcae_reserve");
+  LC_REQUIRE(keep_channels > 0 && keep_channels <= D->cfg.out_channels, "keep_channels out of range");
+  LC_REQUIRE((mean == nullptr) == (stdv == nullptr), "mean and std must be given together");
+  LC_REQUIRE((lat_mean == nullptr) == (lat_std == nullptr), "latent mean and std must be given together");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PlaneSrc src;
+  src.z = latents; src.frame0 = frame0; src.t_take = t_take;
+  src.stride_t = static_cast<long long>(h) * w;
+  src.stride_c = src.stride_t * t_total;
+  src.stride_b = src.stride_c * D->cfg.latent_channels;
+  src.scale = lat_std; src.shift = lat_mean; src.target = target_std;
+  if (D->f32) {
+    Run<float> r;
+    r.D = D; r.st = st; r.n = n;
+    return r.decode(src, h, w, out, keep_channels, mean, stdv, t_take);
+  }
+  Run<bf16> r;
+  r.D = D; r.st = st; r.n = n;
+  return r.decode(src, h, w, out, keep_channels, mean, stdv, t_take);
 }
 
 int lc_dcae_encode(lc_dcae* D, const float* x, int n, int height, int width, float* out, const float* mean,
@@ -623,10 +657,10 @@ int lc_sphere_conv3x3(int precision, const float* x, const float* w, const float
   ep.mode = EPI_UNPATCHIFY; ep.act = act; ep.bias = bias; ep.out = out; ep.rows_per_sample = H * W; ep.n_valid = cout;
   int rc;
   if (f32) {
-    rc = pad_from_nchw<float>(x, reinterpret_cast<float*>(xpad), n, cin, H, W, cp, st);
+    rc = pad_from_nchw<float>(plane_src_4d(x, cin, H * W), reinterpret_cast<float*>(xpad), n, cin, H, W, cp, st);
     if (rc == 0) rc = conv3x3_f32(reinterpret_cast<float*>(xpad), n, H, W, cp, reinterpret_cast<float*>(wm), cout, ep, st);
   } else {
-    rc = pad_from_nchw<bf16>(x, reinterpret_cast<bf16*>(xpad), n, cin, H, W, cp, st);
+    rc = pad_from_nchw<bf16>(plane_src_4d(x, cin, H * W), reinterpret_cast<bf16*>(xpad), n, cin, H, W, cp, st);
     if (rc == 0) rc = conv3x3_bf16(xpad, n, H, W, cp, wm, cout, ep, st);
   }
   cudaStreamSynchronize(st);

@@ -26,10 +26,15 @@ __device__ __forceinline__ void sphere_src(int py, int px, int p, int H, int W, 
 template <typename T>
 __device__ __forceinline__ float ld(const T* p) { return to_f32<T>(*p); }
 
+__device__ __forceinline__ float plane_load(const PlaneSrc& z, int f, int c, int pix) {
+  float v = z.z[z.plane(f, c) + pix];
+  if (z.scale != nullptr) v = __fadd_rn(__fmul_rn(__fdiv_rn(v, z.target), __ldg(z.scale + c)), __ldg(z.shift + c));
+  return v;
+}
+
 // ---------------------------------------------------------------- NCHW f32 latent -> padded NHWC T  (conv_in input)
 template <typename T>
-__global__ void pad_from_nchw_kernel(const float* __restrict__ z, T* __restrict__ out, int n, int C, int H, int W,
-                                     int Cp) {
+__global__ void pad_from_nchw_kernel(PlaneSrc z, T* __restrict__ out, int n, int C, int H, int W, int Cp) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(n) * (H + 2) * (W + 2) * Cp;
   if (i >= total) return;
@@ -43,7 +48,7 @@ __global__ void pad_from_nchw_kernel(const float* __restrict__ z, T* __restrict_
   if (c < C) {
     int sy, sx;
     sphere_src(py, px, 1, H, W, sy, sx);
-    v = z[((static_cast<long long>(f) * C + c) * H + sy) * W + sx];
+    v = plane_load(z, f, c, sy * W + sx);
   }
   out[i] = from_f32<T>(v);
 }
@@ -563,15 +568,15 @@ __global__ void __launch_bounds__(256) pixel_shuffle_kernel(const float* __restr
 
 // ---------------------------------------------------------------- conv_in shortcut: x[p, c] += z[f, c / rep, y, x]
 template <typename T>
-__global__ void in_shortcut_kernel(float* __restrict__ x, T* __restrict__ x_t, const float* __restrict__ z, int n, int HW,
-                                   int C, int Cz, int rep) {
+__global__ void in_shortcut_kernel(float* __restrict__ x, T* __restrict__ x_t, PlaneSrc z, int n, int HW, int C, int Cz,
+                                   int rep) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(n) * HW * C;
   if (i >= total) return;
   const int c = static_cast<int>(i % C);
   const long long p = i / C;
   const int f = static_cast<int>(p / HW), pix = static_cast<int>(p % HW);
-  const float v = x[i] + z[(static_cast<long long>(f) * Cz + c / rep) * HW + pix];
+  const float v = x[i] + plane_load(z, f, c / rep, pix);
   x[i] = v;
   if (x_t != nullptr) x_t[i] = from_f32<T>(v);
 }
@@ -636,8 +641,9 @@ inline unsigned blocks(long long n, int t = 256) { return static_cast<unsigned>(
 }  // namespace
 
 template <typename T>
-int pad_from_nchw(const float* z, T* out, int n, int C, int H, int W, int Cp, cudaStream_t s) {
+int pad_from_nchw(const PlaneSrc& z, T* out, int n, int C, int H, int W, int Cp, cudaStream_t s) {
   const long long total = static_cast<long long>(n) * (H + 2) * (W + 2) * Cp;
+  ProfScope ps(PROF_DEC_PAD, 0.0, static_cast<double>(n) * H * W * C * 4.0 + static_cast<double>(total) * sizeof(T), s);
   pad_from_nchw_kernel<T><<<blocks(total), 256, 0, s>>>(z, out, n, C, H, W, Cp);
   LC_LAUNCH_CHECK();
   return 0;
@@ -646,6 +652,7 @@ template <typename T>
 int pad_from_nhwc(const float* x, T* out, int n, int C, int H, int W, int Cp, cudaStream_t s) {
   LC_REQUIRE(C % 4 == 0 && Cp % 4 == 0, "pad: channels must be multiples of 4");
   const long long total = static_cast<long long>(n) * (H + 2) * (W + 2) * (Cp / 4);
+  ProfScope ps(PROF_DEC_PAD, 0.0, static_cast<double>(n) * H * W * C * 4.0 + static_cast<double>(total) * 4 * sizeof(T), s);
   pad_from_nhwc_kernel<T><<<blocks(total), 256, 0, s>>>(x, out, n, C, H, W, Cp);
   LC_LAUNCH_CHECK();
   return 0;
@@ -654,6 +661,7 @@ template <typename T>
 int halo_fill(T* buf, int n, int H, int W, int Cp, cudaStream_t s) {
   LC_REQUIRE(Cp % 8 == 0, "halo_fill: Cp must be a multiple of 8");
   const long long total = static_cast<long long>(n) * (2 * (W + 2) + 2 * H) * (Cp / 8);
+  ProfScope ps(PROF_DEC_PAD, 0.0, static_cast<double>(total) * 16.0 * sizeof(T), s);
   halo_fill_kernel<T><<<blocks(total), 256, 0, s>>>(buf, n, H, W, Cp);
   LC_LAUNCH_CHECK();
   return 0;
@@ -663,6 +671,8 @@ int dwconv3_glu(const T* in, const float* w, const float* bias, T* out, int n, i
   LC_REQUIRE(C % 8 == 0, "dwconv3_glu: channels must be a multiple of 8");
   constexpr int XT = 4;
   dim3 grid((C / 8 + 31) / 32, (W + 8 * XT - 1) / (8 * XT), n * H);
+  // algorithmic: read [P, C] once, write [P, C/2]
+  ProfScope ps(PROF_DEC_DWGLU, 0.0, static_cast<double>(n) * H * W * C * 1.5 * sizeof(T), s);
   dwconv3_glu_kernel<T, XT><<<grid, 256, 0, s>>>(in, w, bias, out, n, H, W, C);
   LC_LAUNCH_CHECK();
   return 0;
@@ -672,12 +682,16 @@ int multiscale_fused(const float* in, const float* w5, const float* wg, float* o
   LC_REQUIRE(C % 32 == 0, "multiscale projection: channels must be a multiple of 32");
   const long long nblk = static_cast<long long>(n) * H * ((C + 127) / 128);
   LC_REQUIRE(nblk < (1ll << 31), "multiscale projection: too many image rows per call");
+  // algorithmic: read qkv [P, C] once, write the multiscale branch [P, C]
+  ProfScope ps(PROF_DEC_MS, 2.0 * n * H * W * C * (25.0 + 32.0), static_cast<double>(n) * H * W * C * 8.0, s);
   multiscale_fused_kernel<<<static_cast<unsigned>(nblk), 256, 0, s>>>(in, w5, wg, out, n, H, W, C);
   LC_LAUNCH_CHECK();
   return 0;
 }
 template <typename T>
 int linear_attention(const float* qkv, const float* ms, T* out, int n, int HW, int heads, float eps, cudaStream_t s) {
+  // algorithmic: k, v read once (phase 1), q read once (phase 2) of both scales, output [P, 2*heads*32] written
+  ProfScope ps(PROF_DEC_LINATTN, 0.0, static_cast<double>(n) * HW * heads * (2 * 96 * 4.0 + 2 * 32 * sizeof(T)), s);
   linear_attn_kernel<T><<<n * 2 * heads, 256, 0, s>>>(qkv, ms, out, HW, heads, eps);
   LC_LAUNCH_CHECK();
   return 0;
@@ -686,6 +700,9 @@ template <typename T>
 int rmsnorm_rows(const float* y, const float* w, const float* b, float eps, float* resid, float* out_f32, T* out_t,
                  long long P, int C, int relu, cudaStream_t s, int pH, int pW, int pCp) {
   LC_REQUIRE(C % 4 == 0, "rmsnorm: C must be a multiple of 4");
+  // algorithmic: read y; read + write the residual; write the f32 / T copies that were asked for
+  ProfScope ps(PROF_DEC_NORM, 0.0,
+               static_cast<double>(P) * C * (4.0 + (resid ? 8.0 : 0.0) + (out_f32 ? 4.0 : 0.0) + (out_t ? sizeof(T) : 0.0)), s);
   rmsnorm_rows_kernel<T><<<blocks(P, 8), 256, 0, s>>>(y, w, b, eps, resid, out_f32, out_t, P, C, relu, pH, pW, pCp);
   LC_LAUNCH_CHECK();
   return 0;
@@ -695,6 +712,8 @@ int pixel_shuffle_shortcut(const float* conv, const float* xin, float* out, T* o
                            int Cout, cudaStream_t s, int pCp) {
   LC_REQUIRE(Cout % 4 == 0, "pixel_shuffle: C_out must be a multiple of 4");
   const long long total = static_cast<long long>(n) * H * W * (Cout / 4);
+  ProfScope ps(PROF_DEC_SHUFFLE, 0.0,
+               static_cast<double>(n) * H * W * (4.0 * Cout * (8.0 + (out_t ? sizeof(T) : 0.0)) + Cin * 4.0), s);
   pixel_shuffle_kernel<T><<<blocks(total), 256, 0, s>>>(conv, xin, out, out_t, n, H, W, Cin, Cout, 4 * Cout / Cin, pCp);
   LC_LAUNCH_CHECK();
   return 0;
@@ -704,6 +723,8 @@ int pixel_unshuffle_shortcut(const float* conv, const float* xin, float* out, T*
                              int Cout, cudaStream_t s, int pCp) {
   LC_REQUIRE(Cout % 4 == 0 && (4 * Cin) % Cout == 0 && H % 2 == 0 && W % 2 == 0, "pixel_unshuffle: bad geometry");
   const long long total = static_cast<long long>(n) * (H / 2) * (W / 2) * Cout;
+  ProfScope ps(PROF_DEC_SHUFFLE, 0.0,
+               static_cast<double>(n) * H * W * (Cout / 4 + Cin) * 4.0 + static_cast<double>(total) * (4.0 + (out_t ? sizeof(T) : 0.0)), s);
   pixel_unshuffle_kernel<T><<<blocks(total), 256, 0, s>>>(conv, xin, out, out_t, n, H, W, Cin, Cout, 4 * Cin / Cout, pCp);
   LC_LAUNCH_CHECK();
   return 0;
@@ -712,20 +733,22 @@ int enc_out_shortcut(float* out, const float* x, int n, int HW, int C, int L, co
                      float target, cudaStream_t s) {
   LC_REQUIRE(C % L == 0, "encoder out shortcut needs C divisible by latent_channels");
   const long long total = static_cast<long long>(n) * L * HW;
+  ProfScope ps(PROF_DEC_PAD, 0.0, static_cast<double>(total) * 8.0 + static_cast<double>(n) * HW * C * 4.0, s);
   enc_out_shortcut_kernel<<<blocks(total), 256, 0, s>>>(out, x, n, HW, C, L, C / L, mean, stdv, target);
   LC_LAUNCH_CHECK();
   return 0;
 }
 template <typename T>
-int in_shortcut(float* x, T* x_t, const float* z, int n, int HW, int C, int Cz, cudaStream_t s) {
+int in_shortcut(float* x, T* x_t, const PlaneSrc& z, int n, int HW, int C, int Cz, cudaStream_t s) {
   const long long total = static_cast<long long>(n) * HW * C;
+  ProfScope ps(PROF_DEC_PAD, 0.0, static_cast<double>(total) * (8.0 + sizeof(T)) + static_cast<double>(n) * HW * Cz * 4.0, s);
   in_shortcut_kernel<T><<<blocks(total), 256, 0, s>>>(x, x_t, z, n, HW, C, Cz, C / Cz);
   LC_LAUNCH_CHECK();
   return 0;
 }
 
 #define LC_INST(T)                                                                                                   \
-  template int pad_from_nchw<T>(const float*, T*, int, int, int, int, int, cudaStream_t);                            \
+  template int pad_from_nchw<T>(const PlaneSrc&, T*, int, int, int, int, int, cudaStream_t);                          \
   template int pad_from_nhwc<T>(const float*, T*, int, int, int, int, int, cudaStream_t);                            \
   template int halo_fill<T>(T*, int, int, int, int, cudaStream_t);                                                   \
   template int dwconv3_glu<T>(const T*, const float*, const float*, T*, int, int, int, int, cudaStream_t);           \
@@ -736,7 +759,7 @@ int in_shortcut(float* x, T* x_t, const float* z, int n, int HW, int C, int Cz, 
                                          cudaStream_t, int);                                                              \
   template int pixel_unshuffle_shortcut<T>(const float*, const float*, float*, T*, int, int, int, int, int,          \
                                            cudaStream_t, int);                                                       \
-  template int in_shortcut<T>(float*, T*, const float*, int, int, int, int, cudaStream_t);
+  template int in_shortcut<T>(float*, T*, const PlaneSrc&, int, int, int, int, cudaStream_t);
 LC_INST(float)
 LC_INST(bf16)
 #undef LC_INST

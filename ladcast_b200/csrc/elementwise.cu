@@ -385,6 +385,52 @@ __global__ void __launch_bounds__(256) heun_kernel(const float* __restrict__ f, 
   if (x_in_next != nullptr) x_in_next[i] = static_cast<float>(xn * c_in_next);
 }
 
+// x_in = x * c_in  (scale_model_input of step 0, pipeline_AR.py:90)
+__global__ void __launch_bounds__(256) scale_kernel(const float* __restrict__ x, float* __restrict__ out, long long n4,
+                                                    float c) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(x)[i];
+  reinterpret_cast<float4*>(out)[i] = make_float4(v.x * c, v.y * c, v.z * c, v.w * c);
+}
+
+// Heun prologue (edm_sampler.py:44-46, 56-58): x = float64(noise) * t_0 ; x_in = float32(x * c_in(t_0))
+__global__ void __launch_bounds__(256) heun_init_kernel(const float* __restrict__ noise, double* __restrict__ x,
+                                                        float* __restrict__ x_in, long long n, double t0, double c_in) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = static_cast<double>(noise[i]) * t0;
+  x[i] = v;
+  x_in[i] = static_cast<float>(v * c_in);
+}
+
+// AR feedback of roll_out_serial (pipelines/utils.py:560-585): from one sampler output [B, C, T, hw] (normalised
+// latents) write (a) the next step's conditioning = the last t_in frames [B, C, t_in, hw] (unchanged values) and
+// (b) optionally the de-normalised latents (x / target_std) * std[c] + mean[c] in the same layout
+// (inverse_normalize_transform_3D, dataloader/utils.py:233-240; separate div / mul / add like the eager reference).
+__global__ void __launch_bounds__(256) latent_feedback_kernel(const float* __restrict__ s, float* __restrict__ known,
+                                                              float* __restrict__ phys, const float* __restrict__ mean,
+                                                              const float* __restrict__ stdv, float target, int C, int T,
+                                                              int t_in, int hw4, long long n4) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int p = static_cast<int>(i % hw4);
+  long long r = i / hw4;
+  const int t = static_cast<int>(r % T);
+  r /= T;
+  const int c = static_cast<int>(r % C);
+  const long long b = r / C;
+  const float4 v = reinterpret_cast<const float4*>(s)[i];
+  if (known != nullptr && t >= T - t_in)
+    reinterpret_cast<float4*>(known)[((b * C + c) * t_in + (t - (T - t_in))) * hw4 + p] = v;
+  if (phys != nullptr) {
+    const float sd = __ldg(stdv + c), mu = __ldg(mean + c);
+    reinterpret_cast<float4*>(phys)[i] =
+        make_float4(__fadd_rn(__fmul_rn(__fdiv_rn(v.x, target), sd), mu), __fadd_rn(__fmul_rn(__fdiv_rn(v.y, target), sd), mu),
+                    __fadd_rn(__fmul_rn(__fdiv_rn(v.z, target), sd), mu), __fadd_rn(__fmul_rn(__fdiv_rn(v.w, target), sd), mu));
+  }
+}
+
 }  // namespace
 
 template <typename T>
@@ -394,6 +440,7 @@ int layernorm_modulate(const float* x, T* out, int M, int d, float eps, int rows
   LC_REQUIRE(d % 128 == 0 && d <= 2048, "layernorm: d must be a multiple of 128, <= 2048");
   const int nv = d / 128;
   dim3 grid(ceil_div(M, 8 * LN_RPW));
+  ProfScope ps(PROF_LN, 0.0, static_cast<double>(M) * d * (4 + sizeof(T)), s);
 #define LC_LN_CASE(NV)                                                                                            \
   case NV:                                                                                                        \
     layernorm_kernel<T, NV><<<grid, 256, 0, s>>>(x, out, M, d, eps, rows_per_sample, seg_rows, seg_rows_per_sample,   \
@@ -416,6 +463,7 @@ int qk_norm_rope(T* qkv, long long ld, int B, int S, int heads, int head_dim, fl
   LC_REQUIRE(nseg == 1 || nseg == 2, "qk_norm_rope: 1 or 2 segments");
   const long long total = static_cast<long long>(B) * S * 2 * heads;
   RopeSeg s1 = nseg > 1 ? segs[1] : segs[0];
+  ProfScope ps(PROF_ROPE, 0.0, static_cast<double>(total) * 128 * sizeof(T) * 2, s);  // q and k read + written once
   if (sizeof(T) == 2) {
     qk_norm_rope_bf16_kernel<<<static_cast<unsigned>(ceil_div_ll(total / 2, 16)), 256, 0, s>>>(
         reinterpret_cast<bf16*>(qkv), ld, B, S, heads, eps, segs[0], s1, nseg);
@@ -446,6 +494,7 @@ int pack_rope_pairs(const float* cos, const float* sin, uint32_t* out, int n_tok
 template <typename T>
 int patchify(const float* x, T* out, int B, int C, int THW, int Kp, cudaStream_t s) {
   dim3 grid(ceil_div(THW, 32), ceil_div(Kp, 32), B);
+  ProfScope ps(PROF_MISC, 0.0, static_cast<double>(B) * THW * (C * 4.0 + Kp * sizeof(T)), s);
   patchify_kernel<T><<<grid, 256, 0, s>>>(x, out, C, THW, Kp);
   LC_LAUNCH_CHECK();
   return 0;
@@ -453,6 +502,7 @@ int patchify(const float* x, T* out, int B, int C, int THW, int Kp, cudaStream_t
 
 template <typename T>
 int timestep_embed(const float* t, int n_t, int B, T* out, cudaStream_t s) {
+  ProfScope ps(PROF_MISC, 0.0, static_cast<double>(B) * 256 * sizeof(T), s);
   timestep_embed_kernel<T><<<ceil_div(B * 128, 128), 128, 0, s>>>(t, n_t, B, out);
   LC_LAUNCH_CHECK();
   return 0;
@@ -461,6 +511,7 @@ int timestep_embed(const float* t, int n_t, int B, T* out, cudaStream_t s) {
 template <typename T>
 int token_mean(const float* x, int B, int N, int d, T* out, cudaStream_t s) {
   dim3 grid(ceil_div(d, 128), B);
+  ProfScope ps(PROF_MISC, 0.0, static_cast<double>(B) * N * d * 4.0, s);
   token_mean_kernel<T><<<grid, 256, 0, s>>>(x, N, d, out);
   LC_LAUNCH_CHECK();
   return 0;
@@ -470,6 +521,7 @@ template <typename T>
 int gated_add(float* h, const T* a, const float* gate, long long gate_stride, int M, int d, int rows_per_sample,
               cudaStream_t s) {
   const long long n4 = static_cast<long long>(M) * d / 4;
+  ProfScope ps(PROF_MISC, 0.0, static_cast<double>(M) * d * (8.0 + sizeof(T)), s);
   gated_add_kernel<T><<<static_cast<unsigned>(ceil_div_ll(n4, 256)), 256, 0, s>>>(h, a, gate, gate_stride, n4, d,
                                                                                 rows_per_sample);
   LC_LAUNCH_CHECK();
@@ -479,6 +531,7 @@ int gated_add(float* h, const T* a, const float* gate, long long gate_stride, in
 template <typename T>
 int temb_combine(const float* a, const float* b, const float* sc, const float* sh, long long sc_stride, int B, int d,
                  float* out_f32, T* out_silu, cudaStream_t s) {
+  ProfScope ps(PROF_MISC, 0.0, static_cast<double>(B) * d * 16.0, s);
   temb_combine_kernel<T><<<ceil_div(B * d, 256), 256, 0, s>>>(a, b, sc, sh, sc_stride, B, d, out_f32, out_silu);
   LC_LAUNCH_CHECK();
   return 0;
@@ -486,6 +539,7 @@ int temb_combine(const float* a, const float* b, const float* sc, const float* s
 
 template <typename T>
 int cast_rows(const float* x, T* out, long long n, cudaStream_t s) {
+  ProfScope ps(PROF_MISC, 0.0, static_cast<double>(n) * (4.0 + sizeof(T)), s);
   cast_kernel<T><<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s>>>(x, out, n);
   LC_LAUNCH_CHECK();
   return 0;
@@ -495,6 +549,8 @@ int sched_dpmpp2m_step(const float* f, float* x, float* x0_prev, float* x_in_nex
                        cudaStream_t s) {
   LC_REQUIRE(n % 4 == 0, "scheduler: element count must be a multiple of 4");
   const long long n4 = n / 4;
+  // algorithmic bytes: read F, x (+ previous x0 on 2M steps); write x0, x' (+ next x_in)
+  ProfScope ps(PROF_SCHED, 0.0, static_cast<double>(n) * 4.0 * (4 + (c.a_d != 0.f ? 1 : 0) + (x_in_next != nullptr ? 1 : 0)), s);
   dpmpp2m_kernel<<<static_cast<unsigned>(ceil_div_ll(n4, 256)), 256, 0, s>>>(f, x, x0_prev, x_in_next, n4, c);
   LC_LAUNCH_CHECK();
   return 0;
@@ -502,8 +558,39 @@ int sched_dpmpp2m_step(const float* f, float* x, float* x0_prev, float* x_in_nex
 
 int sched_heun_step(const float* f, double* x, double* x_hat, double* d_cur, float* x_in_next, long long n, int phase,
                     double t_cur, double t_next, double c_skip, double c_out, double c_in_next, cudaStream_t s) {
+  // algorithmic bytes: predictor reads F(4) x(8), writes x_hat d_cur x (24) + x_in(4); corrector reads F x x_hat d_cur
+  // (28), writes x (8) + x_in (4)
+  ProfScope ps(PROF_SCHED, 0.0, static_cast<double>(n) * (36.0 + (x_in_next != nullptr ? 4.0 : 0.0)), s);
   heun_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s>>>(f, x, x_hat, d_cur, x_in_next, n, phase, t_cur,
                                                                        t_next, c_skip, c_out, c_in_next);
+  LC_LAUNCH_CHECK();
+  return 0;
+}
+
+int sched_scale_input(const float* x, float* x_in, long long n, float c_in, cudaStream_t s) {
+  LC_REQUIRE(n % 4 == 0, "scheduler: element count must be a multiple of 4");
+  ProfScope ps(PROF_SCHED, 0.0, static_cast<double>(n) * 8.0, s);
+  scale_kernel<<<static_cast<unsigned>(ceil_div_ll(n / 4, 256)), 256, 0, s>>>(x, x_in, n / 4, c_in);
+  LC_LAUNCH_CHECK();
+  return 0;
+}
+
+int sched_heun_init(const float* noise, double* x, float* x_in, long long n, double t0, double c_in, cudaStream_t s) {
+  ProfScope ps(PROF_SCHED, 0.0, static_cast<double>(n) * 16.0, s);
+  heun_init_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s>>>(noise, x, x_in, n, t0, c_in);
+  LC_LAUNCH_CHECK();
+  return 0;
+}
+
+int latent_feedback(const float* samples, float* known, float* phys, const float* mean, const float* stdv, float target,
+                    int B, int C, int T, int t_in, int hw, cudaStream_t s) {
+  LC_REQUIRE(hw % 4 == 0, "latent_feedback: h*w must be a multiple of 4");
+  LC_REQUIRE(t_in >= 1 && t_in <= T, "latent_feedback: need 1 <= T_in <= T_out");
+  LC_REQUIRE(phys == nullptr || (mean != nullptr && stdv != nullptr), "latent_feedback: mean/std required for the de-normalised output");
+  const long long n4 = static_cast<long long>(B) * C * T * (hw / 4);
+  ProfScope ps(PROF_SCHED, 0.0, static_cast<double>(n4) * 16.0 * (1.0 + (phys != nullptr ? 1.0 : 0.0) + static_cast<double>(t_in) / T), s);
+  latent_feedback_kernel<<<static_cast<unsigned>(ceil_div_ll(n4, 256)), 256, 0, s>>>(samples, known, phys, mean, stdv, target, C,
+                                                                                   T, t_in, hw / 4, n4);
   LC_LAUNCH_CHECK();
   return 0;
 }

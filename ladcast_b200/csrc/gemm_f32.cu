@@ -32,7 +32,9 @@ __device__ __forceinline__ void epi_one(const EpiParams& ep, float v, int row, i
       if (n < ep.n_valid) {
         const int r_in = row - sample * ep.rows_per_sample;
         if (ep.ch_scale != nullptr) v = v * __ldg(ep.ch_scale + n) + __ldg(ep.ch_shift + n);
-        reinterpret_cast<float*>(ep.out)[(static_cast<long long>(sample) * ep.n_valid + n) * ep.rows_per_sample + r_in] = v;
+        long long chs;
+        const long long base = epi_unpatch_base(ep, sample, chs);
+        reinterpret_cast<float*>(ep.out)[base + n * chs + r_in] = v;
       }
       break;
   }

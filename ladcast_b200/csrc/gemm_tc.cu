@@ -83,8 +83,8 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& ep, const uint32
   if (KIND == K_UNPATCH) {
     if (row_mine >= M) return;
     const int r_in = row_mine - sample_mine * ep.rows_per_sample;
-    float* op = reinterpret_cast<float*>(ep.out) +
-                (static_cast<long long>(sample_mine) * ep.n_valid + n0) * ep.rows_per_sample + r_in;
+    long long chs;
+    float* op = reinterpret_cast<float*>(ep.out) + epi_unpatch_base(ep, sample_mine, chs) + n0 * chs + r_in;
     const bool has_bias = ep.bias != nullptr, has_scale = ep.ch_scale != nullptr;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -93,7 +93,7 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& ep, const uint32
         if (has_bias) o += __ldg(ep.bias + n0 + j);
         o = act_fast<ACT>(o);
         if (has_scale) o = o * __ldg(ep.ch_scale + n0 + j) + __ldg(ep.ch_shift + n0 + j);
-        op[static_cast<long long>(j) * ep.rows_per_sample] = o;
+        op[j * chs] = o;
       }
     }
     return;
@@ -741,13 +741,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   if (warp == 2) ptx::tmem_dealloc_pair<C::TMEM_COLS>(tmem_base);
 }
 
+// algorithmic HBM bytes of one launch: A once (an implicit conv reads its input once, not 9 times), W once, the output
+// once (read-modify-write epilogues: twice)
+double algorithmic_bytes(int M, int N, int K, const EpiParams& ep, const ConvLoad& cv) {
+  const double a = 2.0 * M * (cv.enabled ? K / 9.0 : static_cast<double>(K));
+  const double out_b = (ep.mode == EPI_GATED_RESID || ep.mode == EPI_RESID_STORE) ? 8.0
+                       : (ep.mode == EPI_UNPATCHIFY || ep.out_f32) ? 4.0 : 2.0;
+  const double n_out = ep.mode == EPI_UNPATCHIFY ? ep.n_valid : N;
+  return a + 2.0 * N * K + out_b * M * n_out;
+}
+
 int launch_pair(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, int M_tiles, int M, int N, int K,
                 int K0, const EpiParams& ep, const ConvLoad& cv, cudaStream_t stream) {
   using C = Cfg2;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDevice<bool> attr_set;
+  if (!attr_set.here()) {
     LC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    attr_set = true;
+    attr_set.here() = true;
   }
   TileSched sched;
   sched.num_m = ceil_div(M_tiles, 2);  // 256-row pair tiles
@@ -761,7 +771,7 @@ int launch_pair(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   const double flops = 2.0 * M * N * (cv.enabled ? 9.0 * cv.c_real : static_cast<double>(K));
   prof_begin(cls, stream);
   gemm_tc2_kernel<<<grid, NUM_THREADS, C::SMEM, stream>>>(a0, a1, w, M, N, K, K0, ep, sched, cv);
-  prof_end(cls, flops, stream);
+  prof_end(cls, flops, stream, algorithmic_bytes(M, N, K, ep, cv));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -770,10 +780,10 @@ template <int BN>
 int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, int M_tiles, int M, int N, int K, int K0,
            const EpiParams& ep, const ConvLoad& cv, cudaStream_t stream) {
   using C = Cfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDevice<bool> attr_set;
+  if (!attr_set.here()) {
     LC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    attr_set = true;
+    attr_set.here() = true;
   }
   TileSched sched;
   sched.num_m = M_tiles;
@@ -785,7 +795,7 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, i
   const double flops = 2.0 * M * N * (cv.enabled ? 9.0 * cv.c_real : static_cast<double>(K));
   prof_begin(cls, stream);
   gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM, stream>>>(a0, a1, w, M, N, K, K0, ep, sched, cv);
-  prof_end(cls, flops, stream);
+  prof_end(cls, flops, stream, algorithmic_bytes(M, N, K, ep, cv));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -793,7 +803,8 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, i
 }  // namespace
 
 int num_sms() {
-  static int n = 0;
+  static PerDevice<int> cache;
+  int& n = cache.here();
   if (n == 0) {
     int dev = 0;
     cudaGetDevice(&dev);

@@ -80,6 +80,7 @@ class AutoencoderDC(CheckpointMixin):
         self._handle = None
         self._reserved = None
         self._sd: Dict[str, torch.Tensor] = {}
+        self._loaded_groups = None  # None = fresh model (random init allowed); else subset of {"decoder", "encoder"}
 
     # ------------------------------------------------------------------ parameters
     def encoder_param_shapes(self) -> Dict[str, Tuple[int, ...]]:
@@ -153,7 +154,22 @@ class AutoencoderDC(CheckpointMixin):
         s["decoder.conv_out.weight"], s["decoder.conv_out.bias"] = (oc, ch[0], 3, 3), (oc,)
         return s
 
+    def _active_shapes(self) -> Dict[str, Tuple[int, ...]]:
+        """Shapes of the sub-modules this instance holds: everything for a fresh model, otherwise only the groups a
+        checkpoint provided (a decoder-only load must NOT grow a random encoder: lc_dcae_encode then fails loudly with
+        'no encoder.* weights were loaded into this handle')."""
+        if self._loaded_groups is None:
+            return self.param_shapes()
+        s: Dict[str, Tuple[int, ...]] = {}
+        if "encoder" in self._loaded_groups:
+            s.update(self.encoder_param_shapes())
+        if "decoder" in self._loaded_groups:
+            s.update(self.decoder_param_shapes())
+        return s
+
     def _materialize(self):
+        if self._loaded_groups is not None:
+            return
         for k, shp in self.param_shapes().items():
             if k not in self._sd:
                 if k.endswith(".weight") and len(shp) > 1:
@@ -185,6 +201,9 @@ class AutoencoderDC(CheckpointMixin):
                     raise RuntimeError(f"Error(s) in loading state_dict: missing {[k for k in grp if k not in state_dict][:5]}")
             if not seen:
                 raise RuntimeError(f"Error(s) in loading state_dict: missing {missing[:5]}")
+        if self._loaded_groups is None:
+            self._sd = {}  # drop a previous random init: only checkpoint tensors may be uploaded from now on
+            self._loaded_groups = set()
         for k, t in state_dict.items():
             if k in shapes and tuple(t.shape) != tuple(shapes[k]):
                 raise RuntimeError(f"size mismatch for {k}: {tuple(t.shape)} vs {tuple(shapes[k])}")
@@ -192,6 +211,11 @@ class AutoencoderDC(CheckpointMixin):
                 self._sd[k] = t.detach().to("cpu", torch.float32).contiguous()
             elif strict:
                 raise RuntimeError(f"unexpected key {k}")
+        for name, grp in (("decoder", self.decoder_param_shapes()), ("encoder", self.encoder_param_shapes())):
+            if grp and all(k in self._sd for k in grp):
+                self._loaded_groups.add(name)
+        if not self._loaded_groups:
+            raise RuntimeError(f"Error(s) in loading state_dict: no complete decoder.* / encoder.* group; missing {missing[:5]}")
         self._release()
         return missing, []
 
@@ -270,7 +294,7 @@ class AutoencoderDC(CheckpointMixin):
         _lib.check(lib.lc_dcae_create(ctypes.byref(cfg), ctypes.byref(h)), "lc_dcae_create")
         with torch.cuda.device(self._device):
             st = _lib.stream()
-            for k in self.param_shapes():
+            for k in self._active_shapes():
                 dv = self._sd[k].to(self._device, torch.float32).contiguous()
                 shp = (ctypes.c_int64 * dv.dim())(*dv.shape)
                 _lib.check(lib.lc_dcae_load(h, k.encode(), _lib.ptr(dv), shp, dv.dim(), st), f"lc_dcae_load({k})")
@@ -313,6 +337,40 @@ class AutoencoderDC(CheckpointMixin):
         oc = self.config.out_channels if self.config.out_channels is not None else self.config.in_channels
         keep = oc - self.static_channels if self.static_channels else oc
         return self._decode_native(z, keep, mean, std)
+
+    def decode_ens_fused(self, latents: torch.Tensor, mean: Optional[torch.Tensor] = None,
+                         std: Optional[torch.Tensor] = None, extract_first: Optional[int] = None,
+                         latent_mean: Optional[torch.Tensor] = None, latent_std: Optional[torch.Tensor] = None,
+                         target_std: float = 0.5, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """`decode_latent_ens` (reference pipelines/utils.py:52-80) in one native pass: latents (B, C, T, h, w) are read
+        in place (no permute / reshape copies), every (b, t < extract_first) frame is decoded and written straight to
+        out (B, 84, extract_first, 8h, 8w), de-normalised with mean / std in the last epilogue.  With latent_mean /
+        latent_std the latents are first mapped back from normalised units, (z / target_std) * std + mean, inside the
+        first kernel (what roll_out_serial does before decoding, pipelines/utils.py:571-577)."""
+        self._ensure_handle()
+        lib = _lib.load()
+        z = latents.to(self._device, torch.float32).contiguous()
+        B, C, T, h, w = z.shape
+        take = T if extract_first is None else int(extract_first)
+        oc = self.config.out_channels if self.config.out_channels is not None else self.config.in_channels
+        keep = oc - self.static_channels if self.static_channels else oc
+        r = self.spatial_compression_ratio
+        if out is None:
+            out = torch.empty(B, keep, take, h * r, w * r, device=self._device, dtype=torch.float32)
+        elif tuple(out.shape) != (B, keep, take, h * r, w * r) or not out.is_contiguous() or out.dtype != torch.float32:
+            raise ValueError("out must be a contiguous float32 tensor of shape (B, keep_channels, extract_first, 8h, 8w)")
+        dev = lambda t: t.to(self._device, torch.float32).contiguous() if t is not None else None  # noqa: E731
+        mean_d, std_d, lm_d, ls_d = dev(mean), dev(std), dev(latent_mean), dev(latent_std)
+        n = B * take
+        with torch.cuda.device(self._device):
+            chunk = min(n, self.MAX_FRAMES_PER_CALL)
+            self._reserve(lib, chunk, h, w)
+            for f0 in range(0, n, chunk):
+                m = min(chunk, n - f0)
+                _lib.check(lib.lc_dcae_decode_ens(self._handle, _lib.ptr(z), B, T, take, f0, m, h, w, _lib.ptr(out), keep,
+                                                  _lib.ptr(mean_d), _lib.ptr(std_d), _lib.ptr(lm_d), _lib.ptr(ls_d),
+                                                  float(target_std), _lib.stream()), "lc_dcae_decode_ens")
+        return out
 
     def _reserve(self, lib, chunk, h, w):
         if self._reserved is None or self._reserved[0] < chunk or self._reserved[1:] != (h, w):

@@ -62,8 +62,13 @@ class LaDCastTransformer3DModel(CheckpointMixin):
         self._geometry = None
         self._cached = None  # (known data_ptr, ...) while inside cached_conditioning()
         self._sd: Dict[str, torch.Tensor] = {}  # filled by load_state_dict, or lazily with a random init
+        self._loaded = False  # a checkpoint was loaded: never paper over missing tensors with a random init
 
     def _materialize(self):
+        """Random initialisation of a FRESH model only (from_config without a checkpoint).  After load_state_dict the
+        missing keys stay missing, so that lc_denoiser_finalize fails loudly ("missing checkpoint tensor")."""
+        if self._loaded:
+            return
         for k, shp in self.param_shapes().items():
             if k not in self._sd:
                 self._sd[k] = self._init_param(k, shp)
@@ -150,6 +155,16 @@ class LaDCastTransformer3DModel(CheckpointMixin):
                 if tuple(t.shape) != tuple(shp):
                     raise RuntimeError(f"size mismatch for {k}: {tuple(t.shape)} vs {tuple(shp)}")
                 self._sd[k] = t.detach().to("cpu", torch.float32).contiguous()
+        if not self._loaded:
+            # tensors a previous random init put there must not survive next to a (partial) checkpoint
+            for k in [k for k in self._sd if k not in state_dict]:
+                del self._sd[k]
+        self._loaded = True
+        if missing:
+            import warnings
+
+            warnings.warn(f"LaDCastTransformer3DModel.load_state_dict(strict=False): {len(missing)} tensors are missing "
+                          f"(e.g. {missing[:3]}); the model will refuse to run until they are loaded")
         self._release()
         return missing, unexpected
 
@@ -274,28 +289,45 @@ class LaDCastTransformer3DModel(CheckpointMixin):
     def cached_conditioning(self, conditioning_tensors, time_elapsed=None, t_out: int = 1):
         """Hoists `prepare` out of a denoising loop: every `forward` inside the block reuses the cached context."""
         self.prepare(conditioning_tensors, time_elapsed, t_out)
-        self._cached = (tuple(conditioning_tensors.shape), t_out)
+        self._cached = self._cache_key(conditioning_tensors, time_elapsed, t_out)
         try:
             yield self
         finally:
             self._cached = None
 
+    @staticmethod
+    def _cache_key(conditioning_tensors, time_elapsed, t_out):
+        """Identity of a prepared context: the conditioning tensor (storage, version, shape), the dates and T_out.  A
+        forward with anything else re-runs `prepare` instead of silently reusing a stale context."""
+        stamps = None
+        if time_elapsed is not None:
+            stamps = tuple(int(v) for v in (time_elapsed.reshape(-1).tolist() if isinstance(time_elapsed, torch.Tensor)
+                                            else time_elapsed))
+        return (conditioning_tensors.data_ptr(), conditioning_tensors._version, tuple(conditioning_tensors.shape),
+                str(conditioning_tensors.device), stamps, int(t_out))
+
     # ------------------------------------------------------------------ forward
     def forward(self, hidden_states: torch.Tensor, timestep: torch.Tensor, conditioning_tensors: torch.Tensor,
                 time_elapsed: Optional[torch.LongTensor] = None, attention_kwargs: Optional[Dict[str, Any]] = None,
                 return_dict: bool = True, coords: Optional[torch.Tensor] = None):
-        B, _, t_out, H, W = hidden_states.shape
+        B, c_in, t_out, H, W = hidden_states.shape
         if conditioning_tensors.shape[0] != B:
             raise ValueError("conditioning_tensors and hidden_states must have the same batch size")
-        if self._cached is None or self._cached != (tuple(conditioning_tensors.shape), t_out):
+        if c_in != self.config.in_channels:
+            raise ValueError(f"hidden_states has {c_in} channels, the model expects in_channels={self.config.in_channels}")
+        if tuple(conditioning_tensors.shape[-2:]) != (H, W):
+            raise ValueError("conditioning_tensors and hidden_states must share the spatial size")
+        if self._cached is None or self._cached != self._cache_key(conditioning_tensors, time_elapsed, t_out):
             self.prepare(conditioning_tensors, time_elapsed, t_out)
+        if self._geometry is None or self._geometry[0] != (conditioning_tensors.shape[2], t_out, H, W):
+            raise _lib.LadcastB200Error("hidden_states geometry differs from the prepared (T_in, T_out, H, W)")
         lib = _lib.load()
         with torch.cuda.device(self._device):
             x = hidden_states.to(self._device, torch.float32).contiguous()
             t = timestep.to(self._device, torch.float32).reshape(-1).contiguous()
             if t.numel() not in (1, B):
                 raise ValueError("timestep must have 1 or batch_size entries")
-            out = torch.empty_like(x)
+            out = torch.empty((B, self.config.out_channels, t_out, H, W), device=self._device, dtype=torch.float32)
             _lib.check(lib.lc_denoiser_forward(self._handle, _lib.ptr(x), _lib.ptr(t), t.numel(), _lib.ptr(out), _lib.stream()),
                        "lc_denoiser_forward")
         if not return_dict:

@@ -37,25 +37,29 @@ def edm_AR_sampler(net, noise_scheduler, batch_size=1, return_seq_len=1, randn_l
         c_out = t32 * sd / (t32**2 + sd**2) ** 0.5
         return float(c_in), float(c_skip), float(c_out), (0.25 * torch.log(t32)).reshape(1)
 
-    x = (latents.to(torch.float64) * t_steps[0]).contiguous()
+    latents = latents.contiguous()
+    x = torch.empty(shape, device=device, dtype=torch.float64)
     x_hat, d_cur = torch.empty_like(x), torch.empty_like(x)
     x_in = torch.empty(shape, device=device, dtype=torch.float32)
     n = num_inference_steps
     with net.cached_conditioning(known_latents, timestamps, t_out=return_seq_len):
         c_in, c_skip, c_out, c_noise = coef(t_steps[0])
-        x_in.copy_((x * c_in).to(torch.float32))
+        # x = float64(noise) * t_0 ; x_in = float32(x * c_in(t_0))   (edm_sampler.py:44-58)
+        _lib.check(lib.lc_sched_heun_init(_lib.ptr(latents), _lib.ptr(x), _lib.ptr(x_in), x.numel(), float(t_steps[0]),
+                                          c_in, _lib.stream()), "lc_sched_heun_init")
         for i in range(n):
             t_cur, t_next = float(t_steps[i]), float(t_steps[i + 1])
             f = net(x_in, c_noise.to(device), known_latents, time_elapsed=timestamps).sample
             second = i < n - 1
-            c_in_n, c_skip_n, c_out_n, c_noise_n = coef(t_steps[i + 1]) if second else (0.0, 0.0, 0.0, None)
-            _lib.check(lib.lc_sched_heun_step(_lib.ptr(f), _lib.ptr(x), _lib.ptr(x_hat), _lib.ptr(d_cur),
-                                              _lib.ptr(x_in) if second else None, x.numel(), 0, t_cur, t_next, c_skip,
-                                              c_out, c_in_n, _lib.stream()), "lc_sched_heun_step")
+            # last step (t_next = 0): Euler only; x_in then receives float32(x), the sampler's return value
+            c_in_n, c_skip_n, c_out_n, c_noise_n = coef(t_steps[i + 1]) if second else (1.0, 0.0, 0.0, None)
+            _lib.check(lib.lc_sched_heun_step(_lib.ptr(f), _lib.ptr(x), _lib.ptr(x_hat), _lib.ptr(d_cur), _lib.ptr(x_in),
+                                              x.numel(), 0, t_cur, t_next, c_skip, c_out, c_in_n, _lib.stream()),
+                       "lc_sched_heun_step")
             if second:
                 f2 = net(x_in, c_noise_n.to(device), known_latents, time_elapsed=timestamps).sample
                 _lib.check(lib.lc_sched_heun_step(_lib.ptr(f2), _lib.ptr(x), _lib.ptr(x_hat), _lib.ptr(d_cur),
                                                   _lib.ptr(x_in), x.numel(), 1, t_cur, t_next, c_skip_n, c_out_n, c_in_n,
                                                   _lib.stream()), "lc_sched_heun_step")
                 c_in, c_skip, c_out, c_noise = c_in_n, c_skip_n, c_out_n, c_noise_n
-    return x.float()
+    return x_in  # == x.float() (written by the last step kernel)

@@ -15,6 +15,11 @@ class AutoRegressive2DPipeline:
         self.ar_model = ar_model
         self.scheduler = scheduler
         self.scheduler_step_kwargs = scheduler_step_kwargs or {}
+        # the reference forwards these to scheduler.step (pipeline_AR.py:100); the fused step kernel is deterministic
+        # and returns tensors, so only the no-op keys of EDMDPMSolverMultistepScheduler.step are accepted
+        bad = [k for k in self.scheduler_step_kwargs if k not in ("generator", "return_dict")]
+        if bad:
+            raise NotImplementedError(f"scheduler_step_kwargs {bad} are not supported by the fused DPM-Solver++ step")
 
     @property
     def _execution_device(self):
@@ -52,14 +57,15 @@ class AutoRegressive2DPipeline:
         sch.set_timesteps(num_inference_steps)
         n = len(sch.timesteps)
         lib = _lib.load()
-        x0_prev = torch.zeros_like(image)
+        x0_prev = torch.empty_like(image)  # written by step 0 (first order: not read), read from step 1 on
         x_in = torch.empty_like(image)
         c_noise = sch.timesteps.to(dev, torch.float32)
         with self.ar_model.cached_conditioning(known_latents, timestamps, t_out=return_seq_len):
             c0 = sch.coefficients(0)
-            torch.mul(image, c0["c_in"], out=x_in)  # scale_model_input of step 0
+            _lib.check(lib.lc_sched_scale_input(_lib.ptr(image), _lib.ptr(x_in), image.numel(), c0["c_in"], _lib.stream()),
+                       "lc_sched_scale_input")  # scale_model_input of step 0; later steps: fused into the step kernel
             for i in range(n):
-                t = c_noise[i : i + 1].expand(batch_size)
+                t = c_noise[i : i + 1]  # one c_noise for the whole batch (the reference expands it to (B,), :92)
                 model_output = self.ar_model(x_in, t, known_latents, time_elapsed=timestamps, return_dict=False)[0]
                 c = sch.coefficients(i)
                 _lib.check(lib.lc_sched_dpmpp2m_step(

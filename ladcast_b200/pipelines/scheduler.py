@@ -109,8 +109,10 @@ class EDMDPMSolverMultistepScheduler:
 
 
 def dpmpp2m_coefficients(n_steps, i, sigmas=None, config=None, lower_order_nums=None):
-    """fp32 scalar coefficients of DPM-Solver++ step i of an n_steps schedule (diffusers step(): first order when
-    i == 0 or i == n-1 [final sigma 0], otherwise the 2M midpoint rule)."""
+    """fp32 scalar coefficients of DPM-Solver++ step i of an n_steps schedule.  Order selection as in diffusers'
+    EDMDPMSolverMultistepScheduler.step: first order at i == 0 (no history yet) and at the last step when
+    `euler_at_final`, or `lower_order_final` with fewer than 15 steps, or `final_sigmas_type == "zero"` (the reference's
+    configuration, where sigma_N = 0 makes the 2M rule undefined); otherwise the 2M midpoint rule."""
     if sigmas is None:
         sch = EDMDPMSolverMultistepScheduler()
         sch.set_timesteps(n_steps)
@@ -126,7 +128,8 @@ def dpmpp2m_coefficients(n_steps, i, sigmas=None, config=None, lower_order_nums=
     h = lam_t - lam_s
     em1 = one * (torch.exp(-h) - 1.0)
     ratio = s_next / s
-    final = i == n_steps - 1
+    final = i == n_steps - 1 and (bool(config.euler_at_final) or (bool(config.lower_order_final) and n_steps < 15)
+                                  or config.final_sigmas_type == "zero")
     first_order = config.solver_order == 1 or lower_order_nums < 1 or final
     a_d = 0.0
     if not first_order:

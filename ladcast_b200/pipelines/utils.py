@@ -74,8 +74,7 @@ def ensemble_AR_sampler(pipeline, sample_size: int, return_seq_len: int, num_inf
     sizes = [batch_size] * (sample_size // batch_size)
     if sample_size % batch_size:
         sizes.append(sample_size % batch_size)
-    samples = torch.empty(sample_size, pipeline.ar_model.config.out_channels, return_seq_len, *known_latents.shape[-2:],
-                          device=device, dtype=pipeline.ar_model.dtype)
+    samples = None
     sampler_kwargs = sampler_kwargs or {}
     scheduler = copy.deepcopy(pipeline.scheduler) if sampler_type == "edm" else pipeline.scheduler
     count = 0
@@ -95,6 +94,10 @@ def ensemble_AR_sampler(pipeline, sample_size: int, return_seq_len: int, num_inf
                            do_edm_style=True, **sampler_kwargs)[0]
         else:
             raise ValueError(f"unknown sampler_type {sampler_type!r}")
+        if n == sample_size:
+            return out  # one batch: the sampler's own output buffer, no gather copy
+        if samples is None:
+            samples = torch.empty(sample_size, *out.shape[1:], device=out.device, dtype=out.dtype)
         samples[count : count + n] = out
         count += n
     return samples
@@ -107,13 +110,13 @@ def decode_latent_ens(encdec_model, latents: torch.Tensor, mean_tensor: Optional
     B, C, T, H, W = latents.shape
     if extract_first is None:
         extract_first = T
+    if hasattr(encdec_model, "decode_ens_fused"):
+        # native path: 5-D in, 5-D out, de-normalisation in the last epilogue — no permute / reshape copies
+        return encdec_model.decode_ens_fused(latents, mean_tensor, std_tensor, extract_first=extract_first)
     z = latents[:, :, :extract_first].to(encdec_model.device).permute(0, 2, 1, 3, 4).reshape(B * extract_first, C, H, W)
-    if hasattr(encdec_model, "decode_fused"):
-        y = encdec_model.decode_fused(z.contiguous(), mean_tensor, std_tensor)
-    else:
-        y = encdec_model.decode(z.contiguous()).sample
-        if mean_tensor is not None:
-            y = y * std_tensor.to(y.device)[None, :, None, None] + mean_tensor.to(y.device)[None, :, None, None]
+    y = encdec_model.decode(z.contiguous()).sample
+    if mean_tensor is not None:
+        y = y * std_tensor.to(y.device)[None, :, None, None] + mean_tensor.to(y.device)[None, :, None, None]
     y = y.reshape(B, extract_first, *y.shape[1:]).permute(0, 2, 1, 3, 4)
     return y
 
@@ -125,6 +128,39 @@ def advance_timestamp(stamp: int, hours: int) -> int:
     s = str(int(stamp))
     t = datetime(int(s[:4]), int(s[4:6]), int(s[6:8]), int(s[8:10])) + timedelta(hours=hours)
     return int(t.strftime("%Y%m%d%H"))
+
+
+@torch.no_grad()
+def rollout_step(pipeline, encdec_model, known: torch.Tensor, stamp: torch.Tensor, ensemble_size: int,
+                 latent_mean: torch.Tensor, latent_std: torch.Tensor, field_mean: Optional[torch.Tensor],
+                 field_std: Optional[torch.Tensor], num_inference_steps: int = 20, return_seq_len: int = 4,
+                 sampler_type: str = "pipeline", member_indices: Optional[Sequence[int]] = None,
+                 return_latent: bool = False, target_std: float = 0.5, t_in: Optional[int] = None,
+                 out: Optional[torch.Tensor] = None):
+    """One AR step of `roll_out_serial` (reference pipelines/utils.py:533-585), entirely in library kernels: sample
+    T_out lead steps for every member, feed the last T_in frames back (lc_latent_feedback), then either de-normalise
+    the latents (return_latent) or decode them — the latent de-normalisation runs inside the decoder's first kernel and
+    the field de-normalisation in its last epilogue, which writes (ens, C, T_out, H, W) directly.
+    All statistics tensors must already live on the device.  Returns (result, next known latents)."""
+    from .. import _lib
+
+    dev = pipeline._execution_device
+    samples = ensemble_AR_sampler(pipeline, sample_size=ensemble_size, return_seq_len=return_seq_len,
+                                  num_inference_steps=num_inference_steps, known_latents=known, timestamps=stamp,
+                                  sampler_type=sampler_type, device=dev, member_indices=member_indices).contiguous()
+    B, C, T, h, w = samples.shape
+    t_in = known.shape[2] if t_in is None else t_in
+    known_next = torch.empty((B, C, t_in, h, w), device=dev, dtype=torch.float32)
+    phys = torch.empty_like(samples) if return_latent else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().lc_latent_feedback(_lib.ptr(samples), _lib.ptr(known_next), _lib.ptr(phys),
+                                                  _lib.ptr(latent_mean), _lib.ptr(latent_std), float(target_std), B, C, T,
+                                                  t_in, h * w, _lib.stream()), "lc_latent_feedback")
+    if return_latent:
+        return phys, known_next
+    fields = encdec_model.decode_ens_fused(samples, field_mean, field_std, latent_mean=latent_mean,
+                                           latent_std=latent_std, target_std=target_std, out=out)
+    return fields, known_next
 
 
 @torch.no_grad()
@@ -154,19 +190,17 @@ def roll_out_latent(pipeline, encdec_model, known_latents: torch.Tensor, init_ti
         reps = min(reps, max_ar_steps)
     t_in = known_latents.shape[2]
     known = known_latents.to(dev, torch.float32, non_blocking=True)
-    lm = latent_mean.to(dev, torch.float32)[None, :, None, None, None]
-    ls = latent_std.to(dev, torch.float32)[None, :, None, None, None]
+    lm = latent_mean.to(dev, torch.float32).contiguous()
+    ls = latent_std.to(dev, torch.float32).contiguous()
+    fm = field_mean.to(dev, torch.float32).contiguous() if field_mean is not None else None
+    fs = field_std.to(dev, torch.float32).contiguous() if field_std is not None else None
     copy_stream = torch.cuda.Stream(device=dev)
-    keep = []
     for step in range(reps):
         stamp = torch.tensor([advance_timestamp(init_timestamp, step * step_size_hour * return_seq_len)])
-        samples = ensemble_AR_sampler(pipeline, sample_size=ensemble_size, return_seq_len=return_seq_len,
-                                      num_inference_steps=num_inference_steps, known_latents=known, timestamps=stamp,
-                                      sampler_type=sampler_type, device=dev, member_indices=member_indices)
-        known = samples[:, :, -t_in:].clone()
-        phys = (samples / target_std) * ls + lm  # latent inverse transform (dataloader/utils.py:233-240)
-        res = phys if return_latent else decode_latent_ens(encdec_model, phys, field_mean, field_std)
-        res = res.contiguous()  # (ens, C, T_out, H, W)
+        res, known = rollout_step(pipeline, encdec_model, known, stamp, ensemble_size, lm, ls, fm, fs,
+                                  num_inference_steps=num_inference_steps, return_seq_len=return_seq_len,
+                                  sampler_type=sampler_type, member_indices=member_indices, return_latent=return_latent,
+                                  target_std=target_std, t_in=t_in)
         if out is None:
             out = torch.empty((reps, *res.shape), dtype=torch.float32, pin_memory=True)
         done = torch.cuda.Event()
@@ -174,8 +208,7 @@ def roll_out_latent(pipeline, encdec_model, known_latents: torch.Tensor, init_ti
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(done)
             out[step].copy_(res, non_blocking=True)
-        res.record_stream(copy_stream)
-        keep.append(res)
+        res.record_stream(copy_stream)  # the allocator may reuse the block only after the copy has drained
     copy_stream.synchronize()
     return out
 
