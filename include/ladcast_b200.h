@@ -186,6 +186,11 @@ LC_API int lc_dcae_encode(lc_dcae* h, const float* x, int n, int height, int wid
  * sum/(H*W) with NaN propagation is formed by the caller.  Zeroes the outputs itself. */
 LC_API int lc_metrics_accumulate(const float* fields, const float* truth, const double* lat_weights, int members,
                                  long long planes, int height, int width, double* sums, double* counts, void* stream);
+/* the same with an explicit distance (in elements) between consecutive members: member m's planes [planes, H*W] start at
+ * fields + m * member_stride.  Reads a member-sharded receive buffer or a slice of a larger tensor in place. */
+LC_API int lc_metrics_accumulate_strided(const float* fields, long long member_stride, const float* truth,
+                                         const double* lat_weights, int members, long long planes, int height, int width,
+                                         double* sums, double* counts, void* stream);
 /* anomaly-correlation terms of get_acc (evaluate/utils.py:122-149): sums/counts [3, planes] fp64 of the NaN-skipping
  * (optionally latitude-weighted) spatial sums of fa*ta, fa^2, ta^2 with fa = forecast - climate, ta = truth - climate */
 LC_API int lc_metrics_acc(const float* forecast, const float* truth, const float* climate, const double* lat_weights,

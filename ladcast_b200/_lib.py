@@ -78,6 +78,7 @@ _OPTIONAL = {
     "lc_dcae_debug_read": ([_vp, _cp, _vp, _i64, _vp], _i),
     "lc_sphere_conv3x3": ([_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "lc_metrics_accumulate": ([_vp, _vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, _vp, _vp], _i),
+    "lc_metrics_accumulate_strided": ([_vp, ctypes.c_longlong, _vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, _vp, _vp], _i),
     "lc_metrics_acc": ([_vp, _vp, _vp, _vp, ctypes.c_longlong, _i, _i, _vp, _vp, _vp], _i),
     "lc_metrics_pointwise": ([_vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, _vp, _vp, _vp], _i),
 }
@@ -130,6 +131,15 @@ def ptr(t):
         raise LadcastB200Error("ladcast_b200 kernels need CUDA tensors; there is no CPU fallback")
     if not t.is_contiguous():
         raise LadcastB200Error("tensor must be contiguous")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def ptr_any(t):
+    """Device pointer of a CUDA tensor that the callee addresses with explicit strides (may be non-contiguous)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise LadcastB200Error("ladcast_b200 kernels need CUDA tensors; there is no CPU fallback")
     return ctypes.c_void_p(t.data_ptr())
 
 

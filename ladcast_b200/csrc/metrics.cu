@@ -2,11 +2,19 @@
 // total.  Reference: evaluate/utils.py:40-118 (pointwise functions) and the assembly loop
 // evaluate/evaluate_ens_gpu.py:339-415 (weights are float64, the SST channel is reduced with nanmean).
 //
-//   fields [M, N, HW] f32  (M members, N = (channel, lead) planes, HW pixels)     truth [N, HW] f32 (NaN allowed)
-// One thread per pixel: the M member values are staged in shared memory (column per thread), the spread is the
-// mean absolute difference over all member pairs — algebraically identical to the reference's sorted formula
-// 2/(M(M-1)) * sum_i (2i - M - 1) x_(i).  Per-pixel values are fp32 (as in the reference), the latitude-weighted
-// spatial sums are fp64: warp-shuffle + shared-memory block reduction, one fp64 atomicAdd per block and metric.
+//   fields: M members x N (channel, lead) planes x HW pixels, f32; member m starts at fields + m * member_stride and
+//   its planes are contiguous ([N, HW]) — a contiguous [M, C, T, H, W] tensor, or the per-member receive slots of
+//   the multi-GPU exchange, are read in place.        truth [N, HW] f32 (NaN allowed)
+//
+// One thread per pixel (consecutive threads = consecutive pixels: every member load is a coalesced 128-B line per
+// warp, all M loads of a thread in flight).  The M member values live in REGISTERS; the spread follows the
+// reference's formulation exactly — sort the members (evaluate/utils.py:86, here a fully unrolled bitonic network on
+// the next power of two, padded with +inf) and form 2/(M(M-1)) * sum_i (2i - M - 1) x_(i) in fp32 (:91-99).  Per-pixel
+// values are fp32 (as in the reference), the latitude-weighted spatial sums are fp64: per-thread accumulation over a
+// few pixels, warp-shuffle + shared-memory block reduction, one fp64 atomicAdd per block and metric.
+// Ensembles larger than 64 members use a shared-memory pairwise kernel (mean |x_i - x_j|, algebraically identical).
+#include <cmath>
+
 #include "../../include/ladcast_b200.h"
 #include "common.cuh"
 
@@ -14,6 +22,7 @@ namespace lc {
 namespace {
 
 constexpr int THREADS = 256;
+constexpr int PIX_PER_THREAD = 4;  // pixels a thread walks over (amortises the fp64 block reduction)
 
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
@@ -21,22 +30,130 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+// ascending bitonic sorting network on MP (power of two) registers; every index is a compile-time constant
+template <int MP>
+__device__ __forceinline__ void sort_network(float (&v)[MP]) {
+#pragma unroll
+  for (int k = 2; k <= MP; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < MP; ++i) {
+        const int l = i ^ j;
+        if (l > i) {
+          const float a = v[i], b = v[l];
+          const float lo = fminf(a, b), hi = fmaxf(a, b);
+          if ((i & k) == 0) { v[i] = lo; v[l] = hi; }
+          else { v[i] = hi; v[l] = lo; }
+        }
+      }
+    }
+  }
+}
+
+// block reduction of NV fp64 values per thread -> atomicAdd into out[k * stride + n]
+template <int NV>
+__device__ __forceinline__ void block_accumulate(const double (&v)[NV], double* __restrict__ first, double* __restrict__ second,
+                                                 long long stride, long long n) {
+  __shared__ double red[NV][THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const double s = warp_sum_d(v[k]);
+    if (lane == 0) red[k][wid] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+    for (int i = 0; i < THREADS / 32; ++i) s += red[threadIdx.x][i];
+    constexpr int HALF = NV / 2;
+    if (threadIdx.x < HALF) atomicAdd(&first[threadIdx.x * stride + n], s);
+    else atomicAdd(&second[(threadIdx.x - HALF) * stride + n], s);
+  }
+}
+
+__device__ __forceinline__ void add_weighted(double (&acc)[8], float msum, float skill, float spread, float y, double w) {
+  // [se, skill, spread, crps] latitude-weighted values + non-NaN counts (nanmean of the SST channel)
+  const float d = msum - y;
+  const double se = static_cast<double>(d * d) * w;
+  const double sk = static_cast<double>(skill) * w;
+  const double sp = static_cast<double>(spread) * w;
+  const double cr = sk - 0.5 * sp;
+  const double vals[4] = {se, sk, sp, cr};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool ok = !isnan(vals[k]);
+    acc[k] += ok ? vals[k] : 0.0;
+    acc[4 + k] += ok ? 1.0 : 0.0;
+  }
+}
+
+template <int MP, bool REDUCE>
+__global__ void __launch_bounds__(THREADS) metrics_sorted_kernel(const float* __restrict__ fields, long long member_stride,
+                                                                 const float* __restrict__ truth,
+                                                                 const double* __restrict__ latw, int M, long long N, int H,
+                                                                 int W, int bpp, double* __restrict__ sums,
+                                                                 double* __restrict__ counts, float* __restrict__ out_skill,
+                                                                 float* __restrict__ out_spread, float* __restrict__ out_mean) {
+  const int HW = H * W;
+  const long long n = blockIdx.x / bpp;
+  const int blk = static_cast<int>(blockIdx.x - n * bpp);
+  const float* base = fields + n * HW;
+  const float inv_m = 1.0f / static_cast<float>(M);
+  const float spread_scale = M > 1 ? 2.0f / (static_cast<float>(M) * static_cast<float>(M - 1)) : 0.f;
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int p = blk * THREADS + threadIdx.x; p < HW; p += bpp * THREADS) {
+    float x[MP];
+#pragma unroll
+    for (int m = 0; m < MP; ++m) x[m] = m < M ? __ldg(base + m * member_stride + p) : INFINITY;
+    const float y = truth != nullptr ? __ldg(truth + n * HW + p) : 0.f;
+    float msum = 0.f, skill = 0.f;
+#pragma unroll
+    for (int m = 0; m < MP; ++m) {
+      if (m < M) {
+        msum += x[m];
+        skill += fabsf(y - x[m]);
+      }
+    }
+    sort_network<MP>(x);
+    float ws = 0.f;
+#pragma unroll
+    for (int m = 0; m < MP; ++m)
+      if (m < M) ws = fmaf(static_cast<float>(2 * (m + 1) - M - 1), x[m], ws);
+    float spread = spread_scale * ws;
+    if (msum != msum) spread = msum;  // a NaN member: torch.sort keeps it and the weighted sum propagates it
+    skill *= inv_m;
+    msum *= inv_m;
+    if (REDUCE) {
+      add_weighted(acc, msum, skill, spread, y, latw[p / W]);
+    } else {
+      if (out_skill) out_skill[n * HW + p] = skill;
+      if (out_spread) out_spread[n * HW + p] = spread;
+      if (out_mean) out_mean[n * HW + p] = msum;
+    }
+  }
+  if (REDUCE) block_accumulate<8>(acc, sums, counts, N, n);
+}
+
+// M > 64: members staged in shared memory (one column per thread), spread = mean absolute pair difference
 template <bool REDUCE>
-__global__ void __launch_bounds__(THREADS) metrics_kernel(const float* __restrict__ fields, const float* __restrict__ truth,
-                                                          const double* __restrict__ latw, int M, long long N, int H,
-                                                          int W, double* __restrict__ sums, double* __restrict__ counts,
-                                                          float* __restrict__ out_skill, float* __restrict__ out_spread,
-                                                          float* __restrict__ out_mean) {
+__global__ void __launch_bounds__(THREADS) metrics_pairwise_kernel(const float* __restrict__ fields, long long member_stride,
+                                                                   const float* __restrict__ truth,
+                                                                   const double* __restrict__ latw, int M, long long N, int H,
+                                                                   int W, int bpp, double* __restrict__ sums,
+                                                                   double* __restrict__ counts, float* __restrict__ out_skill,
+                                                                   float* __restrict__ out_spread, float* __restrict__ out_mean) {
   extern __shared__ float xs[];  // [M][THREADS]
   const int HW = H * W;
-  const long long n = blockIdx.y;
-  const int p = blockIdx.x * THREADS + threadIdx.x;
-  const bool active = p < HW;
-  float msum = 0.f, skill = 0.f, spread = 0.f, y = 0.f;
-  if (active) {
-    y = truth != nullptr ? truth[n * HW + p] : 0.f;
+  const long long n = blockIdx.x / bpp;
+  const int blk = static_cast<int>(blockIdx.x - n * bpp);
+  const float* base = fields + n * HW;
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int p = blk * THREADS + threadIdx.x; p < HW; p += bpp * THREADS) {
+    const float y = truth != nullptr ? truth[n * HW + p] : 0.f;
+    float msum = 0.f, skill = 0.f, spread = 0.f;
     for (int m = 0; m < M; ++m) {
-      const float x = fields[(static_cast<long long>(m) * N + n) * HW + p];
+      const float x = base[m * member_stride + p];
       xs[m * THREADS + threadIdx.x] = x;
       msum += x;
       skill += fabsf(y - x);
@@ -49,59 +166,28 @@ __global__ void __launch_bounds__(THREADS) metrics_kernel(const float* __restric
     if (M > 1) spread = 2.0f * pair / (static_cast<float>(M) * static_cast<float>(M - 1));
     skill /= static_cast<float>(M);
     msum /= static_cast<float>(M);
-  }
-  if (!REDUCE) {
-    if (active) {
+    if (REDUCE) {
+      add_weighted(acc, msum, skill, spread, y, latw[p / W]);
+    } else {
       if (out_skill) out_skill[n * HW + p] = skill;
       if (out_spread) out_spread[n * HW + p] = spread;
       if (out_mean) out_mean[n * HW + p] = msum;
     }
-    return;
   }
-  // [se, skill, spread, crps] weighted sums + non-NaN counts
-  double v[8];
-  {
-    const double w = active ? latw[p / W] : 0.0;
-    const float d = msum - y;
-    const double se = static_cast<double>(d * d) * w;
-    const double sk = static_cast<double>(skill) * w;
-    const double sp = static_cast<double>(spread) * w;
-    const double cr = sk - 0.5 * sp;
-    const double vals[4] = {se, sk, sp, cr};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool ok = active && !isnan(vals[k]);
-      v[k] = ok ? vals[k] : 0.0;
-      v[4 + k] = ok ? 1.0 : 0.0;
-    }
-  }
-  __shared__ double red[8][THREADS / 32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const double s = warp_sum_d(v[k]);
-    if (lane == 0) red[k][wid] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x < 8) {
-    double s = 0.0;
-    for (int i = 0; i < THREADS / 32; ++i) s += red[threadIdx.x][i];
-    if (threadIdx.x < 4) atomicAdd(&sums[threadIdx.x * N + n], s);
-    else atomicAdd(&counts[(threadIdx.x - 4) * N + n], s);
-  }
+  if (REDUCE) block_accumulate<8>(acc, sums, counts, N, n);
 }
 
 // Anomaly correlation coefficient terms (evaluate/utils.py:122-149): per plane, NaN-skipping weighted sums of
 // fa*ta, fa^2, ta^2 (fa = forecast - climate, ta = truth - climate) and their non-NaN counts.
 __global__ void __launch_bounds__(THREADS) acc_kernel(const float* __restrict__ fc, const float* __restrict__ tr,
                                                       const float* __restrict__ cl, const double* __restrict__ latw,
-                                                      long long N, int H, int W, double* __restrict__ sums,
+                                                      long long N, int H, int W, int bpp, double* __restrict__ sums,
                                                       double* __restrict__ counts) {
   const int HW = H * W;
-  const long long n = blockIdx.y;
-  const int p = blockIdx.x * THREADS + threadIdx.x;
+  const long long n = blockIdx.x / bpp;
+  const int blk = static_cast<int>(blockIdx.x - n * bpp);
   double v[6] = {0, 0, 0, 0, 0, 0};
-  if (p < HW) {
+  for (int p = blk * THREADS + threadIdx.x; p < HW; p += bpp * THREADS) {
     const double w = latw != nullptr ? latw[p / W] : 1.0;
     const float c = cl[n * HW + p];
     const float fa = fc[n * HW + p] - c, ta = tr[n * HW + p] - c;
@@ -110,24 +196,48 @@ __global__ void __launch_bounds__(THREADS) acc_kernel(const float* __restrict__ 
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const bool ok = !isnan(vals[k]);
-      v[k] = ok ? vals[k] : 0.0;
-      v[3 + k] = ok ? 1.0 : 0.0;
+      v[k] += ok ? vals[k] : 0.0;
+      v[3 + k] += ok ? 1.0 : 0.0;
     }
   }
-  __shared__ double red[6][THREADS / 32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const double s = warp_sum_d(v[k]);
-    if (lane == 0) red[k][wid] = s;
+  block_accumulate<6>(v, sums, counts, N, n);
+}
+
+int blocks_per_plane(int HW) { return ceil_div(HW, THREADS * PIX_PER_THREAD); }
+
+template <bool REDUCE>
+int launch_metrics(const float* fields, long long member_stride, const float* truth, const double* latw, int M, long long N,
+                   int H, int W, double* sums, double* counts, float* o_skill, float* o_spread, float* o_mean,
+                   cudaStream_t st) {
+  const int bpp = blocks_per_plane(H * W);
+  LC_REQUIRE(N * bpp < (1ll << 31), "too many (channel, lead) planes for one launch");
+  const unsigned grid = static_cast<unsigned>(N * bpp);
+  // algorithmic bytes: every member value and the truth read once (+ per-pixel outputs of the pointwise variant)
+  const double px = static_cast<double>(N) * H * W;
+  ProfScope ps(PROF_METRICS, 0.0, px * 4.0 * (M + (truth ? 1 : 0) + (o_skill ? 1 : 0) + (o_spread ? 1 : 0) + (o_mean ? 1 : 0)), st);
+#define LC_SORTED(MP)                                                                                                      \
+  metrics_sorted_kernel<MP, REDUCE><<<grid, THREADS, 0, st>>>(fields, member_stride, truth, latw, M, N, H, W, bpp, sums, \
+                                                              counts, o_skill, o_spread, o_mean)
+  if (M <= 2) LC_SORTED(2);
+  else if (M <= 4) LC_SORTED(4);
+  else if (M <= 8) LC_SORTED(8);
+  else if (M <= 16) LC_SORTED(16);
+  else if (M <= 32) LC_SORTED(32);
+  else if (M <= 64) LC_SORTED(64);
+  else {
+    const size_t smem = static_cast<size_t>(M) * THREADS * sizeof(float);
+    static PerDevice<size_t> attr;
+    if (smem > 48 * 1024 && smem > attr.here()) {
+      LC_CHECK_CUDA(cudaFuncSetAttribute(metrics_pairwise_kernel<REDUCE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+      attr.here() = smem;
+    }
+    metrics_pairwise_kernel<REDUCE><<<grid, THREADS, smem, st>>>(fields, member_stride, truth, latw, M, N, H, W, bpp, sums,
+                                                                 counts, o_skill, o_spread, o_mean);
   }
-  __syncthreads();
-  if (threadIdx.x < 6) {
-    double s = 0.0;
-    for (int i = 0; i < THREADS / 32; ++i) s += red[threadIdx.x][i];
-    if (threadIdx.x < 3) atomicAdd(&sums[threadIdx.x * N + n], s);
-    else atomicAdd(&counts[(threadIdx.x - 3) * N + n], s);
-  }
+#undef LC_SORTED
+  LC_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace
@@ -137,25 +247,24 @@ using namespace lc;
 
 extern "C" {
 
-int lc_metrics_accumulate(const float* fields, const float* truth, const double* latw, int members, long long planes,
-                          int height, int width, double* sums, double* counts, void* stream) {
+int lc_metrics_accumulate_strided(const float* fields, long long member_stride, const float* truth, const double* latw,
+                                  int members, long long planes, int height, int width, double* sums, double* counts,
+                                  void* stream) {
   LC_REQUIRE(fields && truth && latw && sums && counts, "null argument");
   LC_REQUIRE(members >= 1 && members <= 128, "ensemble size must be in [1, 128]");
-  LC_REQUIRE(planes > 0 && planes <= 65535, "number of (channel, lead) planes must be in [1, 65535] per call");
+  LC_REQUIRE(planes > 0 && height > 0 && width > 0, "bad shape");
+  LC_REQUIRE(member_stride >= planes * height * width || members == 1, "member stride smaller than one member's planes");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t smem = static_cast<size_t>(members) * THREADS * sizeof(float);
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    LC_CHECK_CUDA(cudaFuncSetAttribute(metrics_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr = smem;
-  }
   LC_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * planes, st));
   LC_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(double) * 4 * planes, st));
-  dim3 grid(ceil_div(height * width, THREADS), static_cast<unsigned>(planes));
-  metrics_kernel<true><<<grid, THREADS, smem, st>>>(fields, truth, latw, members, planes, height, width, sums, counts,
-                                                    nullptr, nullptr, nullptr);
-  LC_LAUNCH_CHECK();
-  return 0;
+  return launch_metrics<true>(fields, member_stride, truth, latw, members, planes, height, width, sums, counts, nullptr,
+                              nullptr, nullptr, st);
+}
+
+int lc_metrics_accumulate(const float* fields, const float* truth, const double* latw, int members, long long planes,
+                          int height, int width, double* sums, double* counts, void* stream) {
+  return lc_metrics_accumulate_strided(fields, planes * height * width, truth, latw, members, planes, height, width, sums,
+                                       counts, stream);
 }
 
 int lc_metrics_pointwise(const float* fields, const float* truth, int members, long long planes, int height, int width,
@@ -163,30 +272,23 @@ int lc_metrics_pointwise(const float* fields, const float* truth, int members, l
   LC_REQUIRE(fields != nullptr, "null argument");
   LC_REQUIRE(out_skill == nullptr || truth != nullptr, "CRPS skill needs the truth tensor");
   LC_REQUIRE(members >= 1 && members <= 128, "ensemble size must be in [1, 128]");
-  LC_REQUIRE(planes > 0 && planes <= 65535, "number of planes must be in [1, 65535] per call");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t smem = static_cast<size_t>(members) * THREADS * sizeof(float);
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    LC_CHECK_CUDA(cudaFuncSetAttribute(metrics_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr = smem;
-  }
-  dim3 grid(ceil_div(height * width, THREADS), static_cast<unsigned>(planes));
-  metrics_kernel<false><<<grid, THREADS, smem, st>>>(fields, truth, nullptr, members, planes, height, width, nullptr,
-                                                     nullptr, out_skill, out_spread, out_mean);
-  LC_LAUNCH_CHECK();
-  return 0;
+  LC_REQUIRE(planes > 0 && height > 0 && width > 0, "bad shape");
+  return launch_metrics<false>(fields, planes * height * width, truth, nullptr, members, planes, height, width, nullptr,
+                               nullptr, out_skill, out_spread, out_mean, static_cast<cudaStream_t>(stream));
 }
 
 int lc_metrics_acc(const float* forecast, const float* truth, const float* climate, const double* lat_weights,
                    long long planes, int height, int width, double* sums, double* counts, void* stream) {
   LC_REQUIRE(forecast && truth && climate && sums && counts, "null argument");
-  LC_REQUIRE(planes > 0 && planes <= 65535, "number of planes must be in [1, 65535] per call");
+  LC_REQUIRE(planes > 0 && height > 0 && width > 0, "bad shape");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   LC_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 3 * planes, st));
   LC_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(double) * 3 * planes, st));
-  dim3 grid(ceil_div(height * width, THREADS), static_cast<unsigned>(planes));
-  acc_kernel<<<grid, THREADS, 0, st>>>(forecast, truth, climate, lat_weights, planes, height, width, sums, counts);
+  const int bpp = blocks_per_plane(height * width);
+  LC_REQUIRE(planes * bpp < (1ll << 31), "too many planes for one launch");
+  ProfScope ps(PROF_METRICS, 0.0, static_cast<double>(planes) * height * width * 12.0, st);
+  acc_kernel<<<static_cast<unsigned>(planes * bpp), THREADS, 0, st>>>(forecast, truth, climate, lat_weights, planes, height,
+                                                                     width, bpp, sums, counts);
   LC_LAUNCH_CHECK();
   return 0;
 }

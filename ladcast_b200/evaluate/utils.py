@@ -39,19 +39,10 @@ def _pointwise(forecast, truth, ensemble_dim, want):
                                f.shape[:1] + out_shape)[0].to(torch.float32).contiguous()
     res = {k: torch.empty(out_shape, device=f.device, dtype=torch.float32) for k in want}
     lib = _lib.load()
-    done = 0
-    fv = f.reshape(M, N, H * W)
-    while done < N:  # the kernel takes at most 65535 planes per launch
-        n = min(N - done, 65535)
-        fs = fv[:, done : done + n].contiguous() if n != N else fv
-        ts = t.reshape(N, H * W)[done : done + n].contiguous() if t is not None else None
-        outs = {k: torch.empty((n, H * W), device=f.device, dtype=torch.float32) for k in want}
-        _lib.check(lib.lc_metrics_pointwise(_lib.ptr(fs), _lib.ptr(ts), M, n, H, W, _lib.ptr(outs.get("skill")),
-                                            _lib.ptr(outs.get("spread")), _lib.ptr(outs.get("mean")), _lib.stream()),
+    with torch.cuda.device(f.device):
+        _lib.check(lib.lc_metrics_pointwise(_lib.ptr(f), _lib.ptr(t), M, N, H, W, _lib.ptr(res.get("skill")),
+                                            _lib.ptr(res.get("spread")), _lib.ptr(res.get("mean")), _lib.stream()),
                    "lc_metrics_pointwise")
-        for k in want:
-            res[k].reshape(N, H * W)[done : done + n] = outs[k]
-        done += n
     return res
 
 
@@ -88,17 +79,13 @@ def get_acc(forecast: torch.Tensor, truth: torch.Tensor, climate: torch.Tensor,
         lw = torch.broadcast_to(torch.as_tensor(lat_weight).to(dev, torch.float64).reshape(-1, 1) if torch.as_tensor(lat_weight).numel() == H
                                 else torch.as_tensor(lat_weight).to(dev, torch.float64), (H, 1)).reshape(H).contiguous()
     lib = _lib.load()
-    out = torch.empty(N, device=dev, dtype=torch.float64)
-    done = 0
-    while done < N:
-        n = min(N - done, 65535)
-        s = torch.empty((3, n), device=dev, dtype=torch.float64)
-        k = torch.empty((3, n), device=dev, dtype=torch.float64)
-        _lib.check(lib.lc_metrics_acc(_lib.ptr(f[done : done + n]), _lib.ptr(t[done : done + n]), _lib.ptr(c[done : done + n]),
-                                      _lib.ptr(lw), n, H, W, _lib.ptr(s), _lib.ptr(k), _lib.stream()), "lc_metrics_acc")
-        m = s / k
-        out[done : done + n] = m[0] / torch.sqrt(m[1] * m[2])
-        done += n
+    sm = torch.empty((3, N), device=dev, dtype=torch.float64)
+    cnt = torch.empty((3, N), device=dev, dtype=torch.float64)
+    with torch.cuda.device(dev):
+        _lib.check(lib.lc_metrics_acc(_lib.ptr(f), _lib.ptr(t), _lib.ptr(c), _lib.ptr(lw), N, H, W, _lib.ptr(sm), _lib.ptr(cnt),
+                                      _lib.stream()), "lc_metrics_acc")
+    m = sm / cnt  # nanmean of the three weighted products
+    out = m[0] / torch.sqrt(m[1] * m[2])
     res = out.reshape(shape[:-2])
     return res if lat_weight is not None and torch.as_tensor(lat_weight).dtype == torch.float64 else res.to(torch.float32)
 
@@ -118,23 +105,20 @@ def _tables_from_sums(sums, counts, n_pix, channels, leads, sst_channel):
 
 
 def _local_sums_cuda(fields: torch.Tensor, truth: torch.Tensor, lat_weights: torch.Tensor):
-    """fields [M, N, H, W] f32, truth [N, H, W] f32 -> (sums [4,N], counts [4,N]) fp64 via the CUDA kernel."""
+    """fields [M, N, H, W] f32 (planes of a member contiguous, any member stride), truth [N, H, W] f32 ->
+    (sums [4, N], counts [4, N]) fp64 via the CUDA kernel, read in place (no staging copies)."""
     lib = _lib.load()
     M, N, H, W = fields.shape
+    if fields.dtype != torch.float32 or (M > 1 and fields[0].stride() != (H * W, W, 1)) or fields.stride()[1:] != (H * W, W, 1):
+        fields = fields.to(torch.float32).contiguous()
+    truth = truth.to(fields.device, torch.float32).contiguous()
     sums = torch.empty((4, N), device=fields.device, dtype=torch.float64)
     counts = torch.empty((4, N), device=fields.device, dtype=torch.float64)
     lw = lat_weights.to(fields.device, torch.float64).contiguous()
-    done = 0
-    while done < N:
-        n = min(N - done, 65535)
-        fs = fields[:, done : done + n].contiguous()
-        ts = truth[done : done + n].contiguous()
-        s = torch.empty((4, n), device=fields.device, dtype=torch.float64)
-        c = torch.empty((4, n), device=fields.device, dtype=torch.float64)
-        _lib.check(lib.lc_metrics_accumulate(_lib.ptr(fs), _lib.ptr(ts), _lib.ptr(lw), M, n, H, W, _lib.ptr(s), _lib.ptr(c),
-                                             _lib.stream()), "lc_metrics_accumulate")
-        sums[:, done : done + n], counts[:, done : done + n] = s, c
-        done += n
+    with torch.cuda.device(fields.device):
+        _lib.check(lib.lc_metrics_accumulate_strided(_lib.ptr_any(fields), fields.stride(0) if M > 1 else N * H * W,
+                                                     _lib.ptr(truth), _lib.ptr(lw), M, N, H, W, _lib.ptr(sums),
+                                                     _lib.ptr(counts), _lib.stream()), "lc_metrics_accumulate_strided")
     return sums, counts
 
 
@@ -146,7 +130,10 @@ def ensemble_metrics(fields: torch.Tensor, truth: torch.Tensor, lat_weights=None
     M, C, T, H, W = fields.shape
     if lat_weights is None:
         lat_weights = torch.from_numpy(get_normalized_lat_weights_based_on_cos(np.linspace(-88.5, 90, H)))
-    f = fields.to(torch.float32).reshape(M, C * T, H, W)
+    if not fields.is_cuda:
+        raise _lib.LadcastB200Error("metrics run on CUDA tensors only; there is no CPU fallback")
+    f = fields.to(torch.float32)
+    f = f.reshape(M, C * T, H, W) if f[0].is_contiguous() else f.contiguous().reshape(M, C * T, H, W)
     sums, counts = _local_sums_cuda(f, truth.to(fields.device, torch.float32).reshape(C * T, H, W), torch.as_tensor(lat_weights))
     return _tables_from_sums(sums, counts, H * W, C, T, sst_channel)
 
@@ -156,15 +143,65 @@ def plane_shard(n_planes: int, rank: int, world: int) -> range:
     return range(lo, hi)
 
 
+def exchange_bytes(members, n_planes: int, hw: int, rank: int, world: int) -> int:
+    """fp32 bytes rank `rank` SENDS to other ranks in the member->plane re-shard (its members' values on foreign planes)."""
+    mine = len(plane_shard(n_planes, rank, world))
+    return 4 * hw * members[rank] * (n_planes - mine)
+
+
+@torch.no_grad()
+def reshard_members_to_planes(fields_local: torch.Tensor, members, group=None, out: Optional[torch.Tensor] = None):
+    """The one exchange of the path: fields_local [M_r, N, HW] (this rank's members, all planes) ->
+    [sum(members), n_mine, HW] (all members, this rank's contiguous slice of the N planes).  One grouped NCCL
+    send/recv (ncclGroupStart .. ncclSend/ncclRecv per (member, peer) .. ncclGroupEnd via batch_isend_irecv): every
+    message is a contiguous slice of the source and lands in its final position of the destination, so there is no
+    pack / unpack copy on either side.  Works unchanged on gloo (CPU tests)."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    M_r, N, HW = fields_local.shape
+    mine = plane_shard(N, rank, world)
+    n_mine = len(mine)
+    total = sum(members)
+    first = [sum(members[:q]) for q in range(world)]  # global index of rank q's first member
+    if out is None:
+        out = torch.empty((total, n_mine, HW), dtype=fields_local.dtype, device=fields_local.device)
+    ops = []
+    for q in range(world):
+        pq = plane_shard(N, q, world)
+        if q == rank:
+            continue
+        for m in range(M_r):
+            if len(pq):
+                ops.append(dist.P2POp(dist.isend, fields_local[m, pq.start : pq.stop], _global_rank(group, q), group))
+        for l in range(members[q]):
+            if n_mine:
+                ops.append(dist.P2POp(dist.irecv, out[first[q] + l], _global_rank(group, q), group))
+    if n_mine and M_r:
+        out[first[rank] : first[rank] + M_r].copy_(fields_local[:, mine.start : mine.stop])  # my own share: local copy
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out
+
+
+def _global_rank(group, q):
+    import torch.distributed as dist
+
+    return q if group is None else dist.get_global_rank(group, q)
+
+
 @torch.no_grad()
 def ensemble_metrics_distributed(fields_local: torch.Tensor, truth: torch.Tensor, lat_weights=None, group=None,
                                  sst_channel: Optional[int] = SST_CHANNEL_IDX,
-                                 local_sums_fn: Optional[Callable] = None) -> Dict[str, torch.Tensor]:
+                                 local_sums_fn: Optional[Callable] = None, timings: Optional[dict] = None
+                                 ) -> Dict[str, torch.Tensor]:
     """Members are sharded over ranks (`fields_local` [M_r, C, T, H, W] with possibly different M_r per rank); CRPS
     spread and the ensemble mean need all members per grid point, so the fields are re-sharded once — rank r receives
-    every member's values for its contiguous slice of the C*T (channel, lead) planes (NCCL all-to-all; an
-    all-gather based exchange on backends without all-to-all) — reduced locally, and the [4, planes] partial tables
-    are all-gathered.  Every rank returns the full [C, T] tables."""
+    every member's values for its contiguous slice of the C*T (channel, lead) planes (`reshard_members_to_planes`) —
+    reduced locally by the metrics kernel, and the [8, planes] partial tables are all-gathered.  Every rank returns the
+    full [C, T] tables (reference assembly: evaluate/evaluate_ens_gpu.py:339-415, gather :462-468).
+    `timings` (optional dict) receives CUDA-event milliseconds of the exchange and of the local reduction."""
     import torch.distributed as dist
 
     if local_sums_fn is None:
@@ -177,35 +214,27 @@ def ensemble_metrics_distributed(fields_local: torch.Tensor, truth: torch.Tensor
         lat_weights = torch.from_numpy(get_normalized_lat_weights_based_on_cos(np.linspace(-88.5, 90, H)))
     lat_weights = torch.as_tensor(lat_weights)
     dev = fields_local.device
-    f = fields_local.to(torch.float32).reshape(M_r, N, H * W)
+    f = fields_local.to(torch.float32)
+    f = (f if f.is_contiguous() else f.contiguous()).reshape(M_r, N, H * W)
     counts_m = torch.zeros(world, dtype=torch.int64, device=dev)
     counts_m[rank] = M_r
     dist.all_reduce(counts_m, group=group)
     members = [int(v) for v in counts_m.tolist()]
     mine = plane_shard(N, rank, world)
     n_mine = len(mine)
-    backend = dist.get_backend(group)
-    if backend == "nccl":
-        # send buffer: for destination q, my members' values on q's planes, [M_r, n_q, HW] each, concatenated
-        send = torch.cat([f[:, plane_shard(N, q, world).start : plane_shard(N, q, world).stop].reshape(-1) for q in range(world)])
-        in_split = [M_r * len(plane_shard(N, q, world)) * H * W for q in range(world)]
-        out_split = [members[q] * n_mine * H * W for q in range(world)]
-        recv = torch.empty(sum(out_split), dtype=torch.float32, device=dev)
-        dist.all_to_all_single(recv, send, out_split, in_split, group=group)
-        parts, off = [], 0
-        for q in range(world):
-            parts.append(recv[off : off + out_split[q]].reshape(members[q], n_mine, H * W))
-            off += out_split[q]
-        gathered = torch.cat(parts, dim=0)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if (timings is not None and dev.type == "cuda") else None
+    if ev:
+        ev[0].record()
+    gathered = reshard_members_to_planes(f, members, group)
+    if ev:
+        ev[1].record()
+    t_mine = truth.to(dev, torch.float32).reshape(N, H, W)[mine.start : mine.stop]
+    if n_mine:
+        sums_l, counts_l = local_sums_fn(gathered.reshape(-1, n_mine, H, W), t_mine, lat_weights)
     else:
-        m_max = max(members)
-        pad = torch.zeros((m_max, N, H * W), dtype=torch.float32, device=dev)
-        pad[:M_r] = f
-        bufs = [torch.empty_like(pad) for _ in range(world)]
-        dist.all_gather(bufs, pad, group=group)
-        gathered = torch.cat([bufs[q][: members[q], mine.start : mine.stop] for q in range(world)], dim=0)
-    t_mine = truth.to(dev, torch.float32).reshape(N, H, W)[mine.start : mine.stop].contiguous()
-    sums_l, counts_l = local_sums_fn(gathered.reshape(-1, n_mine, H, W).contiguous(), t_mine, lat_weights)
+        sums_l = counts_l = torch.zeros((4, 0), dtype=torch.float64, device=dev)
+    if ev:
+        ev[2].record()
     n_max = max(len(plane_shard(N, q, world)) for q in range(world))
     packed = torch.zeros((8, n_max), dtype=torch.float64, device=dev)
     packed[:4, :n_mine], packed[4:, :n_mine] = sums_l, counts_l
@@ -213,4 +242,10 @@ def ensemble_metrics_distributed(fields_local: torch.Tensor, truth: torch.Tensor
     dist.all_gather(allp, packed, group=group)
     sums = torch.cat([allp[q][:4, : len(plane_shard(N, q, world))] for q in range(world)], dim=1)
     counts = torch.cat([allp[q][4:, : len(plane_shard(N, q, world))] for q in range(world)], dim=1)
+    if ev:
+        torch.cuda.synchronize(dev)
+        timings["exchange_ms"] = ev[0].elapsed_time(ev[1])
+        timings["kernel_ms"] = ev[1].elapsed_time(ev[2])
+        timings["bytes_sent"] = exchange_bytes(members, N, H * W, rank, world)
+        timings["members"] = members
     return _tables_from_sums(sums, counts, H * W, C, T, sst_channel)
