@@ -7,8 +7,19 @@
 One "step" = one autoregressive step of the rollout for the members resident on a GPU: `num_inference_steps`
 denoiser calls of the DPM-Solver++ sampler (T_out lead steps at once), the scheduler updates, feeding the last frame
 back, latent de-normalisation and the DC-AE decode of every (member, lead) frame.  It yields ens * T_out
-member-6h-steps.  Members shard across GPUs with no communication inside the rollout (weak scaling: every rank
-runs `--ens` members).  Prints ONE JSON line on rank 0.
+member-6h-steps.  Prints ONE JSON line on rank 0 with
+
+  value / ms_per_step  headline (BASELINE config 2): ladcast_375M, `--ens` members PER GPU (weak scaling: members are
+                       independent, no communication inside the rollout), inputs resident in HBM;
+  e2e                  the same through `roll_out_latent` with host buffers (H2D noise, D2H fields every AR step);
+  roofline             tcgen05 GEMM class, live CUDA-event timing per launch; `roofline.secondary`: every other
+                       kernel class (attention / sphere conv vs the bf16 peak, HBM-bound kernels vs the copy peak);
+  metrics              the ensemble-metrics kernel (lat-weighted RMSE / CRPS) on the decoded fields: GB/s vs HBM peak;
+  strong               BASELINE configs 4/5: ladcast_1.6B, a FIXED ensemble (20 and 50 members) sharded over the N
+                       ranks with `member_shard`, plus the one collective of the path — the member->plane re-shard of
+                       the decoded fields (grouped NCCL send/recv) feeding the metrics kernel — timed and checked
+                       against the single-GPU metrics of the gathered fields;
+  cpu_baseline         the oracle port on the host cores (bounded sample + BASELINE config 1 end to end), N=1 only.
 """
 import argparse
 import json
@@ -30,6 +41,25 @@ UNIT = "member-steps/s"
 MODEL_CFG = {
     "375M": dict(num_attention_heads=12, num_layers=2, num_single_layers=4, num_refiner_layers=1),
     "1.6B": dict(num_attention_heads=16, num_layers=5, num_single_layers=10, num_refiner_layers=3),
+}
+
+# kernel classes of lc_prof_collect_all and the roofline that bounds each
+TENSOR_CLASSES = ("gemm_tc", "attention_tc", "sphere_conv_tc")
+CLASS_KERNELS = {
+    "gemm_tc": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05 bf16 GEMM, CTA-pair; denoiser linears + decoder 1x1)",
+    "attention_tc": "attention_tc_kernel (tcgen05 flash attention, D=128)",
+    "sphere_conv_tc": "gemm_tc2_kernel in implicit-GEMM 3x3 sphere-conv mode (DC-AE)",
+    "layernorm": "layernorm_kernel (LayerNorm + AdaLN modulation, fp32 in / bf16 out)",
+    "qk_norm_rope": "qk_norm_rope_bf16_kernel (per-head RMSNorm(q,k) + RoPE, in place)",
+    "scheduler": "dpmpp2m_kernel / scale_kernel / latent_feedback_kernel (fused scheduler step, AR feedback)",
+    "dec_rmsnorm": "rmsnorm_rows_kernel (DC-AE channel RMSNorm + residual)",
+    "dec_multiscale": "multiscale_fused_kernel (DC-AE 5x5 depthwise + grouped 1x1)",
+    "dec_linear_attn": "linear_attn_kernel (DC-AE ReLU linear attention)",
+    "dec_dwconv_glu": "dwconv3_glu_kernel (DC-AE depthwise 3x3 + GLU)",
+    "dec_pixel_shuffle": "pixel_shuffle_kernel (+ shortcut)",
+    "dec_pad": "pad_from_* / halo_fill / in_shortcut kernels (sphere padding)",
+    "metrics": "metrics_sorted_kernel (ensemble mean / CRPS skill / sorted CRPS spread, lat-weighted fp64 reduction)",
+    "misc": "patchify / timestep / pooling / cast kernels",
 }
 
 
@@ -104,10 +134,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_sample(model_name, t_out, n_denoise, repeats=1):
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_reference_sample(model_name, t_out, n_denoise, repeats=1, members=2):
     """The reference algorithm (oracle/ladcast_oracle.py, a CPU fp32 port validated against the unmodified reference)
-    on the host cores: a bounded sample of the same workload — 2 denoiser calls (1 member, T_out lead steps, 2250
-    tokens) + 1 decoded frame — scaled to one member's AR step (n_denoise calls + T_out frames)."""
+    on the host cores with all threads: a bounded, BATCHED sample of the same workload — one denoiser call for
+    `members` members at once (T_out lead steps, 2250 tokens) and the decode of `members` frames in one batch — scaled
+    to those members' AR step (n_denoise calls + members * T_out frames)."""
     from oracle import ladcast_oracle as O
 
     cores = os.cpu_count() or 1
@@ -117,27 +149,55 @@ def cpu_reference_sample(model_name, t_out, n_denoise, repeats=1):
     acfg = O.dcae_config()
     asd = O.make_state_dict(O.dcae_decoder_param_shapes(acfg), 2)
     g = torch.Generator("cpu").manual_seed(0)
-    x = torch.randn((1, 84, t_out, 15, 30), generator=g)
-    cond = torch.randn((1, 84, 1, 15, 30), generator=g) * 0.5
-    z = torch.randn((1, 84, 15, 30), generator=g)
+    B = members
+    x = torch.randn((B, 84, t_out, 15, 30), generator=g)
+    cond = torch.randn((B, 84, 1, 15, 30), generator=g) * 0.5
+    z = torch.randn((B, 84, 15, 30), generator=g)
     ts = torch.tensor([2018010100])
     vals = []
     with torch.no_grad():
-        O.denoiser_forward(sd, cfg, x, torch.tensor([0.5]), cond, ts)  # warm-up
+        O.denoiser_forward(sd, cfg, x[:1], torch.tensor([0.5]), cond[:1], ts)  # warm-up (thread pool, allocator)
         for _ in range(repeats):
             t0 = time.perf_counter()
-            for tt in (0.7, -0.3):
-                O.denoiser_forward(sd, cfg, x, torch.tensor([tt]), cond, ts)
-            t_call = (time.perf_counter() - t0) / 2
+            O.denoiser_forward(sd, cfg, x, torch.tensor([0.7]).expand(B), cond, ts)
+            t_call = time.perf_counter() - t0
             t0 = time.perf_counter()
             O.dcae_decode(asd, acfg, z)
-            t_frame = time.perf_counter() - t0
-            vals.append((t_out / (n_denoise * t_call + t_out * t_frame), t_call, t_frame))
+            t_dec = time.perf_counter() - t0
+            vals.append((B * t_out / (n_denoise * t_call + t_out * t_dec), t_call, t_dec))
     v = sum(a for a, _, _ in vals) / len(vals)
     return {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"oracle port (CPU fp32, torch {torch.__version__}, {cores} threads): 2 denoiser calls B=1 T_out={t_out} "
-                      f"({vals[-1][1]:.2f} s/call) + 1 decoded frame ({vals[-1][2]:.2f} s), scaled to {n_denoise} calls + "
-                      f"{t_out} frames per member AR step"}, vals
+            "sample": f"oracle port (CPU fp32, torch {torch.__version__}, {cores} threads): 1 batched denoiser call B={B} "
+                      f"T_out={t_out} ({vals[-1][1]:.2f} s) + 1 batched decode of {B} frames ({vals[-1][2]:.2f} s), scaled to "
+                      f"{n_denoise} calls + {B * t_out} frames per AR step of {B} members"}, vals
+
+
+def cpu_config1():
+    """BASELINE config 1 end to end through the oracle port: ladcast_375M, ensemble_size=2, num_inference_steps=5,
+    1 lead step (T_out=1), synthetic 84x120x240 input through DCAE encode -> denoise -> decode, fp32, batched."""
+    from oracle import ladcast_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.denoiser_config("375M")
+    sd = O.make_state_dict(O.denoiser_param_shapes(cfg), 1)
+    acfg = O.dcae_config()
+    asd = O.make_state_dict(O.dcae_decoder_param_shapes(acfg), 2)
+    asd.update(O.make_state_dict(O.dcae_encoder_param_shapes(acfg), 3))
+    g = torch.Generator("cpu").manual_seed(0)
+    fields = torch.randn((1, 84, 120, 240), generator=g)
+    static = torch.randn((1, 5, 120, 240), generator=g)
+    lat_mean, lat_std = torch.zeros(84), torch.ones(84)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        z = O.dcae_encode(asd, acfg, fields, static)
+        known = O.normalize_latent(z.permute(1, 0, 2, 3).unsqueeze(0), lat_mean, lat_std, 0.5)
+        t_enc = time.perf_counter() - t0
+        O.rollout(sd, cfg, asd, acfg, known, [0, 1], 2018010100, 1, 1, 5, lat_mean, lat_std, sampler="pipeline")
+        dt = time.perf_counter() - t0
+    return {"seconds": round(dt, 2), "encode_seconds": round(t_enc, 2), "member_steps_per_s": round(2.0 / dt, 4),
+            "config": "BASELINE config 1: 375M, ens=2, 5 denoise steps, T_out=1, encode+denoise+decode, fp32, "
+                      f"{cores} threads (5 denoise steps, so not comparable with the 20-step headline metric)"}
 
 
 def run_reference(args):
@@ -164,6 +224,210 @@ def workload_config(args, world):
             "l2": "working set per step (>1.5 GB of activations) exceeds the 126 MB L2; no explicit flush"}
 
 
+# ------------------------------------------------------------------------------------------------ GPU legs
+class Rollout:
+    """Device-resident AR loop for a list of global member ids: exactly `rollout_step` of the product path."""
+
+    def __init__(self, model_name, members, args, dev, ae=None):
+        from ladcast_b200.models import AutoencoderDC, LaDCastTransformer3DModel
+        from ladcast_b200.pipelines import AutoRegressive2DPipeline, EDMDPMSolverMultistepScheduler
+
+        torch.manual_seed(1234)  # identical random-init weights on every rank
+        self.model = LaDCastTransformer3DModel.from_config(denoiser_kwargs(model_name)).to(dev)
+        self.ae = ae if ae is not None else AutoencoderDC(**DCAE_KW).to(dev)
+        self.pipe = AutoRegressive2DPipeline(self.model, EDMDPMSolverMultistepScheduler())
+        self.members, self.args, self.dev = list(members), args, dev
+        g = torch.Generator("cpu").manual_seed(7)
+        self.known0 = torch.randn((1, 84, 1, 15, 30), generator=g) * 0.5
+        self.lat_mean, self.lat_std = torch.randn(84, generator=g) * 0.1, torch.rand(84, generator=g) + 0.5
+        self.fld_mean, self.fld_std = torch.randn(84, generator=g), torch.rand(84, generator=g) + 0.5
+        self.stats = [t.to(dev).contiguous() for t in (self.lat_mean, self.lat_std, self.fld_mean, self.fld_std)]
+        self.known = self.known0.to(dev)
+        self.out = torch.empty((len(self.members), 84, args.t_out, 120, 240), device=dev) if self.members else None
+        self.stamp = torch.tensor([2018010100])  # the date embedding is recomputed every AR step like the reference
+
+    def step(self):
+        from ladcast_b200.pipelines.utils import rollout_step
+
+        if not self.members:
+            return None
+        a = self.args
+        fields, self.known = rollout_step(self.pipe, self.ae, self.known, self.stamp, len(self.members), *self.stats,
+                                          num_inference_steps=a.denoise_steps, return_seq_len=a.t_out,
+                                          sampler_type="pipeline", member_indices=self.members, out=self.out)
+        return fields
+
+    def release(self):
+        self.model._release()
+        self.model = self.pipe = None
+
+
+def timed_loop(run, steps, warmup, barrier, world, dev, lib, clock_index=None):
+    """W warm-up + K timed AR steps; CUDA events on the launching stream, max over ranks; also the host time spent
+    ENQUEUEING the K steps (launch-bound when it approaches the device time)."""
+    import torch.distributed as dist
+
+    out = None
+    for _ in range(warmup):
+        out = run.step()
+    barrier()
+    clocks = ClockSampler(clock_index) if clock_index is not None else None
+    launches0 = lib.lc_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    h0 = time.perf_counter()
+    for _ in range(steps):
+        out = run.step()
+    host_ms = 1e3 * (time.perf_counter() - h0)
+    e1.record()
+    barrier()
+    launches = lib.lc_launch_count() - launches0
+    clk = clocks.stop() if clocks else None
+    t = torch.tensor([e0.elapsed_time(e1), host_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, host_ms = [float(v) for v in t.tolist()]
+    return out, ms, host_ms, int(launches), clk
+
+
+def profiled_step(run, lib, _lib):
+    """One more identical step with every launch bracketed by CUDA events -> per-class ms / FLOPs / bytes."""
+    lib.lc_prof_enable(1)
+    run.step()
+    torch.cuda.synchronize()
+    classes = _lib.prof_collect()
+    lib.lc_prof_enable(0)
+    return classes
+
+
+def class_rooflines(classes, peaks, step_ms):
+    """roofline objects per kernel class: tensor classes vs the sustained bf16 peak, the rest vs the HBM copy peak."""
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_gb = float(peaks.get("hbm_gbs", 6650.0))
+    src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+    out = {}
+    for name, c in classes.items():
+        ms = c["ms"]
+        if ms <= 0:
+            continue
+        r = {"kernel": CLASS_KERNELS.get(name, name), "launches": c["launches"], "ms": round(ms, 3),
+             "avg_launch_ms": round(ms / c["launches"], 4), "share_of_step": round(ms / step_ms, 4)}
+        if name in TENSOR_CLASSES:
+            ach = c["flops"] / (ms * 1e-3) / 1e12
+            r.update({"bound": "tensor", "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s",
+                      "frac": round(ach / peak_tf, 4), "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)"})
+        else:
+            ach = c["bytes"] / (ms * 1e-3) / 1e9
+            r.update({"bound": "hbm", "achieved": round(ach, 1), "peak": peak_gb, "unit": "GB/s",
+                      "frac": round(ach / peak_gb, 4), "peak_source": f"{src} hbm_gbs", "algorithmic_bytes": c["bytes"]})
+        out[name] = r
+    return out
+
+
+def metrics_leg(fields, lib, _lib, peaks, extra_members=(50,)):
+    """Ensemble-metrics kernel on the decoded fields of the last AR step ([ens, 84, T, 120, 240]) and, for the larger
+    ensemble of config 4, on a synthetic block of the same shape: CUDA-event time and GB/s vs the HBM copy peak.
+    Inputs (fields + truth) exceed the 126 MB L2."""
+    from ladcast_b200.evaluate.utils import ensemble_metrics
+
+    peak_gb = float(peaks.get("hbm_gbs", 6650.0))
+    res = []
+    g = torch.Generator("cpu").manual_seed(11)
+    truth = torch.randn((84, fields.shape[2], 120, 240), generator=g).to(fields.device)
+    cases = [(fields.shape[0], fields)]
+    for m in extra_members:
+        try:
+            cases.append((m, torch.randn((m,) + tuple(fields.shape[1:]), device=fields.device)))
+        except Exception:
+            pass
+    for m, f in cases:
+        for _ in range(3):
+            ensemble_metrics(f, truth)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            tabs = ensemble_metrics(f, truth)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        by = 4.0 * (m + 1) * truth.numel()
+        res.append({"members": m, "planes": 84 * int(fields.shape[2]), "ms": round(ms, 4), "algorithmic_bytes": by,
+                    "achieved": round(by / (ms * 1e-3) / 1e9, 1), "peak": peak_gb, "unit": "GB/s",
+                    "frac": round(by / (ms * 1e-3) / 1e9 / peak_gb, 4), "bound": "hbm",
+                    "note": "includes the two 27 KB memsets and the host-side table assembly launches",
+                    "finite": bool(all(torch.isfinite(v).all() for v in tabs.values()))})
+        del f
+    return res
+
+
+def strong_leg(args, ens_total, rank, world, dev, ae, barrier, lib, _lib, steps, warmup):
+    """BASELINE configs 4/5: ladcast_1.6B, `ens_total` members sharded over the ranks (member_shard), AR steps timed as
+    the headline; then the one exchange of the path + metrics, timed and checked against the single-GPU result."""
+    import torch.distributed as dist
+
+    from ladcast_b200.evaluate.utils import ensemble_metrics, ensemble_metrics_distributed
+    from ladcast_b200.pipelines.utils import member_shard
+
+    members = list(member_shard(ens_total, rank, world))
+    run = Rollout(args.strong_model, members, args, dev, ae=ae)
+    fields, ms, host_ms, launches, _ = timed_loop(run, steps, warmup, barrier, world, dev, lib)
+    step_ms = ms / steps
+    value = ens_total * args.t_out * steps / (ms * 1e-3)
+    per_rank = [len(member_shard(ens_total, r, world)) for r in range(world)]
+    res = {"model": f"ladcast_{args.strong_model}", "ensemble_total": ens_total, "members_per_rank": per_rank,
+           "scaling": "strong", "value": value, "unit": UNIT, "ms_per_step": step_ms, "steps": steps, "warmup": warmup,
+           "host_enqueue_ms_per_step": round(host_ms / steps, 2), "gpu_launches_per_step": launches // max(1, steps),
+           "balance_bound": round(ens_total / (world * max(per_rank)), 4),
+           "step_algorithmic_tflops_per_gpu": round(flops_per_member_step(args.strong_model, args.t_out, args.denoise_steps)
+                                                    * max(per_rank) * args.t_out / (step_ms * 1e-3) / 1e12, 1)}
+    res["limiter"] = ("host launch rate (enqueue time ~ device time)" if host_ms > 0.85 * ms else
+                      "device: the rank with the most members; the host enqueues a step in "
+                      f"{host_ms / steps:.0f} ms of the {step_ms:.0f} ms it takes")
+    # ---- metrics over the sharded ensemble (config 5): exchange + kernel, timed; checked against one GPU
+    g = torch.Generator("cpu").manual_seed(11)
+    truth = torch.randn((84, args.t_out, 120, 240), generator=g).to(dev)
+    if fields is None:
+        fields = torch.empty((0, 84, args.t_out, 120, 240), device=dev)
+    if world > 1:
+        tm = {}
+        for _ in range(2):  # first pass opens the NCCL peer connections
+            tabs = ensemble_metrics_distributed(fields, truth, timings=tm)
+        m_max = max(per_rank)
+        pad = torch.zeros((m_max,) + tuple(fields.shape[1:]), device=dev)
+        pad[: fields.shape[0]] = fields
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad)
+        full = torch.cat([bufs[q][: per_rank[q]] for q in range(world)], dim=0)
+        del bufs, pad
+        want = ensemble_metrics(full, truth)
+        ok = all(torch.allclose(tabs[k], want[k], rtol=1e-9, atol=1e-12, equal_nan=True) for k in want)
+        t = torch.tensor([tm["exchange_ms"], tm["kernel_ms"], float(tm["bytes_sent"]), 0.0 if ok else 1.0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ex_ms, k_ms, by, bad = [float(v) for v in t.tolist()]
+        res["metrics"] = {"exchange_ms": round(ex_ms, 3), "kernel_ms": round(k_ms, 3), "bytes": int(by),
+                          "exchange_gbs_per_gpu": round(by / (ex_ms * 1e-3) / 1e9, 1) if ex_ms > 0 else None,
+                          "matches_single_gpu": bad == 0.0, "rtol": 1e-9,
+                          "what": "ensemble_metrics_distributed on the last AR step's decoded fields (max over ranks; "
+                                  "bytes = fp32 bytes one rank sends) vs ensemble_metrics on the all-gathered fields"}
+        del full
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ensemble_metrics(fields, truth)
+        e0.record()
+        tabs = ensemble_metrics(fields, truth)
+        e1.record()
+        torch.cuda.synchronize()
+        res["metrics"] = {"exchange_ms": 0.0, "kernel_ms": round(e0.elapsed_time(e1), 3), "bytes": 0,
+                          "matches_single_gpu": True, "what": "single GPU: no exchange"}
+    res["finite"] = bool(torch.isfinite(fields).all().item()) and all(bool(torch.isfinite(v).all()) for v in tabs.values())
+    run.release()
+    del run, fields
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -171,11 +435,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="375M", choices=list(MODEL_CFG))
-    ap.add_argument("--ens", type=int, default=20, help="ensemble members per GPU")
+    ap.add_argument("--ens", type=int, default=20, help="ensemble members per GPU (weak-scaling headline)")
     ap.add_argument("--denoise-steps", type=int, default=20)
     ap.add_argument("--t-out", type=int, default=4)
+    ap.add_argument("--strong-model", default="1.6B", choices=list(MODEL_CFG))
+    ap.add_argument("--strong-ens", default="20,50", help="fixed ensemble sizes of the strong-scaling leg (configs 5, 4)")
+    ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-metrics", action="store_true")
     ap.add_argument("--no-roofline", action="store_true", help="skip the extra event-profiled step (for ncu launch lists)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -186,9 +454,7 @@ def main():
     import torch.distributed as dist
 
     from ladcast_b200 import _lib
-    from ladcast_b200.models import AutoencoderDC, LaDCastTransformer3DModel
-    from ladcast_b200.pipelines import AutoRegressive2DPipeline, EDMDPMSolverMultistepScheduler
-    from ladcast_b200.pipelines.utils import decode_latent_ens, ensemble_AR_sampler, roll_out_latent
+    from ladcast_b200.pipelines.utils import roll_out_latent
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -199,103 +465,56 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
-    torch.manual_seed(1234)  # identical random-init weights on every rank
-    model = LaDCastTransformer3DModel.from_config(denoiser_kwargs(args.model)).to(dev)
-    ae = AutoencoderDC(**DCAE_KW).to(dev)
-    pipe = AutoRegressive2DPipeline(model, EDMDPMSolverMultistepScheduler())
-    members = list(range(rank * args.ens, (rank + 1) * args.ens))  # global member ids of this rank
-    g = torch.Generator("cpu").manual_seed(7)
-    known0 = torch.randn((1, 84, 1, 15, 30), generator=g) * 0.5
-    lat_mean, lat_std = torch.randn(84, generator=g) * 0.1, torch.rand(84, generator=g) + 0.5
-    fld_mean, fld_std = torch.randn(84, generator=g), torch.rand(84, generator=g) + 0.5
-    lm, ls = lat_mean.to(dev)[None, :, None, None, None], lat_std.to(dev)[None, :, None, None, None]
-    fm, fs = fld_mean.to(dev), fld_std.to(dev)
-    state = {"known": known0.to(dev), "step": 0}
-
-    def ar_step():
-        stamp = torch.tensor([2018010100 + 0])  # date embedding is recomputed every AR step like the reference
-        s = ensemble_AR_sampler(pipe, sample_size=args.ens, return_seq_len=args.t_out,
-                                num_inference_steps=args.denoise_steps, known_latents=state["known"], timestamps=stamp,
-                                sampler_type="pipeline", device=dev, member_indices=members)
-        state["known"] = s[:, :, -1:].clone()
-        phys = (s / 0.5) * ls + lm
-        fields = decode_latent_ens(ae, phys, fm, fs)
-        state["step"] += 1
-        return fields
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        out = ar_step()
-    barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
-    launches0 = lib.lc_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = ar_step()
-    e1.record()
-    barrier()
-    launches = lib.lc_launch_count() - launches0
-    clk = clocks.stop() if clocks else None
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    finite = bool(torch.isfinite(out).all().item())
-    units = args.ens * args.t_out * args.steps * world
-    value = units / (ms * 1e-3)
-
-    # ---- roofline of the dominant kernel (tcgen05 GEMM): one more identical step with per-launch CUDA events
-    import ctypes
-
-    lib.lc_prof_enable(1)
-    if not args.no_roofline:
-        ar_step()
-    torch.cuda.synchronize()
-    pms, pfl, pln = (ctypes.c_double * 3)(), (ctypes.c_double * 3)(), (ctypes.c_longlong * 3)()
-    _lib.check(lib.lc_prof_collect(pms, pfl, pln), "lc_prof_collect")
-    lib.lc_prof_enable(0)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained"
-    classes = {}
-    for i, nme in enumerate(("gemm_tc", "attention_tc", "sphere_conv_tc")):
-        if pln[i]:
-            classes[nme] = {"launches": int(pln[i]), "ms": round(pms[i], 3), "tflops": round(pfl[i] / (pms[i] * 1e-3) / 1e12, 1)}
-    gemm_ach = pfl[0] / (pms[0] * 1e-3) / 1e12 if pms[0] > 0 else 0.0
+
+    # ---- headline: weak scaling, `--ens` members per GPU (global member ids so that ranks draw distinct noise)
+    members = list(range(rank * args.ens, (rank + 1) * args.ens))
+    run = Rollout(args.model, members, args, dev)
+    out, ms, host_ms, launches, clk = timed_loop(run, args.steps, args.warmup, barrier, world, dev, lib,
+                                                 clock_index=local if rank == 0 else None)
+    finite = bool(torch.isfinite(out).all().item())
+    units = args.ens * args.t_out * args.steps * world
+    value = units / (ms * 1e-3)
     step_ms = ms / args.steps
-    roofline = {"bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05 bf16 GEMM, CTA-pair; denoiser linears + decoder 1x1)",
-                "achieved": round(gemm_ach, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(gemm_ach / peak_tf, 4),
-                "peak_source": peak_src,
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over 36 consecutive launches of this
-                # kernel in a 375M B=20 denoiser call (profiles/r01_gemm_ncu_final.md); only valid for that workload
-                "traffic": 383.1e6 if (args.model == "375M" and args.ens == 20 and args.t_out == 4) else None,
-                "traffic_source": "profiles/r01_gemm_ncu_final.md (ncu, per-launch average, bytes)",
-                "avg_launch_ms": round(pms[0] / max(1, pln[0]), 4), "share_of_step": round(pms[0] / step_ms, 3),
-                "classes": classes,
-                "step_algorithmic_tflops": round(flops_per_member_step(args.model, args.t_out, args.denoise_steps) * args.ens
-                                                 * args.t_out / (step_ms * 1e-3) / 1e12, 1)}
+
+    # ---- rooflines: one more identical step with per-launch CUDA events
+    roofline = None
+    if not args.no_roofline:
+        per_class = class_rooflines(profiled_step(run, lib, _lib), peaks, step_ms)
+        roofline = dict(per_class.get("gemm_tc", {}))
+        # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum per launch) comes from ncu, never from this run:
+        # profiles/r02_*.md hold the per-kernel captures; no constant is pasted here
+        roofline["traffic"] = None
+        roofline["traffic_source"] = "profiles/ (ncu --set full captures, per kernel); not measurable inside bench.py"
+        roofline["secondary"] = [dict(v, **{"class": k}) for k, v in per_class.items() if k != "gemm_tc"]
+        roofline["step_algorithmic_tflops"] = round(flops_per_member_step(args.model, args.t_out, args.denoise_steps)
+                                                    * args.ens * args.t_out / (step_ms * 1e-3) / 1e12, 1)
+
+    # ---- the metrics kernel on the decoded fields
+    metrics = None
+    if not args.no_metrics and rank == 0:
+        metrics = metrics_leg(out, lib, _lib, peaks)
 
     # ---- end to end through the public API with host buffers (H2D of inputs, D2H of decoded fields, each step)
     e2e = None
     if not args.no_e2e:
         k_e2e = min(args.steps, 5)
-        host_known = known0.clone().pin_memory()
+        host_known = run.known0.clone().pin_memory()
         host_out = torch.empty((k_e2e, args.ens, 84, args.t_out, 120, 240), dtype=torch.float32, pin_memory=True)
         barrier()
         t0 = time.perf_counter()
-        roll_out_latent(pipe, ae, host_known, 2018010100, args.ens, lat_mean, lat_std, fld_mean, fld_std,
-                        num_inference_steps=args.denoise_steps, return_seq_len=args.t_out, sampler_type="pipeline",
-                        member_indices=members, out=host_out, max_ar_steps=k_e2e)
+        roll_out_latent(run.pipe, run.ae, host_known, 2018010100, args.ens, run.lat_mean, run.lat_std, run.fld_mean,
+                        run.fld_std, num_inference_steps=args.denoise_steps, return_seq_len=args.t_out,
+                        sampler_type="pipeline", member_indices=members, out=host_out, max_ar_steps=k_e2e)
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], device=dev)
@@ -304,19 +523,37 @@ def main():
         dt = float(tt.item())
         noise_bytes = args.ens * 84 * args.t_out * 15 * 30 * 4
         e2e = {"value": args.ens * args.t_out * k_e2e * world / dt, "unit": UNIT,
-               "h2d_bytes_per_step": noise_bytes + (84 * 15 * 30 * 4 if True else 0),
+               "h2d_bytes_per_step": noise_bytes + 84 * 15 * 30 * 4,
                "d2h_bytes_per_step": args.ens * 84 * args.t_out * 120 * 240 * 4, "steps": k_e2e,
                "api": "ladcast_b200.pipelines.utils.roll_out_latent (pinned host in/out, async D2H per AR step)"}
+        del host_out
+
+    # ---- strong scaling of the north-star configuration (1.6B, fixed ensembles sharded over the ranks)
+    strong = None
+    ae = run.ae
+    run.release()
+    del out
+    torch.cuda.empty_cache()
+    if not args.no_strong:
+        strong = []
+        for i, e in enumerate(int(v) for v in args.strong_ens.split(",") if v):
+            k = min(args.steps, 3 if i == 0 else 2)
+            strong.append(strong_leg(args, e, rank, world, dev, ae, barrier, lib, _lib, steps=k, warmup=3 if i == 0 else 2))
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base, _ = cpu_reference_sample(args.model, args.t_out, args.denoise_steps)
+        try:
+            cpu_base["config1"] = cpu_config1()
+        except Exception as ex:  # the baseline is a report, never a reason to lose the GPU line
+            cpu_base["config1"] = {"error": repr(ex)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
                 "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches),
+                "host_enqueue_ms_per_step": round(host_ms / args.steps, 2), "metrics": metrics, "strong": strong,
                 "clocks": clk, "finite": finite, "impl": "ours"}
         print(json.dumps(line))
     if world > 1:

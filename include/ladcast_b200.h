@@ -212,6 +212,22 @@ LC_API int lc_gemm_bf16out(const void* a, const void* w, const float* bias, void
 /* qkv: [B, S, 3*heads*128] (q|k|v) fp32 (F32) or bf16 (BF16); out: [B, S, heads*128] same dtype. */
 LC_API int lc_attention(int precision, const void* qkv, void* out, int batch, int seq, int heads, void* stream);
 
+/* The index permutations of the path, exported so that the tests can assert them bit-exact:
+ *  - lc_patchify: HunyuanVideoPatchEmbed's flatten(2).transpose(1,2) for patch (1,1,1) (models/embeddings.py:56-59):
+ *    x [B, C, thw] fp32 -> tokens [B*thw, kp] (fp32 or bf16), token n = t*H*W + h*W + w, columns >= C zero;
+ *  - lc_unpatchify_gemm: tokens [B*thw, k] x w[n_out, k]^T (+bias) stored channel-major as [B, n_out, thw] fp32 — the
+ *    proj_out + unpatchify of LaDCast_3D_model.py:1047-1062 (patch size 1: out-feature f = channel c);
+ *  - lc_pixel_(un)shuffle_shortcut: DCUpBlock2d / DCDownBlock2d tails (models/DCAE.py:519-536, 476-490) on NHWC fp32:
+ *    shuffle: conv [n,H,W,4*cout], xin [n,H,W,cin] -> out [n,2H,2W,cout]; unshuffle: conv [n,H,W,cout/4],
+ *    xin [n,H,W,cin] -> out [n,H/2,W/2,cout]. */
+LC_API int lc_patchify(int precision, const float* x, void* tokens, int batch, int channels, int thw, int kp, void* stream);
+LC_API int lc_unpatchify_gemm(int precision, const void* tokens, const void* w, const float* bias, float* out, int batch,
+                              int thw, int n_out, int k, void* stream);
+LC_API int lc_pixel_shuffle_shortcut(const float* conv, const float* xin, float* out, int n, int height, int width, int cin,
+                                     int cout, void* stream);
+LC_API int lc_pixel_unshuffle_shortcut(const float* conv, const float* xin, float* out, int n, int height, int width,
+                                       int cin, int cout, void* stream);
+
 /* One SphereConv2d 3x3 (models/sphere_conv.py:138-192), NCHW fp32 in/out, through the implicit-GEMM path.
  * w: [cout, cin, 3, 3], bias: [cout] or NULL.  Test helper: allocates and synchronises internally. */
 LC_API int lc_sphere_conv3x3(int precision, const float* x, const float* w, const float* bias, float* out, int n, int cin,

@@ -63,6 +63,8 @@ _SIGNATURES = {
     "lc_sched_heun_step": ([_vp, _vp, _vp, _vp, _vp, _i64, _i, _d, _d, _d, _d, _d, _vp], _i),
     "lc_gemm": ([_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
     "lc_attention": ([_i, _vp, _vp, _i, _i, _i, _vp], _i),
+    "lc_patchify": ([_i, _vp, _vp, _i, _i, _i, _i, _vp], _i),
+    "lc_unpatchify_gemm": ([_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
     "lc_gemm_bf16out": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
 }
 
@@ -76,6 +78,8 @@ _OPTIONAL = {
     "lc_dcae_decode_ens": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _f, _vp], _i),
     "lc_dcae_encode": ([_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _f, _vp], _i),
     "lc_dcae_debug_read": ([_vp, _cp, _vp, _i64, _vp], _i),
+    "lc_pixel_shuffle_shortcut": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
+    "lc_pixel_unshuffle_shortcut": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "lc_sphere_conv3x3": ([_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "lc_metrics_accumulate": ([_vp, _vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, _vp, _vp], _i),
     "lc_metrics_accumulate_strided": ([_vp, ctypes.c_longlong, _vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, _vp, _vp], _i),

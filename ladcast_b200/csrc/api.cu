@@ -142,6 +142,24 @@ int lc_gemm_bf16out(const void* a, const void* w, const float* bias, void* c, in
   return gemm_bf16(g, static_cast<cudaStream_t>(stream));
 }
 
+// Test exports of the two index permutations of the denoiser (north star: "index/patch permutations bit-exact").
+int lc_patchify(int precision, const float* x, void* tokens, int batch, int channels, int thw, int kp, void* stream) {
+  LC_REQUIRE(x && tokens && kp >= channels, "bad patchify arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return precision == LC_PRECISION_F32 ? patchify<float>(x, reinterpret_cast<float*>(tokens), batch, channels, thw, kp, st)
+                                       : patchify<bf16>(x, reinterpret_cast<bf16*>(tokens), batch, channels, thw, kp, st);
+}
+
+int lc_unpatchify_gemm(int precision, const void* tokens, const void* w, const float* bias, float* out, int batch, int thw,
+                       int n_out, int k, void* stream) {
+  LC_REQUIRE(tokens && w && out, "null argument");
+  GemmArgs g;
+  g.A0 = tokens; g.lda0 = k; g.K0 = k; g.W = w; g.ldw = k; g.M = batch * thw; g.N = n_out; g.K = k;
+  g.epi.mode = EPI_UNPATCHIFY; g.epi.bias = bias; g.epi.out = out; g.epi.rows_per_sample = thw; g.epi.n_valid = n_out;
+  return precision == LC_PRECISION_F32 ? gemm_f32(g, static_cast<cudaStream_t>(stream))
+                                       : gemm_bf16(g, static_cast<cudaStream_t>(stream));
+}
+
 int lc_debug_gemm_trace(void* buf) { return lc::gemm_set_trace(reinterpret_cast<long long*>(buf)); }
 int lc_debug_attention_trace(void* buf) { return lc::attention_set_trace(reinterpret_cast<long long*>(buf)); }
 int lc_attention(int precision, const void* qkv, void* out, int batch, int seq, int heads, void* stream) {

@@ -640,6 +640,19 @@ int lc_dcae_encode(lc_dcae* D, const float* x, int n, int height, int width, flo
   return rr.encode(x, height, width, out, mean, stdv, target_std);
 }
 
+// Test exports of the decoder / encoder index permutations (NHWC f32 in and out, fp32 arithmetic: one add per element,
+// so the result is bit-identical to torch's pixel_shuffle / pixel_unshuffle formulation, DCAE.py:476-490, 519-536).
+int lc_pixel_shuffle_shortcut(const float* conv, const float* xin, float* out, int n, int H, int W, int cin, int cout,
+                              void* stream) {
+  LC_REQUIRE(conv && xin && out, "null argument");
+  return pixel_shuffle_shortcut<float>(conv, xin, out, nullptr, n, H, W, cin, cout, static_cast<cudaStream_t>(stream));
+}
+int lc_pixel_unshuffle_shortcut(const float* conv, const float* xin, float* out, int n, int H, int W, int cin, int cout,
+                                void* stream) {
+  LC_REQUIRE(conv && xin && out, "null argument");
+  return pixel_unshuffle_shortcut<float>(conv, xin, out, nullptr, n, H, W, cin, cout, static_cast<cudaStream_t>(stream));
+}
+
 // Test export: one 3x3 sphere convolution (+bias, act) NCHW f32 -> NCHW f32 through the implicit-GEMM path.
 int lc_sphere_conv3x3(int precision, const float* x, const float* w, const float* bias, float* out, int n, int cin, int H,
                       int W, int cout, int act, void* stream) {

@@ -830,3 +830,16 @@ def ensemble_metrics(fields: torch.Tensor, truth: torch.Tensor) -> Dict[str, tor
         out["crps_skill"][:, t] = red(skill)
         out["crps"][:, t] = red(skill - 0.5 * spread)
     return out
+
+
+def get_acc(forecast: torch.Tensor, truth: torch.Tensor, climate: torch.Tensor, lat_weight=None) -> torch.Tensor:
+    """get_acc (evaluate/utils.py:122-149): anomaly correlation over the last two dims with nanmean; lat_weight
+    broadcastable [H, 1] (float64 in the scripts, so the products are float64)."""
+    fa, ta = forecast - climate, truth - climate
+    if lat_weight is None:
+        num = torch.nanmean(fa * ta, dim=(-2, -1))
+        den = torch.sqrt(torch.nanmean(fa**2, dim=(-2, -1)) * torch.nanmean(ta**2, dim=(-2, -1)))
+    else:
+        num = torch.nanmean(fa * ta * lat_weight, dim=(-2, -1))
+        den = torch.sqrt(torch.nanmean(fa**2 * lat_weight, dim=(-2, -1)) * torch.nanmean(ta**2 * lat_weight, dim=(-2, -1)))
+    return num / den

@@ -16,6 +16,7 @@ sys.path.insert(0, ROOT)
 
 from diffusers import EDMDPMSolverMultistepScheduler  # noqa: E402  (shim)
 from ladcast.evaluate.utils import (  # noqa: E402
+    get_acc,
     get_normalized_lat_weights_based_on_cos,
     pointwise_crps_skill,
     pointwise_crps_spread,
@@ -198,13 +199,46 @@ def golden_metrics():
     np.savez(os.path.join(OUT, "metrics.npz"), lat_weight=lat_weight.numpy(), **{k: v.numpy() for k, v in tabs.items()})
 
 
+def golden_acc():
+    """The reference's own get_acc (evaluate/utils.py:122-149): lat-weighted and unweighted, NaNs in truth (SST)."""
+    f, t, c = seeded((84, 120, 24), 21), seeded((84, 120, 24), 22), seeded((84, 120, 24), 23, 0.3)
+    t[82, :4] = float("nan")
+    w = torch.from_numpy(get_normalized_lat_weights_based_on_cos(np.linspace(-88.5, 90, 120))).view(-1, 1)
+    np.savez(os.path.join(OUT, "acc.npz"), weighted=get_acc(f, t, c, w).numpy(), unweighted=get_acc(f, t, c).numpy())
+    print("acc", float(get_acc(f, t, c)[0]))
+
+
+def golden_heun8():
+    """edm_AR_sampler (Heun, fp64 state), N = 8 -> 15 denoiser calls, tiny denoiser, ensemble of 2."""
+    cfg, m = build_denoiser("tiny", 11)
+    pipe = AutoRegressive2DPipeline(m, EDMDPMSolverMultistepScheduler())
+    known = seeded((1, 84, 1, 15, 30), 102, 0.5)
+    s = ensemble_AR_sampler(pipe, sample_size=2, return_seq_len=1, num_inference_steps=8, known_latents=known,
+                            timestamps=torch.tensor([2018010100]), sampler_type="edm", device="cpu")
+    np.savez(os.path.join(OUT, "heun8_tiny.npz"), edm_8=s.numpy().astype(np.float32))
+    print("heun8", float(s.abs().mean()))
+
+
+def golden_denoiser_1p6b():
+    """ladcast_1.6B (d=2048, 16 heads, 5+10+3 blocks; 1,605,496,660 parameters) through the unmodified reference:
+    B=1, T_out=1.  Pins the oracle port's 1.6B configuration beyond the parameter count."""
+    cfg, m = build_denoiser("1.6B", 14)
+    x = seeded((1, 84, 1, 15, 30), 100)
+    cond = seeded((1, 84, 1, 15, 30), 101, 0.5)
+    t = torch.tensor([0.2306])
+    ts = torch.tensor([2018070112])
+    out = m(x, t, cond, time_elapsed=ts, return_dict=False)[0]
+    s, a = summary(out)
+    np.savez(os.path.join(OUT, "denoiser_1p6B.npz"), salt=14, B=1, T_out=1, t=t.numpy(), ts=ts.numpy(),
+             out=out.numpy().astype(np.float32), ch_sum=s, ch_abs=a)
+    print("denoiser 1.6B", out.shape, float(out.abs().mean()))
+
+
+ALL = {"sphere": golden_sphere, "embeddings": golden_embeddings, "metrics": golden_metrics, "dcae": golden_dcae,
+       "dcae_encode": golden_dcae_encode, "transforms": golden_transforms, "samplers": golden_samplers,
+       "denoiser": golden_denoiser, "acc": golden_acc, "heun8": golden_heun8, "denoiser_1p6b": golden_denoiser_1p6b}
+
 if __name__ == "__main__":
-    golden_sphere()
-    golden_embeddings()
-    golden_metrics()
-    golden_dcae()
-    golden_dcae_encode()
-    golden_transforms()
-    golden_samplers()
-    golden_denoiser()
+    for name in (sys.argv[1:] or list(ALL)):
+        ALL[name]()
     print("golden vectors written to", OUT)

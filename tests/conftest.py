@@ -17,3 +17,17 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+def record_measured(name, value):
+    """Appends a measured parity figure to gpurun_out/measured.jsonl (read back to set tolerances ~1.2x measured)."""
+    import json
+
+    try:
+        d = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "measured.jsonl"), "a") as f:
+            f.write(json.dumps({"name": name, "value": value}) + "\n")
+    except Exception:
+        pass
+    print(f"[measured] {name} = {value}")

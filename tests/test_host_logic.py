@@ -144,7 +144,7 @@ def _oracle_local_sums(fields, truth, lat_w):
     return sums, counts
 
 
-def _dist_worker(rank, world, port, q):
+def _dist_worker(rank, world, port, q, n_members=5):
     import torch.distributed as dist
 
     from ladcast_b200.evaluate.utils import ensemble_metrics_distributed
@@ -153,10 +153,10 @@ def _dist_worker(rank, world, port, q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     g = torch.Generator("cpu").manual_seed(99)
-    fields = torch.randn((5, 84, 2, 12, 8), generator=g)  # 5 members: ranks get 3 and 2 (uneven on purpose)
+    fields = torch.randn((n_members, 84, 2, 12, 8), generator=g)  # 5 members on 2 ranks: 3 and 2 (uneven on purpose)
     truth = torch.randn((84, 2, 12, 8), generator=g)
     truth[82, 0, 2:4] = float("nan")
-    mine = list(member_shard(5, rank, world))
+    mine = list(member_shard(n_members, rank, world))
     lat_w = torch.from_numpy(O.lat_weights(12))
     tabs = ensemble_metrics_distributed(fields[mine].contiguous(), truth, lat_weights=lat_w, local_sums_fn=_oracle_local_sums)
     want = O.ensemble_metrics(fields, truth)
@@ -165,19 +165,22 @@ def _dist_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_member_sharded_metrics_world2_gloo():
+@pytest.mark.parametrize("world,n_members", [(2, 5), (3, 2)])
+def test_member_sharded_metrics_gloo(world, n_members):
+    """The member -> plane re-shard (grouped send/recv, the same branch NCCL runs) + local reduction + table all-gather
+    reproduce the single-process metrics; (3, 2): one rank owns no member at all, 168 planes split 56/56/56."""
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_dist_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_dist_worker, args=(r, world, port, q, n_members)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in procs]
+    res = [q.get(timeout=180) for _ in procs]
     for p in procs:
         p.join(timeout=60)
-    assert sorted(res) == [(0, True), (1, True)]
+    assert sorted(res) == [(r, True) for r in range(world)]
 
 
 def test_latent_npy_writer_matches_reference_layout(tmp_path):
