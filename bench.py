@@ -228,12 +228,12 @@ def workload_config(args, world):
 class Rollout:
     """Device-resident AR loop for a list of global member ids: exactly `rollout_step` of the product path."""
 
-    def __init__(self, model_name, members, args, dev, ae=None):
+    def __init__(self, model_name, members, args, dev, ae=None, model=None):
         from ladcast_b200.models import AutoencoderDC, LaDCastTransformer3DModel
         from ladcast_b200.pipelines import AutoRegressive2DPipeline, EDMDPMSolverMultistepScheduler
 
         torch.manual_seed(1234)  # identical random-init weights on every rank
-        self.model = LaDCastTransformer3DModel.from_config(denoiser_kwargs(model_name)).to(dev)
+        self.model = model if model is not None else LaDCastTransformer3DModel.from_config(denoiser_kwargs(model_name)).to(dev)
         self.ae = ae if ae is not None else AutoencoderDC(**DCAE_KW).to(dev)
         self.pipe = AutoRegressive2DPipeline(self.model, EDMDPMSolverMultistepScheduler())
         self.members, self.args, self.dev = list(members), args, dev
@@ -362,7 +362,7 @@ def metrics_leg(fields, lib, _lib, peaks, extra_members=(50,)):
     return res
 
 
-def strong_leg(args, ens_total, rank, world, dev, ae, barrier, lib, _lib, steps, warmup):
+def strong_leg(args, ens_total, rank, world, dev, ae, model, barrier, lib, _lib, steps, warmup):
     """BASELINE configs 4/5: ladcast_1.6B, `ens_total` members sharded over the ranks (member_shard), AR steps timed as
     the headline; then the one exchange of the path + metrics, timed and checked against the single-GPU result."""
     import torch.distributed as dist
@@ -371,7 +371,7 @@ def strong_leg(args, ens_total, rank, world, dev, ae, barrier, lib, _lib, steps,
     from ladcast_b200.pipelines.utils import member_shard
 
     members = list(member_shard(ens_total, rank, world))
-    run = Rollout(args.strong_model, members, args, dev, ae=ae)
+    run = Rollout(args.strong_model, members, args, dev, ae=ae, model=model)
     fields, ms, host_ms, launches, _ = timed_loop(run, steps, warmup, barrier, world, dev, lib)
     step_ms = ms / steps
     value = ens_total * args.t_out * steps / (ms * 1e-3)
@@ -422,7 +422,6 @@ def strong_leg(args, ens_total, rank, world, dev, ae, barrier, lib, _lib, steps,
         res["metrics"] = {"exchange_ms": 0.0, "kernel_ms": round(e0.elapsed_time(e1), 3), "bytes": 0,
                           "matches_single_gpu": True, "what": "single GPU: no exchange"}
     res["finite"] = bool(torch.isfinite(fields).all().item()) and all(bool(torch.isfinite(v).all()) for v in tabs.values())
-    run.release()
     del run, fields
     torch.cuda.empty_cache()
     return res
@@ -535,10 +534,15 @@ def main():
     del out
     torch.cuda.empty_cache()
     if not args.no_strong:
+        from ladcast_b200.models import LaDCastTransformer3DModel
+
         strong = []
+        torch.manual_seed(1234)
+        big = LaDCastTransformer3DModel.from_config(denoiser_kwargs(args.strong_model)).to(dev)  # built once, both ensembles
         for i, e in enumerate(int(v) for v in args.strong_ens.split(",") if v):
             k = min(args.steps, 3 if i == 0 else 2)
-            strong.append(strong_leg(args, e, rank, world, dev, ae, barrier, lib, _lib, steps=k, warmup=3 if i == 0 else 2))
+            strong.append(strong_leg(args, e, rank, world, dev, ae, big, barrier, lib, _lib, steps=k, warmup=3 if i == 0 else 2))
+        big._release()
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -114,7 +114,7 @@ LC_API int lc_sched_heun_init(const float* noise, double* x, float* x_in, int64_
 /* AR feedback of roll_out_serial (pipelines/utils.py:560-585) on one sampler output samples[B, C, T_out, hw]
  * (normalised latents): known_next[B, C, T_in, hw] = the last T_in frames (may be NULL); phys[B, C, T_out, hw] =
  * (samples / target_std) * std[c] + mean[c] (inverse_normalize_transform_3D, dataloader/utils.py:233-240; may be
- * NULL).  hw % 4 == 0. */
+ * NULL).  hw must be even. */
 LC_API int lc_latent_feedback(const float* samples, float* known_next, float* phys, const float* mean, const float* std,
                               float target_std, int batch, int channels, int t_out, int t_in, int hw, void* stream);
 /* phase 0: Euler predictor from x (saved to x_hat) ; phase 1: trapezoid corrector.  State in fp64. */

@@ -89,6 +89,11 @@ enum EpiMode {
   EPI_GATED_RESID = 1, // out_f32[orow, n] += gate[b, n] * (acc + bias)   (gate may be null -> 1)
   EPI_UNPATCHIFY = 2,  // out_f32[b, n, row % rows_per_sample] = acc + bias   (token-major -> channel-major)
   EPI_RESID_STORE = 3, // out[orow, n] = act(acc + bias) + resid_f32[orow, n]  (conv shortcut adds)
+  // DC-AE block tail fused into the producing conv / 1x1 GEMM (tensor-core path, N <= one tile so that a CTA holds whole
+  // rows): y = acc * rsqrt(mean_n(acc^2) + norm_eps) * norm_w[n] + norm_b[n];  xres[row, n] += y (fp32 residual stream,
+  // in place, row pitch ldr);  out[orow, n] = T(xres[row, n]) with the usual row remap (next conv's padded input).
+  // Reference: ResBlock / EfficientViTBlock / GLUMBConv tails, models/DCAE.py:356-377, 254-262, 316-324.
+  EPI_NORM_RESID = 4,
 };
 
 struct EpiParams {
@@ -113,7 +118,11 @@ struct EpiParams {
   const float* gate = nullptr;  // [n_samples, gate_stride]
   long long gate_stride = 0;
   const float* resid = nullptr;  // EPI_RESID_STORE
-  long long ldr = 0;
+  long long ldr = 0;             // row pitch of resid / xres
+  float* xres = nullptr;         // EPI_NORM_RESID: fp32 residual stream updated in place (identity row map)
+  const float* norm_w = nullptr; // EPI_NORM_RESID: RMSNorm weight / bias [N]
+  const float* norm_b = nullptr;
+  float norm_eps = 0.f;
   int n_valid = 0;  // EPI_UNPATCHIFY: number of real output channels (<= N)
   // EPI_UNPATCHIFY into a 5-D [B, n_valid, up_T, rows_per_sample] tensor: sample s of this launch is frame
   // (up_frame0 + s) = b * up_T + t and lands in plane (b, n, t).  up_T = 1: plain [samples, n_valid, rows_per_sample].

@@ -5,6 +5,7 @@
 // 3x3 sphere convolutions are implicit GEMMs on the tcgen05 kernel (gemm_tc.cu); 1x1 convolutions are plain
 // GEMMs over pixels; depthwise/grouped/linear-attention/norm kernels are in dcae_kernels.cu.
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <utility>
@@ -46,6 +47,7 @@ struct ResW { ConvW c1, c2; float *n_w = nullptr, *n_b = nullptr; };
 struct Block { int kind = 0; /*0 up, 1 res, 2 evit, 3 down*/ int cin = 0, cout = 0; ConvW up; ResW res; EvitW ev; };
 
 inline int r64(int c) { return (c + 63) / 64 * 64; }
+inline int r8(int c) { return (c + 7) / 8 * 8; }  // row pitch of T-typed GEMM outputs: 16-byte aligned bf16 rows
 
 __global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin, int cp, void* __restrict__ dst, int to_bf16) {
   // w [cout, cin, 3, 3] -> dst [cout, 9*cp], k = (ky*3+kx)*cp + c
@@ -91,6 +93,7 @@ struct lc_dcae {
   float *no_w = nullptr, *no_b = nullptr;
   std::vector<Block> blocks;
   bool has_decoder = false, has_encoder = false;
+  bool fuse_norm = true;  // RMSNorm + residual in the conv / 1x1 epilogue where C <= 256 (LADCAST_B200_FUSE_NORM=0: off)
   ConvW enc_conv_in, enc_conv_out;
   std::vector<Block> enc_blocks;
   int max_frames = 0, h0 = 0, w0 = 0;
@@ -190,6 +193,31 @@ struct Run {
     e.mode = EPI_STORE; e.out_f32 = 1; e.out = out; e.ldo = ld; e.bias = bias;
     return e;
   }
+  // raw conv / 1x1 outputs that only feed a norm or a shuffle are stored as T (bf16 in production, like the
+  // reference's own bf16 autocast), halving their write + read traffic
+  EpiParams store_T(void* out, int ld, const float* bias) const {
+    EpiParams e;
+    e.mode = EPI_STORE; e.out_f32 = sizeof(T) == 4; e.out = out; e.ldo = ld; e.bias = bias;
+    return e;
+  }
+  bool fused_norm_ok(int C) const { return sizeof(T) == 2 && D->fuse_norm && C <= 256 && C % 4 == 0; }
+  EpiParams norm_epilogue(const float* nw, const float* nb, float eps, float* x, int C, void* out_t, int ldo) const {
+    EpiParams e;
+    e.mode = EPI_NORM_RESID; e.norm_w = nw; e.norm_b = nb; e.norm_eps = eps; e.xres = x; e.ldr = C; e.out = out_t; e.ldo = ldo;
+    return e;
+  }
+  int gemm_epi(const void* A, long long lda, long long M, const MatW& mw, const EpiParams& e) const {
+    GemmArgs g;
+    g.A0 = A; g.lda0 = lda; g.K0 = mw.in; g.W = mw.w; g.ldw = mw.in; g.M = static_cast<int>(M); g.N = mw.out; g.K = mw.in;
+    g.epi = e;
+    return gemm_bf16(g, st);
+  }
+  int gemm_T(const void* A, long long lda, long long M, const MatW& mw, void* out, int ldo) const {
+    GemmArgs g;
+    g.A0 = A; g.lda0 = lda; g.K0 = mw.in; g.W = mw.w; g.ldw = mw.in; g.M = static_cast<int>(M); g.N = mw.out; g.K = mw.in;
+    g.epi = store_T(out, ldo, mw.bias);
+    return sizeof(T) == 2 ? gemm_bf16(g, st) : gemm_f32(g, st);
+  }
 
   int res_block(const Block& b, int H, int W) {
     xb_valid = false;
@@ -209,9 +237,18 @@ struct Run {
     e.rows_per_group = H * W; e.group_extra_rows = 2 * (W + 2);
     LC_TRY(conv(padA, H, W, w.c1, e));
     LC_TRY(halo_fill<T>(padB, n, H, W, w.c2.cp, st));
-    LC_TRY(conv(padB, H, W, w.c2, store_f32(D->y.as<float>(), C, nullptr)));
-    // x += norm(y); the new x is also written (as T) into padA's interior: the next 3x3 conv's padded input
-    LC_TRY(rmsnorm_rows<T>(D->y.as<float>(), w.n_w, w.n_b, 1e-5f, x, nullptr, padA, P, C, 0, st, H, W, w.c1.cp));
+    if (fused_norm_ok(C)) {
+      // conv2 + RMSNorm + residual in ONE kernel: a 256-wide N tile holds the whole channel vector of a pixel, so the
+      // epilogue normalises the accumulator rows in place, x += norm(y), and writes T(x) into padA's interior
+      EpiParams f = norm_epilogue(w.n_w, w.n_b, 1e-5f, x, C, padA, w.c1.cp);
+      f.rows_per_sample = W; f.out_rows_per_sample = W + 2; f.out_row_offset = (W + 2) + 1;
+      f.rows_per_group = H * W; f.group_extra_rows = 2 * (W + 2);
+      LC_TRY(conv(padB, H, W, w.c2, f));
+    } else {
+      LC_TRY(conv(padB, H, W, w.c2, store_T(D->y.p, r8(C), nullptr)));
+      // x += norm(y); the new x is also written (as T) into padA's interior: the next 3x3 conv's padded input
+      LC_TRY((rmsnorm_rows<T, T>(D->y.as<T>(), r8(C), w.n_w, w.n_b, 1e-5f, x, nullptr, padA, P, C, 0, st, H, W, w.c1.cp)));
+    }
     padA_valid = true;
     return 0;
   }
@@ -224,18 +261,26 @@ struct Run {
     LC_REQUIRE(HW > D->cfg.head_dim, "quadratic-attention branch (H*W <= head_dim) is not implemented");
     float* x = D->x.as<float>();
     T* xb = D->xb.as<T>();
-    float* y = D->y.as<float>();
+    T* y = D->y.as<T>();
+    const int ldy = r8(C);
     if (!xb_valid) LC_TRY(cast_rows<T>(x, xb, P * C, st));
     xb_valid = true;
-    LC_TRY(gemm(xb, C, P, w.qkv, D->qkv.p, true, ACT_NONE));
-    LC_TRY(multiscale_fused(D->qkv.as<float>(), w.dw5, w.g1, D->ms.as<float>(), n, H, W, 3 * w.inner, st));
-    LC_TRY(linear_attention<T>(D->qkv.as<float>(), D->ms.as<float>(), D->att.as<T>(), n, HW, w.heads, 1e-15f, st));
-    LC_TRY(gemm(D->att.p, 2 * w.inner, P, w.to_out, y, true, ACT_NONE));
-    LC_TRY(rmsnorm_rows<T>(y, w.no_w, w.no_b, 1e-5f, x, nullptr, xb, P, C, 0, st));
+    // q|k|v and the multiscale branch are stored as T; the attention core accumulates in fp32 (DCAE.py:158-175)
+    LC_TRY(gemm_T(xb, C, P, w.qkv, D->qkv.p, 3 * w.inner));
+    LC_TRY(multiscale_fused<T>(D->qkv.as<T>(), w.dw5, w.g1, D->ms.as<T>(), n, H, W, 3 * w.inner, st));
+    LC_TRY(linear_attention<T>(D->qkv.as<T>(), D->ms.as<T>(), D->att.as<T>(), n, HW, w.heads, 1e-15f, st));
+    const bool fuse = fused_norm_ok(C);
+    if (fuse) {
+      LC_TRY(gemm_epi(D->att.p, 2 * w.inner, P, w.to_out, norm_epilogue(w.no_w, w.no_b, 1e-5f, x, C, xb, C)));
+    } else {
+      LC_TRY(gemm_T(D->att.p, 2 * w.inner, P, w.to_out, y, ldy));
+      LC_TRY((rmsnorm_rows<T, T>(y, ldy, w.no_w, w.no_b, 1e-5f, x, nullptr, xb, P, C, 0, st)));
+    }
     LC_TRY(gemm(xb, C, P, w.inv, D->hid.p, false, ACT_SILU));
     LC_TRY(dwconv3_glu<T>(D->hid.as<T>(), w.dw3, w.dw3_b, D->glu.as<T>(), n, H, W, 8 * C, st));
-    LC_TRY(gemm(D->glu.p, 4 * C, P, w.point, y, true, ACT_NONE));
-    return rmsnorm_rows<T>(y, w.n_w, w.n_b, 1e-7f, x, nullptr, xb, P, C, 0, st);
+    if (fuse) return gemm_epi(D->glu.p, 4 * C, P, w.point, norm_epilogue(w.n_w, w.n_b, 1e-7f, x, C, xb, C));
+    LC_TRY(gemm_T(D->glu.p, 4 * C, P, w.point, y, ldy));
+    return rmsnorm_rows<T, T>(y, ldy, w.n_w, w.n_b, 1e-7f, x, nullptr, xb, P, C, 0, st);
   }
 
   int up_block(const Block& b, int& H, int& W, bool next_is_res) {
@@ -244,16 +289,16 @@ struct Run {
     if (padA_valid) LC_TRY(halo_fill<T>(D->padA.as<T>(), n, H, W, b.up.cp, st));
     else LC_TRY(pad_from_nhwc<T>(D->x.as<float>(), D->padA.as<T>(), n, b.cin, H, W, b.up.cp, st));
     padA_valid = false;
-    LC_TRY(conv(D->padA.as<T>(), H, W, b.up, store_f32(D->y.as<float>(), 4 * b.cout, b.up.bias)));
+    LC_TRY(conv(D->padA.as<T>(), H, W, b.up, store_T(D->y.p, 4 * b.cout, b.up.bias)));
     // the shuffled result is also written as T: into padA's interior when a 3x3 conv follows, else as xb rows
     if (next_is_res) {
-      LC_TRY(pixel_shuffle_shortcut<T>(D->y.as<float>(), D->x.as<float>(), D->x2.as<float>(), D->padA.as<T>(), n, H, W,
-                                       b.cin, b.cout, st, r64(b.cout)));
+      LC_TRY((pixel_shuffle_shortcut<T, T>(D->y.as<T>(), D->x.as<float>(), D->x2.as<float>(), D->padA.as<T>(), n, H, W,
+                                           b.cin, b.cout, st, r64(b.cout))));
       padA_valid = true;
       xb_valid = false;
     } else {
-      LC_TRY(pixel_shuffle_shortcut<T>(D->y.as<float>(), D->x.as<float>(), D->x2.as<float>(), D->xb.as<T>(), n, H, W,
-                                       b.cin, b.cout, st));
+      LC_TRY((pixel_shuffle_shortcut<T, T>(D->y.as<T>(), D->x.as<float>(), D->x2.as<float>(), D->xb.as<T>(), n, H, W,
+                                           b.cin, b.cout, st)));
       xb_valid = true;
     }
     std::swap(D->x, D->x2);
@@ -329,8 +374,8 @@ struct Run {
     const int C = D->conv_out.cin;
     const long long P = static_cast<long long>(n) * H * W;
     // norm_out + ReLU written straight into the padded input of conv_out
-    LC_TRY(rmsnorm_rows<T>(D->x.as<float>(), D->no_w, D->no_b, 1e-7f, nullptr, nullptr, D->padA.as<T>(), P, C, 1, st, H, W,
-                           D->conv_out.cp));
+    LC_TRY((rmsnorm_rows<float, T>(D->x.as<float>(), C, D->no_w, D->no_b, 1e-7f, nullptr, nullptr, D->padA.as<T>(), P, C, 1,
+                                   st, H, W, D->conv_out.cp)));
     LC_TRY(halo_fill<T>(D->padA.as<T>(), n, H, W, D->conv_out.cp, st));
     EpiParams e;
     e.mode = EPI_UNPATCHIFY; e.bias = D->conv_out.bias; e.out = out; e.rows_per_sample = H * W;
@@ -472,6 +517,8 @@ int lc_dcae_create(const lc_dcae_cfg* cfg, lc_dcae** out) {
   D->cfg = *cfg;
   D->f32 = cfg->precision == LC_PRECISION_F32;
   D->esz = D->f32 ? 4 : 2;
+  const char* fn = getenv("LADCAST_B200_FUSE_NORM");
+  D->fuse_norm = !(fn != nullptr && fn[0] == '0');
   *out = D;
   return 0;
 }
@@ -515,7 +562,7 @@ int lc_dcae_reserve(lc_dcae* D, int max_frames, int h, int w, void* stream) {
     const size_t H = static_cast<size_t>(h) << (ns - 1 - i), W = static_cast<size_t>(w) << (ns - 1 - i);
     const size_t C = c.stage_channels[i], P = H * W;
     mx_x = std::max(mx_x, P * C);
-    mx_y = std::max(mx_y, P * C);
+    mx_y = std::max(mx_y, P * static_cast<size_t>(r8(static_cast<int>(C))));
     mx_pad = std::max(mx_pad, (H + 2) * (W + 2) * static_cast<size_t>(r64(static_cast<int>(C))));
     if (i < ns - 1) {  // up-block conv runs at the coarser resolution, producing 4*C channels
       const size_t Hc = H / 2, Wc = W / 2, Cc = c.stage_channels[i + 1];
@@ -540,7 +587,7 @@ int lc_dcae_reserve(lc_dcae* D, int max_frames, int h, int w, void* stream) {
       const size_t H = static_cast<size_t>(h) << (ns - 1 - i), W = static_cast<size_t>(w) << (ns - 1 - i);
       const size_t C = c.enc_stage_channels[i], P = H * W;
       mx_x = std::max(mx_x, P * C);
-      mx_y = std::max(mx_y, P * C);
+      mx_y = std::max(mx_y, P * static_cast<size_t>(r8(static_cast<int>(C))));
       mx_xb = std::max(mx_xb, P * C);
       mx_pad = std::max(mx_pad, (H + 2) * (W + 2) * static_cast<size_t>(r64(static_cast<int>(C))));
       if (c.enc_stage_is_evit[i] && c.enc_stage_layers[i] > 0) {
@@ -645,7 +692,7 @@ int lc_dcae_encode(lc_dcae* D, const float* x, int n, int height, int width, flo
 int lc_pixel_shuffle_shortcut(const float* conv, const float* xin, float* out, int n, int H, int W, int cin, int cout,
                               void* stream) {
   LC_REQUIRE(conv && xin && out, "null argument");
-  return pixel_shuffle_shortcut<float>(conv, xin, out, nullptr, n, H, W, cin, cout, static_cast<cudaStream_t>(stream));
+  return pixel_shuffle_shortcut<float, float>(conv, xin, out, nullptr, n, H, W, cin, cout, static_cast<cudaStream_t>(stream));
 }
 int lc_pixel_unshuffle_shortcut(const float* conv, const float* xin, float* out, int n, int H, int W, int cin, int cout,
                                 void* stream) {

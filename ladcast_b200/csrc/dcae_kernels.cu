@@ -232,8 +232,9 @@ __global__ void __launch_bounds__(256, 3) dwconv3_glu_kernel(const T* __restrict
 //            both the transposing stores and the phase-B reads are bank-conflict free);
 //   phase B: warp = (group, 32-pixel half); thread tile 8 px x 4 outputs, outer product over the 32 inputs of the
 //            group: 3 LDS.128 per 32 FFMA (the stand-alone kernel's broadcast reads cost 8 per 32).
-__global__ void __launch_bounds__(256, 3) multiscale_fused_kernel(const float* __restrict__ in, const float* __restrict__ w5,
-                                                               const float* __restrict__ wg, float* __restrict__ out,
+template <typename T>
+__global__ void __launch_bounds__(256, 3) multiscale_fused_kernel(const T* __restrict__ in, const float* __restrict__ w5,
+                                                               const float* __restrict__ wg, T* __restrict__ out,
                                                                int n, int H, int W, int C) {
   __shared__ __align__(16) float ds[128][64];
   __shared__ __align__(16) float ws[4][32][32];  // [group][k][o ^ swizzle(k)]
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(256, 3) multiscale_fused_kernel(const float* _
   }
   const int c = cb + lane * 4;
   const bool c_ok = c < C;
-  const float* base = in + static_cast<long long>(f) * H * W * C + c;
+  const T* base = in + static_cast<long long>(f) * H * W * C + c;
   const int g = warp & 3, half = warp >> 2;
   const int nl = lane & 7, ml = lane >> 3;
   const bool g_ok = cb + g * 32 < C;
@@ -278,14 +279,14 @@ __global__ void __launch_bounds__(256, 3) multiscale_fused_kernel(const float* _
 #pragma unroll
         for (int kx = 0; kx < 5; ++kx)
           wr[kx] = __ldg(reinterpret_cast<const float4*>(w5 + (ky * 5 + (flip ? 4 - kx : kx)) * C + c));
-        const float* rowp = base + static_cast<long long>(sy) * W * C;
+        const T* rowp = base + static_cast<long long>(sy) * W * C;
         int co[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) co[j] = con[j];
         if (rolled) col_offsets<8>(co, x0, 2, W, C, true);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 v = *reinterpret_cast<const float4*>(rowp + co[j]);
+          const float4 v = ld4<T>(rowp + co[j]);
 #pragma unroll
           for (int kx = 0; kx < 5; ++kx) {
             const int o = j - kx;
@@ -324,13 +325,13 @@ __global__ void __launch_bounds__(256, 3) multiscale_fused_kernel(const float* _
 #pragma unroll
         for (int j = 0; j < 4; ++j) a[i][j] = __ffma2_rn(xs[i], w2[j], a[i][j]);
     }
-    float* op = out + ((static_cast<long long>(f) * H + y) * W + seg + px0) * C + cb + g * 32 + nl * 4;
+    T* op = out + ((static_cast<long long>(f) * H + y) * W + seg + px0) * C + cb + g * 32 + nl * 4;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       if (seg + px0 + i < W)
-        *reinterpret_cast<float4*>(op + static_cast<long long>(i) * C) =
-            (i & 1) ? make_float4(a[i >> 1][0].y, a[i >> 1][1].y, a[i >> 1][2].y, a[i >> 1][3].y)
-                    : make_float4(a[i >> 1][0].x, a[i >> 1][1].x, a[i >> 1][2].x, a[i >> 1][3].x);
+        st4<T>(op + static_cast<long long>(i) * C,
+               (i & 1) ? make_float4(a[i >> 1][0].y, a[i >> 1][1].y, a[i >> 1][2].y, a[i >> 1][3].y)
+                       : make_float4(a[i >> 1][0].x, a[i >> 1][1].x, a[i >> 1][2].x, a[i >> 1][3].x));
   }
 }
 
@@ -345,8 +346,8 @@ __global__ void __launch_bounds__(256, 3) multiscale_fused_kernel(const float* _
 //            the finished sums of pixel kl.
 __device__ __forceinline__ float2 relu2(float a, float b) { return make_float2(fmaxf(a, 0.f), fmaxf(b, 0.f)); }
 
-template <typename TO>
-__global__ void __launch_bounds__(256, 2) linear_attn_kernel(const float* __restrict__ qkv, const float* __restrict__ ms,
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256, 2) linear_attn_kernel(const TI* __restrict__ qkv, const TI* __restrict__ ms,
                                                              TO* __restrict__ out, int HW, int heads, float eps) {
   __shared__ __align__(16) float red[8][33][32];  // per-warp partials of S
   __shared__ __align__(16) float S[33][32];
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(256, 2) linear_attn_kernel(const float* __rest
   const int f = blockIdx.x / (2 * heads);
   const int scale = g / heads, hg = g % heads;
   const int C3 = heads * 96;
-  const float* src = (scale ? ms : qkv) + static_cast<long long>(f) * HW * C3 + hg * 96;
+  const TI* src = (scale ? ms : qkv) + static_cast<long long>(f) * HW * C3 + hg * 96;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cl = lane >> 2, kl = lane & 3;
 
@@ -375,10 +376,10 @@ __global__ void __launch_bounds__(256, 2) linear_attn_kernel(const float* __rest
       for (int u = 0; u < U; ++u) {
         v4[u] = ka[u] = kb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p0 + u < HW) {
-          const float* row = src + static_cast<long long>(p0 + u) * C3;
-          v4[u] = *reinterpret_cast<const float4*>(row + 64 + cl * 4);
-          ka[u] = *reinterpret_cast<const float4*>(row + 32 + kl * 8);
-          kb[u] = *reinterpret_cast<const float4*>(row + 32 + kl * 8 + 4);
+          const TI* row = src + static_cast<long long>(p0 + u) * C3;
+          v4[u] = ld4<TI>(row + 64 + cl * 4);
+          ka[u] = ld4<TI>(row + 32 + kl * 8);
+          kb[u] = ld4<TI>(row + 32 + kl * 8 + 4);
         }
       }
 #pragma unroll
@@ -430,9 +431,9 @@ __global__ void __launch_bounds__(256, 2) linear_attn_kernel(const float* __rest
     for (int u = 0; u < 4; ++u) {
       qa[u] = qb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p0 + u < HW) {
-        const float* row = src + static_cast<long long>(p0 + u) * C3 + kl * 8;
-        qa[u] = *reinterpret_cast<const float4*>(row);
-        qb[u] = *reinterpret_cast<const float4*>(row + 4);
+        const TI* row = src + static_cast<long long>(p0 + u) * C3 + kl * 8;
+        qa[u] = ld4<TI>(row);
+        qb[u] = ld4<TI>(row + 4);
       }
     }
     float val[4][5];
@@ -476,19 +477,19 @@ __global__ void __launch_bounds__(256, 2) linear_attn_kernel(const float* __rest
 
 // ---------------------------------------------------------------- channel RMSNorm (+residual) on [P, C] rows
 // y = x_in * rsqrt(mean(x_in^2) + eps) * w + b ; if resid: resid += y (in place) and the result is also written as T.
-template <typename T>
-__global__ void __launch_bounds__(256) rmsnorm_rows_kernel(const float* __restrict__ y, const float* __restrict__ w,
+template <typename TY, typename T>
+__global__ void __launch_bounds__(256) rmsnorm_rows_kernel(const TY* __restrict__ y, int ldy, const float* __restrict__ w,
                                                            const float* __restrict__ b, float eps, float* __restrict__ resid,
                                                            float* __restrict__ out_f32, T* __restrict__ out_t, long long P,
                                                            int C, int relu, int pH, int pW, int pCp) {
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= P) return;
-  const float* yr = y + row * C;
+  const TY* yr = y + row * ldy;
   const int c4 = C / 4;
   float ss = 0.f;
   for (int i = lane; i < c4; i += 32) {
-    const float4 v = *reinterpret_cast<const float4*>(yr + i * 4);
+    const float4 v = ld4<TY>(yr + i * 4);
     ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
   }
 #pragma unroll
@@ -496,7 +497,7 @@ __global__ void __launch_bounds__(256) rmsnorm_rows_kernel(const float* __restri
   const float r = rsqrtf(ss / C + eps);
   for (int i = lane; i < c4; i += 32) {
     const int c = i * 4;
-    const float4 v = *reinterpret_cast<const float4*>(yr + c);
+    const float4 v = ld4<TY>(yr + c);
     const float4 ww = __ldg(reinterpret_cast<const float4*>(w + c));
     const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
     float4 o = make_float4(v.x * r * ww.x + bb.x, v.y * r * ww.y + bb.y, v.z * r * ww.z + bb.z, v.w * r * ww.w + bb.w);
@@ -517,16 +518,15 @@ __global__ void __launch_bounds__(256) rmsnorm_rows_kernel(const float* __restri
         const int yy = static_cast<int>(fy - ff * pH);
         obase = ((ff * (pH + 2) + yy + 1) * (pW + 2) + xx + 1) * pCp;
       }
-      T* ot = out_t + obase + c;
-      ot[0] = from_f32<T>(o.x); ot[1] = from_f32<T>(o.y); ot[2] = from_f32<T>(o.z); ot[3] = from_f32<T>(o.w);
+      st4<T>(out_t + obase + c, o);
     }
   }
 }
 
 // ---------------------------------------------------------------- pixel_shuffle(2) of conv output + shortcut
 // out[f, 2y+i, 2x+j, c] = conv[f, y, x, 4c+2i+j] + x_in[f, y, x, (4c+2i+j) / rep]     (DCAE.py:519-536)
-template <typename T>
-__global__ void __launch_bounds__(256) pixel_shuffle_kernel(const float* __restrict__ conv, const float* __restrict__ xin,
+template <typename TC, typename T>
+__global__ void __launch_bounds__(256) pixel_shuffle_kernel(const TC* __restrict__ conv, const float* __restrict__ xin,
                                                             float* __restrict__ out, T* __restrict__ out_t, int n, int H,
                                                             int W, int Cin, int Cout, int rep, int pCp) {
   // one thread = (input pixel, 4 consecutive output channels): 4 float4 of the conv output -> 4 float4 stores, one
@@ -541,12 +541,12 @@ __global__ void __launch_bounds__(256) pixel_shuffle_kernel(const float* __restr
   const long long fy = pin / W;
   const int y = static_cast<int>(fy % H);
   const long long f = fy / H;
-  const float* cp = conv + pin * (4LL * Cout) + 4 * c;
+  const TC* cp = conv + pin * (4LL * Cout) + 4 * c;
   const float* xp = xin + pin * Cin;
   float v[4][4];  // [channel k][sub-pixel 2i+j]
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float4 t = *reinterpret_cast<const float4*>(cp + 4 * k);
+    const float4 t = ld4<TC>(cp + 4 * k);
     const int ch = 4 * (c + k);
     v[k][0] = t.x + __ldg(xp + (ch + 0) / rep);
     v[k][1] = t.y + __ldg(xp + (ch + 1) / rep);
@@ -677,44 +677,44 @@ int dwconv3_glu(const T* in, const float* w, const float* bias, T* out, int n, i
   LC_LAUNCH_CHECK();
   return 0;
 }
-int multiscale_fused(const float* in, const float* w5, const float* wg, float* out, int n, int H, int W, int C,
-                     cudaStream_t s) {
+template <typename T>
+int multiscale_fused(const T* in, const float* w5, const float* wg, T* out, int n, int H, int W, int C, cudaStream_t s) {
   LC_REQUIRE(C % 32 == 0, "multiscale projection: channels must be a multiple of 32");
   const long long nblk = static_cast<long long>(n) * H * ((C + 127) / 128);
   LC_REQUIRE(nblk < (1ll << 31), "multiscale projection: too many image rows per call");
   // algorithmic: read qkv [P, C] once, write the multiscale branch [P, C]
-  ProfScope ps(PROF_DEC_MS, 2.0 * n * H * W * C * (25.0 + 32.0), static_cast<double>(n) * H * W * C * 8.0, s);
-  multiscale_fused_kernel<<<static_cast<unsigned>(nblk), 256, 0, s>>>(in, w5, wg, out, n, H, W, C);
+  ProfScope ps(PROF_DEC_MS, 2.0 * n * H * W * C * (25.0 + 32.0), static_cast<double>(n) * H * W * C * 2.0 * sizeof(T), s);
+  multiscale_fused_kernel<T><<<static_cast<unsigned>(nblk), 256, 0, s>>>(in, w5, wg, out, n, H, W, C);
   LC_LAUNCH_CHECK();
   return 0;
 }
 template <typename T>
-int linear_attention(const float* qkv, const float* ms, T* out, int n, int HW, int heads, float eps, cudaStream_t s) {
+int linear_attention(const T* qkv, const T* ms, T* out, int n, int HW, int heads, float eps, cudaStream_t s) {
   // algorithmic: k, v read once (phase 1), q read once (phase 2) of both scales, output [P, 2*heads*32] written
-  ProfScope ps(PROF_DEC_LINATTN, 0.0, static_cast<double>(n) * HW * heads * (2 * 96 * 4.0 + 2 * 32 * sizeof(T)), s);
-  linear_attn_kernel<T><<<n * 2 * heads, 256, 0, s>>>(qkv, ms, out, HW, heads, eps);
+  ProfScope ps(PROF_DEC_LINATTN, 0.0, static_cast<double>(n) * HW * heads * (2 * 96 + 2 * 32) * sizeof(T), s);
+  linear_attn_kernel<T, T><<<n * 2 * heads, 256, 0, s>>>(qkv, ms, out, HW, heads, eps);
   LC_LAUNCH_CHECK();
   return 0;
 }
-template <typename T>
-int rmsnorm_rows(const float* y, const float* w, const float* b, float eps, float* resid, float* out_f32, T* out_t,
+template <typename TY, typename T>
+int rmsnorm_rows(const TY* y, int ldy, const float* w, const float* b, float eps, float* resid, float* out_f32, T* out_t,
                  long long P, int C, int relu, cudaStream_t s, int pH, int pW, int pCp) {
-  LC_REQUIRE(C % 4 == 0, "rmsnorm: C must be a multiple of 4");
+  LC_REQUIRE(C % 4 == 0 && ldy % 4 == 0, "rmsnorm: C and the row pitch must be multiples of 4");
   // algorithmic: read y; read + write the residual; write the f32 / T copies that were asked for
   ProfScope ps(PROF_DEC_NORM, 0.0,
-               static_cast<double>(P) * C * (4.0 + (resid ? 8.0 : 0.0) + (out_f32 ? 4.0 : 0.0) + (out_t ? sizeof(T) : 0.0)), s);
-  rmsnorm_rows_kernel<T><<<blocks(P, 8), 256, 0, s>>>(y, w, b, eps, resid, out_f32, out_t, P, C, relu, pH, pW, pCp);
+               static_cast<double>(P) * C * (sizeof(TY) + (resid ? 8.0 : 0.0) + (out_f32 ? 4.0 : 0.0) + (out_t ? sizeof(T) : 0.0)), s);
+  rmsnorm_rows_kernel<TY, T><<<blocks(P, 8), 256, 0, s>>>(y, ldy, w, b, eps, resid, out_f32, out_t, P, C, relu, pH, pW, pCp);
   LC_LAUNCH_CHECK();
   return 0;
 }
-template <typename T>
-int pixel_shuffle_shortcut(const float* conv, const float* xin, float* out, T* out_t, int n, int H, int W, int Cin,
+template <typename TC, typename T>
+int pixel_shuffle_shortcut(const TC* conv, const float* xin, float* out, T* out_t, int n, int H, int W, int Cin,
                            int Cout, cudaStream_t s, int pCp) {
   LC_REQUIRE(Cout % 4 == 0, "pixel_shuffle: C_out must be a multiple of 4");
   const long long total = static_cast<long long>(n) * H * W * (Cout / 4);
   ProfScope ps(PROF_DEC_SHUFFLE, 0.0,
-               static_cast<double>(n) * H * W * (4.0 * Cout * (8.0 + (out_t ? sizeof(T) : 0.0)) + Cin * 4.0), s);
-  pixel_shuffle_kernel<T><<<blocks(total), 256, 0, s>>>(conv, xin, out, out_t, n, H, W, Cin, Cout, 4 * Cout / Cin, pCp);
+               static_cast<double>(n) * H * W * (4.0 * Cout * (sizeof(TC) + 4.0 + (out_t ? sizeof(T) : 0.0)) + Cin * 4.0), s);
+  pixel_shuffle_kernel<TC, T><<<blocks(total), 256, 0, s>>>(conv, xin, out, out_t, n, H, W, Cin, Cout, 4 * Cout / Cin, pCp);
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -752,16 +752,20 @@ int in_shortcut(float* x, T* x_t, const PlaneSrc& z, int n, int HW, int C, int C
   template int pad_from_nhwc<T>(const float*, T*, int, int, int, int, int, cudaStream_t);                            \
   template int halo_fill<T>(T*, int, int, int, int, cudaStream_t);                                                   \
   template int dwconv3_glu<T>(const T*, const float*, const float*, T*, int, int, int, int, cudaStream_t);           \
-  template int linear_attention<T>(const float*, const float*, T*, int, int, int, float, cudaStream_t);              \
-  template int rmsnorm_rows<T>(const float*, const float*, const float*, float, float*, float*, T*, long long, int,  \
-                               int, cudaStream_t, int, int, int);                                                                   \
-  template int pixel_shuffle_shortcut<T>(const float*, const float*, float*, T*, int, int, int, int, int,            \
-                                         cudaStream_t, int);                                                              \
+  template int multiscale_fused<T>(const T*, const float*, const float*, T*, int, int, int, int, cudaStream_t);      \
+  template int linear_attention<T>(const T*, const T*, T*, int, int, int, float, cudaStream_t);                      \
+  template int rmsnorm_rows<T, T>(const T*, int, const float*, const float*, float, float*, float*, T*, long long,   \
+                                  int, int, cudaStream_t, int, int, int);                                            \
+  template int pixel_shuffle_shortcut<T, T>(const T*, const float*, float*, T*, int, int, int, int, int,             \
+                                            cudaStream_t, int);                                                      \
   template int pixel_unshuffle_shortcut<T>(const float*, const float*, float*, T*, int, int, int, int, int,          \
                                            cudaStream_t, int);                                                       \
   template int in_shortcut<T>(float*, T*, const PlaneSrc&, int, int, int, int, cudaStream_t);
 LC_INST(float)
 LC_INST(bf16)
 #undef LC_INST
+// fp32 input rows with a bf16 target (norm_out reads the fp32 residual stream in the bf16 mode)
+template int rmsnorm_rows<float, bf16>(const float*, int, const float*, const float*, float, float*, float*, bf16*, long long,
+                                       int, int, cudaStream_t, int, int, int);
 
 }  // namespace lc

@@ -34,15 +34,18 @@ template <typename T>
 int halo_fill(T* buf, int n, int H, int W, int Cp, cudaStream_t s);
 template <typename T>
 int dwconv3_glu(const T* in, const float* w, const float* bias, T* out, int n, int H, int W, int C, cudaStream_t s);
-int multiscale_fused(const float* in, const float* w5, const float* wg, float* out, int n, int H, int W, int C,
-                     cudaStream_t s);
+// T = activation storage type (bf16 production / float validation): q|k|v and the multiscale branch are stored as T
+// (the reference's own bf16 autocast stores them as bf16 too; the attention core accumulates in fp32, DCAE.py:158-175)
 template <typename T>
-int linear_attention(const float* qkv, const float* ms, T* out, int n, int HW, int heads, float eps, cudaStream_t s);
+int multiscale_fused(const T* in, const float* w5, const float* wg, T* out, int n, int H, int W, int C, cudaStream_t s);
 template <typename T>
-int rmsnorm_rows(const float* y, const float* w, const float* b, float eps, float* resid, float* out_f32, T* out_t,
+int linear_attention(const T* qkv, const T* ms, T* out, int n, int HW, int heads, float eps, cudaStream_t s);
+// y: [P, ldy] rows of type TY (a GEMM / conv output stored as T, or the fp32 residual stream)
+template <typename TY, typename T>
+int rmsnorm_rows(const TY* y, int ldy, const float* w, const float* b, float eps, float* resid, float* out_f32, T* out_t,
                  long long P, int C, int relu, cudaStream_t s, int pH = 0, int pW = 0, int pCp = 0);
-template <typename T>
-int pixel_shuffle_shortcut(const float* conv, const float* xin, float* out, T* out_t, int n, int H, int W, int Cin,
+template <typename TC, typename T>
+int pixel_shuffle_shortcut(const TC* conv, const float* xin, float* out, T* out_t, int n, int H, int W, int Cin,
                            int Cout, cudaStream_t s, int pCp = 0);
 // encoder: DCDownBlock2d tail (H x W = fine resolution) and the Encoder.forward output shortcut (+ normalisation)
 template <typename T>

@@ -411,23 +411,23 @@ __global__ void __launch_bounds__(256) heun_init_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) latent_feedback_kernel(const float* __restrict__ s, float* __restrict__ known,
                                                               float* __restrict__ phys, const float* __restrict__ mean,
                                                               const float* __restrict__ stdv, float target, int C, int T,
-                                                              int t_in, int hw4, long long n4) {
+                                                              int t_in, int hw2, long long n2) {
+  // one thread = two consecutive pixels of a (b, c, t) plane (h*w = 450 is even but not a multiple of 4)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n4) return;
-  const int p = static_cast<int>(i % hw4);
-  long long r = i / hw4;
+  if (i >= n2) return;
+  const int p = static_cast<int>(i % hw2);
+  long long r = i / hw2;
   const int t = static_cast<int>(r % T);
   r /= T;
   const int c = static_cast<int>(r % C);
   const long long b = r / C;
-  const float4 v = reinterpret_cast<const float4*>(s)[i];
+  const float2 v = reinterpret_cast<const float2*>(s)[i];
   if (known != nullptr && t >= T - t_in)
-    reinterpret_cast<float4*>(known)[((b * C + c) * t_in + (t - (T - t_in))) * hw4 + p] = v;
+    reinterpret_cast<float2*>(known)[((b * C + c) * t_in + (t - (T - t_in))) * hw2 + p] = v;
   if (phys != nullptr) {
     const float sd = __ldg(stdv + c), mu = __ldg(mean + c);
-    reinterpret_cast<float4*>(phys)[i] =
-        make_float4(__fadd_rn(__fmul_rn(__fdiv_rn(v.x, target), sd), mu), __fadd_rn(__fmul_rn(__fdiv_rn(v.y, target), sd), mu),
-                    __fadd_rn(__fmul_rn(__fdiv_rn(v.z, target), sd), mu), __fadd_rn(__fmul_rn(__fdiv_rn(v.w, target), sd), mu));
+    reinterpret_cast<float2*>(phys)[i] = make_float2(__fadd_rn(__fmul_rn(__fdiv_rn(v.x, target), sd), mu),
+                                                     __fadd_rn(__fmul_rn(__fdiv_rn(v.y, target), sd), mu));
   }
 }
 
@@ -584,13 +584,13 @@ int sched_heun_init(const float* noise, double* x, float* x_in, long long n, dou
 
 int latent_feedback(const float* samples, float* known, float* phys, const float* mean, const float* stdv, float target,
                     int B, int C, int T, int t_in, int hw, cudaStream_t s) {
-  LC_REQUIRE(hw % 4 == 0, "latent_feedback: h*w must be a multiple of 4");
+  LC_REQUIRE(hw % 2 == 0, "latent_feedback: h*w must be even");
   LC_REQUIRE(t_in >= 1 && t_in <= T, "latent_feedback: need 1 <= T_in <= T_out");
   LC_REQUIRE(phys == nullptr || (mean != nullptr && stdv != nullptr), "latent_feedback: mean/std required for the de-normalised output");
-  const long long n4 = static_cast<long long>(B) * C * T * (hw / 4);
-  ProfScope ps(PROF_SCHED, 0.0, static_cast<double>(n4) * 16.0 * (1.0 + (phys != nullptr ? 1.0 : 0.0) + static_cast<double>(t_in) / T), s);
-  latent_feedback_kernel<<<static_cast<unsigned>(ceil_div_ll(n4, 256)), 256, 0, s>>>(samples, known, phys, mean, stdv, target, C,
-                                                                                   T, t_in, hw / 4, n4);
+  const long long n2 = static_cast<long long>(B) * C * T * (hw / 2);
+  ProfScope ps(PROF_SCHED, 0.0, static_cast<double>(n2) * 8.0 * (1.0 + (phys != nullptr ? 1.0 : 0.0) + static_cast<double>(t_in) / T), s);
+  latent_feedback_kernel<<<static_cast<unsigned>(ceil_div_ll(n2, 256)), 256, 0, s>>>(samples, known, phys, mean, stdv, target, C,
+                                                                                   T, t_in, hw / 2, n2);
   LC_LAUNCH_CHECK();
   return 0;
 }

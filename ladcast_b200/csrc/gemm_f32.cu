@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
 
 int gemm_f32(const GemmArgs& g, cudaStream_t stream) {
   LC_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "empty GEMM");
+  LC_REQUIRE(g.epi.mode != EPI_NORM_RESID, "the fused RMSNorm epilogue exists on the tensor-core path only");
   const int K0 = (g.A1 != nullptr) ? g.K0 : g.K;
   dim3 grid(ceil_div(g.N, TN), ceil_div(g.M, TM));
   gemm_f32_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(g.A0), g.lda0, K0,
@@ -119,6 +120,7 @@ int gemm_f32(const GemmArgs& g, cudaStream_t stream) {
 
 int conv3x3_f32(const float* xpad, int n_frames, int H, int W, int Cp, const float* wmat, int C_out,
                 const EpiParams& epi, cudaStream_t stream) {
+  LC_REQUIRE(epi.mode != EPI_NORM_RESID, "the fused RMSNorm epilogue exists on the tensor-core path only");
   ConvF32 cv;
   cv.enabled = 1; cv.H = H; cv.W = W; cv.Cp = Cp;
   const int M = n_frames * H * W, K = 9 * Cp;

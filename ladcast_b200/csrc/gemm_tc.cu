@@ -71,7 +71,7 @@ __device__ __forceinline__ float act_fast(float v) {
 // Optional in-kernel timeline of pair 0 for tuning (tools/gemm_trace.py): clock64 stamps, [role][tile][4].
 __device__ long long* g_gemm_trace = nullptr;
 
-enum EpiKind { K_STORE_BF16 = 0, K_STORE_F32 = 1, K_GATED = 2, K_RESID = 3, K_UNPATCH = 4, K_QKV = 5 };
+enum EpiKind { K_STORE_BF16 = 0, K_STORE_F32 = 1, K_GATED = 2, K_RESID = 3, K_UNPATCH = 4, K_QKV = 5, K_NORM = 6 };
 
 // One 32x32 accumulator block (lane = row, r[j] = column n0+j).  K_UNPATCH keeps this layout (consecutive rows are
 // contiguous in the channel-major output); every other kind transposes the block through a padded smem tile so
@@ -243,6 +243,59 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& ep, const uint32
   __syncwarp();
 }
 
+// EPI_NORM_RESID chunk: the 32x32 block is transposed through shared memory so that 8 lanes x float4 cover a 128-byte
+// row segment; the row's rstd travels with the row (shuffle), RMSNorm weight / bias with the column.  x += y in place
+// (fp32), the new x is also stored as bf16 at the remapped row (next conv's padded input / next GEMM's operand).
+__device__ __forceinline__ void epilogue_block_norm(const EpiParams& ep, const uint32_t (&r)[32], float* tbuf, int lane,
+                                                    int row_mine, long long orow_mine, float rstd_mine, int n0, int M,
+                                                    int N) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
+  __syncwarp();
+  const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+  const int col = n0 + c4;
+  const bool col_ok = col < N;  // N % 4 == 0 (checked on the host)
+  float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = w4;
+  if (col_ok) {
+    w4 = __ldg(reinterpret_cast<const float4*>(ep.norm_w + col));
+    b4 = __ldg(reinterpret_cast<const float4*>(ep.norm_b + col));
+  }
+  float4 prev[8];
+  long long orows[8];
+  int rows[8];
+  float rs[8];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const int rr = g * 4 + rsub;
+    rows[g] = __shfl_sync(0xffffffffu, row_mine, rr);
+    orows[g] = __shfl_sync(0xffffffffu, orow_mine, rr);
+    rs[g] = __shfl_sync(0xffffffffu, rstd_mine, rr);
+    prev[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rows[g] < M && col_ok && ep.xres != nullptr)
+      prev[g] = *reinterpret_cast<const float4*>(ep.xres + static_cast<long long>(rows[g]) * ep.ldr + col);
+  }
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float* tb = tbuf + (g * 4 + rsub) * 33 + c4;
+    float4 o;
+    o.x = fmaf(tb[0] * rs[g], w4.x, b4.x) + prev[g].x;
+    o.y = fmaf(tb[1] * rs[g], w4.y, b4.y) + prev[g].y;
+    o.z = fmaf(tb[2] * rs[g], w4.z, b4.z) + prev[g].z;
+    o.w = fmaf(tb[3] * rs[g], w4.w, b4.w) + prev[g].w;
+    if (rows[g] < M && col_ok) {
+      if (ep.xres != nullptr) *reinterpret_cast<float4*>(ep.xres + static_cast<long long>(rows[g]) * ep.ldr + col) = o;
+      if (ep.out != nullptr) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&lo);
+        u.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + orows[g] * ep.ldo + col) = u;
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // qkv projection chunk (32 columns of one head, thread = row): bias, then (q/k heads only) per-head RMSNorm with the
 // row's rstd and RoPE on interleaved pairs, bf16, four 16-byte stores.  The rotation factors come from a packed
 // [tokens, 64] half2 (cos, sin) table: 64 B per thread and chunk instead of 256 B of fp32 cos + sin.
@@ -298,6 +351,7 @@ __device__ __forceinline__ void epilogue_qkv_chunk(const EpiParams& ep, const ui
 
 __device__ __forceinline__ int epi_kind(const EpiParams& ep) {
   if (ep.qk_cols > 0) return K_QKV;
+  if (ep.mode == EPI_NORM_RESID) return K_NORM;
   if (ep.mode == EPI_GATED_RESID) return K_GATED;
   if (ep.mode == EPI_UNPATCHIFY) return K_UNPATCH;
   if (ep.mode == EPI_RESID_STORE) return K_RESID;  // f32 output only on the tensor-core path
@@ -347,10 +401,45 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& ep, const ConvLoad
 // Drain one accumulator stage: this warp's 32 rows x (BN/2) columns, TMEM -> registers -> fused epilogue -> global.
 template <int BN>
 __device__ __forceinline__ void epilogue_drain(const EpiParams& ep, int kind, int n_blk, int quarter, int half, int lane,
-                                               float* tbuf, uint32_t tmem_base, int acc, int row, long long orow,
-                                               int sample, int M, int N) {
+                                               float* tbuf, float* tbuf_partner, uint32_t tmem_base, int acc, int row,
+                                               long long orow, int sample, int M, int N) {
   const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                           static_cast<uint32_t>(acc * BN + half * (BN / 2));
+  if (kind == K_NORM) {
+    // the tile holds whole rows (one N tile): pass 1 = sum of squares of this thread's half row, completed with the
+    // partner warp (other column half, same TMEM lanes) through the spare column of the transpose tiles; pass 2 =
+    // normalise + residual + stores.  TMEM is read twice; the conv output never goes to HBM.
+    constexpr int NC = BN / 64;
+    uint32_t r[2][32];
+    float ss4[4] = {0.f, 0.f, 0.f, 0.f};
+    ptx::tmem_ld32(t_addr, r[0]);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      ptx::tmem_ld_wait();
+      if (c + 1 < NC) ptx::tmem_ld32(t_addr + (c + 1) * 32, r[(c + 1) & 1]);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {  // columns >= N are exact zeros (W rows out of bounds are zero-filled by TMA)
+        const float v = __uint_as_float(r[c & 1][j]);
+        ss4[j & 3] = fmaf(v, v, ss4[j & 3]);
+      }
+    }
+    float ss = (ss4[0] + ss4[1]) + (ss4[2] + ss4[3]);
+    tbuf[lane * 33 + 32] = ss;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+    ss += tbuf_partner[lane * 33 + 32];
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");  // both halves have read before a slot is reused
+    const float rstd = rsqrtf(ss / static_cast<float>(N) + ep.norm_eps);
+    const int n_base = n_blk * BN + half * (BN / 2);
+    ptx::tmem_ld32(t_addr, r[0]);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      ptx::tmem_ld_wait();
+      if (c + 1 < NC) ptx::tmem_ld32(t_addr + (c + 1) * 32, r[(c + 1) & 1]);
+      const int n0 = n_base + c * 32;
+      if (n0 < N) epilogue_block_norm(ep, r[c & 1], tbuf, lane, row, orow, rstd, n0, M, N);
+    }
+    return;
+  }
   if (kind == K_QKV) {
     // this warp owns one 128-column head of the tile: pass 1 = sum of squares per row (q/k heads), pass 2 =
     // normalise + rotate + store.  TMEM is read twice; the accumulator never leaves the SM in fp32.
@@ -534,6 +623,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access (= warp id % 4)
     const int half = ew >> 2;      // which half of the tile's columns
     float* tbuf = epi_smem + ew * (32 * 33);
+    float* tbuf_partner = epi_smem + (ew ^ 4) * (32 * 33);
     const int kind = epi_kind(ep);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -545,7 +635,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       epilogue_row(ep, cv, m_blk, quarter, lane, M, row, orow, sample);
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
-      epilogue_drain<BN>(ep, kind, n_blk, quarter, half, lane, tbuf, tmem_base, acc, row, orow, sample, M, N);
+      epilogue_drain<BN>(ep, kind, n_blk, quarter, half, lane, tbuf, tbuf_partner, tmem_base, acc, row, orow, sample, M, N);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
@@ -710,6 +800,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const int quarter = warp & 3;
     const int half = ew >> 2;
     float* tbuf = epi_smem + ew * (32 * 33);
+    float* tbuf_partner = epi_smem + (ew ^ 4) * (32 * 33);
     const int kind = epi_kind(ep);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -726,7 +817,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       if (trace != nullptr && tix < 64) trace[256 + tix * 4 + 1] = clock64();
-      epilogue_drain<BN>(ep, kind, n_blk, quarter, half, lane, tbuf, tmem_base, acc, row, orow, sample, M, N);
+      epilogue_drain<BN>(ep, kind, n_blk, quarter, half, lane, tbuf, tbuf_partner, tmem_base, acc, row, orow, sample, M, N);
       ptx::tc_fence_before();
       __syncwarp();
       if (trace != nullptr && tix < 64) trace[256 + tix * 4 + 2] = clock64();
@@ -745,7 +836,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 // once (read-modify-write epilogues: twice)
 double algorithmic_bytes(int M, int N, int K, const EpiParams& ep, const ConvLoad& cv) {
   const double a = 2.0 * M * (cv.enabled ? K / 9.0 : static_cast<double>(K));
-  const double out_b = (ep.mode == EPI_GATED_RESID || ep.mode == EPI_RESID_STORE) ? 8.0
+  const double out_b = ep.mode == EPI_NORM_RESID ? (ep.xres ? 8.0 : 0.0) + (ep.out ? 2.0 : 0.0)
+                       : (ep.mode == EPI_GATED_RESID || ep.mode == EPI_RESID_STORE) ? 8.0
                        : (ep.mode == EPI_UNPATCHIFY || ep.out_f32) ? 4.0 : 2.0;
   const double n_out = ep.mode == EPI_UNPATCHIFY ? ep.n_valid : N;
   return a + 2.0 * N * K + out_b * M * n_out;
@@ -815,6 +907,15 @@ int num_sms() {
 
 static int pick_bn(int N) { return (N > 128) ? 256 : 128; }
 
+static int check_norm_epilogue(const EpiParams& ep, int N, int bn) {
+  if (ep.mode != EPI_NORM_RESID) return 0;
+  LC_REQUIRE(N <= bn && N % 4 == 0, "fused RMSNorm epilogue needs all output channels in one N tile (N <= 256, N % 4 == 0)");
+  LC_REQUIRE(ep.bias == nullptr && ep.norm_w != nullptr && ep.norm_b != nullptr, "fused RMSNorm epilogue: no GEMM bias, norm weight + bias required");
+  LC_REQUIRE(ep.xres == nullptr || ep.ldr % 4 == 0, "fused RMSNorm epilogue: residual row pitch must be a multiple of 4");
+  LC_REQUIRE(ep.out == nullptr || ep.ldo % 4 == 0, "fused RMSNorm epilogue: output row pitch must be a multiple of 4");
+  return 0;
+}
+
 // CTA pairs pay off once there are enough 256 x 256 tiles to fill the 74 pairs; LADCAST_B200_GEMM_PAIR=0 disables.
 static bool use_pair(int m_tiles, int N) {
   static int mode = -1;
@@ -837,6 +938,7 @@ int gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   const int K0 = (g.A1 != nullptr) ? g.K0 : g.K;
   LC_REQUIRE(g.A1 == nullptr || (K0 % BK == 0 && K0 > 0 && K0 < g.K), "split-K source boundary must be a multiple of 64");
   const int bn = pick_bn(g.N);
+  LC_TRY(check_norm_epilogue(g.epi, g.N, bn));
   CUtensorMap ta0, ta1, tw;
   LC_TRY(make_tmap_2d_bf16(&ta0, g.A0, static_cast<uint64_t>(K0), static_cast<uint64_t>(g.M),
                            static_cast<uint64_t>(g.lda0) * 2, BK, BM));
@@ -882,6 +984,7 @@ int conv3x3_bf16(const void* xpad, int n_frames, int H, int W, int Cp, const voi
   const int M = n_frames * H * W;
   const int K = 9 * Cp;
   const int bn = pick_bn(C_out);
+  LC_TRY(check_norm_epilogue(epi, C_out, bn));
   CUtensorMap ta, tw;
   uint64_t dims[4] = {static_cast<uint64_t>(Cp), static_cast<uint64_t>(W + 2), static_cast<uint64_t>(H + 2),
                       static_cast<uint64_t>(n_frames)};
