@@ -257,6 +257,31 @@ class Rollout:
                                           sampler_type="pipeline", member_indices=self.members, out=self.out)
         return fields
 
+    def probe_host(self, lib):
+        """Host cost of ENQUEUEING one denoiser call into an empty stream (the launch queue of a whole AR step exceeds
+        the driver's queue depth, so timing the enqueue of a full step only measures back-pressure) vs its device time."""
+        B = len(self.members)
+        if B == 0:
+            return None
+        a = self.args
+        known = self.known if self.known.shape[0] == B else self.known.expand(B, -1, -1, -1, -1).contiguous()
+        x = torch.randn((B, 84, a.t_out, 15, 30), device=self.dev)
+        t = torch.full((1,), 0.5, device=self.dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with self.model.cached_conditioning(known, self.stamp, t_out=a.t_out):
+            self.model(x, t, known, time_elapsed=self.stamp)
+            torch.cuda.synchronize()
+            n0 = lib.lc_launch_count()
+            h0 = time.perf_counter()
+            e0.record()
+            self.model(x, t, known, time_elapsed=self.stamp)
+            e1.record()
+            host_us = 1e6 * (time.perf_counter() - h0)
+            torch.cuda.synchronize()
+        return {"host_enqueue_us_per_denoiser_call": round(host_us, 1),
+                "device_us_per_denoiser_call": round(1e3 * e0.elapsed_time(e1), 1),
+                "launches_per_denoiser_call": int(lib.lc_launch_count() - n0)}
+
     def release(self):
         self.model._release()
         self.model = self.pipe = None
@@ -351,12 +376,20 @@ def metrics_leg(fields, lib, _lib, peaks, extra_members=(50,)):
             tabs = ensemble_metrics(f, truth)
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
+        call_ms = e0.elapsed_time(e1) / reps
+        lib.lc_prof_enable(1)  # the reduction kernel alone (CUDA events around its launch)
+        for _ in range(reps):
+            ensemble_metrics(f, truth)
+        torch.cuda.synchronize()
+        k = _lib.prof_collect().get("metrics", {"ms": 0.0, "launches": 1})
+        lib.lc_prof_enable(0)
+        ms = k["ms"] / max(1, k["launches"])
         by = 4.0 * (m + 1) * truth.numel()
-        res.append({"members": m, "planes": 84 * int(fields.shape[2]), "ms": round(ms, 4), "algorithmic_bytes": by,
-                    "achieved": round(by / (ms * 1e-3) / 1e9, 1), "peak": peak_gb, "unit": "GB/s",
-                    "frac": round(by / (ms * 1e-3) / 1e9 / peak_gb, 4), "bound": "hbm",
-                    "note": "includes the two 27 KB memsets and the host-side table assembly launches",
+        res.append({"kernel": CLASS_KERNELS["metrics"], "members": m, "planes": 84 * int(fields.shape[2]),
+                    "kernel_ms": round(ms, 4), "call_ms": round(call_ms, 4), "algorithmic_bytes": by,
+                    "achieved": round(by / (ms * 1e-3) / 1e9, 1) if ms > 0 else None, "peak": peak_gb, "unit": "GB/s",
+                    "frac": round(by / (ms * 1e-3) / 1e9 / peak_gb, 4) if ms > 0 else None, "bound": "hbm",
+                    "note": "call_ms = ensemble_metrics() end to end (memsets, kernel, [C,T] table assembly)",
                     "finite": bool(all(torch.isfinite(v).all() for v in tabs.values()))})
         del f
     return res
@@ -378,13 +411,17 @@ def strong_leg(args, ens_total, rank, world, dev, ae, model, barrier, lib, _lib,
     per_rank = [len(member_shard(ens_total, r, world)) for r in range(world)]
     res = {"model": f"ladcast_{args.strong_model}", "ensemble_total": ens_total, "members_per_rank": per_rank,
            "scaling": "strong", "value": value, "unit": UNIT, "ms_per_step": step_ms, "steps": steps, "warmup": warmup,
-           "host_enqueue_ms_per_step": round(host_ms / steps, 2), "gpu_launches_per_step": launches // max(1, steps),
+           "gpu_launches_per_step": launches // max(1, steps),
            "balance_bound": round(ens_total / (world * max(per_rank)), 4),
            "step_algorithmic_tflops_per_gpu": round(flops_per_member_step(args.strong_model, args.t_out, args.denoise_steps)
                                                     * max(per_rank) * args.t_out / (step_ms * 1e-3) / 1e12, 1)}
-    res["limiter"] = ("host launch rate (enqueue time ~ device time)" if host_ms > 0.85 * ms else
-                      "device: the rank with the most members; the host enqueues a step in "
-                      f"{host_ms / steps:.0f} ms of the {step_ms:.0f} ms it takes")
+    probe = run.probe_host(lib)
+    res["launch_probe"] = probe
+    if probe is not None:
+        ratio = probe["host_enqueue_us_per_denoiser_call"] / max(1e-9, probe["device_us_per_denoiser_call"])
+        res["limiter"] = (f"host launch rate: enqueueing a denoiser call takes {ratio:.2f}x its device time" if ratio > 0.8 else
+                          f"device (the rank with the most members): enqueueing a denoiser call costs {ratio:.2f}x its device "
+                          "time, so the launch queue stays ahead of the GPU")
     # ---- metrics over the sharded ensemble (config 5): exchange + kernel, timed; checked against one GPU
     g = torch.Generator("cpu").manual_seed(11)
     truth = torch.randn((84, args.t_out, 120, 240), generator=g).to(dev)
@@ -484,6 +521,7 @@ def main():
     units = args.ens * args.t_out * args.steps * world
     value = units / (ms * 1e-3)
     step_ms = ms / args.steps
+    launch_probe = run.probe_host(lib)
 
     # ---- rooflines: one more identical step with per-launch CUDA events
     roofline = None
@@ -557,7 +595,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
                 "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches),
-                "host_enqueue_ms_per_step": round(host_ms / args.steps, 2), "metrics": metrics, "strong": strong,
+                "launch_probe": launch_probe, "metrics": metrics, "strong": strong,
                 "clocks": clk, "finite": finite, "impl": "ours"}
         print(json.dumps(line))
     if world > 1:

@@ -46,17 +46,13 @@ __device__ __forceinline__ float4 load4<bf16>(const bf16* p) {
 // normalised and stored (the one-row-per-warp version was DRAM-latency bound: 35 % of HBM peak).
 // Reference: AdaLayerNormZero/ZeroSingle/Continuous (diffusers), LaDCast_3D_model.py:287-302, 524-552, 1044.
 template <typename T, int NV>
-__device__ __forceinline__ void ln_row(const float4 (&vin)[NV], int row, int lane, T* __restrict__ out, int d, float eps,
+__device__ __forceinline__ void ln_row(float4 (&v)[NV], int row, int lane, T* __restrict__ out, int d, float eps,
                                        int rows_per_sample, int seg_rows, int seg_rows_per_sample,
                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                        long long mod_stride, const float* __restrict__ w, const float* __restrict__ b) {
-  float4 v[NV];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    v[i] = vin[i];
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   const float mean = warp_sum(s) / d;
   float q = 0.f;
 #pragma unroll
@@ -86,33 +82,56 @@ __device__ __forceinline__ void ln_row(const float4 (&vin)[NV], int row, int lan
   }
 }
 
-constexpr int LN_RPW = 4;  // rows per warp (8 measured slower: too few blocks for the 9000-row streams)
+constexpr int LN_RPW = 8;      // consecutive rows per warp
+constexpr int LN_STAGES = 2;   // rows of a warp in flight (cp.async ring in shared memory)
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Each warp owns LN_RPW consecutive rows and a private LN_STAGES-deep ring of row buffers in shared memory that
+// cp.async (LDGSTS) fills while the previous row is normalised: the loads need no registers, so the row being
+// processed (NV float4 per lane) and its statistics fit without spills and every warp keeps ~2 rows (12-16 KB) in
+// flight.  (The register double buffer of round 1 spilled 300-800 B per thread at d = 1536 / 2048.)  Every lane reads
+// back exactly the 16-byte chunks it copied itself, so cp.async.wait_group is the only synchronisation needed.
 template <typename T, int NV>
-__global__ void __launch_bounds__(256, 2) layernorm_kernel(const float* __restrict__ x, T* __restrict__ out, int M, int d,
-                                                           float eps, int rows_per_sample, int seg_rows,
-                                                           int seg_rows_per_sample, const float* __restrict__ scale,
-                                                           const float* __restrict__ shift, long long mod_stride,
-                                                           const float* __restrict__ w, const float* __restrict__ b) {
-  const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * LN_RPW;
-  const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256, NV <= 12 ? 2 : 1)
+layernorm_kernel(const float* __restrict__ x, T* __restrict__ out, int M, int d, float eps, int rows_per_sample,
+                 int seg_rows, int seg_rows_per_sample, const float* __restrict__ scale, const float* __restrict__ shift,
+                 long long mod_stride, const float* __restrict__ w, const float* __restrict__ b) {
+  extern __shared__ float4 ln_ring[];  // [8 warps][LN_STAGES][NV * 32]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = (blockIdx.x * 8 + warp) * LN_RPW;
   if (row0 >= M) return;
   const int nrows = min(LN_RPW, M - row0);
-  float4 buf[2][NV];
+  float4* ring = ln_ring + warp * (LN_STAGES * NV * 32);
   const float* xr = x + static_cast<long long>(row0) * d + lane * 4;
+  auto issue = [&](int r) {
+    float4* dst = ring + (r % LN_STAGES) * (NV * 32) + lane;
+    const float* src = xr + static_cast<long long>(r) * d;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) buf[0][i] = *reinterpret_cast<const float4*>(xr + i * 128);
+    for (int i = 0; i < NV; ++i) cp_async16(dst + i * 32, src + i * 128);
+  };
 #pragma unroll
-  for (int r = 0; r < LN_RPW; ++r) {
-    if (r < nrows) {
-      if (r + 1 < nrows) {
+  for (int r = 0; r < LN_STAGES - 1; ++r) {
+    if (r < nrows) issue(r);
+    cp_async_commit();
+  }
+  for (int r = 0; r < nrows; ++r) {
+    if (r + LN_STAGES - 1 < nrows) issue(r + LN_STAGES - 1);
+    cp_async_commit();
+    cp_async_wait<LN_STAGES - 1>();  // row r has landed (groups complete in order)
+    float4 v[NV];
+    const float4* src = ring + (r % LN_STAGES) * (NV * 32) + lane;
 #pragma unroll
-        for (int i = 0; i < NV; ++i)
-          buf[(r + 1) & 1][i] = *reinterpret_cast<const float4*>(xr + static_cast<long long>(r + 1) * d + i * 128);
-      }
-      ln_row<T, NV>(buf[r & 1], row0 + r, lane, out, d, eps, rows_per_sample, seg_rows, seg_rows_per_sample, scale, shift,
-                    mod_stride, w, b);
-    }
+    for (int i = 0; i < NV; ++i) v[i] = src[i * 32];
+    ln_row<T, NV>(v, row0 + r, lane, out, d, eps, rows_per_sample, seg_rows, seg_rows_per_sample, scale, shift,
+                  mod_stride, w, b);
   }
 }
 
@@ -442,10 +461,17 @@ int layernorm_modulate(const float* x, T* out, int M, int d, float eps, int rows
   dim3 grid(ceil_div(M, 8 * LN_RPW));
   ProfScope ps(PROF_LN, 0.0, static_cast<double>(M) * d * (4 + sizeof(T)), s);
 #define LC_LN_CASE(NV)                                                                                            \
-  case NV:                                                                                                        \
-    layernorm_kernel<T, NV><<<grid, 256, 0, s>>>(x, out, M, d, eps, rows_per_sample, seg_rows, seg_rows_per_sample,   \
-                                                 scale, shift, mod_stride, w, b);                                     \
-    break;
+  case NV: {                                                                                                      \
+    constexpr int smem = 8 * LN_STAGES * NV * 32 * 16;                                                            \
+    static PerDevice<bool> attr_set;                                                                              \
+    if (smem > 48 * 1024 && !attr_set.here()) {                                                                   \
+      LC_CHECK_CUDA(cudaFuncSetAttribute(layernorm_kernel<T, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      attr_set.here() = true;                                                                                     \
+    }                                                                                                             \
+    layernorm_kernel<T, NV><<<grid, 256, smem, s>>>(x, out, M, d, eps, rows_per_sample, seg_rows, seg_rows_per_sample, \
+                                                    scale, shift, mod_stride, w, b);                                   \
+    break;                                                                                                        \
+  }
   switch (nv) {
     LC_LN_CASE(1) LC_LN_CASE(2) LC_LN_CASE(3) LC_LN_CASE(4) LC_LN_CASE(5) LC_LN_CASE(6) LC_LN_CASE(7) LC_LN_CASE(8)
     LC_LN_CASE(9) LC_LN_CASE(10) LC_LN_CASE(11) LC_LN_CASE(12) LC_LN_CASE(13) LC_LN_CASE(14) LC_LN_CASE(15)

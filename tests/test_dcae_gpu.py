@@ -6,6 +6,7 @@ import pytest
 import torch
 
 from ladcast_b200 import _lib
+from conftest import record_measured
 from oracle import ladcast_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -82,7 +83,7 @@ def test_dcae_small_vs_oracle(precision, tol):
     torch.cuda.synchronize()
     assert torch.isfinite(out).all()
     r = _rel(out, want)
-    print("dcae small", precision, "rel-L2", r)
+    record_measured(f"dcae_small/{precision}/rel_l2", r)
     assert r < tol
 
 
@@ -96,7 +97,7 @@ def test_dcae_full_bf16_vs_oracle():
     fused = ae.decode_fused(z.cuda(), mean, std)
     torch.cuda.synchronize()
     r = _rel(out, want)
-    print("dcae full bf16 rel-L2", r)
+    record_measured("dcae_full_V0.1.X/bf16/rel_l2", r)
     assert r < 2e-2
     assert _rel(fused, want * std[None, :, None, None] + mean[None, :, None, None]) < 2e-2
 

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import record_measured
 from oracle import ladcast_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -43,7 +44,9 @@ def test_denoiser_tiny_vs_golden(golden_dir, precision):
     out = m(x, torch.from_numpy(g["t"]).cuda(), cond, time_elapsed=torch.from_numpy(g["ts"]), return_dict=False)[0]
     torch.cuda.synchronize()
     assert out.shape == x.shape and torch.isfinite(out).all()
-    assert _rel(out, g["out"]) < TOL[precision]
+    r = _rel(out, g["out"])
+    record_measured(f"denoiser_tiny_golden/{precision}/rel_l2", r)
+    assert r < TOL[precision]
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -108,7 +111,9 @@ def test_denoiser_375M_bf16_vs_oracle():
     want = O.denoiser_forward(sd, cfg, x.cpu(), t, cond.cpu(), ts)
     out = m(x, t.cuda(), cond, time_elapsed=ts).sample
     torch.cuda.synchronize()
-    assert _rel(out, want) < 1e-2
+    r = _rel(out, want)
+    record_measured("denoiser_375M/bf16/rel_l2", r)
+    assert r < 1e-2
 
 
 def test_denoiser_1p6B_bf16_vs_oracle():
@@ -122,7 +127,7 @@ def test_denoiser_1p6B_bf16_vs_oracle():
     out = m(x, t.cuda(), cond, time_elapsed=ts).sample
     torch.cuda.synchronize()
     r = _rel(out, want)
-    print("1.6B bf16 rel-L2", r)
+    record_measured("denoiser_1p6B_T4/bf16/rel_l2", r)
     assert r < 1e-2
 
 

@@ -4,6 +4,7 @@ import ctypes
 import pytest
 import torch
 
+from conftest import record_measured
 from ladcast_b200 import _lib
 
 pytestmark = pytest.mark.gpu
@@ -63,7 +64,10 @@ def test_attention(lib, b, s, heads, prec):
     _lib.check(lib.lc_attention(prec, _lib.ptr(qkv_in), _lib.ptr(out), b, s, heads, _lib.stream()), "lc_attention")
     torch.cuda.synchronize()
     assert torch.isfinite(out.float()).all()
-    assert _rel(out, ref) < tol
+    r = _rel(out, ref)
+    if prec == _lib.PRECISION_BF16:
+        record_measured(f"attention/bf16/b{b}_s{s}_h{heads}/rel_l2", r)
+    assert r < tol
 
 
 def test_dpmpp2m_step(lib):

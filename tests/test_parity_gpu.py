@@ -187,8 +187,8 @@ def test_pixel_shuffle_shortcut_bit_exact(cin, cout):
     x = _seeded((n, cin, H, W), 911).cuda()
     want = F.pixel_shuffle(conv, 2) + F.pixel_shuffle(x.repeat_interleave(4 * cout // cin, dim=1), 2)
     out = torch.full((n, 2 * H, 2 * W, cout), float("nan"), device="cuda")
-    _lib.check(lib.lc_pixel_shuffle_shortcut(_lib.ptr(conv.permute(0, 2, 3, 1).contiguous()),
-                                             _lib.ptr(x.permute(0, 2, 3, 1).contiguous()), _lib.ptr(out), n, H, W, cin, cout,
+    conv_l, x_l = conv.permute(0, 2, 3, 1).contiguous(), x.permute(0, 2, 3, 1).contiguous()  # NHWC (kept alive)
+    _lib.check(lib.lc_pixel_shuffle_shortcut(_lib.ptr(conv_l), _lib.ptr(x_l), _lib.ptr(out), n, H, W, cin, cout,
                                              _lib.stream()), "lc_pixel_shuffle_shortcut")
     torch.cuda.synchronize()
     assert torch.equal(out.permute(0, 3, 1, 2), want)
@@ -204,15 +204,14 @@ def test_pixel_unshuffle_shortcut_index_map(cin, cout):
     n, H, W = 2, 8, 12
     conv = _seeded((n, cout // 4, H, W), 920).cuda()
     x = _seeded((n, cin, H, W), 921).cuda()
-    zeros = torch.zeros_like(x)
     out = torch.full((n, H // 2, W // 2, cout), float("nan"), device="cuda")
     args = (n, H, W, cin, cout, _lib.stream())
-    _lib.check(lib.lc_pixel_unshuffle_shortcut(_lib.ptr(conv.permute(0, 2, 3, 1).contiguous()),
-                                               _lib.ptr(zeros.permute(0, 2, 3, 1).contiguous()), _lib.ptr(out), *args), "unshuffle")
+    conv_l, x_l = conv.permute(0, 2, 3, 1).contiguous(), x.permute(0, 2, 3, 1).contiguous()  # NHWC (kept alive)
+    zeros_l = torch.zeros_like(x_l)
+    _lib.check(lib.lc_pixel_unshuffle_shortcut(_lib.ptr(conv_l), _lib.ptr(zeros_l), _lib.ptr(out), *args), "unshuffle")
     torch.cuda.synchronize()
     assert torch.equal(out.permute(0, 3, 1, 2), F.pixel_unshuffle(conv, 2))
-    _lib.check(lib.lc_pixel_unshuffle_shortcut(_lib.ptr(conv.permute(0, 2, 3, 1).contiguous()),
-                                               _lib.ptr(x.permute(0, 2, 3, 1).contiguous()), _lib.ptr(out), *args), "unshuffle")
+    _lib.check(lib.lc_pixel_unshuffle_shortcut(_lib.ptr(conv_l), _lib.ptr(x_l), _lib.ptr(out), *args), "unshuffle")
     torch.cuda.synchronize()
     g = 4 * cin // cout
     want = F.pixel_unshuffle(conv, 2) + F.pixel_unshuffle(x, 2).unflatten(1, (-1, g)).mean(dim=2)

@@ -27,7 +27,7 @@ for name in models:
         _, ms, host_ms, launches, _ = bench.timed_loop(run, 2, 2, torch.cuda.synchronize, 1, dev, lib)
         cls = bench.profiled_step(run, lib, _lib)
         r = {"model": name, "members": B, "ms_per_step": ms / 2, "member_steps_per_s": B * 4 * 2 / (ms * 1e-3),
-             "per_member_ms": ms / 2 / B, "host_enqueue_ms_per_step": host_ms / 2, "launches_per_step": launches // 2,
+             "per_member_ms": ms / 2 / B, "launch_probe": run.probe_host(lib), "launches_per_step": launches // 2,
              "tflops": {k: round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) for k, v in cls.items() if v["flops"] > 0},
              "class_ms": {k: round(v["ms"], 2) for k, v in cls.items()}}
         print(json.dumps(r), flush=True)
