@@ -5,12 +5,18 @@
 #include "kernels.h"
 
 #include <atomic>
+#include <cstdlib>
 #include <vector>
 
 namespace lc {
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 const char* last_error() { return g_err.c_str(); }
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("LADCAST_B200_PDL"); return e != nullptr && e[0] == '1'; }();
+  return on;
+}
 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }

@@ -92,6 +92,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();  // q|k|v are produced by the preceding kernel: nothing global is touched above this line
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -326,7 +327,7 @@ int attention_bf16(const bf16* qkv, int B, int S, int heads, int head_dim, bf16*
                            static_cast<uint64_t>(3) * d * 2, 64, 128));
   dim3 grid(ceil_div(S, 2 * BQ), heads, B);
   prof_begin(PROF_ATTN, s);
-  attention_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(tm, S, heads, out_p, Np, out_c);
+  LC_CHECK_CUDA(launch_kernel(attention_tc_kernel, grid, NUM_THREADS, SMEM_BYTES, s, tm, S, heads, out_p, Np, out_c));
   prof_end(PROF_ATTN, 4.0 * B * heads * static_cast<double>(S) * S * HD, s, 8.0 * B * S * d);  // q, k, v in + o out (bf16)
   LC_LAUNCH_CHECK();
   return 0;

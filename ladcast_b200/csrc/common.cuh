@@ -7,6 +7,7 @@
 
 #include <cstdio>
 #include <string>
+#include <utility>
 
 namespace lc {
 
@@ -202,6 +203,35 @@ struct PerDevice {
   V v[LC_MAX_DEVICES] = {};
   V& here() { return v[current_device()]; }
 };
+
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every hot-path kernel calls pdl_grid_sync() after its block-local setup (barrier init, TMEM allocation, tensor-map
+// prefetch, index math) and BEFORE its first global-memory access: griddepcontrol.wait blocks until the preceding grid
+// of the stream has completed and flushed, then griddepcontrol.launch_dependents lets the NEXT grid's CTAs be
+// scheduled as soon as every CTA of this grid is resident — so a kernel's launch latency and prologue overlap the
+// tail of its predecessor while all memory ordering stays that of the stream.  (Triggering only after the wait keeps
+// at most one dependent grid waiting on the SMs.)  Both instructions are no-ops for a grid launched without the
+// attribute; launch_kernel() sets it when LADCAST_B200_PDL=1.
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---------------------------------------------------------------- lightweight per-class kernel timing (bench only)
 // When enabled, every launch of the library is bracketed with CUDA events on its stream; durations, algorithmic FLOPs

@@ -35,6 +35,7 @@ __device__ __forceinline__ float plane_load(const PlaneSrc& z, int f, int c, int
 // ---------------------------------------------------------------- NCHW f32 latent -> padded NHWC T  (conv_in input)
 template <typename T>
 __global__ void pad_from_nchw_kernel(PlaneSrc z, T* __restrict__ out, int n, int C, int H, int W, int Cp) {
+  pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(n) * (H + 2) * (W + 2) * Cp;
   if (i >= total) return;
@@ -57,6 +58,7 @@ __global__ void pad_from_nchw_kernel(PlaneSrc z, T* __restrict__ out, int n, int
 template <typename T>
 __global__ void pad_from_nhwc_kernel(const float* __restrict__ x, T* __restrict__ out, int n, int C, int H, int W,
                                      int Cp) {
+  pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // one thread per 4 channels
   const int c4 = Cp / 4;
   const long long total = static_cast<long long>(n) * (H + 2) * (W + 2) * c4;
@@ -81,6 +83,7 @@ __global__ void pad_from_nhwc_kernel(const float* __restrict__ x, T* __restrict_
 // from its own interior (after a conv epilogue wrote the interior directly).
 template <typename T>
 __global__ void halo_fill_kernel(T* __restrict__ buf, int n, int H, int W, int Cp) {
+  pdl_grid_sync();
   // halo positions per frame: 2 full rows (W+2) + 2 columns x H
   const int per_frame = 2 * (W + 2) + 2 * H;
   const int c8 = Cp / 8;
@@ -173,6 +176,7 @@ template <typename T, int XT>
 __global__ void __launch_bounds__(256, 3) dwconv3_glu_kernel(const T* __restrict__ in, const float* __restrict__ w,
                                                           const float* __restrict__ bias, T* __restrict__ out, int n,
                                                           int H, int W, int C) {
+  pdl_grid_sync();
   const int Co = C / 2;
   const int c = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
   const int x0 = (blockIdx.y * 8 + (threadIdx.x >> 5)) * XT;
@@ -236,6 +240,7 @@ template <typename T>
 __global__ void __launch_bounds__(256, 3) multiscale_fused_kernel(const T* __restrict__ in, const float* __restrict__ w5,
                                                                const float* __restrict__ wg, T* __restrict__ out,
                                                                int n, int H, int W, int C) {
+  pdl_grid_sync();
   __shared__ __align__(16) float ds[128][64];
   __shared__ __align__(16) float ws[4][32][32];  // [group][k][o ^ swizzle(k)]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -349,6 +354,7 @@ __device__ __forceinline__ float2 relu2(float a, float b) { return make_float2(f
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256, 2) linear_attn_kernel(const TI* __restrict__ qkv, const TI* __restrict__ ms,
                                                              TO* __restrict__ out, int HW, int heads, float eps) {
+  pdl_grid_sync();
   __shared__ __align__(16) float red[8][33][32];  // per-warp partials of S
   __shared__ __align__(16) float S[33][32];
   const int g = blockIdx.x % (2 * heads);
@@ -482,6 +488,7 @@ __global__ void __launch_bounds__(256) rmsnorm_rows_kernel(const TY* __restrict_
                                                            const float* __restrict__ b, float eps, float* __restrict__ resid,
                                                            float* __restrict__ out_f32, T* __restrict__ out_t, long long P,
                                                            int C, int relu, int pH, int pW, int pCp) {
+  pdl_grid_sync();
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= P) return;
@@ -495,31 +502,33 @@ __global__ void __launch_bounds__(256) rmsnorm_rows_kernel(const TY* __restrict_
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float r = rsqrtf(ss / C + eps);
+  // output row: plain [P, C] rows, or (pCp > 0) the interior of a sphere-padded [n, pH+2, pW+2, pCp] conv input
+  // (row -> (frame, y, x) once per row: the 64-bit divisions used to sit inside the channel loop)
+  long long obase = row * C;
+  if (pCp > 0) {
+    const long long fy = row / pW;
+    const int xx = static_cast<int>(row - fy * pW);
+    const long long ff = fy / pH;
+    const int yy = static_cast<int>(fy - ff * pH);
+    obase = ((ff * (pH + 2) + yy + 1) * (pW + 2) + xx + 1) * pCp;
+  }
+  float* rrow = resid != nullptr ? resid + row * C : nullptr;
+  float* frow = out_f32 != nullptr ? out_f32 + row * C : nullptr;
+  T* trow = out_t != nullptr ? out_t + obase : nullptr;
   for (int i = lane; i < c4; i += 32) {
     const int c = i * 4;
     const float4 v = ld4<TY>(yr + c);
     const float4 ww = __ldg(reinterpret_cast<const float4*>(w + c));
     const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
     float4 o = make_float4(v.x * r * ww.x + bb.x, v.y * r * ww.y + bb.y, v.z * r * ww.z + bb.z, v.w * r * ww.w + bb.w);
-    if (resid != nullptr) {
-      float4 h = *reinterpret_cast<float4*>(resid + row * C + c);
+    if (rrow != nullptr) {
+      const float4 h = *reinterpret_cast<const float4*>(rrow + c);
       o.x += h.x; o.y += h.y; o.z += h.z; o.w += h.w;
-      *reinterpret_cast<float4*>(resid + row * C + c) = o;
+      *reinterpret_cast<float4*>(rrow + c) = o;
     }
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + row * C + c) = o;
-    if (out_t != nullptr) {
-      // plain [P, C] rows, or (pCp > 0) the interior of a sphere-padded [n, pH+2, pW+2, pCp] conv input
-      long long obase = row * C;
-      if (pCp > 0) {
-        const long long fy = row / pW;
-        const int xx = static_cast<int>(row - fy * pW);
-        const long long ff = fy / pH;
-        const int yy = static_cast<int>(fy - ff * pH);
-        obase = ((ff * (pH + 2) + yy + 1) * (pW + 2) + xx + 1) * pCp;
-      }
-      st4<T>(out_t + obase + c, o);
-    }
+    if (frow != nullptr) *reinterpret_cast<float4*>(frow + c) = o;
+    if (trow != nullptr) st4<T>(trow + c, o);
   }
 }
 
@@ -529,6 +538,7 @@ template <typename TC, typename T>
 __global__ void __launch_bounds__(256) pixel_shuffle_kernel(const TC* __restrict__ conv, const float* __restrict__ xin,
                                                             float* __restrict__ out, T* __restrict__ out_t, int n, int H,
                                                             int W, int Cin, int Cout, int rep, int pCp) {
+  pdl_grid_sync();
   // one thread = (input pixel, 4 consecutive output channels): 4 float4 of the conv output -> 4 float4 stores, one
   // per sub-pixel (i, j)
   const int c4n = Cout / 4;
@@ -570,6 +580,7 @@ __global__ void __launch_bounds__(256) pixel_shuffle_kernel(const TC* __restrict
 template <typename T>
 __global__ void in_shortcut_kernel(float* __restrict__ x, T* __restrict__ x_t, PlaneSrc z, int n, int HW, int C, int Cz,
                                    int rep) {
+  pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(n) * HW * C;
   if (i >= total) return;
@@ -589,6 +600,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) pixel_unshuffle_kernel(const float* __restrict__ conv, const float* __restrict__ xin,
                                                               float* __restrict__ out, T* __restrict__ out_t, int n, int H,
                                                               int W, int Cin, int Cout, int g, int pCp) {
+  pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int Ho = H / 2, Wo = W / 2, Cq = Cout / 4;
   const long long total = static_cast<long long>(n) * Ho * Wo * Cout;
@@ -621,6 +633,7 @@ __global__ void __launch_bounds__(256) pixel_unshuffle_kernel(const float* __res
 __global__ void __launch_bounds__(256) enc_out_shortcut_kernel(float* __restrict__ out, const float* __restrict__ x, int n,
                                                                int HW, int C, int L, int g, const float* __restrict__ mean,
                                                                const float* __restrict__ stdv, float target) {
+  pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(n) * L * HW;
   if (i >= total) return;
@@ -644,7 +657,7 @@ template <typename T>
 int pad_from_nchw(const PlaneSrc& z, T* out, int n, int C, int H, int W, int Cp, cudaStream_t s) {
   const long long total = static_cast<long long>(n) * (H + 2) * (W + 2) * Cp;
   ProfScope ps(PROF_DEC_PAD, 0.0, static_cast<double>(n) * H * W * C * 4.0 + static_cast<double>(total) * sizeof(T), s);
-  pad_from_nchw_kernel<T><<<blocks(total), 256, 0, s>>>(z, out, n, C, H, W, Cp);
+  LC_CHECK_CUDA(launch_kernel(pad_from_nchw_kernel<T>, blocks(total), 256, 0, s, z, out, n, C, H, W, Cp));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -653,7 +666,7 @@ int pad_from_nhwc(const float* x, T* out, int n, int C, int H, int W, int Cp, cu
   LC_REQUIRE(C % 4 == 0 && Cp % 4 == 0, "pad: channels must be multiples of 4");
   const long long total = static_cast<long long>(n) * (H + 2) * (W + 2) * (Cp / 4);
   ProfScope ps(PROF_DEC_PAD, 0.0, static_cast<double>(n) * H * W * C * 4.0 + static_cast<double>(total) * 4 * sizeof(T), s);
-  pad_from_nhwc_kernel<T><<<blocks(total), 256, 0, s>>>(x, out, n, C, H, W, Cp);
+  LC_CHECK_CUDA(launch_kernel(pad_from_nhwc_kernel<T>, blocks(total), 256, 0, s, x, out, n, C, H, W, Cp));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -662,7 +675,7 @@ int halo_fill(T* buf, int n, int H, int W, int Cp, cudaStream_t s) {
   LC_REQUIRE(Cp % 8 == 0, "halo_fill: Cp must be a multiple of 8");
   const long long total = static_cast<long long>(n) * (2 * (W + 2) + 2 * H) * (Cp / 8);
   ProfScope ps(PROF_DEC_PAD, 0.0, static_cast<double>(total) * 16.0 * sizeof(T), s);
-  halo_fill_kernel<T><<<blocks(total), 256, 0, s>>>(buf, n, H, W, Cp);
+  LC_CHECK_CUDA(launch_kernel(halo_fill_kernel<T>, blocks(total), 256, 0, s, buf, n, H, W, Cp));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -673,7 +686,7 @@ int dwconv3_glu(const T* in, const float* w, const float* bias, T* out, int n, i
   dim3 grid((C / 8 + 31) / 32, (W + 8 * XT - 1) / (8 * XT), n * H);
   // algorithmic: read [P, C] once, write [P, C/2]
   ProfScope ps(PROF_DEC_DWGLU, 0.0, static_cast<double>(n) * H * W * C * 1.5 * sizeof(T), s);
-  dwconv3_glu_kernel<T, XT><<<grid, 256, 0, s>>>(in, w, bias, out, n, H, W, C);
+  LC_CHECK_CUDA(launch_kernel(dwconv3_glu_kernel<T, XT>, grid, 256, 0, s, in, w, bias, out, n, H, W, C));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -684,7 +697,7 @@ int multiscale_fused(const T* in, const float* w5, const float* wg, T* out, int 
   LC_REQUIRE(nblk < (1ll << 31), "multiscale projection: too many image rows per call");
   // algorithmic: read qkv [P, C] once, write the multiscale branch [P, C]
   ProfScope ps(PROF_DEC_MS, 2.0 * n * H * W * C * (25.0 + 32.0), static_cast<double>(n) * H * W * C * 2.0 * sizeof(T), s);
-  multiscale_fused_kernel<T><<<static_cast<unsigned>(nblk), 256, 0, s>>>(in, w5, wg, out, n, H, W, C);
+  LC_CHECK_CUDA(launch_kernel(multiscale_fused_kernel<T>, static_cast<unsigned>(nblk), 256, 0, s, in, w5, wg, out, n, H, W, C));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -692,7 +705,7 @@ template <typename T>
 int linear_attention(const T* qkv, const T* ms, T* out, int n, int HW, int heads, float eps, cudaStream_t s) {
   // algorithmic: k, v read once (phase 1), q read once (phase 2) of both scales, output [P, 2*heads*32] written
   ProfScope ps(PROF_DEC_LINATTN, 0.0, static_cast<double>(n) * HW * heads * (2 * 96 + 2 * 32) * sizeof(T), s);
-  linear_attn_kernel<T, T><<<n * 2 * heads, 256, 0, s>>>(qkv, ms, out, HW, heads, eps);
+  LC_CHECK_CUDA(launch_kernel(linear_attn_kernel<T, T>, n * 2 * heads, 256, 0, s, qkv, ms, out, HW, heads, eps));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -703,7 +716,7 @@ int rmsnorm_rows(const TY* y, int ldy, const float* w, const float* b, float eps
   // algorithmic: read y; read + write the residual; write the f32 / T copies that were asked for
   ProfScope ps(PROF_DEC_NORM, 0.0,
                static_cast<double>(P) * C * (sizeof(TY) + (resid ? 8.0 : 0.0) + (out_f32 ? 4.0 : 0.0) + (out_t ? sizeof(T) : 0.0)), s);
-  rmsnorm_rows_kernel<TY, T><<<blocks(P, 8), 256, 0, s>>>(y, ldy, w, b, eps, resid, out_f32, out_t, P, C, relu, pH, pW, pCp);
+  LC_CHECK_CUDA(launch_kernel(rmsnorm_rows_kernel<TY, T>, blocks(P, 8), 256, 0, s, y, ldy, w, b, eps, resid, out_f32, out_t, P, C, relu, pH, pW, pCp));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -714,7 +727,7 @@ int pixel_shuffle_shortcut(const TC* conv, const float* xin, float* out, T* out_
   const long long total = static_cast<long long>(n) * H * W * (Cout / 4);
   ProfScope ps(PROF_DEC_SHUFFLE, 0.0,
                static_cast<double>(n) * H * W * (4.0 * Cout * (sizeof(TC) + 4.0 + (out_t ? sizeof(T) : 0.0)) + Cin * 4.0), s);
-  pixel_shuffle_kernel<TC, T><<<blocks(total), 256, 0, s>>>(conv, xin, out, out_t, n, H, W, Cin, Cout, 4 * Cout / Cin, pCp);
+  LC_CHECK_CUDA(launch_kernel(pixel_shuffle_kernel<TC, T>, blocks(total), 256, 0, s, conv, xin, out, out_t, n, H, W, Cin, Cout, 4 * Cout / Cin, pCp));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -725,7 +738,7 @@ int pixel_unshuffle_shortcut(const float* conv, const float* xin, float* out, T*
   const long long total = static_cast<long long>(n) * (H / 2) * (W / 2) * Cout;
   ProfScope ps(PROF_DEC_SHUFFLE, 0.0,
                static_cast<double>(n) * H * W * (Cout / 4 + Cin) * 4.0 + static_cast<double>(total) * (4.0 + (out_t ? sizeof(T) : 0.0)), s);
-  pixel_unshuffle_kernel<T><<<blocks(total), 256, 0, s>>>(conv, xin, out, out_t, n, H, W, Cin, Cout, 4 * Cin / Cout, pCp);
+  LC_CHECK_CUDA(launch_kernel(pixel_unshuffle_kernel<T>, blocks(total), 256, 0, s, conv, xin, out, out_t, n, H, W, Cin, Cout, 4 * Cin / Cout, pCp));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -734,7 +747,7 @@ int enc_out_shortcut(float* out, const float* x, int n, int HW, int C, int L, co
   LC_REQUIRE(C % L == 0, "encoder out shortcut needs C divisible by latent_channels");
   const long long total = static_cast<long long>(n) * L * HW;
   ProfScope ps(PROF_DEC_PAD, 0.0, static_cast<double>(total) * 8.0 + static_cast<double>(n) * HW * C * 4.0, s);
-  enc_out_shortcut_kernel<<<blocks(total), 256, 0, s>>>(out, x, n, HW, C, L, C / L, mean, stdv, target);
+  LC_CHECK_CUDA(launch_kernel(enc_out_shortcut_kernel, blocks(total), 256, 0, s, out, x, n, HW, C, L, C / L, mean, stdv, target));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -742,7 +755,7 @@ template <typename T>
 int in_shortcut(float* x, T* x_t, const PlaneSrc& z, int n, int HW, int C, int Cz, cudaStream_t s) {
   const long long total = static_cast<long long>(n) * HW * C;
   ProfScope ps(PROF_DEC_PAD, 0.0, static_cast<double>(total) * (8.0 + sizeof(T)) + static_cast<double>(n) * HW * Cz * 4.0, s);
-  in_shortcut_kernel<T><<<blocks(total), 256, 0, s>>>(x, x_t, z, n, HW, C, Cz, C / Cz);
+  LC_CHECK_CUDA(launch_kernel(in_shortcut_kernel<T>, blocks(total), 256, 0, s, x, x_t, z, n, HW, C, Cz, C / Cz));
   LC_LAUNCH_CHECK();
   return 0;
 }

@@ -3,6 +3,7 @@
 // warp-shuffle reductions; fp32 statistics regardless of the storage type.
 #include <cuda_fp16.h>
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace lc {
 namespace {
@@ -82,56 +83,56 @@ __device__ __forceinline__ void ln_row(float4 (&v)[NV], int row, int lane, T* __
   }
 }
 
-constexpr int LN_RPW = 8;      // consecutive rows per warp
-constexpr int LN_STAGES = 2;   // rows of a warp in flight (cp.async ring in shared memory)
+constexpr int LN_STAGES = 3;   // rows of a warp in flight (bulk-async ring in shared memory)
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
-               "l"(gmem_src)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// Each warp owns LN_RPW consecutive rows and a private LN_STAGES-deep ring of row buffers in shared memory that
-// cp.async (LDGSTS) fills while the previous row is normalised: the loads need no registers, so the row being
-// processed (NV float4 per lane) and its statistics fit without spills and every warp keeps ~2 rows (12-16 KB) in
-// flight.  (The register double buffer of round 1 spilled 300-800 B per thread at d = 1536 / 2048.)  Every lane reads
-// back exactly the 16-byte chunks it copied itself, so cp.async.wait_group is the only synchronisation needed.
+// Each warp owns a contiguous range of rows and a private LN_STAGES-deep ring of row buffers in shared memory.  Lane 0
+// streams whole rows (d * 4 bytes, one contiguous cp.async.bulk = one TMA request per row) into the ring, completion
+// is signalled on a per-stage mbarrier; the warp normalises row r while rows r+1 .. r+LN_STAGES-1 are in flight.
+// The loads need neither registers nor LSU issue slots, so the row being processed (NV float4 per lane) fits without
+// spills (the register double buffer of round 1 spilled 300-800 B per thread at d = 1536 / 2048) and every SM keeps
+// 8 warps x 3 rows (144-192 KB) in flight.  The grid is one wave: rows are split evenly over all resident warps.
 template <typename T, int NV>
-__global__ void __launch_bounds__(256, NV <= 12 ? 2 : 1)
+__global__ void __launch_bounds__(256, 1)
 layernorm_kernel(const float* __restrict__ x, T* __restrict__ out, int M, int d, float eps, int rows_per_sample,
                  int seg_rows, int seg_rows_per_sample, const float* __restrict__ scale, const float* __restrict__ shift,
-                 long long mod_stride, const float* __restrict__ w, const float* __restrict__ b) {
-  extern __shared__ float4 ln_ring[];  // [8 warps][LN_STAGES][NV * 32]
+                 long long mod_stride, const float* __restrict__ w, const float* __restrict__ b, int rows_per_warp) {
+  pdl_grid_sync();
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  constexpr int ROW_BYTES = NV * 512;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = (blockIdx.x * 8 + warp) * LN_RPW;
-  if (row0 >= M) return;
-  const int nrows = min(LN_RPW, M - row0);
-  float4* ring = ln_ring + warp * (LN_STAGES * NV * 32);
-  const float* xr = x + static_cast<long long>(row0) * d + lane * 4;
-  auto issue = [&](int r) {
-    float4* dst = ring + (r % LN_STAGES) * (NV * 32) + lane;
-    const float* src = xr + static_cast<long long>(r) * d;
+  float4* ring = reinterpret_cast<float4*>(ln_smem) + warp * (LN_STAGES * NV * 32);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + 8 * LN_STAGES * ROW_BYTES) + warp * LN_STAGES;
+  const long long row0 = (static_cast<long long>(blockIdx.x) * 8 + warp) * rows_per_warp;
+  if (row0 >= M) return;  // warp-uniform; no block-wide barrier is used anywhere in this kernel
+  const int nrows = static_cast<int>(min(static_cast<long long>(rows_per_warp), M - row0));
+  if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) cp_async16(dst + i * 32, src + i * 128);
+    for (int s = 0; s < LN_STAGES; ++s) ptx::mbar_init(&bars[s], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncwarp();
+  const float* xr = x + row0 * d;
+  auto issue = [&](int r) {  // lane 0 only
+    const int st = r % LN_STAGES;
+    ptx::mbar_expect_tx(&bars[st], ROW_BYTES);
+    ptx::bulk_load(ring + st * (NV * 32), xr + static_cast<long long>(r) * d, ROW_BYTES, &bars[st]);
   };
+  if (lane == 0) {
 #pragma unroll
-  for (int r = 0; r < LN_STAGES - 1; ++r) {
-    if (r < nrows) issue(r);
-    cp_async_commit();
+    for (int r = 0; r < LN_STAGES - 1; ++r)
+      if (r < nrows) issue(r);
   }
   for (int r = 0; r < nrows; ++r) {
-    if (r + LN_STAGES - 1 < nrows) issue(r + LN_STAGES - 1);
-    cp_async_commit();
-    cp_async_wait<LN_STAGES - 1>();  // row r has landed (groups complete in order)
+    // stage (r - 1) % LN_STAGES was read by every lane in the previous iteration (__syncwarp below): refill it
+    if (lane == 0 && r + LN_STAGES - 1 < nrows) issue(r + LN_STAGES - 1);
+    ptx::mbar_wait(&bars[r % LN_STAGES], (r / LN_STAGES) & 1);
     float4 v[NV];
     const float4* src = ring + (r % LN_STAGES) * (NV * 32) + lane;
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = src[i * 32];
-    ln_row<T, NV>(v, row0 + r, lane, out, d, eps, rows_per_sample, seg_rows, seg_rows_per_sample, scale, shift,
-                  mod_stride, w, b);
+    ln_row<T, NV>(v, static_cast<int>(row0) + r, lane, out, d, eps, rows_per_sample, seg_rows, seg_rows_per_sample, scale,
+                  shift, mod_stride, w, b);
+    __syncwarp();
   }
 }
 
@@ -141,6 +142,7 @@ layernorm_kernel(const float* __restrict__ x, T* __restrict__ out, int M, int d,
 template <typename T>
 __global__ void __launch_bounds__(256) qk_norm_rope_kernel(T* __restrict__ qkv, long long ld, int B, int S, int heads,
                                                            float eps, RopeSeg s0, RopeSeg s1, int nseg) {
+  pdl_grid_sync();
   const long long gw = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const long long total = static_cast<long long>(B) * S * 2 * heads;
@@ -188,6 +190,7 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 }
 __global__ void __launch_bounds__(256) qk_norm_rope_bf16_kernel(bf16* __restrict__ qkv, long long ld, int B, int S,
                                                                 int heads, float eps, RopeSeg s0, RopeSeg s1, int nseg) {
+  pdl_grid_sync();
   const unsigned total = static_cast<unsigned>(B) * S * heads;  // (token row, head) units
   const unsigned unit = blockIdx.x * 16u + (threadIdx.x >> 4);
   const int sub = threadIdx.x & 15;
@@ -262,6 +265,7 @@ __global__ void __launch_bounds__(256) qk_norm_rope_bf16_kernel(bf16* __restrict
 template <typename T>
 __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ x, T* __restrict__ out, int C, int THW,
                                                        int Kp) {
+  pdl_grid_sync();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -280,6 +284,7 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
 // ---------------------------------------------------------------- Timesteps(256, flip_sin_to_cos, shift 0): [cos | sin]
 template <typename T>
 __global__ void timestep_embed_kernel(const float* __restrict__ t, int n_t, int B, T* __restrict__ out) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * 128) return;
   const int b = i >> 7, k = i & 127;
@@ -292,6 +297,7 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t, int n_t, int 
 // ---------------------------------------------------------------- mean over tokens: [B,N,d] f32 -> [B,d] T
 template <typename T>
 __global__ void __launch_bounds__(256) token_mean_kernel(const float* __restrict__ x, int N, int d, T* __restrict__ out) {
+  pdl_grid_sync();
   __shared__ float part[8][32 * 4 + 4];
   const int b = blockIdx.y;
   const int c = blockIdx.x * 128 + (threadIdx.x & 31) * 4;
@@ -321,6 +327,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) gated_add_kernel(float* __restrict__ h, const T* __restrict__ a,
                                                         const float* __restrict__ gate, long long gate_stride,
                                                         long long n4, int d, int rows_per_sample) {
+  pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const long long e = i * 4;
@@ -338,6 +345,7 @@ template <typename T>
 __global__ void temb_combine_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                     const float* __restrict__ sc, const float* __restrict__ sh, long long sc_stride,
                                     int B, int d, float* __restrict__ out_f32, T* __restrict__ out_silu) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * d) return;
   const int r = i / d, c = i - r * d;
@@ -349,6 +357,7 @@ __global__ void temb_combine_kernel(const float* __restrict__ a, const float* __
 
 template <typename T>
 __global__ void cast_kernel(const float* __restrict__ x, T* __restrict__ out, long long n) {
+  pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = from_f32<T>(x[i]);
 }
@@ -359,6 +368,7 @@ __global__ void cast_kernel(const float* __restrict__ x, T* __restrict__ out, lo
 __global__ void __launch_bounds__(256) dpmpp2m_kernel(const float* __restrict__ f, float* __restrict__ x,
                                                       float* __restrict__ x0_prev, float* __restrict__ x_in_next,
                                                       long long n4, SchedCoef c) {
+  pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 fv = reinterpret_cast<const float4*>(f)[i];
@@ -383,6 +393,7 @@ __global__ void __launch_bounds__(256) heun_kernel(const float* __restrict__ f, 
                                                    double* __restrict__ x_hat, double* __restrict__ d_cur,
                                                    float* __restrict__ x_in_next, long long n, int phase, double t_cur,
                                                    double t_next, double c_skip, double c_out, double c_in_next) {
+  pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double fv = static_cast<double>(f[i]);
@@ -407,6 +418,7 @@ __global__ void __launch_bounds__(256) heun_kernel(const float* __restrict__ f, 
 // x_in = x * c_in  (scale_model_input of step 0, pipeline_AR.py:90)
 __global__ void __launch_bounds__(256) scale_kernel(const float* __restrict__ x, float* __restrict__ out, long long n4,
                                                     float c) {
+  pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -416,6 +428,7 @@ __global__ void __launch_bounds__(256) scale_kernel(const float* __restrict__ x,
 // Heun prologue (edm_sampler.py:44-46, 56-58): x = float64(noise) * t_0 ; x_in = float32(x * c_in(t_0))
 __global__ void __launch_bounds__(256) heun_init_kernel(const float* __restrict__ noise, double* __restrict__ x,
                                                         float* __restrict__ x_in, long long n, double t0, double c_in) {
+  pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double v = static_cast<double>(noise[i]) * t0;
@@ -431,6 +444,7 @@ __global__ void __launch_bounds__(256) latent_feedback_kernel(const float* __res
                                                               float* __restrict__ phys, const float* __restrict__ mean,
                                                               const float* __restrict__ stdv, float target, int C, int T,
                                                               int t_in, int hw2, long long n2) {
+  pdl_grid_sync();
   // one thread = two consecutive pixels of a (b, c, t) plane (h*w = 450 is even but not a multiple of 4)
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n2) return;
@@ -458,18 +472,21 @@ int layernorm_modulate(const float* x, T* out, int M, int d, float eps, int rows
                        int seg_rows, int seg_rows_per_sample) {
   LC_REQUIRE(d % 128 == 0 && d <= 2048, "layernorm: d must be a multiple of 128, <= 2048");
   const int nv = d / 128;
-  dim3 grid(ceil_div(M, 8 * LN_RPW));
+  // one wave: the rows are split evenly over every warp that can be resident (8 warps per CTA, one CTA per SM)
+  const int warps = 8 * num_sms();
+  const int rpw = ceil_div(M, warps) < 4 ? 4 : ceil_div(M, warps);
+  dim3 grid(ceil_div(M, 8 * rpw));
   ProfScope ps(PROF_LN, 0.0, static_cast<double>(M) * d * (4 + sizeof(T)), s);
 #define LC_LN_CASE(NV)                                                                                            \
   case NV: {                                                                                                      \
-    constexpr int smem = 8 * LN_STAGES * NV * 32 * 16;                                                            \
+    constexpr int smem = 8 * LN_STAGES * NV * 512 + 8 * LN_STAGES * 8;                                            \
     static PerDevice<bool> attr_set;                                                                              \
     if (smem > 48 * 1024 && !attr_set.here()) {                                                                   \
       LC_CHECK_CUDA(cudaFuncSetAttribute(layernorm_kernel<T, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
       attr_set.here() = true;                                                                                     \
     }                                                                                                             \
-    layernorm_kernel<T, NV><<<grid, 256, smem, s>>>(x, out, M, d, eps, rows_per_sample, seg_rows, seg_rows_per_sample, \
-                                                    scale, shift, mod_stride, w, b);                                   \
+    LC_CHECK_CUDA(launch_kernel(layernorm_kernel<T, NV>, grid, 256, smem, s, x, out, M, d, eps, rows_per_sample, seg_rows, seg_rows_per_sample, \
+                                                    scale, shift, mod_stride, w, b, rpw));                              \
     break;                                                                                                        \
   }
   switch (nv) {
@@ -491,13 +508,13 @@ int qk_norm_rope(T* qkv, long long ld, int B, int S, int heads, int head_dim, fl
   RopeSeg s1 = nseg > 1 ? segs[1] : segs[0];
   ProfScope ps(PROF_ROPE, 0.0, static_cast<double>(total) * 128 * sizeof(T) * 2, s);  // q and k read + written once
   if (sizeof(T) == 2) {
-    qk_norm_rope_bf16_kernel<<<static_cast<unsigned>(ceil_div_ll(total / 2, 16)), 256, 0, s>>>(
-        reinterpret_cast<bf16*>(qkv), ld, B, S, heads, eps, segs[0], s1, nseg);
+    LC_CHECK_CUDA(launch_kernel(qk_norm_rope_bf16_kernel, static_cast<unsigned>(ceil_div_ll(total / 2, 16)), 256, 0, s, 
+        reinterpret_cast<bf16*>(qkv), ld, B, S, heads, eps, segs[0], s1, nseg));
     LC_LAUNCH_CHECK();
     return 0;
   }
-  qk_norm_rope_kernel<T><<<static_cast<unsigned>(ceil_div_ll(total, 8)), 256, 0, s>>>(qkv, ld, B, S, heads, eps, segs[0],
-                                                                                     s1, nseg);
+  LC_CHECK_CUDA(launch_kernel(qk_norm_rope_kernel<T>, static_cast<unsigned>(ceil_div_ll(total, 8)), 256, 0, s, qkv, ld, B, S, heads, eps, segs[0],
+                                                                                     s1, nseg));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -506,13 +523,14 @@ int qk_norm_rope(T* qkv, long long ld, int B, int S, int heads, int head_dim, fl
 // half2 (cos, sin) per rotation pair for the fused qkv epilogue
 __global__ void pack_rope_pairs_kernel(const float* __restrict__ cs, const float* __restrict__ sn, uint32_t* __restrict__ out,
                                        int n) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * 64) return;
   const __half2 h = __floats2half2_rn(cs[2 * i], sn[2 * i]);
   out[i] = *reinterpret_cast<const uint32_t*>(&h);
 }
 int pack_rope_pairs(const float* cos, const float* sin, uint32_t* out, int n_tokens, cudaStream_t s) {
-  pack_rope_pairs_kernel<<<ceil_div(n_tokens * 64, 256), 256, 0, s>>>(cos, sin, out, n_tokens);
+  LC_CHECK_CUDA(launch_kernel(pack_rope_pairs_kernel, ceil_div(n_tokens * 64, 256), 256, 0, s, cos, sin, out, n_tokens));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -521,7 +539,7 @@ template <typename T>
 int patchify(const float* x, T* out, int B, int C, int THW, int Kp, cudaStream_t s) {
   dim3 grid(ceil_div(THW, 32), ceil_div(Kp, 32), B);
   ProfScope ps(PROF_MISC, 0.0, static_cast<double>(B) * THW * (C * 4.0 + Kp * sizeof(T)), s);
-  patchify_kernel<T><<<grid, 256, 0, s>>>(x, out, C, THW, Kp);
+  LC_CHECK_CUDA(launch_kernel(patchify_kernel<T>, grid, 256, 0, s, x, out, C, THW, Kp));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -529,7 +547,7 @@ int patchify(const float* x, T* out, int B, int C, int THW, int Kp, cudaStream_t
 template <typename T>
 int timestep_embed(const float* t, int n_t, int B, T* out, cudaStream_t s) {
   ProfScope ps(PROF_MISC, 0.0, static_cast<double>(B) * 256 * sizeof(T), s);
-  timestep_embed_kernel<T><<<ceil_div(B * 128, 128), 128, 0, s>>>(t, n_t, B, out);
+  LC_CHECK_CUDA(launch_kernel(timestep_embed_kernel<T>, ceil_div(B * 128, 128), 128, 0, s, t, n_t, B, out));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -538,7 +556,7 @@ template <typename T>
 int token_mean(const float* x, int B, int N, int d, T* out, cudaStream_t s) {
   dim3 grid(ceil_div(d, 128), B);
   ProfScope ps(PROF_MISC, 0.0, static_cast<double>(B) * N * d * 4.0, s);
-  token_mean_kernel<T><<<grid, 256, 0, s>>>(x, N, d, out);
+  LC_CHECK_CUDA(launch_kernel(token_mean_kernel<T>, grid, 256, 0, s, x, N, d, out));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -548,8 +566,8 @@ int gated_add(float* h, const T* a, const float* gate, long long gate_stride, in
               cudaStream_t s) {
   const long long n4 = static_cast<long long>(M) * d / 4;
   ProfScope ps(PROF_MISC, 0.0, static_cast<double>(M) * d * (8.0 + sizeof(T)), s);
-  gated_add_kernel<T><<<static_cast<unsigned>(ceil_div_ll(n4, 256)), 256, 0, s>>>(h, a, gate, gate_stride, n4, d,
-                                                                                rows_per_sample);
+  LC_CHECK_CUDA(launch_kernel(gated_add_kernel<T>, static_cast<unsigned>(ceil_div_ll(n4, 256)), 256, 0, s, h, a, gate, gate_stride, n4, d,
+                                                                                rows_per_sample));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -558,7 +576,7 @@ template <typename T>
 int temb_combine(const float* a, const float* b, const float* sc, const float* sh, long long sc_stride, int B, int d,
                  float* out_f32, T* out_silu, cudaStream_t s) {
   ProfScope ps(PROF_MISC, 0.0, static_cast<double>(B) * d * 16.0, s);
-  temb_combine_kernel<T><<<ceil_div(B * d, 256), 256, 0, s>>>(a, b, sc, sh, sc_stride, B, d, out_f32, out_silu);
+  LC_CHECK_CUDA(launch_kernel(temb_combine_kernel<T>, ceil_div(B * d, 256), 256, 0, s, a, b, sc, sh, sc_stride, B, d, out_f32, out_silu));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -566,7 +584,7 @@ int temb_combine(const float* a, const float* b, const float* sc, const float* s
 template <typename T>
 int cast_rows(const float* x, T* out, long long n, cudaStream_t s) {
   ProfScope ps(PROF_MISC, 0.0, static_cast<double>(n) * (4.0 + sizeof(T)), s);
-  cast_kernel<T><<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s>>>(x, out, n);
+  LC_CHECK_CUDA(launch_kernel(cast_kernel<T>, static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s, x, out, n));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -577,7 +595,7 @@ int sched_dpmpp2m_step(const float* f, float* x, float* x0_prev, float* x_in_nex
   const long long n4 = n / 4;
   // algorithmic bytes: read F, x (+ previous x0 on 2M steps); write x0, x' (+ next x_in)
   ProfScope ps(PROF_SCHED, 0.0, static_cast<double>(n) * 4.0 * (4 + (c.a_d != 0.f ? 1 : 0) + (x_in_next != nullptr ? 1 : 0)), s);
-  dpmpp2m_kernel<<<static_cast<unsigned>(ceil_div_ll(n4, 256)), 256, 0, s>>>(f, x, x0_prev, x_in_next, n4, c);
+  LC_CHECK_CUDA(launch_kernel(dpmpp2m_kernel, static_cast<unsigned>(ceil_div_ll(n4, 256)), 256, 0, s, f, x, x0_prev, x_in_next, n4, c));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -587,8 +605,8 @@ int sched_heun_step(const float* f, double* x, double* x_hat, double* d_cur, flo
   // algorithmic bytes: predictor reads F(4) x(8), writes x_hat d_cur x (24) + x_in(4); corrector reads F x x_hat d_cur
   // (28), writes x (8) + x_in (4)
   ProfScope ps(PROF_SCHED, 0.0, static_cast<double>(n) * (36.0 + (x_in_next != nullptr ? 4.0 : 0.0)), s);
-  heun_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s>>>(f, x, x_hat, d_cur, x_in_next, n, phase, t_cur,
-                                                                       t_next, c_skip, c_out, c_in_next);
+  LC_CHECK_CUDA(launch_kernel(heun_kernel, static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s, f, x, x_hat, d_cur, x_in_next, n, phase, t_cur,
+                                                                       t_next, c_skip, c_out, c_in_next));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -596,14 +614,14 @@ int sched_heun_step(const float* f, double* x, double* x_hat, double* d_cur, flo
 int sched_scale_input(const float* x, float* x_in, long long n, float c_in, cudaStream_t s) {
   LC_REQUIRE(n % 4 == 0, "scheduler: element count must be a multiple of 4");
   ProfScope ps(PROF_SCHED, 0.0, static_cast<double>(n) * 8.0, s);
-  scale_kernel<<<static_cast<unsigned>(ceil_div_ll(n / 4, 256)), 256, 0, s>>>(x, x_in, n / 4, c_in);
+  LC_CHECK_CUDA(launch_kernel(scale_kernel, static_cast<unsigned>(ceil_div_ll(n / 4, 256)), 256, 0, s, x, x_in, n / 4, c_in));
   LC_LAUNCH_CHECK();
   return 0;
 }
 
 int sched_heun_init(const float* noise, double* x, float* x_in, long long n, double t0, double c_in, cudaStream_t s) {
   ProfScope ps(PROF_SCHED, 0.0, static_cast<double>(n) * 16.0, s);
-  heun_init_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s>>>(noise, x, x_in, n, t0, c_in);
+  LC_CHECK_CUDA(launch_kernel(heun_init_kernel, static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s, noise, x, x_in, n, t0, c_in));
   LC_LAUNCH_CHECK();
   return 0;
 }
@@ -615,8 +633,8 @@ int latent_feedback(const float* samples, float* known, float* phys, const float
   LC_REQUIRE(phys == nullptr || (mean != nullptr && stdv != nullptr), "latent_feedback: mean/std required for the de-normalised output");
   const long long n2 = static_cast<long long>(B) * C * T * (hw / 2);
   ProfScope ps(PROF_SCHED, 0.0, static_cast<double>(n2) * 8.0 * (1.0 + (phys != nullptr ? 1.0 : 0.0) + static_cast<double>(t_in) / T), s);
-  latent_feedback_kernel<<<static_cast<unsigned>(ceil_div_ll(n2, 256)), 256, 0, s>>>(samples, known, phys, mean, stdv, target, C,
-                                                                                   T, t_in, hw / 2, n2);
+  LC_CHECK_CUDA(launch_kernel(latent_feedback_kernel, static_cast<unsigned>(ceil_div_ll(n2, 256)), 256, 0, s, samples, known, phys, mean, stdv, target, C,
+                                                                                   T, t_in, hw / 2, n2));
   LC_LAUNCH_CHECK();
   return 0;
 }

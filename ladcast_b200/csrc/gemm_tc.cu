@@ -545,6 +545,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();  // everything above overlaps the previous kernel's tail; operands are only touched below
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -715,6 +716,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   ptx::cluster_sync();  // peer's barriers are initialised and its TMEM is allocated
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();  // everything above overlaps the previous kernel's tail; operands are only touched below
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -862,7 +864,7 @@ int launch_pair(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   const int cls = cv.enabled ? PROF_CONV : PROF_GEMM;
   const double flops = 2.0 * M * N * (cv.enabled ? 9.0 * cv.c_real : static_cast<double>(K));
   prof_begin(cls, stream);
-  gemm_tc2_kernel<<<grid, NUM_THREADS, C::SMEM, stream>>>(a0, a1, w, M, N, K, K0, ep, sched, cv);
+  LC_CHECK_CUDA(launch_kernel(gemm_tc2_kernel, grid, NUM_THREADS, C::SMEM, stream, a0, a1, w, M, N, K, K0, ep, sched, cv));
   prof_end(cls, flops, stream, algorithmic_bytes(M, N, K, ep, cv));
   LC_LAUNCH_CHECK();
   return 0;
@@ -886,7 +888,7 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, i
   const int cls = cv.enabled ? PROF_CONV : PROF_GEMM;
   const double flops = 2.0 * M * N * (cv.enabled ? 9.0 * cv.c_real : static_cast<double>(K));
   prof_begin(cls, stream);
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM, stream>>>(a0, a1, w, M, N, K, K0, ep, sched, cv);
+  LC_CHECK_CUDA(launch_kernel(gemm_tc_kernel<BN>, grid, NUM_THREADS, C::SMEM, stream, a0, a1, w, M, N, K, K0, ep, sched, cv));
   prof_end(cls, flops, stream, algorithmic_bytes(M, N, K, ep, cv));
   LC_LAUNCH_CHECK();
   return 0;

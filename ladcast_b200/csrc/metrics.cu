@@ -8,8 +8,8 @@
 //
 // One thread per pixel (consecutive threads = consecutive pixels: every member load is a coalesced 128-B line per
 // warp, all M loads of a thread in flight).  The M member values live in REGISTERS; the spread follows the
-// reference's formulation exactly — sort the members (evaluate/utils.py:86, here a fully unrolled bitonic network on
-// the next power of two, padded with +inf) and form 2/(M(M-1)) * sum_i (2i - M - 1) x_(i) in fp32 (:91-99).  Per-pixel
+// reference's formulation exactly — sort the members (evaluate/utils.py:86, here a fully unrolled merge-exchange
+// network for exactly M values) and form 2/(M(M-1)) * sum_i (2i - M - 1) x_(i) in fp32 (:91-99).  Per-pixel
 // values are fp32 (as in the reference), the latitude-weighted spatial sums are fp64: per-thread accumulation over a
 // few pixels, warp-shuffle + shared-memory block reduction, one fp64 atomicAdd per block and metric.
 // Ensembles larger than 64 members use a shared-memory pairwise kernel (mean |x_i - x_j|, algebraically identical).
@@ -30,24 +30,39 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
-// ascending bitonic sorting network on MP (power of two) registers; every index is a compile-time constant
-template <int MP>
-__device__ __forceinline__ void sort_network(float (&v)[MP]) {
-#pragma unroll
-  for (int k = 2; k <= MP; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll
-      for (int i = 0; i < MP; ++i) {
-        const int l = i ^ j;
-        if (l > i) {
-          const float a = v[i], b = v[l];
-          const float lo = fminf(a, b), hi = fmaxf(a, b);
-          if ((i & k) == 0) { v[i] = lo; v[l] = hi; }
-          else { v[i] = hi; v[l] = lo; }
-        }
+// Sorting network for EXACTLY M values in registers: Knuth's merge exchange (TAOCP 5.2.2, Algorithm M = Batcher's
+// odd-even merge sort for arbitrary n): 97 comparators for 20 members, 395 for 50 (a bitonic network padded to the next
+// power of two needs 240 / 672).  The comparator list is built at compile time; after full unrolling every index is
+// a constant, so the values never leave the register file.
+template <int M>
+struct MergeExchangeNet {
+  static constexpr int kMax = M * 6 * 6 / 4 + 8;  // >= M * ceil(log2 M)^2 / 4 comparators
+  int n = 0;
+  int a[kMax] = {}, b[kMax] = {};
+  constexpr MergeExchangeNet() {
+    int t = 0;
+    while ((1 << t) < M) ++t;
+    if (M < 2) return;
+    for (int p = 1 << (t - 1); p > 0; p >>= 1) {
+      int q = 1 << (t - 1), r = 0, d = p;
+      while (true) {
+        for (int i = 0; i < M - d; ++i)
+          if ((i & p) == r) { a[n] = i; b[n] = i + d; ++n; }
+        if (q == p) break;
+        d = q - p; q >>= 1; r = p;
       }
     }
+  }
+};
+
+template <int M>
+__device__ __forceinline__ void sort_network(float (&v)[M]) {
+  constexpr MergeExchangeNet<M> net;
+#pragma unroll
+  for (int c = 0; c < net.n; ++c) {
+    const float lo = fminf(v[net.a[c]], v[net.b[c]]), hi = fmaxf(v[net.a[c]], v[net.b[c]]);
+    v[net.a[c]] = lo;
+    v[net.b[c]] = hi;
   }
 }
 
@@ -88,13 +103,14 @@ __device__ __forceinline__ void add_weighted(double (&acc)[8], float msum, float
   }
 }
 
-template <int MP, bool REDUCE>
+template <int M, bool REDUCE>
 __global__ void __launch_bounds__(THREADS) metrics_sorted_kernel(const float* __restrict__ fields, long long member_stride,
                                                                  const float* __restrict__ truth,
-                                                                 const double* __restrict__ latw, int M, long long N, int H,
+                                                                 const double* __restrict__ latw, long long N, int H,
                                                                  int W, int bpp, double* __restrict__ sums,
                                                                  double* __restrict__ counts, float* __restrict__ out_skill,
                                                                  float* __restrict__ out_spread, float* __restrict__ out_mean) {
+  pdl_grid_sync();
   const int HW = H * W;
   const long long n = blockIdx.x / bpp;
   const int blk = static_cast<int>(blockIdx.x - n * bpp);
@@ -103,23 +119,20 @@ __global__ void __launch_bounds__(THREADS) metrics_sorted_kernel(const float* __
   const float spread_scale = M > 1 ? 2.0f / (static_cast<float>(M) * static_cast<float>(M - 1)) : 0.f;
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int p = blk * THREADS + threadIdx.x; p < HW; p += bpp * THREADS) {
-    float x[MP];
+    float x[M];
 #pragma unroll
-    for (int m = 0; m < MP; ++m) x[m] = m < M ? __ldg(base + m * member_stride + p) : INFINITY;
+    for (int m = 0; m < M; ++m) x[m] = __ldg(base + m * member_stride + p);
     const float y = truth != nullptr ? __ldg(truth + n * HW + p) : 0.f;
     float msum = 0.f, skill = 0.f;
 #pragma unroll
-    for (int m = 0; m < MP; ++m) {
-      if (m < M) {
-        msum += x[m];
-        skill += fabsf(y - x[m]);
-      }
+    for (int m = 0; m < M; ++m) {
+      msum += x[m];
+      skill += fabsf(y - x[m]);
     }
-    sort_network<MP>(x);
+    sort_network<M>(x);
     float ws = 0.f;
 #pragma unroll
-    for (int m = 0; m < MP; ++m)
-      if (m < M) ws = fmaf(static_cast<float>(2 * (m + 1) - M - 1), x[m], ws);
+    for (int m = 0; m < M; ++m) ws = fmaf(static_cast<float>(2 * (m + 1) - M - 1), x[m], ws);
     float spread = spread_scale * ws;
     if (msum != msum) spread = msum;  // a NaN member: torch.sort keeps it and the weighted sum propagates it
     skill *= inv_m;
@@ -143,6 +156,7 @@ __global__ void __launch_bounds__(THREADS) metrics_pairwise_kernel(const float* 
                                                                    int W, int bpp, double* __restrict__ sums,
                                                                    double* __restrict__ counts, float* __restrict__ out_skill,
                                                                    float* __restrict__ out_spread, float* __restrict__ out_mean) {
+  pdl_grid_sync();
   extern __shared__ float xs[];  // [M][THREADS]
   const int HW = H * W;
   const long long n = blockIdx.x / bpp;
@@ -183,6 +197,7 @@ __global__ void __launch_bounds__(THREADS) acc_kernel(const float* __restrict__ 
                                                       const float* __restrict__ cl, const double* __restrict__ latw,
                                                       long long N, int H, int W, int bpp, double* __restrict__ sums,
                                                       double* __restrict__ counts) {
+  pdl_grid_sync();
   const int HW = H * W;
   const long long n = blockIdx.x / bpp;
   const int blk = static_cast<int>(blockIdx.x - n * bpp);
@@ -215,15 +230,18 @@ int launch_metrics(const float* fields, long long member_stride, const float* tr
   // algorithmic bytes: every member value and the truth read once (+ per-pixel outputs of the pointwise variant)
   const double px = static_cast<double>(N) * H * W;
   ProfScope ps(PROF_METRICS, 0.0, px * 4.0 * (M + (truth ? 1 : 0) + (o_skill ? 1 : 0) + (o_spread ? 1 : 0) + (o_mean ? 1 : 0)), st);
-#define LC_SORTED(MP)                                                                                                      \
-  metrics_sorted_kernel<MP, REDUCE><<<grid, THREADS, 0, st>>>(fields, member_stride, truth, latw, M, N, H, W, bpp, sums, \
-                                                              counts, o_skill, o_spread, o_mean)
-  if (M <= 2) LC_SORTED(2);
-  else if (M <= 4) LC_SORTED(4);
-  else if (M <= 8) LC_SORTED(8);
-  else if (M <= 16) LC_SORTED(16);
-  else if (M <= 32) LC_SORTED(32);
-  else if (M <= 64) LC_SORTED(64);
+#define LC_SORTED(MM)                                                                                                   \
+  case MM:                                                                                                              \
+    LC_CHECK_CUDA(launch_kernel(metrics_sorted_kernel<MM, REDUCE>, grid, THREADS, 0, st, fields, member_stride, truth, latw, N, H, W, bpp, sums, \
+                                                                counts, o_skill, o_spread, o_mean));                     \
+    break;
+#define LC_SORTED8(B) LC_SORTED(B) LC_SORTED(B + 1) LC_SORTED(B + 2) LC_SORTED(B + 3) LC_SORTED(B + 4) LC_SORTED(B + 5) \
+    LC_SORTED(B + 6) LC_SORTED(B + 7)
+  if (M <= 64) {
+    switch (M) {
+      LC_SORTED8(1) LC_SORTED8(9) LC_SORTED8(17) LC_SORTED8(25) LC_SORTED8(33) LC_SORTED8(41) LC_SORTED8(49) LC_SORTED8(57)
+    }
+  }
   else {
     const size_t smem = static_cast<size_t>(M) * THREADS * sizeof(float);
     static PerDevice<size_t> attr;
@@ -232,9 +250,10 @@ int launch_metrics(const float* fields, long long member_stride, const float* tr
                                          static_cast<int>(smem)));
       attr.here() = smem;
     }
-    metrics_pairwise_kernel<REDUCE><<<grid, THREADS, smem, st>>>(fields, member_stride, truth, latw, M, N, H, W, bpp, sums,
-                                                                 counts, o_skill, o_spread, o_mean);
+    LC_CHECK_CUDA(launch_kernel(metrics_pairwise_kernel<REDUCE>, grid, THREADS, smem, st, fields, member_stride, truth, latw, M, N, H, W, bpp, sums,
+                                                                 counts, o_skill, o_spread, o_mean));
   }
+#undef LC_SORTED8
 #undef LC_SORTED
   LC_LAUNCH_CHECK();
   return 0;
@@ -287,8 +306,8 @@ int lc_metrics_acc(const float* forecast, const float* truth, const float* clima
   const int bpp = blocks_per_plane(height * width);
   LC_REQUIRE(planes * bpp < (1ll << 31), "too many planes for one launch");
   ProfScope ps(PROF_METRICS, 0.0, static_cast<double>(planes) * height * width * 12.0, st);
-  acc_kernel<<<static_cast<unsigned>(planes * bpp), THREADS, 0, st>>>(forecast, truth, climate, lat_weights, planes, height,
-                                                                     width, bpp, sums, counts);
+  LC_CHECK_CUDA(launch_kernel(acc_kernel, static_cast<unsigned>(planes * bpp), THREADS, 0, st, forecast, truth, climate, lat_weights, planes, height,
+                                                                     width, bpp, sums, counts));
   LC_LAUNCH_CHECK();
   return 0;
 }

@@ -1,6 +1,9 @@
 """Tensor-level pieces of `ladcast.dataloader.utils` that the rollout callers use (reference
 dataloader/utils.py:223-306 and the static-field preparation of pipelines/pred_rollout.py:260-291).  The xarray / zarr
-front end (`xarr_to_tensor`, `tensor_to_xarr`, `filter_time_range`) is out of scope.
+front end is replaced by an array front end with the same channel layout and NaN conventions: a
+"field set" is a plain mapping {variable name -> array}, atmospheric variables (time, level, lat, lon), surface
+variables (time, lat, lon) — what `np.load(..., mmap_mode="r")` of per-variable .npy files or a zarr group's arrays
+give — see `fields_to_tensor` / `tensor_to_fields` / `select_init_times`.
 
 Inside `roll_out_latent` / `encode_fused` / `decode_fused` these transforms are fused into CUDA epilogues; the functions
 here are the reference-compatible host API for everything around that."""
@@ -96,3 +99,121 @@ def prepare_static_conditioning(lsm: Optional[torch.Tensor], orography: Optional
     mean = static.mean(dim=(1, 2), keepdim=True)
     std = static.std(dim=(1, 2), keepdim=True)
     return (static - mean) / std
+
+
+SST_FILL_VALUE = -2.0  # normalised sea-surface temperature over land (dataloader/utils.py:399-404, weather_dataset.py)
+
+
+def _to_tensor(a) -> torch.Tensor:
+    if isinstance(a, torch.Tensor):
+        return a
+    import numpy as np
+
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def fields_to_tensor(fields: Dict, variable_names: Optional[List[str]] = None, level_index: Optional[List[int]] = None,
+                     normalization_param_dict: Optional[Dict] = None, mean_tensor: Optional[torch.Tensor] = None,
+                     std_tensor: Optional[torch.Tensor] = None, static_conditioning_tensor: Optional[torch.Tensor] = None,
+                     crop_south_pole: bool = False) -> torch.Tensor:
+    """Array counterpart of `xarr_to_tensor` (reference dataloader/utils.py:357-448): stacks a field set into the
+    model's (C, T, H, W) layout — variables in `variable_names` order (default: VAR_LIST entries present), an
+    atmospheric variable contributing one channel per selected level, time-independent entries skipped — then
+    standardises per channel, replaces the NaNs of `sea_surface_temperature` (land) by -2 AFTER normalisation and
+    optionally appends the static conditioning channels (C_s, H, W) broadcast over time.
+    level_index: positions along the level axis to keep (the reference selects by level value on the xarray side).
+    crop_south_pole: drop latitude row 0 of a 121-row grid (pred_rollout.py crops `[1:]`)."""
+    names = [n for n in (variable_names or VAR_LIST) if n in fields]
+    parts, sst_channel, c = [], None, 0
+    for name in names:
+        a = _to_tensor(fields[name]).to(torch.float32)
+        if a.dim() == 4:  # (time, level, lat, lon) -> (level, time, lat, lon)
+            if level_index is not None:
+                a = a[:, level_index]
+            a = a.permute(1, 0, 2, 3)
+        elif a.dim() == 3:  # (time, lat, lon)
+            if name == "sea_surface_temperature":
+                sst_channel = c
+            a = a.unsqueeze(0)
+        else:
+            continue  # static (lat, lon) entries such as land_sea_mask have no time axis
+        parts.append(a)
+        c += a.shape[0]
+    if not parts:
+        raise ValueError("no time-dependent variable found in the field set")
+    x = torch.cat(parts, dim=0)
+    if crop_south_pole:
+        x = x[:, :, 1:]
+    if normalization_param_dict is not None:
+        mean_tensor, std_tensor = precompute_mean_std(normalization_param_dict,
+                                                      [n for n in names if n != "land_sea_mask" and _to_tensor(fields[n]).dim() >= 3])
+    if mean_tensor is not None:
+        if mean_tensor.numel() != x.shape[0]:
+            raise ValueError(f"{mean_tensor.numel()} channel statistics for {x.shape[0]} channels")
+        x = normalize_transform_3D(x, mean_tensor.to(x.dtype), std_tensor.to(x.dtype))
+        if sst_channel is not None:
+            x[sst_channel] = torch.nan_to_num(x[sst_channel], nan=SST_FILL_VALUE)
+    if static_conditioning_tensor is not None:
+        st = static_conditioning_tensor.to(x.dtype).unsqueeze(1).expand(-1, x.shape[1], -1, -1)
+        x = torch.cat([x, st], dim=0)
+    return x
+
+
+def tensor_to_fields(x: torch.Tensor, variable_names: List[str], n_levels: Dict[str, int],
+                     normalization_param_dict: Optional[Dict] = None, mean_tensor: Optional[torch.Tensor] = None,
+                     std_tensor: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """Array counterpart of `tensor_to_xarr` (reference dataloader/utils.py:452-513): (C, T, H, W) -> field set on the
+    host, de-normalised first if statistics are given.  n_levels[name] = number of level channels of an atmospheric
+    variable (absent / 0 = surface variable)."""
+    if normalization_param_dict is not None:
+        mean_tensor, std_tensor = precompute_mean_std(normalization_param_dict, variable_names)
+    if mean_tensor is not None:
+        x = inverse_normalize_transform_3D(x, mean_tensor.to(x.device), std_tensor.to(x.device))
+    x = x.cpu()
+    out, c = {}, 0
+    for name in variable_names:
+        k = int(n_levels.get(name, 0))
+        if k > 0:
+            out[name] = x[c : c + k].permute(1, 0, 2, 3)  # (time, level, lat, lon)
+            c += k
+        else:
+            out[name] = x[c]
+            c += 1
+    if c != x.shape[0]:
+        raise ValueError("Mismatch in the number of variables.")
+    return out
+
+
+def select_init_times(times, num_samples_per_month: int, enforce_year=None) -> List:
+    """Forecast init times as `filter_time_range` picks them (reference dataloader/utils.py:517-597): for every month
+    present in `times`, `num_samples_per_month` days evenly spaced from the 1st up to (excluding) the last day of the
+    month, at 00 and 12 UTC, never beyond the last available time.  `times`: datetimes (or anything
+    datetime.fromisoformat / numpy datetime64 convertible); returns a sorted list of datetime objects."""
+    import calendar
+    from datetime import datetime
+
+    import numpy as np
+
+    def as_dt(t):
+        if isinstance(t, datetime):
+            return t
+        if isinstance(t, np.datetime64):
+            return t.astype("datetime64[s]").astype(datetime)
+        return datetime.fromisoformat(str(t))
+
+    ts = [as_dt(t) for t in times]
+    if enforce_year is not None:
+        ts = [t for t in ts if t.year == int(enforce_year)]
+    if not ts:
+        return []
+    last = max(as_dt(t) for t in times)
+    picked = []
+    for yr, mo in sorted({(t.year, t.month) for t in ts}):
+        days = np.round(np.linspace(1, calendar.monthrange(yr, mo)[1], num_samples_per_month, endpoint=False)).astype(int)
+        days[0] = 1
+        for day in days:
+            for hour in (0, 12):
+                dt = datetime(yr, mo, int(day), hour)
+                if dt <= last:
+                    picked.append(dt)
+    return sorted(picked)

@@ -65,6 +65,13 @@ def get_crps(forecast: torch.Tensor, truth: torch.Tensor, ensemble_dim: int = 0)
 
 
 @torch.no_grad()
+def ensemble_mean(forecast: torch.Tensor, ensemble_dim: int = 0) -> torch.Tensor:
+    """Mean over the ensemble dimension on the device (the pointwise mode of the metrics kernel) — what
+    roll_out_serial(return_ensemble_mean=True) keeps of every decoded block (pipelines/utils.py:608-630)."""
+    return _pointwise(forecast, None, ensemble_dim, ("mean",))["mean"]
+
+
+@torch.no_grad()
 def get_acc(forecast: torch.Tensor, truth: torch.Tensor, climate: torch.Tensor,
             lat_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Anomaly correlation coefficient over the last two (spatial) dims with nanmean semantics (reference

@@ -136,7 +136,7 @@ def rollout_step(pipeline, encdec_model, known: torch.Tensor, stamp: torch.Tenso
                  field_std: Optional[torch.Tensor], num_inference_steps: int = 20, return_seq_len: int = 4,
                  sampler_type: str = "pipeline", member_indices: Optional[Sequence[int]] = None,
                  return_latent: bool = False, target_std: float = 0.5, t_in: Optional[int] = None,
-                 out: Optional[torch.Tensor] = None):
+                 out: Optional[torch.Tensor] = None, extract_first: Optional[int] = None):
     """One AR step of `roll_out_serial` (reference pipelines/utils.py:533-585), entirely in library kernels: sample
     T_out lead steps for every member, feed the last T_in frames back (lc_latent_feedback), then either de-normalise
     the latents (return_latent) or decode them — the latent de-normalisation runs inside the decoder's first kernel and
@@ -157,9 +157,9 @@ def rollout_step(pipeline, encdec_model, known: torch.Tensor, stamp: torch.Tenso
                                                   _lib.ptr(latent_mean), _lib.ptr(latent_std), float(target_std), B, C, T,
                                                   t_in, h * w, _lib.stream()), "lc_latent_feedback")
     if return_latent:
-        return phys, known_next
-    fields = encdec_model.decode_ens_fused(samples, field_mean, field_std, latent_mean=latent_mean,
-                                           latent_std=latent_std, target_std=target_std, out=out)
+        return (phys if extract_first in (None, T) else phys[:, :, :extract_first]), known_next
+    fields = encdec_model.decode_ens_fused(samples, field_mean, field_std, extract_first=extract_first,
+                                           latent_mean=latent_mean, latent_std=latent_std, target_std=target_std, out=out)
     return fields, known_next
 
 
@@ -169,7 +169,8 @@ def roll_out_latent(pipeline, encdec_model, known_latents: torch.Tensor, init_ti
                     field_std: Optional[torch.Tensor] = None, num_inference_steps: int = 20, return_seq_len: int = 4,
                     total_lead_time_hour: int = 240, step_size_hour: int = 6, sampler_type: str = "pipeline",
                     member_indices: Optional[Sequence[int]] = None, return_latent: bool = False, target_std: float = 0.5,
-                    out: Optional[torch.Tensor] = None, max_ar_steps: Optional[int] = None):
+                    out: Optional[torch.Tensor] = None, max_ar_steps: Optional[int] = None,
+                    return_ensemble_mean: bool = False):
     """Tensor-in / tensor-out core of `roll_out_serial` (reference pipelines/utils.py:533-654): the AR loop
     [sample -> feed the last T_in frames back -> de-normalise -> decode] from already encoded, normalised
     `known_latents` (1, C, T_in, h, w) given on the HOST or the device.
@@ -178,9 +179,15 @@ def roll_out_latent(pipeline, encdec_model, known_latents: torch.Tensor, init_ti
     s*T_out+1 .. (s+1)*T_out (decoded fields in physical units, or de-normalised latents when return_latent).
     `rollout_as_lead_major(out)` gives the reference's (ensemble, C, lead, H, W) view.  Each AR step's block is one
     contiguous asynchronous device->host copy on a side stream that overlaps the next AR step's compute.
-    `member_indices`: global member ids owned by this process (multi-GPU member sharding)."""
+    `member_indices`: global member ids owned by this process (multi-GPU member sharding).
+    `return_ensemble_mean` (reference :299, :608-630): only the ensemble mean of every decoded block leaves the device
+    (shape (n_ar_steps, 1, C, T_out, H, W)); the mean over members is taken by the metrics kernel's pointwise mode.
+    When T_out does not divide the number of lead steps, the last block's surplus frames are not decoded (the
+    reference's `pred_selection`, :536-537) and stay NaN in the output."""
     import math
 
+    if return_latent and return_ensemble_mean:
+        raise ValueError("return_ensemble_mean must be False when return_latent is True.")
     dev = pipeline._execution_device
     total = total_lead_time_hour // step_size_hour
     if total_lead_time_hour % step_size_hour != 0:
@@ -197,17 +204,28 @@ def roll_out_latent(pipeline, encdec_model, known_latents: torch.Tensor, init_ti
     copy_stream = torch.cuda.Stream(device=dev)
     for step in range(reps):
         stamp = torch.tensor([advance_timestamp(init_timestamp, step * step_size_hour * return_seq_len)])
+        sel = min(return_seq_len, total - step * return_seq_len)  # lead steps of this block that exist (pred_selection)
         res, known = rollout_step(pipeline, encdec_model, known, stamp, ensemble_size, lm, ls, fm, fs,
                                   num_inference_steps=num_inference_steps, return_seq_len=return_seq_len,
                                   sampler_type=sampler_type, member_indices=member_indices, return_latent=return_latent,
-                                  target_std=target_std, t_in=t_in)
+                                  target_std=target_std, t_in=t_in, extract_first=sel)
+        if return_ensemble_mean:
+            from ..evaluate.utils import ensemble_mean
+
+            res = ensemble_mean(res).unsqueeze(0)  # (1, C, sel, H, W), reduced on the device
         if out is None:
-            out = torch.empty((reps, *res.shape), dtype=torch.float32, pin_memory=True)
+            shape = (reps, res.shape[0], res.shape[1], return_seq_len, *res.shape[3:])
+            out = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+            if total % return_seq_len:
+                out[-1].fill_(float("nan"))
         done = torch.cuda.Event()
         done.record(torch.cuda.current_stream(dev))
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(done)
-            out[step].copy_(res, non_blocking=True)
+            if sel == return_seq_len:
+                out[step].copy_(res, non_blocking=True)
+            else:
+                out[step][:, :, :sel].copy_(res, non_blocking=True)
         res.record_stream(copy_stream)  # the allocator may reuse the block only after the copy has drained
     copy_stream.synchronize()
     return out
@@ -229,16 +247,56 @@ def encode_initial_condition(encdec_model, input_fields: torch.Tensor, static_fi
 
 
 def roll_out_serial(pipeline, encdec_model, input_fields: torch.Tensor, static_fields: Optional[torch.Tensor],
-                    init_timestamp: int, ensemble_size: int, latent_mean: torch.Tensor, latent_std: torch.Tensor,
-                    field_mean: Optional[torch.Tensor] = None, field_std: Optional[torch.Tensor] = None, **kw):
-    """Tensor-in / tensor-out `roll_out_serial` (reference pipelines/utils.py:250-661 without the xarray layer):
-    encode the initial condition, normalise it, then run `roll_out_latent`.  `input_fields` (C, T_in, H, W) are the
-    standardised fields of the T_in input times; returns (rollout, known_latents)."""
-    known = encode_initial_condition(encdec_model, input_fields, static_fields, latent_mean, latent_std,
-                                     kw.get("target_std", 0.5))
-    out = roll_out_latent(pipeline, encdec_model, known, init_timestamp, ensemble_size, latent_mean, latent_std,
-                          field_mean, field_std, **kw)
-    return out, known
+                    init_timestamp, ensemble_size: int, latent_mean: torch.Tensor, latent_std: torch.Tensor,
+                    field_mean: Optional[torch.Tensor] = None, field_std: Optional[torch.Tensor] = None,
+                    noise_level: float = 0.0, generator: Optional[torch.Generator] = None,
+                    reference_layout: bool = False, raw_fields: Optional[torch.Tensor] = None, **kw):
+    """Tensor-in / tensor-out `roll_out_serial` (reference pipelines/utils.py:250-661 without the xarray layer): encode
+    the initial condition (+ static channels), normalise it, optionally perturb it, then run `roll_out_latent`.
+
+    input_fields: standardised fields of the T_in input times, (C, T_in, H, W) for one forecast or
+    (n_init, C, T_in, H, W) with `init_timestamp` a sequence for the reference's loop over init times (:445).
+    noise_level (:518-528): known latents += randn * noise_level * latent_std (drawn from `generator` on the host).
+    Keyword options of `roll_out_latent` pass through (num_inference_steps, return_seq_len, total_lead_time_hour,
+    return_latent, return_ensemble_mean, sampler_type, member_indices, ...).
+
+    Returns (rollout, known_latents) — the AR-blocked host tensor of `roll_out_latent` (stacked over init times when
+    several are given) — or, with reference_layout=True, the reference's `return_tensor=True` result: a tensor
+    (n_init, return_size, C, lead+1, H, W) whose slot 0 holds the un-normalised input field of the forecast time
+    (`raw_fields`, (n_init,) C, H, W; NaN if not given) or, for return_latent, the encoded initial latent (:466-497)."""
+    multi = input_fields.dim() == 5
+    fields = input_fields if multi else input_fields.unsqueeze(0)
+    stamps = list(init_timestamp) if multi else [init_timestamp]
+    if len(stamps) != fields.shape[0]:
+        raise ValueError("one init_timestamp per forecast is required")
+    target_std = kw.get("target_std", 0.5)
+    outs, knowns = [], []
+    for i, stamp in enumerate(stamps):
+        known = encode_initial_condition(encdec_model, fields[i], static_fields, latent_mean, latent_std, target_std)
+        knowns.append(known)
+        start = known
+        if noise_level and noise_level > 0:
+            noise = torch.randn(known.shape, generator=generator, dtype=torch.float32)
+            start = known + (noise * noise_level * latent_std.to(torch.float32).reshape(1, -1, 1, 1, 1)).to(known.device)
+        outs.append(roll_out_latent(pipeline, encdec_model, start, int(stamp), ensemble_size, latent_mean, latent_std,
+                                    field_mean, field_std, **kw))
+    if not reference_layout:
+        if multi:
+            return torch.stack(outs, dim=0), torch.cat(knowns, dim=0)
+        return outs[0], knowns[0]
+    total = kw.get("total_lead_time_hour", 240) // kw.get("step_size_hour", 6)
+    res = []
+    for i, o in enumerate(outs):
+        lead = rollout_as_lead_major(o, total)  # (return_size, C, total, H, W)
+        first = torch.full_like(lead[:, :, :1], float("nan"))
+        if kw.get("return_latent", False):
+            z0 = (knowns[i][0, :, -1].cpu() / target_std) * latent_std.reshape(-1, 1, 1) + latent_mean.reshape(-1, 1, 1)
+            first[:] = z0[None, :, None]
+        elif raw_fields is not None:
+            rf = raw_fields[i] if raw_fields.dim() == 4 else raw_fields
+            first[:] = rf.to("cpu", torch.float32)[None, :, None]
+        res.append(torch.cat([first, lead], dim=2))
+    return torch.stack(res, dim=0)
 
 
 def save_latents_npy(path_dir: str, init_timestamp: int, initial_latent: torch.Tensor, rollout: torch.Tensor) -> str:

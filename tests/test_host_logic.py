@@ -268,3 +268,35 @@ def test_dataloader_transforms_vs_reference_golden(golden_dir):
     assert torch.allclose(st.mean(dim=(1, 2)), torch.zeros(5), atol=1e-5)
     assert torch.allclose(st.std(dim=(1, 2)), torch.ones(5), atol=1e-5)
     assert prepare_static_conditioning(None, None) is None
+
+
+def test_array_front_end_matches_reference_conventions():
+    """f-4: fields_to_tensor / tensor_to_fields / select_init_times — channel order (6 x 13 levels, then surface),
+    normalisation, SST NaN -> -2 after normalisation, static channels appended, inverse round trip, init-time picks."""
+    from datetime import datetime, timedelta
+
+    from ladcast_b200.dataloader.utils import VAR_LIST, fields_to_tensor, select_init_times, tensor_to_fields
+
+    g = torch.Generator("cpu").manual_seed(3)
+    T, L, H, W = 2, 13, 6, 8
+    fields = {n: torch.randn(T, L, H, W, generator=g) for n in VAR_LIST[:6]}
+    fields.update({n: torch.randn(T, H, W, generator=g) for n in VAR_LIST[6:]})
+    fields["sea_surface_temperature"][:, :2] = float("nan")
+    fields["land_sea_mask"] = torch.rand(H, W, generator=g)  # static entry: skipped
+    mean, std = torch.randn(84, generator=g), torch.rand(84, generator=g) + 0.5
+    static = torch.randn(5, H, W, generator=g)
+    x = fields_to_tensor(fields, mean_tensor=mean, std_tensor=std, static_conditioning_tensor=static)
+    assert x.shape == (89, T, H, W)
+    assert torch.allclose(x[13 + 4], (fields["specific_humidity"][:, 4] - mean[17]) / std[17])
+    assert torch.equal(x[82, :, :2], torch.full((T, 2, W), -2.0)) and not torch.isnan(x).any()
+    assert torch.allclose(x[82, :, 2:], (fields["sea_surface_temperature"][:, 2:] - mean[82]) / std[82])
+    assert torch.equal(x[84:, 1], static)
+    back = tensor_to_fields(x[:84], VAR_LIST, {n: 13 for n in VAR_LIST[:6]}, mean_tensor=mean, std_tensor=std)
+    assert torch.allclose(back["temperature"], fields["temperature"], atol=1e-5) and back["2m_temperature"].shape == (T, H, W)
+    sub = fields_to_tensor(fields, variable_names=["temperature", "2m_temperature"], level_index=[0, 12])
+    assert sub.shape == (3, T, H, W) and torch.equal(sub[1], fields["temperature"][:, 12])
+    times = [datetime(2018, 1, 1) + timedelta(hours=6 * i) for i in range(4 * 59)]  # Jan + Feb 2018
+    picks = select_init_times(times, 3)
+    assert picks[:4] == [datetime(2018, 1, 1, 0), datetime(2018, 1, 1, 12), datetime(2018, 1, 11, 0), datetime(2018, 1, 11, 12)]
+    assert all(p <= times[-1] for p in picks) and len(picks) == 12
+    assert select_init_times(times, 3, enforce_year=2019) == []

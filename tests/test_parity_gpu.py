@@ -293,3 +293,64 @@ def test_metrics_nan_member_propagates():
     mask = ~torch.isnan(want)
     assert torch.allclose(sp[mask], want[mask], rtol=1e-5, atol=1e-6)
     assert torch.isnan(get_crps(f.cuda(), torch.zeros(1, 4, 16, 8).cuda(), 0).cpu()[1, 3, 4])
+
+
+# ------------------------------------------------------------------------------------------- roll_out_serial options
+def _tiny_rollout_setup(precision="fp32"):
+    from ladcast_b200.models import AutoencoderDC
+    from ladcast_b200.pipelines import AutoRegressive2DPipeline, EDMDPMSolverMultistepScheduler
+
+    cfg, sd, m = _denoiser("tiny", 11, precision)
+    acfg = O.dcae_config("tiny")
+    asd = O.make_state_dict(O.dcae_decoder_param_shapes(acfg), 21)
+    asd.update(O.make_state_dict(O.dcae_encoder_param_shapes(acfg), 23))
+    ae = AutoencoderDC(**acfg)
+    ae.load_state_dict(asd)
+    ae.to("cuda").set_precision(precision)
+    pipe = AutoRegressive2DPipeline(m, EDMDPMSolverMultistepScheduler())
+    stats = (_seeded((84,), 31) * 0.1, _seeded((84,), 32).abs() + 0.5, _seeded((84,), 33), _seeded((84,), 34).abs() + 0.5)
+    return (cfg, sd, acfg, asd), pipe, ae, stats
+
+
+def test_roll_out_serial_options():
+    """The reference's roll_out_serial switches (pipelines/utils.py): T_out not dividing the lead count (pred_selection,
+    :536-537), return_ensemble_mean (:608-630), noise_level (:518-528), several init times (:445), return_tensor layout
+    with the t = 0 slot (:466-497) — FP32 validation mode, tiny models, against the oracle rollout."""
+    from ladcast_b200.pipelines.utils import encode_initial_condition, roll_out_latent, roll_out_serial, rollout_as_lead_major
+
+    (cfg, sd, acfg, asd), pipe, ae, (lm, ls, fm, fs) = _tiny_rollout_setup()
+    fields = _seeded((2, 84, 1, 120, 240), 501)  # two init times, (n_init, C, T_in, H, W)
+    static = _seeded((5, 120, 240), 502)
+    stamps = [2018010100, 2018063018]
+    kw = dict(num_inference_steps=3, return_seq_len=2, total_lead_time_hour=18)  # 3 lead steps, T_out = 2 -> blocks 2 + 1
+    out, known = roll_out_serial(pipe, ae, fields.cuda(), static.cuda(), stamps, 2, lm, ls, fm, fs, **kw)
+    assert out.shape == (2, 2, 2, 84, 2, 120, 240) and known.shape == (2, 84, 1, 15, 30)
+    for i in range(2):
+        z = O.dcae_encode(asd, acfg, fields[i].permute(1, 0, 2, 3), static.unsqueeze(0))
+        kn = O.normalize_latent(z.permute(1, 0, 2, 3).unsqueeze(0), lm, ls, 0.5)
+        _, want = O.rollout(sd, cfg, asd, acfg, kn, [0, 1], stamps[i], 3, 2, 3, lm, ls, fm, fs, sampler="pipeline")
+        got = rollout_as_lead_major(out[i], 3)
+        assert got.shape == want.shape == (2, 84, 3, 120, 240)
+        assert _rel(got, want) < 2e-3
+        assert torch.isnan(out[i][-1][:, :, 1]).all()  # the surplus frame of the last block is never decoded
+    # ensemble mean only
+    mean_out, _ = roll_out_serial(pipe, ae, fields[0].cuda(), static.cuda(), stamps[0], 2, lm, ls, fm, fs,
+                                  return_ensemble_mean=True, **kw)
+    assert mean_out.shape == (2, 1, 84, 2, 120, 240)
+    assert torch.allclose(rollout_as_lead_major(mean_out, 3)[0], rollout_as_lead_major(out[0], 3).mean(0), rtol=1e-5, atol=1e-5)
+    # reference return_tensor layout: (n_init, return_size, C, lead + 1, H, W), slot 0 = raw input field
+    raw = _seeded((2, 84, 120, 240), 503)
+    ref_layout = roll_out_serial(pipe, ae, fields.cuda(), static.cuda(), stamps, 2, lm, ls, fm, fs, reference_layout=True,
+                                 raw_fields=raw, **kw)
+    assert ref_layout.shape == (2, 2, 84, 4, 120, 240)
+    assert torch.equal(ref_layout[1, 0, :, 0], raw[1]) and torch.equal(ref_layout[:, :, :, 1:], torch.stack(
+        [rollout_as_lead_major(out[i], 3) for i in range(2)]))
+    # latent perturbation: same as rolling out from the perturbed latents
+    g = torch.Generator("cpu").manual_seed(77)
+    pert, kn0 = roll_out_serial(pipe, ae, fields[0].cuda(), static.cuda(), stamps[0], 2, lm, ls, fm, fs, noise_level=0.1,
+                                generator=g, return_latent=True, **kw)
+    noise = torch.randn(kn0.shape, generator=torch.Generator("cpu").manual_seed(77))
+    manual = roll_out_latent(pipe, ae, kn0 + (noise * 0.1 * ls.reshape(1, -1, 1, 1, 1)).cuda(), stamps[0], 2, lm, ls, fm, fs,
+                             return_latent=True, **kw)
+    assert torch.equal(pert[0], manual[0]) and _rel(pert[0], roll_out_latent(pipe, ae, kn0, stamps[0], 2, lm, ls, fm, fs,
+                                                                               return_latent=True, **kw)[0]) > 1e-3

@@ -46,7 +46,11 @@ SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "nse
 
 
 def load(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """.ncu-rep (converted through `ncu -i ... --page raw --csv`) or an already converted raw-page .csv"""
+    if path.endswith(".csv"):
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     return rows[0], rows[1], rows[2:]
 
