@@ -228,6 +228,14 @@ LC_API int lc_pixel_shuffle_shortcut(const float* conv, const float* xin, float*
 LC_API int lc_pixel_unshuffle_shortcut(const float* conv, const float* xin, float* out, int n, int height, int width,
                                        int cin, int cout, void* stream);
 
+/* LayerNorm (no affine, biased variance, eps) of x [rows, d] fp32 followed by the AdaLN modulation
+ * y * (1 + scale[b, :]) + shift[b, :] with b = row / rows_per_sample (scale / shift rows `mod_stride` floats apart;
+ * NULL = none), or by an affine w, b [d]; out is fp32 (F32) or bf16 (BF16).  The denoiser's norm1 / norm2 / norm_out
+ * (diffusers AdaLayerNormZero / ZeroSingle / Continuous; LaDCast_3D_model.py:287-302, 524-552, 1044).  d % 128 == 0. */
+LC_API int lc_layernorm_modulate(int precision, const float* x, void* out, int rows, int d, float eps, int rows_per_sample,
+                                 const float* scale, const float* shift, int64_t mod_stride, const float* w,
+                                 const float* b, void* stream);
+
 /* One SphereConv2d 3x3 (models/sphere_conv.py:138-192), NCHW fp32 in/out, through the implicit-GEMM path.
  * w: [cout, cin, 3, 3], bias: [cout] or NULL.  Test helper: allocates and synchronises internally. */
 LC_API int lc_sphere_conv3x3(int precision, const float* x, const float* w, const float* bias, float* out, int n, int cin,

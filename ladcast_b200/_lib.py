@@ -63,6 +63,7 @@ _SIGNATURES = {
     "lc_sched_heun_step": ([_vp, _vp, _vp, _vp, _vp, _i64, _i, _d, _d, _d, _d, _d, _vp], _i),
     "lc_gemm": ([_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
     "lc_attention": ([_i, _vp, _vp, _i, _i, _i, _vp], _i),
+    "lc_layernorm_modulate": ([_i, _vp, _vp, _i, _i, _f, _i, _vp, _vp, _i64, _vp, _vp, _vp], _i),
     "lc_patchify": ([_i, _vp, _vp, _i, _i, _i, _i, _vp], _i),
     "lc_unpatchify_gemm": ([_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),
     "lc_gemm_bf16out": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp], _i),

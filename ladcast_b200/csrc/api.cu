@@ -166,6 +166,18 @@ int lc_unpatchify_gemm(int precision, const void* tokens, const void* w, const f
                                        : gemm_bf16(g, static_cast<cudaStream_t>(stream));
 }
 
+// Test / micro-benchmark export of the LayerNorm + modulation kernel (AdaLayerNormZero / Continuous: LN without affine,
+// eps, then y * (1 + scale[b]) + shift[b]; or an affine LN when w / b are given).
+int lc_layernorm_modulate(int precision, const float* x, void* out, int rows, int d, float eps, int rows_per_sample,
+                          const float* scale, const float* shift, int64_t mod_stride, const float* w, const float* b,
+                          void* stream) {
+  LC_REQUIRE(x && out, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return precision == LC_PRECISION_F32
+             ? layernorm_modulate<float>(x, reinterpret_cast<float*>(out), rows, d, eps, rows_per_sample, scale, shift, mod_stride, w, b, st)
+             : layernorm_modulate<bf16>(x, reinterpret_cast<bf16*>(out), rows, d, eps, rows_per_sample, scale, shift, mod_stride, w, b, st);
+}
+
 int lc_debug_gemm_trace(void* buf) { return lc::gemm_set_trace(reinterpret_cast<long long*>(buf)); }
 int lc_debug_attention_trace(void* buf) { return lc::attention_set_trace(reinterpret_cast<long long*>(buf)); }
 int lc_attention(int precision, const void* qkv, void* out, int batch, int seq, int heads, void* stream) {

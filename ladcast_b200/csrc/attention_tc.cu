@@ -19,6 +19,8 @@
 //                 per element), lazy rescale of O (only when the row max grows by more than 2^8), P (bf16) stored
 //                 back to TMEM over S.  Final O / l epilogue per tile.  576 threads leave 96 registers per thread.
 //   TMEM columns: S_A/P_A 0..127, S_B/P_B 128..255, O_A 256..383, O_B 384..511.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 #include "tmap.h"
@@ -72,6 +74,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
   const int n_tiles = (S + BKV - 1) / BKV;
   const int row_base = b * S;
   long long* trace = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0 ? g_trace : nullptr;
+  if (warp == 0) LC_TRACE(3, 0, 0);  // role 3: CTA life cycle — entry, set-up done, O complete, last store issued
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm);
@@ -93,6 +96,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_grid_sync();  // q|k|v are produced by the preceding kernel: nothing global is touched above this line
+  if (warp == 0) LC_TRACE(3, 0, 1);
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -268,6 +272,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
     }
     ptx::mbar_wait(o_full, 0);
     ptx::tc_fence_after();
+    LC_TRACE(3, 0, 2);
     // row sum = the two halves' partial sums (same alpha sequence in both); Q's shared memory is dead by now
     float* lx = reinterpret_cast<float*>(sQ);
     lx[(t * 2 + hh) * 128 + r] = l;
@@ -299,6 +304,342 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
         }
       }
     }
+    LC_TRACE(3, 0, 3);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+
+// ------------------------------------------------------------------------------------------------ persistent variant
+// Same tile algorithm, but ONE CTA per SM walks over (sample, head, 256-query block) work items, so that per-item
+// set-up and drain are paid once per CTA or overlap the next item instead of costing ~21 % of every CTA's life
+// (in-kernel timeline of the one-item kernel: 62 k cycles of steady-state steps in a 79 k-cycle CTA):
+//   * barriers, TMEM and the K/V ring persist; the producer streams the next item's K/V right behind the current one
+//     and re-loads Q as soon as the item's last S = Q K^T has completed (q_empty);
+//   * the next item's first S tiles are issued straight after the current item's last P V; its first P V waits for
+//     the epilogue to drain O (o_empty[tile]);
+//   * the epilogue no longer issues 16-byte stores scattered over 128 rows per warp instruction (LSU-bound, ~7.6 k
+//     cycles): O / l is packed to bf16 into a swizzled 32 KB staging tile and written by TMA tensor stores (3-D maps
+//     {d, tokens of the stream, samples}: rows past the stream's token count are clipped by the hardware, which also
+//     splits a tile that straddles the pred | cond boundary).  The staging tile is one slot of the K/V ring: the
+//     producer passes the slot that follows V_{n-1} of every item to the softmax warps instead of filling it (ring
+//     order K_0 V_0 ... K_{n-1} V_{n-1} [O staging]), tile A then tile B use it, and tile B's store releases it — so
+//     all 5 slots carry K/V in the steady state and no extra shared memory is needed.
+// Shared memory: Q 2 x 32 KB, ring 5 x 32 KB (as the one-item kernel).
+constexpr int RING_P = 5;
+constexpr int SMEM_BYTES_P = 2 * TILE_BYTES + RING_P * TILE_BYTES + 256 + XCH_BYTES;
+
+__global__ void __maxnreg__(96)
+attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_p,
+                               const __grid_constant__ CUtensorMap tm_c, int S, int heads, int n_qb, int n_items, int Np,
+                               int has_cond, bf16* __restrict__ out_c) {
+  extern __shared__ uint8_t smem_raw[];
+  if ((ptx::smem_u32(smem_raw) & 1023u) != 0) __trap();  // swizzled TMA tiles need 1024-byte alignment
+  uint8_t* sQ = smem_raw;                                  // [2][TILE_BYTES]
+  uint8_t* sR = sQ + 2 * TILE_BYTES;                       // [RING_P][TILE_BYTES]: K_0 V_0 ... K_{n-1} V_{n-1} [O staging]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sR + RING_P * TILE_BYTES);
+  uint64_t* q_full = bars;                   // 1
+  uint64_t* q_empty = bars + 1;              // 1
+  uint64_t* r_full = bars + 2;               // RING_P
+  uint64_t* r_empty = r_full + RING_P;       // RING_P
+  uint64_t* s_full = r_empty + RING_P;       // [tile]
+  uint64_t* p_full = s_full + 2;             // [tile] (8 arrivals: one per softmax warp)
+  uint64_t* o_full = p_full + 2;             // [tile]
+  uint64_t* o_empty = o_full + 2;            // [tile] (8 arrivals)
+  uint64_t* stg_empty = o_empty + 2;         // 1: tile A's store has read the staging slot (tile B may write it)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_empty + 1);
+  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = heads * HD;
+  const int n_tiles = (S + BKV - 1) / BKV;
+  long long* trace = blockIdx.x == 0 && lane == 0 ? g_trace : nullptr;
+  if (warp == 0) LC_TRACE(3, 0, 0);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm);
+    ptx::prefetch_tmap(&tm_p);
+    if (has_cond) ptx::prefetch_tmap(&tm_c);
+    ptx::mbar_init(q_full, 1);
+    ptx::mbar_init(q_empty, 1);
+    for (int i = 0; i < RING_P; ++i) {
+      ptx::mbar_init(&r_full[i], 1);
+      ptx::mbar_init(&r_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&p_full[i], 8);
+      ptx::mbar_init(&o_full[i], 1);
+      ptx::mbar_init(&o_empty[i], 8);
+    }
+    ptx::mbar_init(stg_empty, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();  // q|k|v are produced by the preceding kernel: nothing global is touched above this line
+  if (warp == 0) LC_TRACE(3, 0, 1);
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int st = 0, k = 0;
+    uint32_t ph = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+      const int qb = item % n_qb, bh = item / n_qb;
+      const int h = bh % heads, b = bh / heads;
+      const int row_base = b * S, q0 = qb * (2 * BQ);
+      if (k > 0) ptx::mbar_wait(q_empty, (k - 1) & 1);  // every S = Q K^T of the previous item has completed
+      ptx::mbar_expect_tx(q_full, 2 * TILE_BYTES);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        ptx::tma_load_2d(sQ + t * TILE_BYTES, &tm, q_full, h * HD, row_base + q0 + t * BQ);
+        ptx::tma_load_2d(sQ + t * TILE_BYTES + SUB_BYTES, &tm, q_full, h * HD + 64, row_base + q0 + t * BQ);
+      }
+      for (int j = 0; j < n_tiles; ++j) {
+        const int kr = row_base + j * BKV;
+#pragma unroll
+        for (int kv = 0; kv < 2; ++kv) {  // 0: K_j, 1: V_j
+          ptx::mbar_wait(&r_empty[st], ph ^ 1);
+          const int col = (kv + 1) * d + h * HD;
+          uint8_t* dst = sR + st * TILE_BYTES;
+          ptx::mbar_expect_tx(&r_full[st], TILE_BYTES);
+          ptx::tma_load_2d(dst, &tm, &r_full[st], col, kr);
+          ptx::tma_load_2d(dst + SUB_BYTES, &tm, &r_full[st], col + 64, kr);
+          if (++st == RING_P) { st = 0; ph ^= 1; }
+        }
+      }
+      // the slot behind V_{n-1} is handed to the softmax warps as the item's output staging tile
+      ptx::mbar_wait(&r_empty[st], ph ^ 1);
+      ptx::mbar_arrive(&r_full[st]);
+      if (++st == RING_P) { st = 0; ph ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(128, BKV, 0, 0);  // A = Q (K-major), B = K (K-major)
+    constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(128, HD, 0, 1);   // A = P (TMEM), B = V (MN-major)
+    const uint32_t q_addr = ptx::smem_u32(sQ), r_addr = ptx::smem_u32(sR);
+    auto issue_qk = [&](int t, int slot) {
+      const uint32_t k_addr = r_addr + slot * TILE_BYTES;
+      const uint32_t d_tmem = tmem_base + COL_S + static_cast<uint32_t>(t * 128);
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const uint32_t off = (kk >> 2) * SUB_BYTES + (kk & 3) * 32;
+        ptx::umma_f16(d_tmem, ptx::make_smem_desc(q_addr + t * TILE_BYTES + off, 16, 1024),
+                      ptx::make_smem_desc(k_addr + off, 16, 1024), idesc_qk, kk != 0 ? 1u : 0u);
+      }
+      ptx::umma_commit(&s_full[t]);
+    };
+    auto issue_pv = [&](int t, int slot, bool first) {
+      const uint32_t v_addr = r_addr + slot * TILE_BYTES;
+      const uint32_t d_tmem = tmem_base + COL_O + static_cast<uint32_t>(t * 128);
+      const uint32_t a_tmem = tmem_base + COL_S + static_cast<uint32_t>(t * 128);
+#pragma unroll
+      for (int kk = 0; kk < BKV / 16; ++kk)
+        ptx::umma_f16_ts(d_tmem, a_tmem + kk * 8, ptx::make_smem_desc(v_addr + kk * 2048, SUB_BYTES, 1024), idesc_pv,
+                         (first && kk == 0) ? 0u : 1u);
+    };
+    int st = 0, k = 0;
+    uint32_t ph = 0, sc = 0;  // sc: running (item, step) count = phase counter of s_full / p_full
+    auto advance = [&]() { if (++st == RING_P) { st = 0; ph ^= 1; } };
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+      ptx::mbar_wait(q_full, k & 1);
+      ptx::mbar_wait(&r_full[st], ph);
+      ptx::tc_fence_after();
+      // the S columns are free: the previous item's last P V were issued before (the tensor pipe runs in order)
+      issue_qk(0, st);
+      issue_qk(1, st);
+      ptx::umma_commit(&r_empty[st]);
+      if (n_tiles == 1) ptx::umma_commit(q_empty);
+      advance();
+      for (int j = 0; j < n_tiles; ++j, ++sc) {
+        const int v_slot = st;
+        ptx::mbar_wait(&r_full[v_slot], ph);
+        advance();
+        const int k_slot = st;  // K_{j+1}
+        const uint32_t k_ph = ph;
+        const bool more = j + 1 < n_tiles;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          ptx::mbar_wait(&p_full[t], sc & 1);
+          if (j == 0 && k > 0) ptx::mbar_wait(&o_empty[t], (k - 1) & 1);  // the epilogue has drained O_t
+          ptx::tc_fence_after();
+          if (k == 0) LC_TRACE(0, j, 2 * t);
+          issue_pv(t, v_slot, j == 0);
+          if (!more) ptx::umma_commit(&o_full[t]);
+          if (t == 1) ptx::umma_commit(&r_empty[v_slot]);
+          if (more) {
+            if (t == 0) {
+              ptx::mbar_wait(&r_full[k_slot], k_ph);
+              ptx::tc_fence_after();
+            }
+            issue_qk(t, k_slot);
+            if (t == 1) {
+              ptx::umma_commit(&r_empty[k_slot]);
+              if (j + 2 == n_tiles) ptx::umma_commit(q_empty);  // the item's last S tiles: Q may be replaced
+            }
+          }
+          if (k == 0) LC_TRACE(0, j, 2 * t + 1);
+        }
+        if (more) advance();
+      }
+      advance();  // the slot behind V_{n-1} is the item's output staging tile (owned by the softmax warps)
+    }
+  } else if (warp >= 2) {
+    // ===================== softmax + epilogue =====================
+    const int idx = warp - 2;
+    const int t = idx >> 3;          // 0: tile A (warps 2-9), 1: tile B (warps 10-17)
+    const int hh = (idx >> 2) & 1;   // key half of the row this thread exponentiates
+    const int quarter = warp & 3;    // TMEM lane quarter this warp may access (= warp id % 4)
+    if (idx & 7) trace = nullptr;    // one traced warp per tile
+    const int r = quarter * 32 + lane;
+    const uint32_t pair_bar = 1 + t * 4 + quarter;  // named barrier of the two warps sharing these 32 rows
+    const uint32_t tile_bar = 9 + t;                // named barrier of the tile's 8 warps
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const float scale_log2 = 0.08838834764831845f * 1.4426950408889634f;
+    const uint32_t s_addr = tmem_base + lane_addr + COL_S + static_cast<uint32_t>(t * 128);
+    const uint32_t o_addr = tmem_base + lane_addr + COL_O + static_cast<uint32_t>(t * 128 + hh * 64);
+    uint32_t sc = 0;
+    int k = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++k) {
+      const int qb = item % n_qb, bh = item / n_qb;
+      const int h = bh % heads, b = bh / heads;
+      const int q0 = qb * (2 * BQ);
+      long long* tr = k == 0 ? trace : nullptr;
+      float m_used = -INFINITY, l = 0.f;
+      for (int j = 0; j < n_tiles; ++j, ++sc) {
+        if (tr != nullptr) tr[((1 + t) * 64 + j) * 4 + 0] = clock64();
+        ptx::mbar_wait(&s_full[t], sc & 1);
+        ptx::tc_fence_after();
+        if (tr != nullptr) tr[((1 + t) * 64 + j) * 4 + 1] = clock64();
+        const int n_valid = S - j * BKV;  // keys >= n_valid are padding (only ever true for the last tile)
+        uint32_t sreg[2][32];
+        ptx::tmem_ld32(s_addr + hh * 64, sreg[0]);
+        ptx::tmem_ld32(s_addr + hh * 64 + 32, sreg[1]);
+        ptx::tmem_ld_wait();
+        if (n_valid < BKV) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (hh * 64 + c * 32 + i >= n_valid) sreg[c][i] = 0xff800000u;  // -inf
+        }
+        float mxs[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mxs[i & 3] = fmaxf(mxs[i & 3], __uint_as_float(sreg[c][i]));
+        float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
+        xch[(t * 2 + hh) * 128 + r] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        mx = fmaxf(mx, xch[(t * 2 + (1 - hh)) * 128 + r]);
+        if (tr != nullptr) tr[((1 + t) * 64 + j) * 4 + 2] = clock64();
+        const float m_new = fmaxf(m_used, mx * scale_log2);
+        const bool need = __any_sync(0xffffffffu, m_new > m_used + RESCALE_THRESHOLD);
+        float alpha = 1.f;
+        if (need) {
+          alpha = (m_used == -INFINITY) ? 0.f : exp2f(m_used - m_new);
+          m_used = m_new;
+        }
+        const float neg_m = -m_used;
+        float ps[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 64; i += 2) {
+          const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(sreg[i >> 5][i & 31]), scale_log2, neg_m));
+          const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(sreg[i >> 5][(i & 31) + 1]), scale_log2, neg_m));
+          ps[(i >> 1) & 3] += p0 + p1;
+          __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&pb);
+        }
+        if (need && j > 0) {  // rare: rescale this thread's 64 columns of O (quiescent: PV_t(j-1) has completed)
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            ptx::tmem_ld32(o_addr + c * 32, o);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            ptx::tmem_st32(o_addr + c * 32, o);
+          }
+        }
+        ptx::tmem_st32(s_addr + hh * 32, pk);
+        l = l * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&p_full[t]);
+        if (tr != nullptr) tr[((1 + t) * 64 + j) * 4 + 3] = clock64();
+      }
+      // ---- epilogue of the item: O_t / l -> bf16 -> swizzled staging tile -> TMA tensor stores
+      ptx::mbar_wait(&o_full[t], k & 1);
+      ptx::tc_fence_after();
+      if (tr != nullptr) tr[(3 * 64 + 0) * 4 + 2] = clock64();
+      xch[(t * 2 + hh) * 128 + r] = l;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      const float inv = 1.0f / (l + xch[(t * 2 + (1 - hh)) * 128 + r]);
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // both have read before the slots are reused
+      // staging tile = ring position k * (2 n + 1) + 2 n (behind the item's last V); tile A first, then tile B
+      const int pos = k * (2 * n_tiles + 1) + 2 * n_tiles;
+      const int stg_slot = pos % RING_P;
+      ptx::mbar_wait(&r_full[stg_slot], (pos / RING_P) & 1);
+      if (t == 1) ptx::mbar_wait(stg_empty, k & 1);  // tile A's stores have read the tile
+      uint8_t* sO = sR + stg_slot * TILE_BYTES;
+      uint8_t* srow = sO + hh * SUB_BYTES + r * 128;
+      // The one tile per (sample, head) that straddles the pred | cond boundary: its pred rows go through the TMA store
+      // (clipped at Np), its cond rows would need a negative start coordinate in the cond map, so the few threads that
+      // own them store their 128 bytes directly.
+      const int tok0 = q0 + t * BQ, tok = tok0 + r;
+      bf16* direct = nullptr;
+      if (has_cond && tok0 < Np && tok >= Np && tok < S)
+        direct = out_c + (static_cast<long long>(b) * (S - Np) + (tok - Np)) * d + h * HD + hh * 64;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        ptx::tmem_ld32(o_addr + c * 32, o);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 pkt;
+          __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+          __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+          __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+          __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+          pkt.x = *reinterpret_cast<uint32_t*>(&t0);
+          pkt.y = *reinterpret_cast<uint32_t*>(&t1);
+          pkt.z = *reinterpret_cast<uint32_t*>(&t2);
+          pkt.w = *reinterpret_cast<uint32_t*>(&t3);
+          const int chunk = c * 4 + (i >> 3);  // 16-byte chunk of the 128-byte row, 128B-swizzled like a TMA tile
+          *reinterpret_cast<uint4*>(srow + ((chunk ^ (r & 7)) << 4)) = pkt;
+          if (direct != nullptr) *reinterpret_cast<uint4*>(direct + c * 32 + i) = pkt;
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&o_empty[t]);  // O_t may be overwritten by the next item's first P V
+      ptx::fence_proxy_async();                      // staging writes -> visible to the TMA (async proxy)
+      asm volatile("bar.sync %0, 256;" ::"r"(tile_bar) : "memory");
+      if ((idx & 7) == 0 && lane == 0) {
+        // rows beyond the stream's length are clipped by the tensor map (coordinates are never negative)
+        if (tok0 < Np) {
+          ptx::tma_store_3d(&tm_p, sO, h * HD, tok0, b);
+          ptx::tma_store_3d(&tm_p, sO + SUB_BYTES, h * HD + 64, tok0, b);
+        } else if (has_cond && tok0 < S) {
+          ptx::tma_store_3d(&tm_c, sO, h * HD, tok0 - Np, b);
+          ptx::tma_store_3d(&tm_c, sO + SUB_BYTES, h * HD + 64, tok0 - Np, b);
+        }
+        ptx::bulk_commit();
+        ptx::bulk_wait_read();
+        if (t == 0) ptx::mbar_arrive(stg_empty);           // tile B may write the staging tile now
+        else ptx::mbar_arrive(&r_empty[stg_slot]);         // back to the producer: the slot carries K/V again
+        if (tr != nullptr) tr[(3 * 64 + 0) * 4 + 3] = clock64();
+      }
+    }
   }
 
   ptx::tc_fence_before();
@@ -316,19 +657,61 @@ int attention_set_trace(long long* buf) {
 int attention_bf16(const bf16* qkv, int B, int S, int heads, int head_dim, bf16* out_p, int Np, bf16* out_c,
                    cudaStream_t s) {
   LC_REQUIRE(head_dim == HD, "attention: head_dim must be 128");
-  static PerDevice<bool> attr_set;
-  if (!attr_set.here()) {
-    LC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set.here() = true;
-  }
   const int d = heads * HD;
   CUtensorMap tm;
   LC_TRY(make_tmap_2d_bf16(&tm, qkv, static_cast<uint64_t>(3) * d, static_cast<uint64_t>(B) * S,
                            static_cast<uint64_t>(3) * d * 2, 64, 128));
-  dim3 grid(ceil_div(S, 2 * BQ), heads, B);
+  const double flops = 4.0 * B * heads * static_cast<double>(S) * S * HD, bytes = 8.0 * B * S * d;  // q, k, v in + o out
+  static const int variant = [] { const char* e = getenv("LADCAST_B200_ATTN"); return (e != nullptr && e[0] == '6') ? 6 : 7; }();
+  if (variant == 6) {  // one work item per CTA (round 1)
+    static PerDevice<bool> attr_set;
+    if (!attr_set.here()) {
+      LC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      attr_set.here() = true;
+    }
+    dim3 grid(ceil_div(S, 2 * BQ), heads, B);
+    prof_begin(PROF_ATTN, s);
+    LC_CHECK_CUDA(launch_kernel(attention_tc_kernel, grid, NUM_THREADS, SMEM_BYTES, s, tm, S, heads, out_p, Np, out_c));
+    prof_end(PROF_ATTN, flops, s, bytes);
+    LC_LAUNCH_CHECK();
+    return 0;
+  }
+  // persistent: one CTA per SM over (sample, head, query block) items; outputs through 3-D TMA store maps
+  // {d, tokens of the stream, samples} so that the hardware clips rows past the stream's length
+  static PerDevice<bool> attr_set_p;
+  if (!attr_set_p.here()) {
+    LC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_P));
+    attr_set_p.here() = true;
+  }
+  if (Np == 0) {  // every token belongs to the second stream (context refiner): treat it as the only stream
+    out_p = out_c;
+    out_c = nullptr;
+    Np = S;
+  }
+  LC_REQUIRE(out_p != nullptr && Np >= 1 && Np <= S && (out_c != nullptr || Np == S), "attention: bad pred / cond split");
+  CUtensorMap tm_p, tm_c;
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(d), static_cast<uint64_t>(Np), static_cast<uint64_t>(B)};
+    uint64_t strides[2] = {static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(Np) * d * 2};
+    uint32_t box[3] = {64, 128, 1};
+    LC_TRY(make_tmap_bf16(&tm_p, out_p, 3, dims, strides, box));
+  }
+  const int has_cond = (Np < S) ? 1 : 0;
+  if (has_cond) {
+    uint64_t dims[3] = {static_cast<uint64_t>(d), static_cast<uint64_t>(S - Np), static_cast<uint64_t>(B)};
+    uint64_t strides[2] = {static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(S - Np) * d * 2};
+    uint32_t box[3] = {64, 128, 1};
+    LC_TRY(make_tmap_bf16(&tm_c, out_c, 3, dims, strides, box));
+  } else {
+    tm_c = tm_p;
+  }
+  const int n_qb = ceil_div(S, 2 * BQ);
+  const int n_items = n_qb * heads * B;
+  const int grid = n_items < num_sms() ? n_items : num_sms();
   prof_begin(PROF_ATTN, s);
-  LC_CHECK_CUDA(launch_kernel(attention_tc_kernel, grid, NUM_THREADS, SMEM_BYTES, s, tm, S, heads, out_p, Np, out_c));
-  prof_end(PROF_ATTN, 4.0 * B * heads * static_cast<double>(S) * S * HD, s, 8.0 * B * S * d);  // q, k, v in + o out (bf16)
+  LC_CHECK_CUDA(launch_kernel(attention_tc_persistent_kernel, dim3(grid), NUM_THREADS, SMEM_BYTES_P, s, tm, tm_p, tm_c, S, heads,
+                              n_qb, n_items, Np, has_cond, out_c));
+  prof_end(PROF_ATTN, flops, s, bytes);
   LC_LAUNCH_CHECK();
   return 0;
 }

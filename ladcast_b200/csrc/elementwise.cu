@@ -2,6 +2,7 @@
 // token pooling, gated residual, temb combine; and the fused scheduler steps.  All vectorised (128-bit) with
 // warp-shuffle reductions; fp32 statistics regardless of the storage type.
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -44,7 +45,11 @@ __device__ __forceinline__ float4 load4<bf16>(const bf16* p) {
 // ---------------------------------------------------------------- LayerNorm (+ AdaLN modulation | affine)
 // One warp per row at a time, the row (d = NV*128 floats) lives in registers; two-pass variance (biased), as
 // nn.LayerNorm.  Each warp walks over RPW consecutive rows with the next row's loads in flight while the current row is
-// normalised and stored (the one-row-per-warp version was DRAM-latency bound: 35 % of HBM peak).
+// normalised (in place) and stored (the one-row-per-warp version was DRAM-latency bound: 35 % of HBM peak).
+// Round 2 tried two shared-memory rings in front of this (cp.async per lane; one TMA bulk copy per row with a per-warp
+// mbarrier ring): both were SLOWER (3.0-3.4 TB/s stand-alone against 4.1 TB/s here; tools/bench_ln.py) — plain 128-bit
+// loads from 16 warps per SM keep more bytes in flight than 8 warps x 3 rows — so the register pipeline stays, now
+// without spills (the row is normalised in its buffer; d = 2048 runs one CTA per SM with the full register file).
 // Reference: AdaLayerNormZero/ZeroSingle/Continuous (diffusers), LaDCast_3D_model.py:287-302, 524-552, 1044.
 template <typename T, int NV>
 __device__ __forceinline__ void ln_row(float4 (&v)[NV], int row, int lane, T* __restrict__ out, int d, float eps,
@@ -83,56 +88,34 @@ __device__ __forceinline__ void ln_row(float4 (&v)[NV], int row, int lane, T* __
   }
 }
 
-constexpr int LN_STAGES = 3;   // rows of a warp in flight (bulk-async ring in shared memory)
+constexpr int LN_RPW = 4;  // rows per warp (8 measured slower: too few blocks for the 9000-row streams)
 
-// Each warp owns a contiguous range of rows and a private LN_STAGES-deep ring of row buffers in shared memory.  Lane 0
-// streams whole rows (d * 4 bytes, one contiguous cp.async.bulk = one TMA request per row) into the ring, completion
-// is signalled on a per-stage mbarrier; the warp normalises row r while rows r+1 .. r+LN_STAGES-1 are in flight.
-// The loads need neither registers nor LSU issue slots, so the row being processed (NV float4 per lane) fits without
-// spills (the register double buffer of round 1 spilled 300-800 B per thread at d = 1536 / 2048) and every SM keeps
-// 8 warps x 3 rows (144-192 KB) in flight.  The grid is one wave: rows are split evenly over all resident warps.
 template <typename T, int NV>
-__global__ void __launch_bounds__(256, 1)
-layernorm_kernel(const float* __restrict__ x, T* __restrict__ out, int M, int d, float eps, int rows_per_sample,
-                 int seg_rows, int seg_rows_per_sample, const float* __restrict__ scale, const float* __restrict__ shift,
-                 long long mod_stride, const float* __restrict__ w, const float* __restrict__ b, int rows_per_warp) {
+__global__ void __launch_bounds__(256, NV <= 12 ? 2 : 1) layernorm_kernel(const float* __restrict__ x, T* __restrict__ out, int M, int d,
+                                                           float eps, int rows_per_sample, int seg_rows,
+                                                           int seg_rows_per_sample, const float* __restrict__ scale,
+                                                           const float* __restrict__ shift, long long mod_stride,
+                                                           const float* __restrict__ w, const float* __restrict__ b) {
   pdl_grid_sync();
-  extern __shared__ __align__(128) uint8_t ln_smem[];
-  constexpr int ROW_BYTES = NV * 512;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4* ring = reinterpret_cast<float4*>(ln_smem) + warp * (LN_STAGES * NV * 32);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + 8 * LN_STAGES * ROW_BYTES) + warp * LN_STAGES;
-  const long long row0 = (static_cast<long long>(blockIdx.x) * 8 + warp) * rows_per_warp;
-  if (row0 >= M) return;  // warp-uniform; no block-wide barrier is used anywhere in this kernel
-  const int nrows = static_cast<int>(min(static_cast<long long>(rows_per_warp), M - row0));
-  if (lane == 0) {
+  const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * LN_RPW;
+  const int lane = threadIdx.x & 31;
+  if (row0 >= M) return;
+  const int nrows = min(LN_RPW, M - row0);
+  float4 buf[2][NV];
+  const float* xr = x + static_cast<long long>(row0) * d + lane * 4;
 #pragma unroll
-    for (int s = 0; s < LN_STAGES; ++s) ptx::mbar_init(&bars[s], 1);
-    ptx::fence_barrier_init();
-  }
-  __syncwarp();
-  const float* xr = x + row0 * d;
-  auto issue = [&](int r) {  // lane 0 only
-    const int st = r % LN_STAGES;
-    ptx::mbar_expect_tx(&bars[st], ROW_BYTES);
-    ptx::bulk_load(ring + st * (NV * 32), xr + static_cast<long long>(r) * d, ROW_BYTES, &bars[st]);
-  };
-  if (lane == 0) {
+  for (int i = 0; i < NV; ++i) buf[0][i] = *reinterpret_cast<const float4*>(xr + i * 128);
 #pragma unroll
-    for (int r = 0; r < LN_STAGES - 1; ++r)
-      if (r < nrows) issue(r);
-  }
-  for (int r = 0; r < nrows; ++r) {
-    // stage (r - 1) % LN_STAGES was read by every lane in the previous iteration (__syncwarp below): refill it
-    if (lane == 0 && r + LN_STAGES - 1 < nrows) issue(r + LN_STAGES - 1);
-    ptx::mbar_wait(&bars[r % LN_STAGES], (r / LN_STAGES) & 1);
-    float4 v[NV];
-    const float4* src = ring + (r % LN_STAGES) * (NV * 32) + lane;
+  for (int r = 0; r < LN_RPW; ++r) {
+    if (r < nrows) {
+      if (r + 1 < nrows) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = src[i * 32];
-    ln_row<T, NV>(v, static_cast<int>(row0) + r, lane, out, d, eps, rows_per_sample, seg_rows, seg_rows_per_sample, scale,
-                  shift, mod_stride, w, b);
-    __syncwarp();
+        for (int i = 0; i < NV; ++i)
+          buf[(r + 1) & 1][i] = *reinterpret_cast<const float4*>(xr + static_cast<long long>(r + 1) * d + i * 128);
+      }
+      ln_row<T, NV>(buf[r & 1], row0 + r, lane, out, d, eps, rows_per_sample, seg_rows, seg_rows_per_sample, scale, shift,
+                    mod_stride, w, b);
+    }
   }
 }
 
@@ -472,23 +455,13 @@ int layernorm_modulate(const float* x, T* out, int M, int d, float eps, int rows
                        int seg_rows, int seg_rows_per_sample) {
   LC_REQUIRE(d % 128 == 0 && d <= 2048, "layernorm: d must be a multiple of 128, <= 2048");
   const int nv = d / 128;
-  // one wave: the rows are split evenly over every warp that can be resident (8 warps per CTA, one CTA per SM)
-  const int warps = 8 * num_sms();
-  const int rpw = ceil_div(M, warps) < 4 ? 4 : ceil_div(M, warps);
-  dim3 grid(ceil_div(M, 8 * rpw));
+  dim3 grid(ceil_div(M, 8 * LN_RPW));
   ProfScope ps(PROF_LN, 0.0, static_cast<double>(M) * d * (4 + sizeof(T)), s);
 #define LC_LN_CASE(NV)                                                                                            \
-  case NV: {                                                                                                      \
-    constexpr int smem = 8 * LN_STAGES * NV * 512 + 8 * LN_STAGES * 8;                                            \
-    static PerDevice<bool> attr_set;                                                                              \
-    if (smem > 48 * 1024 && !attr_set.here()) {                                                                   \
-      LC_CHECK_CUDA(cudaFuncSetAttribute(layernorm_kernel<T, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-      attr_set.here() = true;                                                                                     \
-    }                                                                                                             \
-    LC_CHECK_CUDA(launch_kernel(layernorm_kernel<T, NV>, grid, 256, smem, s, x, out, M, d, eps, rows_per_sample, seg_rows, seg_rows_per_sample, \
-                                                    scale, shift, mod_stride, w, b, rpw));                              \
-    break;                                                                                                        \
-  }
+  case NV:                                                                                                        \
+    LC_CHECK_CUDA(launch_kernel(layernorm_kernel<T, NV>, grid, 256, 0, s, x, out, M, d, eps, rows_per_sample, seg_rows, \
+                                seg_rows_per_sample, scale, shift, mod_stride, w, b));                            \
+    break;
   switch (nv) {
     LC_LN_CASE(1) LC_LN_CASE(2) LC_LN_CASE(3) LC_LN_CASE(4) LC_LN_CASE(5) LC_LN_CASE(6) LC_LN_CASE(7) LC_LN_CASE(8)
     LC_LN_CASE(9) LC_LN_CASE(10) LC_LN_CASE(11) LC_LN_CASE(12) LC_LN_CASE(13) LC_LN_CASE(14) LC_LN_CASE(15)

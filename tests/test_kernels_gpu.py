@@ -92,3 +92,28 @@ def test_dpmpp2m_step(lib):
                                              _lib.stream()), "sched")
     torch.cuda.synchronize()
     assert _rel(x.cpu(), want) < 1e-6
+
+
+@pytest.mark.parametrize("rows,d,rps", [(37, 256, 10), (450, 1536, 450), (2250 * 3 + 5, 1536, 2250), (1000, 2048, 333)])
+@pytest.mark.parametrize("prec", [_lib.PRECISION_F32, _lib.PRECISION_BF16], ids=["f32", "bf16"])
+def test_layernorm_modulate(lib, rows, d, rps, prec):
+    """LayerNorm (no affine) + AdaLN modulation, and the affine variant, against torch in float64."""
+    g = torch.Generator("cpu").manual_seed(rows + d)
+    x = (torch.randn(rows, d, generator=g) * 2 + 0.3).cuda()
+    nb = (rows + rps - 1) // rps
+    mod = torch.randn(nb, 3 * d, generator=g).cuda() * 0.5
+    w, b = torch.randn(d, generator=g).cuda(), torch.randn(d, generator=g).cuda()
+    dt = torch.float32 if prec == _lib.PRECISION_F32 else torch.bfloat16
+    tol = 2e-6 if prec == _lib.PRECISION_F32 else 4e-3
+    ln = torch.nn.functional.layer_norm(x.double(), (d,), eps=1e-6)
+    sample = torch.arange(rows, device="cuda") // rps
+    want_mod = ln * (1 + mod[sample, d : 2 * d].double()) + mod[sample, :d].double()
+    out = torch.full((rows, d), float("nan"), device="cuda", dtype=dt)
+    _lib.check(lib.lc_layernorm_modulate(prec, _lib.ptr(x), _lib.ptr(out), rows, d, 1e-6, rps, _lib.ptr_any(mod[:, d:]), _lib.ptr(mod),
+                                         3 * d, None, None, _lib.stream()), "lc_layernorm_modulate")
+    torch.cuda.synchronize()
+    assert _rel(out, want_mod) < tol
+    _lib.check(lib.lc_layernorm_modulate(prec, _lib.ptr(x), _lib.ptr(out), rows, d, 1e-6, 1 << 30, None, None, 0, _lib.ptr(w),
+                                         _lib.ptr(b), _lib.stream()), "lc_layernorm_modulate")
+    torch.cuda.synchronize()
+    assert _rel(out, ln * w.double() + b.double()) < tol

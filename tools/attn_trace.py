@@ -10,7 +10,7 @@ qkv = torch.randn(b, s, 3 * d, device="cuda").bfloat16()
 out = torch.empty(b, s, d, device="cuda", dtype=torch.bfloat16)
 for _ in range(2):
     _lib.check(lib.lc_attention(0, _lib.ptr(qkv), _lib.ptr(out), b, s, h, _lib.stream()))
-tr = torch.zeros(3, 64, 4, dtype=torch.int64, device="cuda")
+tr = torch.zeros(4, 64, 4, dtype=torch.int64, device="cuda")
 lib.lc_debug_attention_trace.argtypes = [ctypes.c_void_p]
 lib.lc_debug_attention_trace(_lib.ptr(tr))
 _lib.check(lib.lc_attention(0, _lib.ptr(qkv), _lib.ptr(out), b, s, h, _lib.stream()))
@@ -27,3 +27,8 @@ for j in range(n):
     print(f"{j:3d} | {m[0]:7d} {m[1]:7d} {m[2]:7d} {m[3]:7d} | {a[0]:7d} {a[1]:7d} {a[2]:7d} {a[3]:7d} | {bb[0]:7d} {bb[1]:7d} {bb[2]:7d} {bb[3]:7d}")
 print("softmax A: wait-for-S / load / compute per step:",
       [(int(t[1, j, 1] - t[1, j, 0]), int(t[1, j, 2] - t[1, j, 1]), int(t[1, j, 3] - t[1, j, 2])) for j in range(4, 10)])
+life = [int(x) - int(t[3, 0, 0]) for x in t[3, 0]]
+steady = (int(t[0, n - 2, 0]) - int(t[0, 3, 0])) / (n - 5)
+print(f"CTA life cycle (cycles from entry): set-up done {life[1]}, first S wait {t0 - int(t[3, 0, 0])}, O complete {life[2]}, "
+      f"last store issued {life[3]}; steady-state step {steady:.0f} cycles; {n} steps -> "
+      f"{100 * (1 - n * steady / max(1, life[3])):.1f} % of the CTA's life is prologue / epilogue / pipeline fill")
