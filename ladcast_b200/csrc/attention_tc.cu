@@ -324,13 +324,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
 //   * the epilogue no longer issues 16-byte stores scattered over 128 rows per warp instruction (LSU-bound, ~7.6 k
 //     cycles): O / l is packed to bf16 into a swizzled 32 KB staging tile and written by TMA tensor stores (3-D maps
 //     {d, tokens of the stream, samples}: rows past the stream's token count are clipped by the hardware, which also
-//     splits a tile that straddles the pred | cond boundary).  The staging tile is one slot of the K/V ring: the
-//     producer passes the slot that follows V_{n-1} of every item to the softmax warps instead of filling it (ring
-//     order K_0 V_0 ... K_{n-1} V_{n-1} [O staging]), tile A then tile B use it, and tile B's store releases it — so
-//     all 5 slots carry K/V in the steady state and no extra shared memory is needed.
+//     splits a tile that straddles the pred | cond boundary).  The staging tiles are slots of the K/V ring: the
+//     producer passes the two slots that follow V_{n-1} of every item to the softmax warps instead of filling them
+//     (ring order K_0 V_0 ... K_{n-1} V_{n-1} [O_A staging] [O_B staging]) — all 5 slots carry K/V in the steady
+//     state and no extra shared memory is needed;
+//   * the thread that issues a tile's TMA stores does not wait for them: it returns the staging slot to the producer
+//     (cp.async.bulk.wait_group.read + arrive) only after the wait for the next item's first S tile, when the ~1.9 k
+//     cycles the stores need to drain the tile have long passed.  (A dedicated 19th store warp was tried instead: the
+//     item boundary got 1-2.7 k cycles shorter but every softmax step 180 cycles longer — no net gain.)
 // Shared memory: Q 2 x 32 KB, ring 5 x 32 KB (as the one-item kernel).
 constexpr int RING_P = 5;
 constexpr int SMEM_BYTES_P = 2 * TILE_BYTES + RING_P * TILE_BYTES + 256 + XCH_BYTES;
+constexpr int NUM_THREADS_P = NUM_THREADS;
 
 __global__ void __maxnreg__(96)
 attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_p,
@@ -349,8 +354,7 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __g
   uint64_t* p_full = s_full + 2;             // [tile] (8 arrivals: one per softmax warp)
   uint64_t* o_full = p_full + 2;             // [tile]
   uint64_t* o_empty = o_full + 2;            // [tile] (8 arrivals)
-  uint64_t* stg_empty = o_empty + 2;         // 1: tile A's store has read the staging slot (tile B may write it)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_empty + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
   float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -375,7 +379,6 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __g
       ptx::mbar_init(&o_full[i], 1);
       ptx::mbar_init(&o_empty[i], 8);
     }
-    ptx::mbar_init(stg_empty, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -414,35 +417,54 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __g
           if (++st == RING_P) { st = 0; ph ^= 1; }
         }
       }
-      // the slot behind V_{n-1} is handed to the softmax warps as the item's output staging tile
-      ptx::mbar_wait(&r_empty[st], ph ^ 1);
-      ptx::mbar_arrive(&r_full[st]);
-      if (++st == RING_P) { st = 0; ph ^= 1; }
+      // the two slots behind V_{n-1} are handed to the softmax warps as the item's output staging tiles (A, B)
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        ptx::mbar_wait(&r_empty[st], ph ^ 1);
+        ptx::mbar_arrive(&r_full[st]);
+        if (++st == RING_P) { st = 0; ph ^= 1; }
+      }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // The whole warp walks the loop converged (waits, counters, addresses are warp-uniform) and ONE elected lane issues:
+    // inside an elect.sync region the compiler keeps descriptors in uniform registers, so a K-step costs ~4 SASS
+    // instructions.  With the loop inside `if (lane == 0)` every MMA was preceded by a ~15-instruction
+    // ELECT / R2UR.BROADCAST sequence and the issue thread, not the tensor pipe, set the pace (81-94 cycles per M128
+    // MMA against the 68 the pipe needs).
     constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(128, BKV, 0, 0);  // A = Q (K-major), B = K (K-major)
     constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(128, HD, 0, 1);   // A = P (TMEM), B = V (MN-major)
+    constexpr uint32_t desc_hi = ptx::smem_desc_hi(1024);
     const uint32_t q_addr = ptx::smem_u32(sQ), r_addr = ptx::smem_u32(sR);
     auto issue_qk = [&](int t, int slot) {
-      const uint32_t k_addr = r_addr + slot * TILE_BYTES;
+      const uint32_t a_lo = ptx::smem_desc_lo(q_addr + t * TILE_BYTES, 16);
+      const uint32_t b_lo = ptx::smem_desc_lo(r_addr + slot * TILE_BYTES, 16);
       const uint32_t d_tmem = tmem_base + COL_S + static_cast<uint32_t>(t * 128);
+      if (ptx::elect_one()) {
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        const uint32_t off = (kk >> 2) * SUB_BYTES + (kk & 3) * 32;
-        ptx::umma_f16(d_tmem, ptx::make_smem_desc(q_addr + t * TILE_BYTES + off, 16, 1024),
-                      ptx::make_smem_desc(k_addr + off, 16, 1024), idesc_qk, kk != 0 ? 1u : 0u);
+        for (int kk = 0; kk < 8; ++kk) {  // 128 head dims = 2 sub-tiles x 4 K-steps of 16
+          const uint32_t off = ((kk >> 2) * SUB_BYTES + (kk & 3) * 32) >> 4;
+          ptx::umma_f16_lh(d_tmem, a_lo + off, b_lo + off, desc_hi, idesc_qk, kk != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&s_full[t]);
       }
-      ptx::umma_commit(&s_full[t]);
+      __syncwarp();
     };
     auto issue_pv = [&](int t, int slot, bool first) {
-      const uint32_t v_addr = r_addr + slot * TILE_BYTES;
+      const uint32_t b_lo = ptx::smem_desc_lo(r_addr + slot * TILE_BYTES, SUB_BYTES);
       const uint32_t d_tmem = tmem_base + COL_O + static_cast<uint32_t>(t * 128);
       const uint32_t a_tmem = tmem_base + COL_S + static_cast<uint32_t>(t * 128);
+      if (ptx::elect_one()) {
 #pragma unroll
-      for (int kk = 0; kk < BKV / 16; ++kk)
-        ptx::umma_f16_ts(d_tmem, a_tmem + kk * 8, ptx::make_smem_desc(v_addr + kk * 2048, SUB_BYTES, 1024), idesc_pv,
-                         (first && kk == 0) ? 0u : 1u);
+        for (int kk = 0; kk < BKV / 16; ++kk)  // 128 keys = 8 K-steps of 16 (16 key rows x 128 B = 2 KB per sub-tile)
+          ptx::umma_f16_ts_lh(d_tmem, a_tmem + kk * 8, b_lo + ((kk * 2048) >> 4), desc_hi, idesc_pv,
+                              (first && kk == 0) ? 0u : 1u);
+      }
+      __syncwarp();
+    };
+    auto commit = [&](uint64_t* bar) {
+      if (ptx::elect_one()) ptx::umma_commit(bar);
+      __syncwarp();
     };
     int st = 0, k = 0;
     uint32_t ph = 0, sc = 0;  // sc: running (item, step) count = phase counter of s_full / p_full
@@ -454,8 +476,8 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __g
       // the S columns are free: the previous item's last P V were issued before (the tensor pipe runs in order)
       issue_qk(0, st);
       issue_qk(1, st);
-      ptx::umma_commit(&r_empty[st]);
-      if (n_tiles == 1) ptx::umma_commit(q_empty);
+      commit(&r_empty[st]);
+      if (n_tiles == 1) commit(q_empty);
       advance();
       for (int j = 0; j < n_tiles; ++j, ++sc) {
         const int v_slot = st;
@@ -471,8 +493,8 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __g
           ptx::tc_fence_after();
           if (k == 0) LC_TRACE(0, j, 2 * t);
           issue_pv(t, v_slot, j == 0);
-          if (!more) ptx::umma_commit(&o_full[t]);
-          if (t == 1) ptx::umma_commit(&r_empty[v_slot]);
+          if (!more) commit(&o_full[t]);
+          if (t == 1) commit(&r_empty[v_slot]);
           if (more) {
             if (t == 0) {
               ptx::mbar_wait(&r_full[k_slot], k_ph);
@@ -480,15 +502,16 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __g
             }
             issue_qk(t, k_slot);
             if (t == 1) {
-              ptx::umma_commit(&r_empty[k_slot]);
-              if (j + 2 == n_tiles) ptx::umma_commit(q_empty);  // the item's last S tiles: Q may be replaced
+              commit(&r_empty[k_slot]);
+              if (j + 2 == n_tiles) commit(q_empty);  // the item's last S tiles: Q may be replaced
             }
           }
           if (k == 0) LC_TRACE(0, j, 2 * t + 1);
         }
         if (more) advance();
       }
-      advance();  // the slot behind V_{n-1} is the item's output staging tile (owned by the softmax warps)
+      advance();  // the two slots behind V_{n-1} are the item's output staging tiles (owned by the softmax warps)
+      advance();
     }
   } else if (warp >= 2) {
     // ===================== softmax + epilogue =====================
@@ -500,6 +523,8 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __g
     const int r = quarter * 32 + lane;
     const uint32_t pair_bar = 1 + t * 4 + quarter;  // named barrier of the two warps sharing these 32 rows
     const uint32_t tile_bar = 9 + t;                // named barrier of the tile's 8 warps
+    const bool storer = (idx & 7) == 0 && lane == 0;  // issues the tile's TMA stores
+    int pending_slot = -1;                            // staging slot whose stores may still be reading it
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const float scale_log2 = 0.08838834764831845f * 1.4426950408889634f;
     const uint32_t s_addr = tmem_base + lane_addr + COL_S + static_cast<uint32_t>(t * 128);
@@ -517,6 +542,12 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __g
         ptx::mbar_wait(&s_full[t], sc & 1);
         ptx::tc_fence_after();
         if (tr != nullptr) tr[((1 + t) * 64 + j) * 4 + 1] = clock64();
+        if (trace != nullptr && k == 1 && j == 0) trace[(3 * 64 + 1 + t) * 4 + 3] = clock64();  // next item's first S ready
+        if (pending_slot >= 0) {  // (storer only) the previous item's stores have drained the staging tile by now
+          ptx::bulk_wait_read();
+          ptx::mbar_arrive(&r_empty[pending_slot]);  // back to the producer: the slot carries K/V again
+          pending_slot = -1;
+        }
         const int n_valid = S - j * BKV;  // keys >= n_valid are padding (only ever true for the last tile)
         uint32_t sreg[2][32];
         ptx::tmem_ld32(s_addr + hh * 64, sreg[0]);
@@ -579,16 +610,17 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __g
       // ---- epilogue of the item: O_t / l -> bf16 -> swizzled staging tile -> TMA tensor stores
       ptx::mbar_wait(&o_full[t], k & 1);
       ptx::tc_fence_after();
+      if (tr != nullptr) tr[(3 * 64 + 3 + t) * 4 + 0] = clock64();  // O_t complete
       if (tr != nullptr) tr[(3 * 64 + 0) * 4 + 2] = clock64();
       xch[(t * 2 + hh) * 128 + r] = l;
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
       const float inv = 1.0f / (l + xch[(t * 2 + (1 - hh)) * 128 + r]);
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");  // both have read before the slots are reused
-      // staging tile = ring position k * (2 n + 1) + 2 n (behind the item's last V); tile A first, then tile B
-      const int pos = k * (2 * n_tiles + 1) + 2 * n_tiles;
+      // staging tile of tile t = ring position k * (2 n + 2) + 2 n + t (behind the item's last V)
+      const int pos = k * (2 * n_tiles + 2) + 2 * n_tiles + t;
       const int stg_slot = pos % RING_P;
       ptx::mbar_wait(&r_full[stg_slot], (pos / RING_P) & 1);
-      if (t == 1) ptx::mbar_wait(stg_empty, k & 1);  // tile A's stores have read the tile
+      if (tr != nullptr) tr[(3 * 64 + 1 + t) * 4 + 0] = clock64();
       uint8_t* sO = sR + stg_slot * TILE_BYTES;
       uint8_t* srow = sO + hh * SUB_BYTES + r * 128;
       // The one tile per (sample, head) that straddles the pred | cond boundary: its pred rows go through the TMA store
@@ -622,9 +654,11 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __g
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&o_empty[t]);  // O_t may be overwritten by the next item's first P V
-      ptx::fence_proxy_async();                      // staging writes -> visible to the TMA (async proxy)
+      if (tr != nullptr) tr[(3 * 64 + 1 + t) * 4 + 1] = clock64();
+      ptx::fence_proxy_async();  // staging writes -> visible to the TMA (async proxy)
       asm volatile("bar.sync %0, 256;" ::"r"(tile_bar) : "memory");
-      if ((idx & 7) == 0 && lane == 0) {
+      if (tr != nullptr) tr[(3 * 64 + 1 + t) * 4 + 2] = clock64();
+      if (storer) {
         // rows beyond the stream's length are clipped by the tensor map (coordinates are never negative)
         if (tok0 < Np) {
           ptx::tma_store_3d(&tm_p, sO, h * HD, tok0, b);
@@ -634,11 +668,13 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __g
           ptx::tma_store_3d(&tm_c, sO + SUB_BYTES, h * HD + 64, tok0 - Np, b);
         }
         ptx::bulk_commit();
-        ptx::bulk_wait_read();
-        if (t == 0) ptx::mbar_arrive(stg_empty);           // tile B may write the staging tile now
-        else ptx::mbar_arrive(&r_empty[stg_slot]);         // back to the producer: the slot carries K/V again
+        pending_slot = stg_slot;
         if (tr != nullptr) tr[(3 * 64 + 0) * 4 + 3] = clock64();
       }
+    }
+    if (pending_slot >= 0) {  // last item: the stores must have read the tile before the CTA's shared memory goes away
+      ptx::bulk_wait_read();
+      ptx::mbar_arrive(&r_empty[pending_slot]);
     }
   }
 
@@ -709,7 +745,7 @@ int attention_bf16(const bf16* qkv, int B, int S, int heads, int head_dim, bf16*
   const int n_items = n_qb * heads * B;
   const int grid = n_items < num_sms() ? n_items : num_sms();
   prof_begin(PROF_ATTN, s);
-  LC_CHECK_CUDA(launch_kernel(attention_tc_persistent_kernel, dim3(grid), NUM_THREADS, SMEM_BYTES_P, s, tm, tm_p, tm_c, S, heads,
+  LC_CHECK_CUDA(launch_kernel(attention_tc_persistent_kernel, dim3(grid), NUM_THREADS_P, SMEM_BYTES_P, s, tm, tm_p, tm_c, S, heads,
                               n_qb, n_items, Np, has_cond, out_c));
   prof_end(PROF_ATTN, flops, s, bytes);
   LC_LAUNCH_CHECK();

@@ -32,3 +32,10 @@ steady = (int(t[0, n - 2, 0]) - int(t[0, 3, 0])) / (n - 5)
 print(f"CTA life cycle (cycles from entry): set-up done {life[1]}, first S wait {t0 - int(t[3, 0, 0])}, O complete {life[2]}, "
       f"last store issued {life[3]}; steady-state step {steady:.0f} cycles; {n} steps -> "
       f"{100 * (1 - n * steady / max(1, life[3])):.1f} % of the CTA's life is prologue / epilogue / pipeline fill")
+if int(t[3, 1, 0]) > 0:  # persistent kernel: item boundary of the first item (cycles from CTA entry)
+    e = int(t[3, 0, 0])
+    for tt, nm in ((0, "A"), (1, "B")):
+        print(f"tile {nm}: O complete {int(t[3, 3 + tt, 0]) - e}, staging acquired {int(t[3, 1 + tt, 0]) - e}, staging written "
+              f"{int(t[3, 1 + tt, 1]) - e}, tile barrier passed {int(t[3, 1 + tt, 2]) - e}, stores read {int(t[3, 3 + tt, 1]) - e}, "
+              f"first S of the next item seen {int(t[3, 1 + tt, 3]) - e}")
+    print(f"last softmax step of item 0 ends at A {int(t[1, n - 1, 3]) - e} / B {int(t[2, n - 1, 3]) - e}")
