@@ -596,9 +596,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // the whole warp walks the loop converged and one elected lane issues: inside an elect.sync region the compiler
+    // keeps the descriptors in uniform registers (1-3 SASS instructions between MMAs instead of a ~20-instruction
+    // ELECT / R2UR.BROADCAST sequence per MMA)
     constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, 0, 0);
+    constexpr uint32_t desc_hi = ptx::smem_desc_hi(1024);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -610,18 +614,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t a_base = ptx::smem_u32(smem_a + stage * C::STAGE_A);
-        const uint32_t b_base = ptx::smem_u32(smem_b + stage * C::STAGE_B);
+        const uint32_t a_lo = ptx::smem_desc_lo(ptx::smem_u32(smem_a + stage * C::STAGE_A), 16);
+        const uint32_t b_lo = ptx::smem_desc_lo(ptx::smem_u32(smem_b + stage * C::STAGE_B), 16);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-          const uint64_t da = ptx::make_smem_desc(a_base + kk * UMMA_K * 2, 16, 1024);
-          const uint64_t db = ptx::make_smem_desc(b_base + kk * UMMA_K * 2, 16, 1024);
-          ptx::umma_f16(d_tmem, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < BK / UMMA_K; ++kk)
+            ptx::umma_f16_lh(d_tmem, a_lo + ((kk * UMMA_K * 2) >> 4), b_lo + ((kk * UMMA_K * 2) >> 4), desc_hi, idesc,
+                             (kb | kk) != 0 ? 1u : 0u);
+          ptx::umma_commit(&empty_bar[stage]);
+          if (kb == num_kb - 1) ptx::umma_commit(&tmem_full[acc]);
         }
-        ptx::umma_commit(&empty_bar[stage]);
+        __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
-      ptx::umma_commit(&tmem_full[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= EPI_WARP0) {
@@ -768,14 +773,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0 && leader) {
+  } else if (warp == 1 && leader) {
     // ===================== MMA issuer (leader CTA only) =====================
+    // converged warp + elect.sync-guarded issue (uniform-datapath descriptors), as in the single-CTA kernel
     constexpr uint32_t idesc = ptx::make_idesc_bf16(2 * BM, BN, 0, 0);
+    constexpr uint32_t desc_hi = ptx::smem_desc_hi(1024);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    long long* trace = pair_id == 0 ? g_gemm_trace : nullptr;
+    long long* trace = (pair_id == 0 && lane == 0) ? g_gemm_trace : nullptr;
     int tix = 0;
     for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++tix) {
       if (trace != nullptr && tix < 64) trace[tix * 4 + 0] = clock64();
@@ -787,18 +794,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
         if (trace != nullptr && tix < 64 && kb == 0) trace[tix * 4 + 2] = clock64();
-        const uint32_t a_base = ptx::smem_u32(smem_a + stage * C::STAGE_A);
-        const uint32_t b_base = ptx::smem_u32(smem_b + stage * C::STAGE_B);
+        const uint32_t a_lo = ptx::smem_desc_lo(ptx::smem_u32(smem_a + stage * C::STAGE_A), 16);
+        const uint32_t b_lo = ptx::smem_desc_lo(ptx::smem_u32(smem_b + stage * C::STAGE_B), 16);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-          const uint64_t da = ptx::make_smem_desc(a_base + kk * UMMA_K * 2, 16, 1024);
-          const uint64_t db = ptx::make_smem_desc(b_base + kk * UMMA_K * 2, 16, 1024);
-          ptx::umma_f16_pair(d_tmem, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < BK / UMMA_K; ++kk)
+            ptx::umma_f16_pair_lh(d_tmem, a_lo + ((kk * UMMA_K * 2) >> 4), b_lo + ((kk * UMMA_K * 2) >> 4), desc_hi, idesc,
+                                  (kb | kk) != 0 ? 1u : 0u);
+          ptx::umma_commit_pair(&empty_bar[stage]);
+          if (kb == num_kb - 1) ptx::umma_commit_pair(&tmem_full[acc]);
         }
-        ptx::umma_commit_pair(&empty_bar[stage]);
+        __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
-      ptx::umma_commit_pair(&tmem_full[acc]);
       if (trace != nullptr && tix < 64) trace[tix * 4 + 3] = clock64();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
