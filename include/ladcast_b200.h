@@ -111,6 +111,9 @@ LC_API int lc_sched_dpmpp2m_step(const float* f, float* x, float* x0_prev, float
 LC_API int lc_sched_scale_input(const float* x, float* x_in, int64_t n, float c_in, void* stream);
 /* Heun prologue (edm_sampler.py:44-58): x = float64(noise) * t_0 ; x_in = float32(x * c_in(t_0)) */
 LC_API int lc_sched_heun_init(const float* noise, double* x, float* x_in, int64_t n, double t0, double c_in, void* stream);
+/* Heun stochastic churn (edm_sampler.py:67-76, deterministic=False): x += k * noise (fp64, k = sqrt(t_hat^2 - t_cur^2) *
+ * S_noise) ; x_in = float32(x * c_in(t_hat)) */
+LC_API int lc_sched_heun_churn(double* x, const double* noise, float* x_in, int64_t n, double k, double c_in, void* stream);
 /* AR feedback of roll_out_serial (pipelines/utils.py:560-585) on one sampler output samples[B, C, T_out, hw]
  * (normalised latents): known_next[B, C, T_in, hw] = the last T_in frames (may be NULL); phys[B, C, T_out, hw] =
  * (samples / target_std) * std[c] + mean[c] (inverse_normalize_transform_3D, dataloader/utils.py:233-240; may be

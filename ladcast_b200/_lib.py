@@ -50,6 +50,7 @@ _SIGNATURES = {
     "lc_debug_attention_trace": ([_vp], _i),
     "lc_sched_scale_input": ([_vp, _vp, _i64, _f, _vp], _i),
     "lc_sched_heun_init": ([_vp, _vp, _vp, _i64, _d, _d, _vp], _i),
+    "lc_sched_heun_churn": ([_vp, _vp, _vp, _i64, _d, _d, _vp], _i),
     "lc_latent_feedback": ([_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _vp], _i),
     "lc_denoiser_create": ([ctypes.POINTER(DenoiserCfg), ctypes.POINTER(_vp)], _i),
     "lc_denoiser_destroy": ([_vp], None),

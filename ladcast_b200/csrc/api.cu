@@ -122,6 +122,11 @@ int lc_sched_heun_init(const float* noise, double* x, float* x_in, int64_t n, do
   return sched_heun_init(noise, x, x_in, n, t0, c_in, static_cast<cudaStream_t>(stream));
 }
 
+int lc_sched_heun_churn(double* x, const double* noise, float* x_in, int64_t n, double k, double c_in, void* stream) {
+  LC_REQUIRE(x && noise && x_in, "null argument");
+  return sched_heun_churn(x, noise, x_in, n, k, c_in, static_cast<cudaStream_t>(stream));
+}
+
 int lc_latent_feedback(const float* samples, float* known_next, float* phys, const float* mean, const float* stdv,
                        float target_std, int batch, int channels, int t_out, int t_in, int hw, void* stream) {
   LC_REQUIRE(samples && (known_next || phys), "null argument");

@@ -419,6 +419,18 @@ __global__ void __launch_bounds__(256) heun_init_kernel(const float* __restrict_
   x_in[i] = static_cast<float>(v * c_in);
 }
 
+// Stochastic churn of the Heun sampler (edm_sampler.py:67-76, deterministic=False): x_hat = x_cur + k * noise with
+// k = sqrt(t_hat^2 - t_cur^2) * S_noise and float64 noise (randn_like of the fp64 state); x_in = float32(x_hat * c_in(t_hat)).
+__global__ void __launch_bounds__(256) heun_churn_kernel(double* __restrict__ x, const double* __restrict__ noise,
+                                                         float* __restrict__ x_in, long long n, double k, double c_in) {
+  pdl_grid_sync();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = x[i] + k * noise[i];
+  x[i] = v;
+  x_in[i] = static_cast<float>(v * c_in);
+}
+
 // AR feedback of roll_out_serial (pipelines/utils.py:560-585): from one sampler output [B, C, T, hw] (normalised
 // latents) write (a) the next step's conditioning = the last t_in frames [B, C, t_in, hw] (unchanged values) and
 // (b) optionally the de-normalised latents (x / target_std) * std[c] + mean[c] in the same layout
@@ -595,6 +607,13 @@ int sched_scale_input(const float* x, float* x_in, long long n, float c_in, cuda
 int sched_heun_init(const float* noise, double* x, float* x_in, long long n, double t0, double c_in, cudaStream_t s) {
   ProfScope ps(PROF_SCHED, 0.0, static_cast<double>(n) * 16.0, s);
   LC_CHECK_CUDA(launch_kernel(heun_init_kernel, static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s, noise, x, x_in, n, t0, c_in));
+  LC_LAUNCH_CHECK();
+  return 0;
+}
+
+int sched_heun_churn(double* x, const double* noise, float* x_in, long long n, double k, double c_in, cudaStream_t s) {
+  ProfScope ps(PROF_SCHED, 0.0, static_cast<double>(n) * 28.0, s);
+  LC_CHECK_CUDA(launch_kernel(heun_churn_kernel, static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, s, x, noise, x_in, n, k, c_in));
   LC_LAUNCH_CHECK();
   return 0;
 }

@@ -60,6 +60,7 @@ int sched_heun_step(const float* f, double* x, double* x_hat, double* d_cur, flo
 // x_in = x * c_in (scale_model_input of the first step); Heun prologue x = f64(noise) * t0, x_in = f32(x * c_in)
 int sched_scale_input(const float* x, float* x_in, long long n, float c_in, cudaStream_t s);
 int sched_heun_init(const float* noise, double* x, float* x_in, long long n, double t0, double c_in, cudaStream_t s);
+int sched_heun_churn(double* x, const double* noise, float* x_in, long long n, double k, double c_in, cudaStream_t s);
 // AR feedback: next conditioning frames + optional de-normalised copy of a sampler output [B, C, T, hw]
 int latent_feedback(const float* samples, float* known, float* phys, const float* mean, const float* stdv, float target,
                     int B, int C, int T, int t_in, int hw, cudaStream_t s);

@@ -97,6 +97,35 @@ def get_acc(forecast: torch.Tensor, truth: torch.Tensor, climate: torch.Tensor,
     return res if lat_weight is not None and torch.as_tensor(lat_weight).dtype == torch.float64 else res.to(torch.float32)
 
 
+def climatology_to_timeseries(clim, start_time, lead_time, interval=6, exclude_start=True, hours=(0, 6, 12, 18)):
+    """Array form of the reference's `climatology_to_timeseries` (evaluate/utils.py:152-201; xarray is not in this image):
+    `clim` [366 (dayofyear 1..366), len(hours), ...] (tensor or ndarray) -> ([nt, ...] climatology along the forecast
+    valid times start_time (+ interval) ... start_time + lead_time h, list of datetimes).  The selection is by
+    (dayofyear, hour) LABEL exactly like `ds.sel(dayofyear=..., hour=...)`: an hour that is not in `hours` raises."""
+    from datetime import datetime, timedelta
+
+    if clim.ndim < 2:
+        raise ValueError("Dataset must have both 'dayofyear' and 'hour' dims")
+    if isinstance(start_time, np.datetime64):
+        start = start_time.astype("datetime64[s]").astype(datetime)
+    else:
+        start = start_time if isinstance(start_time, datetime) else datetime.fromisoformat(str(start_time))
+    n = int(lead_time) // int(interval)
+    times = [start + timedelta(hours=int(interval) * k) for k in range(n + 1)]
+    if exclude_start:
+        times = times[1:]
+    hour_index = {int(h): i for i, h in enumerate(hours)}
+    try:
+        hi = [hour_index[t.hour] for t in times]
+    except KeyError as e:
+        raise KeyError(f"hour {e.args[0]} is not a climatology hour {tuple(hours)}") from None
+    di = [t.timetuple().tm_yday - 1 for t in times]
+    if isinstance(clim, torch.Tensor):
+        idx = (torch.as_tensor(di, device=clim.device), torch.as_tensor(hi, device=clim.device))
+        return clim[idx], times
+    return np.asarray(clim)[np.asarray(di), np.asarray(hi)], times
+
+
 def _tables_from_sums(sums, counts, n_pix, channels, leads, sst_channel):
     """sums/counts [4, C*T] fp64 -> dict of [C, T] fp64 tables: mean over pixels, nanmean for the SST channel, NaN
     propagation elsewhere (torch.mean semantics)."""

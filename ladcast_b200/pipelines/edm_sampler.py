@@ -1,6 +1,7 @@
 """Drop-in for `ladcast.pipelines.edm_sampler.edm_AR_sampler` (reference pipelines/edm_sampler.py:11-120): EDM Heun
 sampler, sampler state in float64, 2N-1 denoiser calls.  The fp64 predictor/corrector updates run in
-`lc_sched_heun_step`; stochastic churn (deterministic=False) is not part of the reference's call sites."""
+`lc_sched_heun_step`; the stochastic-churn branch (deterministic=False, edm_sampler.py:67-76) adds
+`lc_sched_heun_churn` before each predictor (noise drawn by the caller's `randn_like` on the fp64 state)."""
 from typing import List, Optional, Union
 
 import torch
@@ -19,14 +20,13 @@ def edm_AR_sampler(net, noise_scheduler, batch_size=1, return_seq_len=1, randn_l
             f"You have passed a list of generators of length {len(generator)}, but requested an effective batch"
             f" size of {batch_size}. Make sure the batch size matches the length of the generators.")
     assert known_latents is not None, "known_latents must be provided"
-    if not deterministic:
-        raise NotImplementedError("stochastic churn is not implemented (the reference always samples deterministically)")
     if isinstance(device, str):
         device = torch.device(device)
     shape = (batch_size, net.config.out_channels, return_seq_len, *known_latents.shape[-2:])
     latents = randn_tensor(shape, generator=generator, device=device, dtype=net.dtype)
     noise_scheduler.set_timesteps(num_inference_steps, device=device)
-    t_steps = noise_scheduler.sigmas.to(torch.float64)  # CPU, float32 values widened
+    sig32 = noise_scheduler.sigmas.to(torch.float32).cpu()
+    t_steps = sig32.to(torch.float64)  # CPU, float32 values widened
     sd = float(noise_scheduler.config.sigma_data)
     lib = _lib.load()
 
@@ -49,6 +49,16 @@ def edm_AR_sampler(net, noise_scheduler, batch_size=1, return_seq_len=1, randn_l
                                           c_in, _lib.stream()), "lc_sched_heun_init")
         for i in range(n):
             t_cur, t_next = float(t_steps[i]), float(t_steps[i + 1])
+            if not deterministic:
+                # increase the noise level temporarily: t_hat, gamma and the noise scale in float32 like the reference
+                gamma = min(S_churn / num_inference_steps, 2.0**0.5 - 1) if S_min <= float(sig32[i]) <= S_max else 0
+                t_hat = sig32[i] + gamma * sig32[i]
+                k = float((t_hat**2 - sig32[i] ** 2).sqrt() * S_noise)
+                eps = randn_like(x).contiguous()  # fp64; drawn every step (also when gamma == 0) like the reference
+                c_in, c_skip, c_out, c_noise = coef(t_hat)
+                _lib.check(lib.lc_sched_heun_churn(_lib.ptr(x), _lib.ptr(eps), _lib.ptr(x_in), x.numel(), k, c_in,
+                                                   _lib.stream()), "lc_sched_heun_churn")
+                t_cur = float(t_hat)
             f = net(x_in, c_noise.to(device), known_latents, time_elapsed=timestamps).sample
             second = i < n - 1
             # last step (t_next = 0): Euler only; x_in then receives float32(x), the sampler's return value

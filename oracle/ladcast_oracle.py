@@ -694,9 +694,10 @@ def dpmpp2m_sample(net, noise: torch.Tensor, n_steps: int, trace: Optional[list]
     return x
 
 
-def heun_sample(net, noise: torch.Tensor, n_steps: int) -> torch.Tensor:
-    """edm_AR_sampler (edm_sampler.py:44-120), deterministic branch: float64 state, 2N-1 net calls with a (1,)
-    c_noise broadcast over the batch."""
+def heun_sample(net, noise: torch.Tensor, n_steps: int, deterministic: bool = True, S_churn=0.0, S_min=0.0,
+                S_max=float("inf"), S_noise=0.0, randn_like=torch.randn_like) -> torch.Tensor:
+    """edm_AR_sampler (edm_sampler.py:44-120): float64 state, 2N-1 net calls with a (1,) c_noise broadcast over the
+    batch; deterministic=False adds the stochastic churn of :67-76 (t_hat, gamma in float32)."""
     t_steps = karras_sigmas(n_steps)
     x_next = noise.to(torch.float64) * t_steps[0]
 
@@ -707,12 +708,16 @@ def heun_sample(net, noise: torch.Tensor, n_steps: int) -> torch.Tensor:
 
     for i in range(n_steps):
         t_cur, t_nxt = t_steps[i], t_steps[i + 1]
-        x_hat = x_next
-        d_cur = (x_hat - den(x_hat, t_cur)) / t_cur
-        x_next = x_hat + (t_nxt - t_cur) * d_cur
+        x_hat, t_hat = x_next, t_cur
+        if not deterministic:
+            gamma = min(S_churn / n_steps, 2.0**0.5 - 1) if S_min <= float(t_cur) <= S_max else 0
+            t_hat = t_cur + gamma * t_cur
+            x_hat = x_next + (t_hat**2 - t_cur**2).sqrt() * S_noise * randn_like(x_next)
+        d_cur = (x_hat - den(x_hat, t_hat)) / t_hat
+        x_next = x_hat + (t_nxt - t_hat) * d_cur
         if i < n_steps - 1:
             d_prime = (x_next - den(x_next, t_nxt)) / t_nxt
-            x_next = x_hat + (t_nxt - t_cur) * (0.5 * d_cur + 0.5 * d_prime)
+            x_next = x_hat + (t_nxt - t_hat) * (0.5 * d_cur + 0.5 * d_prime)
     return x_next.float()
 
 
@@ -727,7 +732,7 @@ def member_noise(members: Sequence[int], shape_tail: Sequence[int], dtype=torch.
 
 
 def ensemble_sample(sd: SD, cfg: dict, members: Sequence[int], T_out: int, n_steps: int, known: torch.Tensor,
-                    timestamp: int, sampler: str = "pipeline") -> torch.Tensor:
+                    timestamp: int, sampler: str = "pipeline", sampler_kwargs: Optional[dict] = None) -> torch.Tensor:
     """ensemble_AR_sampler (pipelines/utils.py:665-742) for an explicit list of global member indices."""
     B = len(members)
     kn = known.expand(B, *known.shape[1:]) if known.shape[0] == 1 else known
@@ -737,7 +742,7 @@ def ensemble_sample(sd: SD, cfg: dict, members: Sequence[int], T_out: int, n_ste
     if sampler == "pipeline":
         return dpmpp2m_sample(net, noise, n_steps)
     if sampler == "edm":
-        return heun_sample(net, noise, n_steps)
+        return heun_sample(net, noise, n_steps, **(sampler_kwargs or {}))
     raise ValueError(sampler)
 
 

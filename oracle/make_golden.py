@@ -219,6 +219,28 @@ def golden_heun8():
     print("heun8", float(s.abs().mean()))
 
 
+def churn_noise_fn(seed=777):
+    """randn_like for the churn goldens: fp64 draws from one seeded CPU generator, in call order."""
+    g = torch.Generator("cpu").manual_seed(seed)
+    return lambda x: torch.randn(x.shape, generator=g, dtype=x.dtype).to(x.device)
+
+
+CHURN_KW = dict(deterministic=False, S_churn=4.0, S_min=0.05, S_max=50.0, S_noise=1.003)
+
+
+def golden_heun_churn():
+    """edm_AR_sampler with stochastic churn (deterministic=False, edm_sampler.py:67-76): N = 6, tiny denoiser,
+    ensemble of 2; S_min / S_max chosen so that some steps have gamma = 0 and some gamma > 0."""
+    cfg, m = build_denoiser("tiny", 11)
+    pipe = AutoRegressive2DPipeline(m, EDMDPMSolverMultistepScheduler())
+    known = seeded((1, 84, 1, 15, 30), 102, 0.5)
+    s = ensemble_AR_sampler(pipe, sample_size=2, return_seq_len=1, num_inference_steps=6, known_latents=known,
+                            timestamps=torch.tensor([2018010100]), sampler_type="edm", device="cpu",
+                            sampler_kwargs=dict(CHURN_KW, randn_like=churn_noise_fn()))
+    np.savez(os.path.join(OUT, "heun_churn_tiny.npz"), edm_churn_6=s.numpy().astype(np.float32))
+    print("heun churn", float(s.abs().mean()))
+
+
 def golden_denoiser_1p6b():
     """ladcast_1.6B (d=2048, 16 heads, 5+10+3 blocks; 1,605,496,660 parameters) through the unmodified reference:
     B=1, T_out=1.  Pins the oracle port's 1.6B configuration beyond the parameter count."""
@@ -236,7 +258,7 @@ def golden_denoiser_1p6b():
 
 ALL = {"sphere": golden_sphere, "embeddings": golden_embeddings, "metrics": golden_metrics, "dcae": golden_dcae,
        "dcae_encode": golden_dcae_encode, "transforms": golden_transforms, "samplers": golden_samplers,
-       "denoiser": golden_denoiser, "acc": golden_acc, "heun8": golden_heun8, "denoiser_1p6b": golden_denoiser_1p6b}
+       "denoiser": golden_denoiser, "acc": golden_acc, "heun8": golden_heun8, "heun_churn": golden_heun_churn, "denoiser_1p6b": golden_denoiser_1p6b}
 
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(ALL)):

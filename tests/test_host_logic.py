@@ -300,3 +300,27 @@ def test_array_front_end_matches_reference_conventions():
     assert picks[:4] == [datetime(2018, 1, 1, 0), datetime(2018, 1, 1, 12), datetime(2018, 1, 11, 0), datetime(2018, 1, 11, 12)]
     assert all(p <= times[-1] for p in picks) and len(picks) == 12
     assert select_init_times(times, 3, enforce_year=2019) == []
+
+
+def test_climatology_to_timeseries_array_form():
+    """evaluate/utils.py:152-201 without xarray: selection by (dayofyear, hour) label along the forecast valid times,
+    start excluded by default, leap day and the year wrap included; pandas (the reference's own time arithmetic) as
+    the checker."""
+    import pandas as pd
+
+    from ladcast_b200.evaluate.utils import climatology_to_timeseries
+
+    clim = np.arange(366 * 4 * 3, dtype=np.float32).reshape(366, 4, 3)
+    for start, lead, excl in (("2020-02-28T12", 48, True), ("2019-12-31T06", 36, False), ("2018-01-01T00", 240, True)):
+        got, times = climatology_to_timeseries(clim, start, lead, exclude_start=excl)
+        idx = pd.date_range(start=pd.to_datetime(start), end=pd.to_datetime(start) + pd.Timedelta(hours=lead), freq="6h")
+        idx = idx[1:] if excl else idx
+        assert [pd.Timestamp(t) for t in times] == list(idx)
+        want = np.stack([clim[d - 1, h // 6] for d, h in zip(idx.dayofyear, idx.hour)])
+        assert np.array_equal(got, want)
+        got_t, _ = climatology_to_timeseries(torch.from_numpy(clim), start, lead, exclude_start=excl)
+        assert np.array_equal(got_t.numpy(), want)
+    with pytest.raises(KeyError):
+        climatology_to_timeseries(clim, "2018-01-01T03", 12)
+    with pytest.raises(ValueError):
+        climatology_to_timeseries(np.zeros(4), "2018-01-01T00", 12)

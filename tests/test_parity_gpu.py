@@ -131,6 +131,28 @@ def test_heun8_vs_reference_golden(golden_dir, precision, tol):
     assert r < tol
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 5e-2)])
+def test_heun_churn_vs_reference_golden(golden_dir, precision, tol):
+    """Stochastic churn (deterministic=False, edm_sampler.py:67-76): `lc_sched_heun_churn` + the Heun kernels against the
+    unmodified reference on the same seeded fp64 churn noise (drawn on the CPU in call order, moved to the device)."""
+    from ladcast_b200.pipelines import AutoRegressive2DPipeline, EDMDPMSolverMultistepScheduler
+    from ladcast_b200.pipelines.utils import ensemble_AR_sampler
+
+    g = np.load(os.path.join(golden_dir, "heun_churn_tiny.npz"))
+    cfg, sd, m = _denoiser("tiny", 11, precision)
+    pipe = AutoRegressive2DPipeline(m, EDMDPMSolverMultistepScheduler())
+    gen = torch.Generator("cpu").manual_seed(777)
+    kw = dict(deterministic=False, S_churn=4.0, S_min=0.05, S_max=50.0, S_noise=1.003,
+              randn_like=lambda x: torch.randn(x.shape, generator=gen, dtype=x.dtype).to(x.device))
+    s = ensemble_AR_sampler(pipe, sample_size=2, return_seq_len=1, num_inference_steps=6,
+                            known_latents=_seeded((1, 84, 1, 15, 30), 102, 0.5).cuda(),
+                            timestamps=torch.tensor([2018010100]), sampler_type="edm", device="cuda", sampler_kwargs=kw)
+    torch.cuda.synchronize()
+    r = _rel(s, g["edm_churn_6"])
+    record_measured(f"heun_churn/{precision}/rel_l2", r)
+    assert r < tol
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_denoiser_1p6B_vs_reference_golden(golden_dir, precision):
     g = np.load(os.path.join(golden_dir, "denoiser_1p6B.npz"))
