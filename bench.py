@@ -449,6 +449,21 @@ def strong_leg(args, ens_total, rank, world, dev, ae, model, barrier, lib, _lib,
                           "what": "ensemble_metrics_distributed on the last AR step's decoded fields (max over ranks; "
                                   "bytes = fp32 bytes one rank sends) vs ensemble_metrics on the all-gathered fields"}
         del full
+        # the same metrics with NO exchange step: peer-memory reads inside the reduction kernel (exchange="p2p")
+        try:
+            tp = {}
+            for _ in range(3):  # first pass maps the peers' buffers (CUDA IPC)
+                tabs_p = ensemble_metrics_distributed(fields, truth, timings=tp, exchange="p2p")
+            okp = all(torch.allclose(tabs_p[k], want[k], rtol=1e-9, atol=1e-12, equal_nan=True) for k in want)
+            t = torch.tensor([tp["kernel_ms"], 0.0 if okp else 1.0], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res["metrics"]["p2p_fused"] = {
+                "kernel_ms": round(float(t[0]), 3), "exchange_ms": 0.0, "matches_single_gpu": float(t[1]) == 0.0,
+                "remote_gbs_per_gpu": round(by / (float(t[0]) * 1e-3) / 1e9, 1) if float(t[0]) > 0 else None,
+                "what": "lc_metrics_accumulate_ptrs: every rank reduces its plane slice reading the other ranks' members "
+                        "in place over NVLink (CUDA-IPC peer memory) - exchange and reduction are one kernel"}
+        except Exception as ex:  # never lose the bench line to the optional path
+            res["metrics"]["p2p_fused"] = {"error": repr(ex)[:300]}
     else:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ensemble_metrics(fields, truth)

@@ -194,6 +194,14 @@ LC_API int lc_metrics_accumulate(const float* fields, const float* truth, const 
 LC_API int lc_metrics_accumulate_strided(const float* fields, long long member_stride, const float* truth,
                                          const double* lat_weights, int members, long long planes, int height, int width,
                                          double* sums, double* counts, void* stream);
+/* the same with one base pointer per member (HOST array of `members` <= 64 DEVICE pointers; member m's planes
+ * [planes, H*W] are contiguous at member_ptrs[m]).  A pointer may address another GPU's memory mapped into this process
+ * (CUDA IPC / peer access): with members sharded over GPUs (evaluate/evaluate_ens_gpu.py:462-468 gathers them instead)
+ * every rank reduces its slice of the planes reading the other ranks' members in place over NVLink — the member->plane
+ * exchange and the reduction are one kernel, no gathered copy. */
+LC_API int lc_metrics_accumulate_ptrs(const float* const* member_ptrs, const float* truth, const double* lat_weights,
+                                      int members, long long planes, int height, int width, double* sums, double* counts,
+                                      void* stream);
 /* anomaly-correlation terms of get_acc (evaluate/utils.py:122-149): sums/counts [3, planes] fp64 of the NaN-skipping
  * (optionally latitude-weighted) spatial sums of fa*ta, fa^2, ta^2 with fa = forecast - climate, ta = truth - climate */
 LC_API int lc_metrics_acc(const float* forecast, const float* truth, const float* climate, const double* lat_weights,

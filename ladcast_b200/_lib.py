@@ -85,6 +85,7 @@ _OPTIONAL = {
     "lc_sphere_conv3x3": ([_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "lc_metrics_accumulate": ([_vp, _vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, _vp, _vp], _i),
     "lc_metrics_accumulate_strided": ([_vp, ctypes.c_longlong, _vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, _vp, _vp], _i),
+    "lc_metrics_accumulate_ptrs": ([_vp, _vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, _vp, _vp], _i),
     "lc_metrics_acc": ([_vp, _vp, _vp, _vp, ctypes.c_longlong, _i, _i, _vp, _vp, _vp], _i),
     "lc_metrics_pointwise": ([_vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, _vp, _vp, _vp], _i),
 }

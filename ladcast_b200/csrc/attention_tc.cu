@@ -20,6 +20,7 @@
 //                 back to TMEM over S.  Final O / l epilogue per tile.  576 threads leave 96 registers per thread.
 //   TMEM columns: S_A/P_A 0..127, S_B/P_B 128..255, O_A 256..383, O_B 384..511.
 #include <cstdlib>
+#include <type_traits>
 
 #include "kernels.h"
 #include "ptx.cuh"
@@ -334,9 +335,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, int S, int heads, bf
 //     item boundary got 1-2.7 k cycles shorter but every softmax step 180 cycles longer — no net gain.)
 // Shared memory: Q 2 x 32 KB, ring 5 x 32 KB (as the one-item kernel).
 constexpr int RING_P = 5;
+constexpr int ATTN_POLY_DEFAULT = 0;
+constexpr int ATTN_SPLIT_DEFAULT = 1;
 constexpr int SMEM_BYTES_P = 2 * TILE_BYTES + RING_P * TILE_BYTES + 256 + XCH_BYTES;
 constexpr int NUM_THREADS_P = NUM_THREADS;
 
+// POLY > 0: every POLY-th element of a row's exponentials is computed by ptx::ex2_poly on the FMA / ALU pipes — the
+// softmax step is bound by the MUFU pipe (16 ex2 / clk / SM against 128 x 128 exponentials per tile step, the same
+// ~1 k cycles the tensor pipe needs for the step's 16 MMAs), so moving a fraction off it shortens the serial
+// softmax -> P V -> Q K^T chain of a tile.
+// SPLIT: a thread owns keys [32 hh, 32 hh + 32) and [64 + 32 hh, 64 + 32 hh + 32) of its row instead of one 64-key
+// half, and P is handed to the tensor pipe in two 64-key chunks (p_half, then p_full): the first four K-steps of
+// O += P V run while the second chunk is still being exponentiated.
+template <int POLY, bool SPLIT>
 __global__ void __maxnreg__(96)
 attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_p,
                                const __grid_constant__ CUtensorMap tm_c, int S, int heads, int n_qb, int n_items, int Np,
@@ -354,7 +365,8 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __g
   uint64_t* p_full = s_full + 2;             // [tile] (8 arrivals: one per softmax warp)
   uint64_t* o_full = p_full + 2;             // [tile]
   uint64_t* o_empty = o_full + 2;            // [tile] (8 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+  uint64_t* p_half = o_empty + 2;            // [tile] (8 arrivals; SPLIT: the first 64 keys of P are in TMEM)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_half + 2);
   float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -378,6 +390,7 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __g
       ptx::mbar_init(&p_full[i], 8);
       ptx::mbar_init(&o_full[i], 1);
       ptx::mbar_init(&o_empty[i], 8);
+      ptx::mbar_init(&p_half[i], 8);
     }
     ptx::fence_barrier_init();
   }
@@ -450,13 +463,13 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __g
       }
       __syncwarp();
     };
-    auto issue_pv = [&](int t, int slot, bool first) {
+    auto issue_pv = [&](int t, int slot, bool first, int kk0, int kk1) {
       const uint32_t b_lo = ptx::smem_desc_lo(r_addr + slot * TILE_BYTES, SUB_BYTES);
       const uint32_t d_tmem = tmem_base + COL_O + static_cast<uint32_t>(t * 128);
       const uint32_t a_tmem = tmem_base + COL_S + static_cast<uint32_t>(t * 128);
       if (ptx::elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < BKV / 16; ++kk)  // 128 keys = 8 K-steps of 16 (16 key rows x 128 B = 2 KB per sub-tile)
+        for (int kk = kk0; kk < kk1; ++kk)  // 128 keys = 8 K-steps of 16 (16 key rows x 128 B = 2 KB per sub-tile)
           ptx::umma_f16_ts_lh(d_tmem, a_tmem + kk * 8, b_lo + ((kk * 2048) >> 4), desc_hi, idesc_pv,
                               (first && kk == 0) ? 0u : 1u);
       }
@@ -488,11 +501,22 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __g
         const bool more = j + 1 < n_tiles;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          ptx::mbar_wait(&p_full[t], sc & 1);
-          if (j == 0 && k > 0) ptx::mbar_wait(&o_empty[t], (k - 1) & 1);  // the epilogue has drained O_t
-          ptx::tc_fence_after();
-          if (k == 0) LC_TRACE(0, j, 2 * t);
-          issue_pv(t, v_slot, j == 0);
+          if (SPLIT) {
+            ptx::mbar_wait(&p_half[t], sc & 1);
+            if (j == 0 && k > 0) ptx::mbar_wait(&o_empty[t], (k - 1) & 1);  // the epilogue has drained O_t
+            ptx::tc_fence_after();
+            if (k == 0) LC_TRACE(0, j, 2 * t);
+            issue_pv(t, v_slot, j == 0, 0, 4);
+            ptx::mbar_wait(&p_full[t], sc & 1);
+            ptx::tc_fence_after();
+            issue_pv(t, v_slot, false, 4, 8);
+          } else {
+            ptx::mbar_wait(&p_full[t], sc & 1);
+            if (j == 0 && k > 0) ptx::mbar_wait(&o_empty[t], (k - 1) & 1);  // the epilogue has drained O_t
+            ptx::tc_fence_after();
+            if (k == 0) LC_TRACE(0, j, 2 * t);
+            issue_pv(t, v_slot, j == 0, 0, 8);
+          }
           if (!more) commit(&o_full[t]);
           if (t == 1) commit(&r_empty[v_slot]);
           if (more) {
@@ -549,16 +573,18 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __g
           pending_slot = -1;
         }
         const int n_valid = S - j * BKV;  // keys >= n_valid are padding (only ever true for the last tile)
+        // key offset of sreg[c][0]: one 64-key half, or (SPLIT) 32 keys of each 64-key chunk
+        const int key0 = SPLIT ? hh * 32 : hh * 64, key1 = SPLIT ? 64 + hh * 32 : hh * 64 + 32;
         uint32_t sreg[2][32];
-        ptx::tmem_ld32(s_addr + hh * 64, sreg[0]);
-        ptx::tmem_ld32(s_addr + hh * 64 + 32, sreg[1]);
+        ptx::tmem_ld32(s_addr + key0, sreg[0]);
+        ptx::tmem_ld32(s_addr + key1, sreg[1]);
         ptx::tmem_ld_wait();
         if (n_valid < BKV) {
 #pragma unroll
           for (int c = 0; c < 2; ++c)
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (hh * 64 + c * 32 + i >= n_valid) sreg[c][i] = 0xff800000u;  // -inf
+              if ((c == 0 ? key0 : key1) + i >= n_valid) sreg[c][i] = 0xff800000u;  // -inf
         }
         float mxs[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
@@ -580,26 +606,52 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __g
         const float neg_m = -m_used;
         float ps[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[32];
+        auto exps = [&](auto lo) {  // exponentials + bf16 packing of elements [lo, lo + 32) of this thread's 64
+          constexpr int LO = decltype(lo)::value;
 #pragma unroll
-        for (int i = 0; i < 64; i += 2) {
-          const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(sreg[i >> 5][i & 31]), scale_log2, neg_m));
-          const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(sreg[i >> 5][(i & 31) + 1]), scale_log2, neg_m));
-          ps[(i >> 1) & 3] += p0 + p1;
-          __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&pb);
-        }
-        if (need && j > 0) {  // rare: rescale this thread's 64 columns of O (quiescent: PV_t(j-1) has completed)
+          for (int i = LO; i < LO + 32; i += 2) {
+            const float x0 = fmaf(__uint_as_float(sreg[i >> 5][i & 31]), scale_log2, neg_m);
+            const float x1 = fmaf(__uint_as_float(sreg[i >> 5][(i & 31) + 1]), scale_log2, neg_m);
+            const float p0 = (POLY > 0 && (i % POLY) == POLY - 1) ? ptx::ex2_poly(x0) : ptx::ex2_approx(x0);
+            const float p1 = (POLY > 0 && ((i + 1) % POLY) == POLY - 1) ? ptx::ex2_poly(x1) : ptx::ex2_approx(x1);
+            ps[(i >> 1) & 3] += p0 + p1;
+            __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&pb);
+          }
+        };
+        exps(std::integral_constant<int, 0>{});
+        if (SPLIT && need && j > 0) {  // rare: the O rescale must precede the FIRST chunk's hand-over
 #pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            ptx::tmem_ld32(o_addr + c * 32, o);
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[16];
+            ptx::tmem_ld16(o_addr + c * 16, o);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            ptx::tmem_st32(o_addr + c * 32, o);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            ptx::tmem_st16r(o_addr + c * 16, o);
           }
         }
-        ptx::tmem_st32(s_addr + hh * 32, pk);
+        if (SPLIT) {  // P of keys [0, 64) (this thread: P columns [16 hh, 16 hh + 16)) -> tensor pipe
+          ptx::tmem_st16<0>(s_addr + hh * 16, pk);
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&p_half[t]);
+        }
+        exps(std::integral_constant<int, 32>{});
+        if (!SPLIT && need && j > 0) {  // rare: rescale this thread's 64 columns of O (quiescent: PV_t(j-1) has completed)
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[16];
+            ptx::tmem_ld16(o_addr + c * 16, o);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            ptx::tmem_st16r(o_addr + c * 16, o);
+          }
+        }
+        if (SPLIT) ptx::tmem_st16<16>(s_addr + 32 + hh * 16, pk);  // P of keys [64, 128)
+        else ptx::tmem_st32(s_addr + hh * 32, pk);
         l = l * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
@@ -714,9 +766,18 @@ int attention_bf16(const bf16* qkv, int B, int S, int heads, int head_dim, bf16*
   }
   // persistent: one CTA per SM over (sample, head, query block) items; outputs through 3-D TMA store maps
   // {d, tokens of the stream, samples} so that the hardware clips rows past the stream's length
+  // LADCAST_B200_ATTN_POLY = n: every n-th exponential on the FMA / ALU pipes (0 = all on the MUFU)
+  static const int poly = [] { const char* e = getenv("LADCAST_B200_ATTN_POLY"); return e != nullptr ? atoi(e) : ATTN_POLY_DEFAULT; }();
+  static const int split = [] { const char* e = getenv("LADCAST_B200_ATTN_SPLIT"); return e != nullptr ? atoi(e) : ATTN_SPLIT_DEFAULT; }();
+  auto kern = split ? (poly == 2 ? attention_tc_persistent_kernel<2, true> : poly == 3 ? attention_tc_persistent_kernel<3, true>
+                     : poly == 4 ? attention_tc_persistent_kernel<4, true> : poly == 8 ? attention_tc_persistent_kernel<8, true>
+                                                                                      : attention_tc_persistent_kernel<0, true>)
+                    : (poly == 2 ? attention_tc_persistent_kernel<2, false> : poly == 3 ? attention_tc_persistent_kernel<3, false>
+                     : poly == 4 ? attention_tc_persistent_kernel<4, false> : poly == 8 ? attention_tc_persistent_kernel<8, false>
+                                                                                       : attention_tc_persistent_kernel<0, false>);
   static PerDevice<bool> attr_set_p;
   if (!attr_set_p.here()) {
-    LC_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_P));
+    LC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_P));
     attr_set_p.here() = true;
   }
   if (Np == 0) {  // every token belongs to the second stream (context refiner): treat it as the only stream
@@ -745,7 +806,7 @@ int attention_bf16(const bf16* qkv, int B, int S, int heads, int head_dim, bf16*
   const int n_items = n_qb * heads * B;
   const int grid = n_items < num_sms() ? n_items : num_sms();
   prof_begin(PROF_ATTN, s);
-  LC_CHECK_CUDA(launch_kernel(attention_tc_persistent_kernel, dim3(grid), NUM_THREADS_P, SMEM_BYTES_P, s, tm, tm_p, tm_c, S, heads,
+  LC_CHECK_CUDA(launch_kernel(kern, dim3(grid), NUM_THREADS_P, SMEM_BYTES_P, s, tm, tm_p, tm_c, S, heads,
                               n_qb, n_items, Np, has_cond, out_c));
   prof_end(PROF_ATTN, flops, s, bytes);
   LC_LAUNCH_CHECK();

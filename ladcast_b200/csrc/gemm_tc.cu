@@ -404,6 +404,25 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& ep, const ConvLoad
   orow = epi_out_row(ep, row, sample);
 }
 
+// Read-modify-write epilogues (gated fp32 residual, residual + store): pull this warp's slice of the NEXT tile's
+// residual rows (32 rows x BN/2 fp32 columns = 4 lines per lane) into L2 while the current tile is drained.  Each warp
+// walks its 4 column blocks with one DRAM round trip per block; with K = 1536 that chain (not the tensor pipe) set
+// the pace of the out-projections (54 % tensor-active, profiles/r02_kernels.md) — from L2 the round trip is ~3x shorter.
+template <int BN>
+__device__ __forceinline__ void epilogue_prefetch(const EpiParams& ep, const ConvLoad& cv, int kind, int m_blk, int n_blk,
+                                                  int quarter, int half, int lane, int M, int N) {
+  if ((kind != K_GATED && kind != K_RESID) || !ep.prefetch) return;
+  int row, sample;
+  long long orow;
+  epilogue_row(ep, cv, m_blk, quarter, lane, M, row, orow, sample);
+  if (row >= M) return;
+  const float* base = kind == K_GATED ? reinterpret_cast<const float*>(ep.out) + orow * ep.ldo : ep.resid + orow * ep.ldr;
+  const int c0 = n_blk * BN + half * (BN / 2);
+#pragma unroll
+  for (int c = 0; c < BN / 2; c += 32)
+    if (c0 + c < N) ptx::prefetch_l2(base + c0 + c);
+}
+
 // Drain one accumulator stage: this warp's 32 rows x (BN/2) columns, TMEM -> registers -> fused epilogue -> global.
 template <int BN>
 __device__ __forceinline__ void epilogue_drain(const EpiParams& ep, int kind, int n_blk, int quarter, int half, int lane,
@@ -645,8 +664,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int row, sample;
       long long orow;
       epilogue_row(ep, cv, m_blk, quarter, lane, M, row, orow, sample);
+      if (tile == static_cast<int>(blockIdx.x)) epilogue_prefetch<BN>(ep, cv, kind, m_blk, n_blk, quarter, half, lane, M, N);
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
+      if (tile + static_cast<int>(gridDim.x) < num_tiles) {
+        int m_nx, n_nx;
+        sched.decode(tile + gridDim.x, m_nx, n_nx);
+        epilogue_prefetch<BN>(ep, cv, kind, m_nx, n_nx, quarter, half, lane, M, N);
+      }
       epilogue_drain<BN>(ep, kind, n_blk, quarter, half, lane, tbuf, tbuf_partner, tmem_base, acc, row, orow, sample, M, N);
       ptx::tc_fence_before();
       __syncwarp();
@@ -829,10 +854,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       int row, sample;
       long long orow;
       epilogue_row(ep, cv, m_blk, quarter, lane, M, row, orow, sample);
+      if (tix == 0) epilogue_prefetch<BN>(ep, cv, kind, m_blk, n_blk, quarter, half, lane, M, N);
       if (trace != nullptr && tix < 64) trace[256 + tix * 4 + 0] = clock64();
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       if (trace != nullptr && tix < 64) trace[256 + tix * 4 + 1] = clock64();
+      if (tile + num_pairs < num_tiles) {
+        int mp_nx, n_nx;
+        sched.decode(tile + num_pairs, mp_nx, n_nx);
+        epilogue_prefetch<BN>(ep, cv, kind, mp_nx * 2 + static_cast<int>(cta_rank), n_nx, quarter, half, lane, M, N);
+      }
       epilogue_drain<BN>(ep, kind, n_blk, quarter, half, lane, tbuf, tbuf_partner, tmem_base, acc, row, orow, sample, M, N);
       ptx::tc_fence_before();
       __syncwarp();
@@ -877,8 +908,11 @@ int launch_pair(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
   const int cls = cv.enabled ? PROF_CONV : PROF_GEMM;
   const double flops = 2.0 * M * N * (cv.enabled ? 9.0 * cv.c_real : static_cast<double>(K));
+  static const bool epi_prefetch = [] { const char* e = getenv("LADCAST_B200_EPI_PREFETCH"); return !(e != nullptr && e[0] == '0'); }();
+  EpiParams epl = ep;
+  epl.prefetch = epi_prefetch ? 1 : 0;
   prof_begin(cls, stream);
-  LC_CHECK_CUDA(launch_kernel(gemm_tc2_kernel, grid, NUM_THREADS, C::SMEM, stream, a0, a1, w, M, N, K, K0, ep, sched, cv));
+  LC_CHECK_CUDA(launch_kernel(gemm_tc2_kernel, grid, NUM_THREADS, C::SMEM, stream, a0, a1, w, M, N, K, K0, epl, sched, cv));
   prof_end(cls, flops, stream, algorithmic_bytes(M, N, K, ep, cv));
   LC_LAUNCH_CHECK();
   return 0;

@@ -103,25 +103,35 @@ __device__ __forceinline__ void add_weighted(double (&acc)[8], float msum, float
   }
 }
 
-template <int M, bool REDUCE>
-__global__ void __launch_bounds__(THREADS) metrics_sorted_kernel(const float* __restrict__ fields, long long member_stride,
-                                                                 const float* __restrict__ truth,
-                                                                 const double* __restrict__ latw, long long N, int H,
-                                                                 int W, int bpp, double* __restrict__ sums,
-                                                                 double* __restrict__ counts, float* __restrict__ out_skill,
-                                                                 float* __restrict__ out_spread, float* __restrict__ out_mean) {
-  pdl_grid_sync();
+// member m of plane n, pixel p: (a) strided members of one allocation, (b) one base pointer per member — the members
+// of other GPUs are read IN PLACE over NVLink (peer memory mapped through CUDA IPC), so the member->plane exchange and
+// the reduction are one kernel and the gathered copy never exists.
+struct StridedMembers {
+  const float* base;
+  long long member_stride;
+  __device__ __forceinline__ float operator()(int m, long long off) const { return __ldg(base + m * member_stride + off); }
+};
+constexpr int MAX_PTR_MEMBERS = 64;
+struct MemberPtrs {
+  const float* p[MAX_PTR_MEMBERS];
+};
+
+template <int M, bool REDUCE, typename Load>
+__device__ __forceinline__ void metrics_sorted_body(const Load& load, const float* __restrict__ truth,
+                                                    const double* __restrict__ latw, long long N, int H, int W, int bpp,
+                                                    double* __restrict__ sums, double* __restrict__ counts,
+                                                    float* __restrict__ out_skill, float* __restrict__ out_spread,
+                                                    float* __restrict__ out_mean) {
   const int HW = H * W;
   const long long n = blockIdx.x / bpp;
   const int blk = static_cast<int>(blockIdx.x - n * bpp);
-  const float* base = fields + n * HW;
   const float inv_m = 1.0f / static_cast<float>(M);
   const float spread_scale = M > 1 ? 2.0f / (static_cast<float>(M) * static_cast<float>(M - 1)) : 0.f;
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int p = blk * THREADS + threadIdx.x; p < HW; p += bpp * THREADS) {
     float x[M];
 #pragma unroll
-    for (int m = 0; m < M; ++m) x[m] = __ldg(base + m * member_stride + p);
+    for (int m = 0; m < M; ++m) x[m] = load(m, n * HW + p);
     const float y = truth != nullptr ? __ldg(truth + n * HW + p) : 0.f;
     float msum = 0.f, skill = 0.f;
 #pragma unroll
@@ -146,6 +156,30 @@ __global__ void __launch_bounds__(THREADS) metrics_sorted_kernel(const float* __
     }
   }
   if (REDUCE) block_accumulate<8>(acc, sums, counts, N, n);
+}
+
+template <int M, bool REDUCE>
+__global__ void __launch_bounds__(THREADS) metrics_sorted_kernel(const float* __restrict__ fields, long long member_stride,
+                                                                 const float* __restrict__ truth,
+                                                                 const double* __restrict__ latw, long long N, int H,
+                                                                 int W, int bpp, double* __restrict__ sums,
+                                                                 double* __restrict__ counts, float* __restrict__ out_skill,
+                                                                 float* __restrict__ out_spread, float* __restrict__ out_mean) {
+  pdl_grid_sync();
+  metrics_sorted_body<M, REDUCE>(StridedMembers{fields, member_stride}, truth, latw, N, H, W, bpp, sums, counts, out_skill,
+                                 out_spread, out_mean);
+}
+
+// members given by pointer (local or peer memory): member m's planes are contiguous [N, HW] at ptrs.p[m]
+template <int M>
+__global__ void __launch_bounds__(THREADS) metrics_sorted_ptr_kernel(const __grid_constant__ MemberPtrs ptrs,
+                                                                     const float* __restrict__ truth,
+                                                                     const double* __restrict__ latw, long long N, int H,
+                                                                     int W, int bpp, double* __restrict__ sums,
+                                                                     double* __restrict__ counts) {
+  pdl_grid_sync();
+  auto load = [&ptrs](int m, long long off) { return ptrs.p[m][off]; };
+  metrics_sorted_body<M, true>(load, truth, latw, N, H, W, bpp, sums, counts, nullptr, nullptr, nullptr);
 }
 
 // M > 64: members staged in shared memory (one column per thread), spread = mean absolute pair difference
@@ -259,6 +293,27 @@ int launch_metrics(const float* fields, long long member_stride, const float* tr
   return 0;
 }
 
+int launch_metrics_ptrs(const MemberPtrs& ptrs, const float* truth, const double* latw, int M, long long N, int H, int W,
+                        double* sums, double* counts, cudaStream_t st) {
+  const int bpp = blocks_per_plane(H * W);
+  LC_REQUIRE(N * bpp < (1ll << 31), "too many (channel, lead) planes for one launch");
+  const unsigned grid = static_cast<unsigned>(N * bpp);
+  ProfScope ps(PROF_METRICS, 0.0, static_cast<double>(N) * H * W * 4.0 * (M + 1), st);
+#define LC_SORTED(MM)                                                                                                       \
+  case MM:                                                                                                                  \
+    LC_CHECK_CUDA(launch_kernel(metrics_sorted_ptr_kernel<MM>, grid, THREADS, 0, st, ptrs, truth, latw, N, H, W, bpp, sums, counts)); \
+    break;
+#define LC_SORTED8(B) LC_SORTED(B) LC_SORTED(B + 1) LC_SORTED(B + 2) LC_SORTED(B + 3) LC_SORTED(B + 4) LC_SORTED(B + 5) \
+    LC_SORTED(B + 6) LC_SORTED(B + 7)
+  switch (M) {
+    LC_SORTED8(1) LC_SORTED8(9) LC_SORTED8(17) LC_SORTED8(25) LC_SORTED8(33) LC_SORTED8(41) LC_SORTED8(49) LC_SORTED8(57)
+  }
+#undef LC_SORTED8
+#undef LC_SORTED
+  LC_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace
 }  // namespace lc
 
@@ -284,6 +339,20 @@ int lc_metrics_accumulate(const float* fields, const float* truth, const double*
                           int height, int width, double* sums, double* counts, void* stream) {
   return lc_metrics_accumulate_strided(fields, planes * height * width, truth, latw, members, planes, height, width, sums,
                                        counts, stream);
+}
+
+int lc_metrics_accumulate_ptrs(const float* const* member_ptrs, const float* truth, const double* latw, int members,
+                               long long planes, int height, int width, double* sums, double* counts, void* stream) {
+  LC_REQUIRE(member_ptrs && truth && latw && sums && counts, "null argument");
+  LC_REQUIRE(members >= 1 && members <= MAX_PTR_MEMBERS, "ensemble size must be in [1, 64] for the pointer form");
+  LC_REQUIRE(planes > 0 && height > 0 && width > 0, "bad shape");
+  MemberPtrs ptrs;
+  for (int m = 0; m < MAX_PTR_MEMBERS; ++m) ptrs.p[m] = m < members ? member_ptrs[m] : nullptr;
+  for (int m = 0; m < members; ++m) LC_REQUIRE(ptrs.p[m] != nullptr, "null member pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LC_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * planes, st));
+  LC_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(double) * 4 * planes, st));
+  return launch_metrics_ptrs(ptrs, truth, latw, members, planes, height, width, sums, counts, st);
 }
 
 int lc_metrics_pointwise(const float* fields, const float* truth, int members, long long planes, int height, int width,

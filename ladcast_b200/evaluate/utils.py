@@ -221,6 +221,61 @@ def reshard_members_to_planes(fields_local: torch.Tensor, members, group=None, o
     return out
 
 
+_PEER_VIEWS: dict = {}
+
+
+def peer_views(t: torch.Tensor, group=None):
+    """Maps every rank's tensor `t` (same role on each rank, any shape) into this process: returns a list with one
+    tensor per rank — this rank's own `t` and CUDA-IPC views of the others' device memory (one node, peer access over
+    NVLink).  Collective; the mapping is cached per (storage address, size) so a reused output buffer is exchanged once."""
+    import torch.distributed as dist
+    from torch.multiprocessing.reductions import reduce_tensor
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    key = (t.data_ptr(), tuple(t.shape), t.dtype, id(group))
+    flag = torch.tensor([0 if key in _PEER_VIEWS else 1], device=t.device)
+    dist.all_reduce(flag, group=group)  # any rank without a cached mapping -> everybody re-exchanges handles
+    if int(flag.item()) == 0:
+        return _PEER_VIEWS[key][0]
+    objs = [None] * world
+    dist.all_gather_object(objs, reduce_tensor(t), group=group)
+    views = [t if q == rank else objs[q][0](*objs[q][1]) for q in range(world)]
+    probe = torch.empty(1, device=t.device, dtype=t.dtype)
+    for q, v in enumerate(views):
+        if q == rank:
+            continue
+        if not torch.cuda.can_device_access_peer(t.device.index, v.device.index):
+            raise _lib.LadcastB200Error(f"GPU {t.device.index} cannot access GPU {v.device.index} as a peer")
+        probe.copy_(v.reshape(-1)[:1])  # a device-to-device copy makes torch enable peer access local <-> q
+    torch.cuda.synchronize(t.device)
+    _PEER_VIEWS[key] = (views, t)  # keeps the source alive as long as the mapping is cached
+    return views
+
+
+@torch.no_grad()
+def _local_sums_peer(views, members, n_planes: int, mine: range, truth_mine: torch.Tensor, lat_weights: torch.Tensor, H, W):
+    """sums/counts [4, len(mine)] of this rank's plane slice with every member read where it lies: views[q] is rank q's
+    [M_q, N, HW] fp32 field block (peer memory for q != rank)."""
+    import ctypes
+
+    lib = _lib.load()
+    dev = truth_mine.device
+    n_mine = len(mine)
+    ptrs = []
+    for q, v in enumerate(views):
+        for l in range(members[q]):
+            ptrs.append(v.data_ptr() + 4 * (l * n_planes + mine.start) * H * W)
+    arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+    sums = torch.empty((4, n_mine), device=dev, dtype=torch.float64)
+    counts = torch.empty((4, n_mine), device=dev, dtype=torch.float64)
+    lw = lat_weights.to(dev, torch.float64).contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(lib.lc_metrics_accumulate_ptrs(arr, _lib.ptr(truth_mine), _lib.ptr(lw), len(ptrs), n_mine, H, W,
+                                                  _lib.ptr(sums), _lib.ptr(counts), _lib.stream()),
+                   "lc_metrics_accumulate_ptrs")
+    return sums, counts
+
+
 def _global_rank(group, q):
     import torch.distributed as dist
 
@@ -230,14 +285,19 @@ def _global_rank(group, q):
 @torch.no_grad()
 def ensemble_metrics_distributed(fields_local: torch.Tensor, truth: torch.Tensor, lat_weights=None, group=None,
                                  sst_channel: Optional[int] = SST_CHANNEL_IDX,
-                                 local_sums_fn: Optional[Callable] = None, timings: Optional[dict] = None
-                                 ) -> Dict[str, torch.Tensor]:
+                                 local_sums_fn: Optional[Callable] = None, timings: Optional[dict] = None,
+                                 exchange: str = "nccl") -> Dict[str, torch.Tensor]:
     """Members are sharded over ranks (`fields_local` [M_r, C, T, H, W] with possibly different M_r per rank); CRPS
     spread and the ensemble mean need all members per grid point, so the fields are re-sharded once — rank r receives
     every member's values for its contiguous slice of the C*T (channel, lead) planes (`reshard_members_to_planes`) —
     reduced locally by the metrics kernel, and the [8, planes] partial tables are all-gathered.  Every rank returns the
     full [C, T] tables (reference assembly: evaluate/evaluate_ens_gpu.py:339-415, gather :462-468).
-    `timings` (optional dict) receives CUDA-event milliseconds of the exchange and of the local reduction."""
+    `timings` (optional dict) receives CUDA-event milliseconds of the exchange and of the local reduction.
+    exchange="p2p" (one node, CUDA): no exchange step at all — the other ranks' field blocks are mapped into this
+    process (`peer_views`) and `lc_metrics_accumulate_ptrs` reads every member of this rank's plane slice in place over
+    NVLink, so the transfer overlaps the reduction pixel by pixel and the gathered copy (a write + a read of
+    M * planes/world * H * W * 4 B per rank) never exists.  `fields_local` must then be fp32-contiguous and must not be
+    overwritten by its owner until the call has returned on every rank (the function ends with a barrier)."""
     import torch.distributed as dist
 
     if local_sums_fn is None:
@@ -259,18 +319,40 @@ def ensemble_metrics_distributed(fields_local: torch.Tensor, truth: torch.Tensor
     mine = plane_shard(N, rank, world)
     n_mine = len(mine)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if (timings is not None and dev.type == "cuda") else None
-    if ev:
-        ev[0].record()
-    gathered = reshard_members_to_planes(f, members, group)
-    if ev:
-        ev[1].record()
-    t_mine = truth.to(dev, torch.float32).reshape(N, H, W)[mine.start : mine.stop]
-    if n_mine:
-        sums_l, counts_l = local_sums_fn(gathered.reshape(-1, n_mine, H, W), t_mine, lat_weights)
+    t_mine = truth.to(dev, torch.float32).reshape(N, H, W)[mine.start : mine.stop].contiguous()
+    if exchange == "p2p":
+        if dev.type != "cuda":
+            raise _lib.LadcastB200Error("exchange='p2p' needs CUDA tensors (peer memory over NVLink)")
+        if sum(members) > 64:
+            raise _lib.LadcastB200Error("exchange='p2p' supports up to 64 members in total")
+        views = peer_views(f if M_r > 0 else torch.zeros(1, device=dev), group)  # a rank without members shares a dummy
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)  # every rank's fields are complete before anybody reads them
+        if ev:
+            ev[0].record()
+            ev[1].record()
+        if n_mine:
+            sums_l, counts_l = _local_sums_peer(views, members, N, mine, t_mine, lat_weights, H, W)
+        else:
+            sums_l = counts_l = torch.zeros((4, 0), dtype=torch.float64, device=dev)
+        if ev:
+            ev[2].record()
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)  # peers have finished reading this rank's fields
+    elif exchange == "nccl":
+        if ev:
+            ev[0].record()
+        gathered = reshard_members_to_planes(f, members, group)
+        if ev:
+            ev[1].record()
+        if n_mine:
+            sums_l, counts_l = local_sums_fn(gathered.reshape(-1, n_mine, H, W), t_mine, lat_weights)
+        else:
+            sums_l = counts_l = torch.zeros((4, 0), dtype=torch.float64, device=dev)
+        if ev:
+            ev[2].record()
     else:
-        sums_l = counts_l = torch.zeros((4, 0), dtype=torch.float64, device=dev)
-    if ev:
-        ev[2].record()
+        raise ValueError(f"unknown exchange {exchange!r}")
     n_max = max(len(plane_shard(N, q, world)) for q in range(world))
     packed = torch.zeros((8, n_max), dtype=torch.float64, device=dev)
     packed[:4, :n_mine], packed[4:, :n_mine] = sums_l, counts_l
