@@ -340,10 +340,12 @@ constexpr int ATTN_SPLIT_DEFAULT = 1;
 constexpr int SMEM_BYTES_P = 2 * TILE_BYTES + RING_P * TILE_BYTES + 256 + XCH_BYTES;
 constexpr int NUM_THREADS_P = NUM_THREADS;
 
-// POLY > 0: every POLY-th element of a row's exponentials is computed by ptx::ex2_poly on the FMA / ALU pipes — the
-// softmax step is bound by the MUFU pipe (16 ex2 / clk / SM against 128 x 128 exponentials per tile step, the same
-// ~1 k cycles the tensor pipe needs for the step's 16 MMAs), so moving a fraction off it shortens the serial
-// softmax -> P V -> Q K^T chain of a tile.
+// POLY > 0: every POLY-th element of a row's exponentials is computed by ptx::ex2_poly on the FMA / ALU pipes instead
+// of the MUFU (16 ex2 / clk / SM against 128 x 128 exponentials per tile step).  Measured on B200 (B=20, S=2250, H=12,
+// profiles/r02_attn_ab.log): every period tried (2, 3, 4, 8) is SLOWER than the all-MUFU form (1063 -> 976-1048 TFLOP/s;
+// with the split hand-over 1114 -> 999-1111): the softmax step is issue- / latency-bound, not MUFU-throughput-bound, and
+// the 8 extra FMA / ALU instructions per element cost more than the MUFU slot they free.  Kept as an experiment
+// (LADCAST_B200_ATTN_POLY=3), off by default.
 // SPLIT: a thread owns keys [32 hh, 32 hh + 32) and [64 + 32 hh, 64 + 32 hh + 32) of its row instead of one 64-key
 // half, and P is handed to the tensor pipe in two 64-key chunks (p_half, then p_full): the first four K-steps of
 // O += P V run while the second chunk is still being exponentiated.
@@ -586,6 +588,24 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __g
             for (int i = 0; i < 32; ++i)
               if ((c == 0 ? key0 : key1) + i >= n_valid) sreg[c][i] = 0xff800000u;  // -inf
         }
+        float neg_m = -m_used;
+        float ps[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[32];
+        auto exps = [&](auto lo) {  // exponentials + bf16 packing of elements [lo, lo + 32) of this thread's 64
+          constexpr int LO = decltype(lo)::value;
+#pragma unroll
+          for (int i = LO; i < LO + 32; i += 2) {
+            const float x0 = fmaf(__uint_as_float(sreg[i >> 5][i & 31]), scale_log2, neg_m);
+            const float x1 = fmaf(__uint_as_float(sreg[i >> 5][(i & 31) + 1]), scale_log2, neg_m);
+            const float p0 = (POLY > 0 && (i % POLY) == POLY - 1) ? ptx::ex2_poly(x0) : ptx::ex2_approx(x0);
+            const float p1 = (POLY > 0 && ((i + 1) % POLY) == POLY - 1) ? ptx::ex2_poly(x1) : ptx::ex2_approx(x1);
+            ps[(i >> 1) & 3] += p0 + p1;
+            __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&pb);
+          }
+        };
+        // (Measured and dropped: exponentiating the first chunk speculatively against the previous running maximum
+        // while the row maximum is still being exchanged — 1009 vs 1135 TFLOP/s, the extra live registers spill.)
         float mxs[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int c = 0; c < 2; ++c)
@@ -602,23 +622,8 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm, const __g
         if (need) {
           alpha = (m_used == -INFINITY) ? 0.f : exp2f(m_used - m_new);
           m_used = m_new;
+          neg_m = -m_used;
         }
-        const float neg_m = -m_used;
-        float ps[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t pk[32];
-        auto exps = [&](auto lo) {  // exponentials + bf16 packing of elements [lo, lo + 32) of this thread's 64
-          constexpr int LO = decltype(lo)::value;
-#pragma unroll
-          for (int i = LO; i < LO + 32; i += 2) {
-            const float x0 = fmaf(__uint_as_float(sreg[i >> 5][i & 31]), scale_log2, neg_m);
-            const float x1 = fmaf(__uint_as_float(sreg[i >> 5][(i & 31) + 1]), scale_log2, neg_m);
-            const float p0 = (POLY > 0 && (i % POLY) == POLY - 1) ? ptx::ex2_poly(x0) : ptx::ex2_approx(x0);
-            const float p1 = (POLY > 0 && ((i + 1) % POLY) == POLY - 1) ? ptx::ex2_poly(x1) : ptx::ex2_approx(x1);
-            ps[(i >> 1) & 3] += p0 + p1;
-            __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&pb);
-          }
-        };
         exps(std::integral_constant<int, 0>{});
         if (SPLIT && need && j > 0) {  // rare: the O rescale must precede the FIRST chunk's hand-over
 #pragma unroll 1
@@ -769,12 +774,8 @@ int attention_bf16(const bf16* qkv, int B, int S, int heads, int head_dim, bf16*
   // LADCAST_B200_ATTN_POLY = n: every n-th exponential on the FMA / ALU pipes (0 = all on the MUFU)
   static const int poly = [] { const char* e = getenv("LADCAST_B200_ATTN_POLY"); return e != nullptr ? atoi(e) : ATTN_POLY_DEFAULT; }();
   static const int split = [] { const char* e = getenv("LADCAST_B200_ATTN_SPLIT"); return e != nullptr ? atoi(e) : ATTN_SPLIT_DEFAULT; }();
-  auto kern = split ? (poly == 2 ? attention_tc_persistent_kernel<2, true> : poly == 3 ? attention_tc_persistent_kernel<3, true>
-                     : poly == 4 ? attention_tc_persistent_kernel<4, true> : poly == 8 ? attention_tc_persistent_kernel<8, true>
-                                                                                      : attention_tc_persistent_kernel<0, true>)
-                    : (poly == 2 ? attention_tc_persistent_kernel<2, false> : poly == 3 ? attention_tc_persistent_kernel<3, false>
-                     : poly == 4 ? attention_tc_persistent_kernel<4, false> : poly == 8 ? attention_tc_persistent_kernel<8, false>
-                                                                                       : attention_tc_persistent_kernel<0, false>);
+  auto kern = !split ? attention_tc_persistent_kernel<0, false>
+              : poly == 3 ? attention_tc_persistent_kernel<3, true> : attention_tc_persistent_kernel<0, true>;
   static PerDevice<bool> attr_set_p;
   if (!attr_set_p.here()) {
     LC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_P));

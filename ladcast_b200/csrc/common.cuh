@@ -124,6 +124,7 @@ struct EpiParams {
   const float* norm_w = nullptr; // EPI_NORM_RESID: RMSNorm weight / bias [N]
   const float* norm_b = nullptr;
   float norm_eps = 0.f;
+  int stage_bf16 = 0;  // CTA-pair kernel, bf16 outputs: rows staged through shared memory, coalesced write-back (LADCAST_B200_EPI_STAGE=0: off)
   int prefetch = 1;  // read-modify-write epilogues: L2 prefetch of the next tile's residual rows (LADCAST_B200_EPI_PREFETCH=0: off)
   int n_valid = 0;  // EPI_UNPATCHIFY: number of real output channels (<= N)
   // EPI_UNPATCHIFY into a 5-D [B, n_valid, up_T, rows_per_sample] tensor: sample s of this launch is frame

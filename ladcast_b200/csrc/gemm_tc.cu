@@ -305,10 +305,46 @@ __device__ __forceinline__ void epilogue_block_norm(const EpiParams& ep, const u
 // qkv projection chunk (32 columns of one head, thread = row): bias, then (q/k heads only) per-head RMSNorm with the
 // row's rstd and RoPE on interleaved pairs, bf16, four 16-byte stores.  The rotation factors come from a packed
 // [tokens, 64] half2 (cos, sin) table: 64 B per thread and chunk instead of 256 B of fp32 cos + sin.
+
+// Staged bf16 write-back (see drain_bf16_staged): a warp's 32 rows x 64 columns sit in its 4 KB staging tile as
+// [row][8 x 16-byte chunk ^ (row & 7)]; lane = (row-in-group rsub = lane / 8, chunk kq = lane % 8): 8 lanes cover one
+// contiguous 128-byte row segment, four rows per instruction.
+struct StagedRows {
+  long long orows[8];
+  bool ok[8];
+};
+__device__ __forceinline__ StagedRows staged_rows(int lane, int row, long long orow, int M) {
+  StagedRows sr;
+  const int rsub = lane >> 3;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const int rr = g * 4 + rsub;
+    sr.ok[g] = __shfl_sync(0xffffffffu, row, rr) < M;
+    sr.orows[g] = __shfl_sync(0xffffffffu, orow, rr);
+  }
+  return sr;
+}
+__device__ __forceinline__ void staged_put(uint8_t* buf, int lane, int chunk, const uint4& pk) {
+  *reinterpret_cast<uint4*>(buf + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = pk;
+}
+__device__ __forceinline__ void staged_writeback(const EpiParams& ep, const uint8_t* buf, int lane, int n0_64,
+                                                 const StagedRows& sr) {
+  const int rsub = lane >> 3, kq = lane & 7;
+  __syncwarp();
+  bf16* gbase = reinterpret_cast<bf16*>(ep.out) + n0_64 + kq * 8;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const int rr = g * 4 + rsub;
+    const uint4 val = *reinterpret_cast<const uint4*>(buf + rr * 128 + ((kq ^ (rr & 7)) << 4));
+    if (sr.ok[g]) *reinterpret_cast<uint4*>(gbase + sr.orows[g] * ep.ldo) = val;
+  }
+  __syncwarp();
+}
+
 // Reference: LaDCast_3D_model.py:92-169 (to_q/k/v, norm_q/k, apply_rotary_emb).
 __device__ __forceinline__ void epilogue_qkv_chunk(const EpiParams& ep, const uint32_t (&r)[32], bool row_ok,
                                                    long long orow, int tok, float rstd, int n0, int colh0, bool is_qk,
-                                                   const float* nw) {
+                                                   const float* nw, uint8_t* stage = nullptr, int lane = 0, int cpar = 0) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
@@ -340,7 +376,7 @@ __device__ __forceinline__ void epilogue_qkv_chunk(const EpiParams& ep, const ui
       }
     }
   }
-  if (!row_ok) return;
+  if (!row_ok && stage == nullptr) return;
   uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + orow * ep.ldo + n0);
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
@@ -351,7 +387,8 @@ __device__ __forceinline__ void epilogue_qkv_chunk(const EpiParams& ep, const ui
     pk.y = *reinterpret_cast<uint32_t*>(&t1);
     pk.z = *reinterpret_cast<uint32_t*>(&t2);
     pk.w = *reinterpret_cast<uint32_t*>(&t3);
-    op[j >> 3] = pk;
+    if (stage != nullptr) staged_put(stage, lane, cpar * 4 + (j >> 3), pk);
+    else op[j >> 3] = pk;
   }
 }
 
@@ -364,12 +401,64 @@ __device__ __forceinline__ int epi_kind(const EpiParams& ep) {
   return ep.out_f32 ? K_STORE_F32 : K_STORE_BF16;
 }
 
+// bf16 output, full column slice: bias / activation / packing as in epilogue_block, but the packed rows go through a
+// per-warp 4 KB staging tile (32 rows x 128 B, 16-byte chunks XOR-swizzled by row so that both directions are bank-
+// conflict free) and are written back with 8 lanes x 16 B covering one contiguous 128-byte row segment, four rows per
+// instruction.  The direct form (each thread stores 16 B of its own row: 32 different lines per warp instruction)
+// keeps the LSU busy for ~7-8 k cycles per 128x256 tile — with K = 1536 that is most of the 11-14 k-cycle epilogue, which
+// then back-pressures the MMA issuer through the two accumulator stages (tools/gemm_trace.py: 1.5-2.7 k of every
+// ~16 k-cycle tile waiting for a free accumulator).
+template <int BN, int ACT>
+__device__ __forceinline__ void drain_bf16_staged(const EpiParams& ep, uint32_t t_addr, int n_base, float* tbuf, int lane,
+                                                  int row, long long orow, int M) {
+  constexpr int NC = BN / 64;
+  uint8_t* buf = reinterpret_cast<uint8_t*>(tbuf);
+  const StagedRows sr = staged_rows(lane, row, orow, M);
+  const bool has_bias = ep.bias != nullptr;
+  uint32_t r[2][32];
+  ptx::tmem_ld32(t_addr, r[0]);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    ptx::tmem_ld_wait();
+    if (c + 1 < NC) ptx::tmem_ld32(t_addr + (c + 1) * 32, r[(c + 1) & 1]);
+    const int n0 = n_base + c * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = __uint_as_float(r[c & 1][j + q]);
+      if (has_bias) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j + 4));
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+      __nv_bfloat162 t0 = __floats2bfloat162_rn(act_fast<ACT>(v[0]), act_fast<ACT>(v[1]));
+      __nv_bfloat162 t1 = __floats2bfloat162_rn(act_fast<ACT>(v[2]), act_fast<ACT>(v[3]));
+      __nv_bfloat162 t2 = __floats2bfloat162_rn(act_fast<ACT>(v[4]), act_fast<ACT>(v[5]));
+      __nv_bfloat162 t3 = __floats2bfloat162_rn(act_fast<ACT>(v[6]), act_fast<ACT>(v[7]));
+      uint4 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&t0);
+      pk.y = *reinterpret_cast<uint32_t*>(&t1);
+      pk.z = *reinterpret_cast<uint32_t*>(&t2);
+      pk.w = *reinterpret_cast<uint32_t*>(&t3);
+      staged_put(buf, lane, (c & 1) * 4 + (j >> 3), pk);
+    }
+    // 64 columns of the 32 rows are staged: write them back as whole 128-byte row segments
+    if (c & 1) staged_writeback(ep, buf, lane, n0 - 32, sr);
+  }
+}
+
 // Chunk loop of one accumulator stage with the TMEM load of chunk c+1 in flight while chunk c is processed; kind and
 // activation are compile-time so the loop body is straight-line code.
 template <int BN, int KIND, int ACT>
 __device__ __forceinline__ void drain_loop(const EpiParams& ep, uint32_t t_addr, int n_base, float* tbuf, int lane, int row,
                                            long long orow, int sample, int M, int N) {
   constexpr int NC = BN / 64;
+  if (KIND == K_STORE_BF16 && ep.stage_bf16 && n_base + BN / 2 <= N && (ep.ldo & 7) == 0) {
+    drain_bf16_staged<BN, ACT>(ep, t_addr, n_base, tbuf, lane, row, orow, M);
+    return;
+  }
   uint32_t r[2][32];
   ptx::tmem_ld32(t_addr, r[0]);
 #pragma unroll
@@ -495,12 +584,17 @@ __device__ __forceinline__ void epilogue_drain(const EpiParams& ep, int kind, in
     const int tok = row % ep.rows_per_sample;
     const bool row_ok = row < M;
     if (head0 < N) {
+      const bool staged = ep.stage_bf16 && (ep.ldo & 7) == 0;
+      uint8_t* buf = staged ? reinterpret_cast<uint8_t*>(tbuf) : nullptr;
+      StagedRows sr;
+      if (staged) sr = staged_rows(lane, row, orow, M);
       ptx::tmem_ld32(t_addr, r[0]);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         ptx::tmem_ld_wait();
         if (c + 1 < 4) ptx::tmem_ld32(t_addr + (c + 1) * 32, r[(c + 1) & 1]);
-        epilogue_qkv_chunk(ep, r[c & 1], row_ok, orow, tok, rstd, head0 + c * 32, c * 32, is_qk, nw);
+        epilogue_qkv_chunk(ep, r[c & 1], row_ok, orow, tok, rstd, head0 + c * 32, c * 32, is_qk, nw, buf, lane, c & 1);
+        if (staged && (c & 1)) staged_writeback(ep, buf, lane, head0 + (c - 1) * 32, sr);
       }
     }
   } else {
@@ -909,8 +1003,10 @@ int launch_pair(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap&
   const int cls = cv.enabled ? PROF_CONV : PROF_GEMM;
   const double flops = 2.0 * M * N * (cv.enabled ? 9.0 * cv.c_real : static_cast<double>(K));
   static const bool epi_prefetch = [] { const char* e = getenv("LADCAST_B200_EPI_PREFETCH"); return !(e != nullptr && e[0] == '0'); }();
+  static const bool epi_stage = [] { const char* e = getenv("LADCAST_B200_EPI_STAGE"); return !(e != nullptr && e[0] == '0'); }();
   EpiParams epl = ep;
   epl.prefetch = epi_prefetch ? 1 : 0;
+  epl.stage_bf16 = epi_stage ? 1 : 0;
   prof_begin(cls, stream);
   LC_CHECK_CUDA(launch_kernel(gemm_tc2_kernel, grid, NUM_THREADS, C::SMEM, stream, a0, a1, w, M, N, K, K0, epl, sched, cv));
   prof_end(cls, flops, stream, algorithmic_bytes(M, N, K, ep, cv));
