@@ -81,11 +81,11 @@ struct lc_denoiser {
   std::vector<DualW> dual;
   std::vector<SingleW> single;
   int mod_dim = 0, kp_in = 96;
-  // RMSNorm(q,k)+RoPE fused into the qkv GEMM epilogue (gemm_tc.cu K_QKV, thread-per-row, packed half2 rotation
-  // table).  Measured in-step A/B on B200 (375M, B=20): 505.0 vs 508.3 ms per AR step, i.e. +0.6 % — the K=1536
-  // projections' epilogue becomes their critical path (GEMM class 1157 vs 1217 TFLOP/s) and eats most of the
-  // 19 ms of the removed HBM-bound kernel.  Within box-to-box noise, so off by default; LADCAST_B200_FUSE_QK=1
-  // turns it on.
+  // RMSNorm(q,k)+RoPE fused into the qkv GEMM epilogue (gemm_tc.cu K_QKV: one pass over tensor memory, values kept as
+  // packed bf16 pairs, staged coalesced stores).  Measured in-step A/B on B200 (375M, B=20), three epilogue forms over
+  // two rounds: always +0.6 % (477.5 vs 480.5 ms per AR step): the norm / rotation arithmetic of a 128x256 tile on 8
+  // epilogue warps (~2x the plain epilogue) exceeds the K=1536 main loop it has to hide under, and the qkv GEMMs give
+  // back the 18 ms of the removed HBM-bound kernel (GEMM class 256 -> 275 ms).  Off by default; LADCAST_B200_FUSE_QK=1.
   bool fuse_qk = false;
   // single-stream blocks: pred and cond rows in one GEMM launch per projection (LADCAST_B200_MERGE_STREAMS=0: off)
   bool merge_streams = true;

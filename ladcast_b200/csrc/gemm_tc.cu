@@ -392,6 +392,75 @@ __device__ __forceinline__ void epilogue_qkv_chunk(const EpiParams& ep, const ui
   }
 }
 
+// Fused qkv epilogue in ONE pass over tensor memory: this warp owns one 128-column head of the tile and each thread a
+// full head row.  Pass over TMEM: bias, sum of squares (fp32), values kept as 64 packed bf16 pairs in registers (the
+// reference's own autocast rounds the projection output to bf16 before the RMSNorm).  Then from registers: q/k heads
+// are normalised and rotated (packed half2 (cos, sin) table), every head is staged and written back as whole 128-byte
+// row segments.  The two-pass form read TMEM twice and its scattered 16-byte stores made the epilogue the K=1536
+// projections' critical path.
+__device__ __forceinline__ void drain_qkv_single_pass(const EpiParams& ep, uint32_t t_addr, int head0, bool is_qk,
+                                                      const float* nw, float* tbuf, int lane, int row, long long orow,
+                                                      int M) {
+  uint8_t* buf = reinterpret_cast<uint8_t*>(tbuf);
+  const bool row_ok = row < M;
+  const int tok = row % ep.rows_per_sample;
+  uint32_t pkd[64];
+  float ss[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {  // one 32-column load in flight at a time: the 64 packed pairs need the registers
+    uint32_t r[32];
+    ptx::tmem_ld32(t_addr + c * 32, r);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + head0 + c * 32 + j));
+      const float t0 = __uint_as_float(r[j]) + b4.x, t1 = __uint_as_float(r[j + 1]) + b4.y;
+      const float t2 = __uint_as_float(r[j + 2]) + b4.z, t3 = __uint_as_float(r[j + 3]) + b4.w;
+      ss[0] = fmaf(t0, t0, ss[0]); ss[1] = fmaf(t1, t1, ss[1]); ss[2] = fmaf(t2, t2, ss[2]); ss[3] = fmaf(t3, t3, ss[3]);
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(t0, t1), p1 = __floats2bfloat162_rn(t2, t3);
+      pkd[c * 16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&p0);
+      pkd[c * 16 + (j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
+    }
+  }
+  if (is_qk) {
+    const float rstd = rsqrtf(((ss[0] + ss[1]) + (ss[2] + ss[3])) * (1.0f / 128.0f) + ep.qk_eps);
+    const uint4* cs = (ep.rope_cs != nullptr && row_ok)
+                          ? reinterpret_cast<const uint4*>(ep.rope_cs + static_cast<long long>(tok) * 64) : nullptr;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {  // 8 features = 4 rotation pairs per step
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(nw + q * 8));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(nw + q * 8 + 4));
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      uint4 c4 = make_uint4(0u, 0u, 0u, 0u);
+      if (cs != nullptr) c4 = __ldg(cs + q);
+      const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pkd[q * 4 + k]));
+        float a = x.x * rstd * wv[2 * k], b = x.y * rstd * wv[2 * k + 1];
+        if (cs != nullptr) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&cw[k]));  // (cos, sin)
+          const float ra = a * f.x - b * f.y, rb = b * f.x + a * f.y;
+          a = ra;
+          b = rb;
+        }
+        __nv_bfloat162 o = __floats2bfloat162_rn(a, b);
+        pkd[q * 4 + k] = *reinterpret_cast<uint32_t*>(&o);
+      }
+    }
+  }
+  const StagedRows sr = staged_rows(lane, row, orow, M);
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {  // two groups of 64 columns through the 4 KB staging tile
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch)
+      staged_put(buf, lane, ch, make_uint4(pkd[g * 32 + ch * 4], pkd[g * 32 + ch * 4 + 1], pkd[g * 32 + ch * 4 + 2],
+                                           pkd[g * 32 + ch * 4 + 3]));
+    staged_writeback(ep, buf, lane, head0 + g * 64, sr);
+  }
+}
+
 __device__ __forceinline__ int epi_kind(const EpiParams& ep) {
   if (ep.qk_cols > 0) return K_QKV;
   if (ep.mode == EPI_NORM_RESID) return K_NORM;
@@ -560,6 +629,10 @@ __device__ __forceinline__ void epilogue_drain(const EpiParams& ep, int kind, in
     const int head0 = n_blk * BN + half * (BN / 2);
     const bool is_qk = head0 < ep.qk_cols;
     const float* nw = (head0 < ep.qk_cols / 2) ? ep.qk_wq : ep.qk_wk;
+    if (ep.stage_bf16 && (ep.ldo & 7) == 0) {
+      if (head0 < N) drain_qkv_single_pass(ep, t_addr, head0, is_qk, nw, tbuf, lane, row, orow, M);
+      return;
+    }
     float rstd = 1.f;
     uint32_t r[2][32];
     if (is_qk && head0 < N) {

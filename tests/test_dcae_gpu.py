@@ -73,7 +73,7 @@ def test_dcae_tiny_vs_golden(golden_dir):
 SMALL = O.dcae_config("tiny")
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 8.5e-3)])  # measured 1.4e-6 / 6.3e-3
 def test_dcae_small_vs_oracle(precision, tol):
     cfg, sd, ae = _ae(SMALL, 22, precision)
     z = _seeded((3, 84, 15, 30), 500)
@@ -98,8 +98,8 @@ def test_dcae_full_bf16_vs_oracle():
     torch.cuda.synchronize()
     r = _rel(out, want)
     record_measured("dcae_full_V0.1.X/bf16/rel_l2", r)
-    assert r < 2e-2
-    assert _rel(fused, want * std[None, :, None, None] + mean[None, :, None, None]) < 2e-2
+    assert r < 1e-2  # north_star per-call budget; measured 7.9e-3 (profiles/r02_measured_parity.jsonl)
+    assert _rel(fused, want * std[None, :, None, None] + mean[None, :, None, None]) < 1e-2
 
 
 def test_dcae_decode_160_latents_batch_consistency():

@@ -53,7 +53,7 @@ def test_attention(lib, b, s, heads, prec):
     if prec == _lib.PRECISION_BF16:
         qkv_in = qkv.bfloat16().contiguous()
         out = torch.zeros(b, s, d, device="cuda", dtype=torch.bfloat16)
-        tol = 1.5e-2
+        tol = 3e-3  # measured 1.8e-3 .. 2.3e-3 (profiles/r02_measured_parity.jsonl); P and the output are bf16
     else:
         qkv_in = qkv
         out = torch.zeros(b, s, d, device="cuda")

@@ -80,3 +80,38 @@ def test_get_acc_vs_oracle():
     got_u = get_acc(f.cuda(), t.cuda(), c.cuda())
     assert torch.allclose(got_w.cpu(), want_w, rtol=1e-6, atol=1e-9)
     assert torch.allclose(got_u.cpu(), want_u, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("M", [1, 7, 20, 50])
+def test_metrics_pointer_form_matches_strided(M):
+    """lc_metrics_accumulate_ptrs (one base pointer per member: the form that reads peer-GPU members in place) against
+    lc_metrics_accumulate_strided on the same values, with the members scattered over separate allocations and a plane
+    offset as in the distributed reduction: bit-identical tables."""
+    import ctypes
+
+    from ladcast_b200 import _lib
+    from ladcast_b200.evaluate.utils import get_normalized_lat_weights_based_on_cos
+
+    lib = _lib.load()
+    N, H, W, n0, n_mine = 12, 120, 48, 3, 5  # a rank's slice [n0, n0 + n_mine) of N planes
+    fields = _seeded((M, N, H, W), 300 + M).cuda()
+    truth = _seeded((N, H, W), 301).cuda()
+    truth[4, 7:9, 5:11] = float("nan")
+    lw = torch.from_numpy(get_normalized_lat_weights_based_on_cos(np.linspace(-88.5, 90, H))).cuda()
+    blocks = [fields[m].clone() for m in range(M)]  # every member in its own allocation
+    ptrs = (ctypes.c_void_p * M)(*[b.data_ptr() + 4 * n0 * H * W for b in blocks])
+    t_mine = truth[n0 : n0 + n_mine].contiguous()
+    s1, c1 = [torch.empty((4, n_mine), device="cuda", dtype=torch.float64) for _ in range(2)]
+    s2, c2 = [torch.empty((4, n_mine), device="cuda", dtype=torch.float64) for _ in range(2)]
+    _lib.check(lib.lc_metrics_accumulate_ptrs(ptrs, _lib.ptr(t_mine), _lib.ptr(lw), M, n_mine, H, W, _lib.ptr(s1),
+                                              _lib.ptr(c1), _lib.stream()), "lc_metrics_accumulate_ptrs")
+    sl = fields[:, n0 : n0 + n_mine]
+    _lib.check(lib.lc_metrics_accumulate_strided(_lib.ptr_any(sl), fields.stride(0), _lib.ptr(t_mine), _lib.ptr(lw), M,
+                                                 n_mine, H, W, _lib.ptr(s2), _lib.ptr(c2), _lib.stream()),
+               "lc_metrics_accumulate_strided")
+    torch.cuda.synchronize()
+    assert torch.equal(c1, c2)
+    assert torch.allclose(s1, s2, rtol=1e-12, atol=0, equal_nan=True)  # fp64 atomics: order of block sums may differ
+    with pytest.raises(_lib.LadcastB200Error):
+        _lib.check(lib.lc_metrics_accumulate_ptrs(ptrs, _lib.ptr(t_mine), _lib.ptr(lw), 65, n_mine, H, W, _lib.ptr(s1),
+                                                  _lib.ptr(c1), _lib.stream()), "lc_metrics_accumulate_ptrs")

@@ -10,6 +10,9 @@ for i in 1 2; do
     LADCAST_B200_FUSE_QK=$fq timeout 600 python bench.py --no-cpu-baseline --no-strong --no-e2e --no-metrics > gpurun_out/r02i_bench_fq${fq}_$i.json 2> gpurun_out/r02i_bench.err; echo "fq=$fq rc=$?"
   done
 done
+for fq in 0 1; do
+  LADCAST_B200_PDL=1 LADCAST_B200_FUSE_QK=$fq timeout 600 python bench.py --no-cpu-baseline --no-strong --no-e2e --no-metrics > gpurun_out/r02i_bench_fq${fq}_pdl.json 2> gpurun_out/r02i_bench.err; echo "pdl fq=$fq rc=$?"
+done
 python - <<'PY'
 import json,glob
 for f in sorted(glob.glob('gpurun_out/r02i_bench_fq*_*.json')):
