@@ -228,7 +228,7 @@ def workload_config(args, world):
 class Rollout:
     """Device-resident AR loop for a list of global member ids: exactly `rollout_step` of the product path."""
 
-    def __init__(self, model_name, members, args, dev, ae=None, model=None):
+    def __init__(self, model_name, members, args, dev, ae=None, model=None, out=None):
         from ladcast_b200.models import AutoencoderDC, LaDCastTransformer3DModel
         from ladcast_b200.pipelines import AutoRegressive2DPipeline, EDMDPMSolverMultistepScheduler
 
@@ -243,7 +243,8 @@ class Rollout:
         self.fld_mean, self.fld_std = torch.randn(84, generator=g), torch.rand(84, generator=g) + 0.5
         self.stats = [t.to(dev).contiguous() for t in (self.lat_mean, self.lat_std, self.fld_mean, self.fld_std)]
         self.known = self.known0.to(dev)
-        self.out = torch.empty((len(self.members), 84, args.t_out, 120, 240), device=dev) if self.members else None
+        self.out = out if out is not None else (
+            torch.empty((len(self.members), 84, args.t_out, 120, 240), device=dev) if self.members else None)
         self.stamp = torch.tensor([2018010100])  # the date embedding is recomputed every AR step like the reference
 
     def step(self):
@@ -404,11 +405,23 @@ def strong_leg(args, ens_total, rank, world, dev, ae, model, barrier, lib, _lib,
     from ladcast_b200.pipelines.utils import member_shard
 
     members = list(member_shard(ens_total, rank, world))
-    run = Rollout(args.strong_model, members, args, dev, ae=ae, model=model)
+    per_rank = [len(member_shard(ens_total, r, world)) for r in range(world)]
+    out_buf = None
+    if world > 1:  # (collective: every rank takes part, also one without members)
+        # decoded fields are produced straight into this rank's peer-visible buffer (CUDA IPC), so the fused
+        # peer-memory metrics below read them in place: no staging copy on either side
+        try:
+            from ladcast_b200.evaluate.utils import _peer_buffer
+
+            pb = _peer_buffer(max(per_rank) * 84 * args.t_out * 120 * 240, dev)
+            if members:
+                out_buf = pb.tensor[: len(members) * 84 * args.t_out * 120 * 240].view(len(members), 84, args.t_out, 120, 240)
+        except Exception:
+            out_buf = None
+    run = Rollout(args.strong_model, members, args, dev, ae=ae, model=model, out=out_buf)
     fields, ms, host_ms, launches, _ = timed_loop(run, steps, warmup, barrier, world, dev, lib)
     step_ms = ms / steps
     value = ens_total * args.t_out * steps / (ms * 1e-3)
-    per_rank = [len(member_shard(ens_total, r, world)) for r in range(world)]
     res = {"model": f"ladcast_{args.strong_model}", "ensemble_total": ens_total, "members_per_rank": per_rank,
            "scaling": "strong", "value": value, "unit": UNIT, "ms_per_step": step_ms, "steps": steps, "warmup": warmup,
            "gpu_launches_per_step": launches // max(1, steps),
@@ -452,13 +465,14 @@ def strong_leg(args, ens_total, rank, world, dev, ae, model, barrier, lib, _lib,
         # the same metrics with NO exchange step: peer-memory reads inside the reduction kernel (exchange="p2p")
         try:
             tp = {}
-            for _ in range(3):  # first pass maps the peers' buffers (CUDA IPC)
+            for _ in range(3):  # first pass allocates + maps the peer-visible buffers (CUDA IPC)
                 tabs_p = ensemble_metrics_distributed(fields, truth, timings=tp, exchange="p2p")
             okp = all(torch.allclose(tabs_p[k], want[k], rtol=1e-9, atol=1e-12, equal_nan=True) for k in want)
-            t = torch.tensor([tp["kernel_ms"], 0.0 if okp else 1.0], device=dev)
+            t = torch.tensor([tp["kernel_ms"], 0.0 if okp else 1.0, tp["exchange_ms"]], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             res["metrics"]["p2p_fused"] = {
-                "kernel_ms": round(float(t[0]), 3), "exchange_ms": 0.0, "matches_single_gpu": float(t[1]) == 0.0,
+                "kernel_ms": round(float(t[0]), 3), "stage_and_barrier_ms": round(float(t[2]), 3),
+                "fields_in_peer_buffer": out_buf is not None, "matches_single_gpu": float(t[1]) == 0.0,
                 "remote_gbs_per_gpu": round(by / (float(t[0]) * 1e-3) / 1e9, 1) if float(t[0]) > 0 else None,
                 "what": "lc_metrics_accumulate_ptrs: every rank reduces its plane slice reading the other ranks' members "
                         "in place over NVLink (CUDA-IPC peer memory) - exchange and reduction are one kernel"}
@@ -614,6 +628,12 @@ def main():
                 "clocks": clk, "finite": finite, "impl": "ours"}
         print(json.dumps(line))
     if world > 1:
+        try:
+            from ladcast_b200.evaluate.utils import release_peer_buffers
+
+            release_peer_buffers()
+        except Exception:
+            pass
         dist.destroy_process_group()
 
 

@@ -17,6 +17,7 @@
 #ifndef LADCAST_B200_H_
 #define LADCAST_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__GNUC__)
@@ -194,6 +195,18 @@ LC_API int lc_metrics_accumulate(const float* fields, const float* truth, const 
 LC_API int lc_metrics_accumulate_strided(const float* fields, long long member_stride, const float* truth,
                                          const double* lat_weights, int members, long long planes, int height, int width,
                                          double* sums, double* counts, void* stream);
+/* Peer-visible device buffers for the fused metrics exchange (one node, one process per GPU): the owner allocates
+ * `bytes` of device memory and gets a 64-byte CUDA-IPC handle to hand to the other processes (any byte transport);
+ * lc_ipc_open maps an owner's buffer for kernels of the CALLER's current GPU (cudaIpcOpenMemHandle with lazy peer
+ * access: loads go over NVLink / NVSwitch).  Close every opened mapping before the owner frees. */
+LC_API int lc_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);
+LC_API int lc_ipc_open(const unsigned char* handle64, void** dev_ptr);
+LC_API int lc_ipc_close(void* dev_ptr);
+LC_API int lc_ipc_free(void* dev_ptr);
+/* Lets kernels launched on the CURRENT device dereference memory of `peer_device` (cudaDeviceEnablePeerAccess;
+ * already-enabled is not an error).  Needed once per peer before lc_metrics_accumulate_ptrs is given pointers into
+ * another GPU's memory (e.g. CUDA-IPC mappings of the other ranks' decoded fields). */
+LC_API int lc_enable_peer_access(int peer_device);
 /* the same with one base pointer per member (HOST array of `members` <= 64 DEVICE pointers; member m's planes
  * [planes, H*W] are contiguous at member_ptrs[m]).  A pointer may address another GPU's memory mapped into this process
  * (CUDA IPC / peer access): with members sharded over GPUs (evaluate/evaluate_ens_gpu.py:462-468 gathers them instead)

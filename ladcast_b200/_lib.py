@@ -85,6 +85,11 @@ _OPTIONAL = {
     "lc_sphere_conv3x3": ([_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "lc_metrics_accumulate": ([_vp, _vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, _vp, _vp], _i),
     "lc_metrics_accumulate_strided": ([_vp, ctypes.c_longlong, _vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, _vp, _vp], _i),
+    "lc_enable_peer_access": ([_i], _i),
+    "lc_ipc_alloc": ([ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p), _vp], _i),
+    "lc_ipc_open": ([_vp, ctypes.POINTER(ctypes.c_void_p)], _i),
+    "lc_ipc_close": ([_vp], _i),
+    "lc_ipc_free": ([_vp], _i),
     "lc_metrics_accumulate_ptrs": ([_vp, _vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, _vp, _vp], _i),
     "lc_metrics_acc": ([_vp, _vp, _vp, _vp, ctypes.c_longlong, _i, _i, _vp, _vp, _vp], _i),
     "lc_metrics_pointwise": ([_vp, _vp, _i, ctypes.c_longlong, _i, _i, _vp, _vp, _vp, _vp], _i),

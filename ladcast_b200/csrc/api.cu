@@ -1,4 +1,5 @@
 // Remaining C-ABI entry points: version/error, scheduler steps, low-level op exports used by the parity tests.
+#include <cstring>
 #include <string>
 
 #include "../../include/ladcast_b200.h"
@@ -125,6 +126,60 @@ int lc_sched_heun_init(const float* noise, double* x, float* x_in, int64_t n, do
 int lc_sched_heun_churn(double* x, const double* noise, float* x_in, int64_t n, double k, double c_in, void* stream) {
   LC_REQUIRE(x && noise && x_in, "null argument");
   return sched_heun_churn(x, noise, x_in, n, k, c_in, static_cast<cudaStream_t>(stream));
+}
+
+// ---- peer-visible device buffers (CUDA IPC): the owner allocates and exports, every other process of the node opens
+// the handle ON ITS OWN GPU with lazy peer access, which maps the owner's memory for this GPU's kernels over NVLink.
+int lc_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64) {
+  LC_REQUIRE(dev_ptr != nullptr && handle64 != nullptr && bytes > 0, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  LC_CHECK_CUDA(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    LC_CHECK_CUDA(e);
+  }
+  memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  return 0;
+}
+
+int lc_ipc_open(const unsigned char* handle64, void** dev_ptr) {
+  LC_REQUIRE(dev_ptr != nullptr && handle64 != nullptr, "bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  LC_CHECK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *dev_ptr = p;
+  return 0;
+}
+
+int lc_ipc_close(void* dev_ptr) {
+  if (dev_ptr != nullptr) LC_CHECK_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return 0;
+}
+
+int lc_ipc_free(void* dev_ptr) {
+  if (dev_ptr != nullptr) LC_CHECK_CUDA(cudaFree(dev_ptr));
+  return 0;
+}
+
+int lc_enable_peer_access(int peer_device) {
+  int dev = 0;
+  LC_CHECK_CUDA(cudaGetDevice(&dev));
+  if (peer_device == dev) return 0;
+  int can = 0;
+  LC_CHECK_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+  LC_REQUIRE(can != 0, "the current GPU cannot access the requested peer GPU (no NVLink / PCIe peer path)");
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    (void)cudaGetLastError();  // not an error: somebody (torch, NCCL) enabled it before
+    return 0;
+  }
+  LC_CHECK_CUDA(e);
+  return 0;
 }
 
 int lc_latent_feedback(const float* samples, float* known_next, float* phys, const float* mean, const float* stdv,

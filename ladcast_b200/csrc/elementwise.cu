@@ -88,19 +88,20 @@ __device__ __forceinline__ void ln_row(float4 (&v)[NV], int row, int lane, T* __
   }
 }
 
-constexpr int LN_RPW = 4;  // rows per warp (8 measured slower: too few blocks for the 9000-row streams)
+constexpr int LN_RPW = 4;  // max rows per warp (8 measured slower: too few blocks for the 9000-row streams); the launcher
+                           // picks 4, 2 or 1 per launch so that small row counts (2-3 members per GPU) still fill whole waves
 
 template <typename T, int NV>
 __global__ void __launch_bounds__(256, NV <= 12 ? 2 : 1) layernorm_kernel(const float* __restrict__ x, T* __restrict__ out, int M, int d,
                                                            float eps, int rows_per_sample, int seg_rows,
                                                            int seg_rows_per_sample, const float* __restrict__ scale,
                                                            const float* __restrict__ shift, long long mod_stride,
-                                                           const float* __restrict__ w, const float* __restrict__ b) {
+                                                           const float* __restrict__ w, const float* __restrict__ b, int rpw) {
   pdl_grid_sync();
-  const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * LN_RPW;
+  const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * rpw;
   const int lane = threadIdx.x & 31;
   if (row0 >= M) return;
-  const int nrows = min(LN_RPW, M - row0);
+  const int nrows = min(rpw, M - row0);
   float4 buf[2][NV];
   const float* xr = x + static_cast<long long>(row0) * d + lane * 4;
 #pragma unroll
@@ -467,12 +468,22 @@ int layernorm_modulate(const float* x, T* out, int M, int d, float eps, int rows
                        int seg_rows, int seg_rows_per_sample) {
   LC_REQUIRE(d % 128 == 0 && d <= 2048, "layernorm: d must be a multiple of 128, <= 2048");
   const int nv = d / 128;
-  dim3 grid(ceil_div(M, 8 * LN_RPW));
+  // rows per warp: the largest of 4 / 2 / 1 whose grid fills >= 90 % of its last wave (else the best-filling one)
+  const int slots = num_sms() * (nv <= 12 ? 2 : 1);
+  int rpw = LN_RPW;
+  double best = -1.0;
+  for (int cand = LN_RPW; cand >= 1; cand >>= 1) {
+    const int blocks = ceil_div(M, 8 * cand);
+    const double eff = static_cast<double>(blocks) / (static_cast<double>(ceil_div(blocks, slots)) * slots);
+    if (eff >= 0.9) { rpw = cand; break; }
+    if (eff > best) { best = eff; rpw = cand; }
+  }
+  dim3 grid(ceil_div(M, 8 * rpw));
   ProfScope ps(PROF_LN, 0.0, static_cast<double>(M) * d * (4 + sizeof(T)), s);
 #define LC_LN_CASE(NV)                                                                                            \
   case NV:                                                                                                        \
     LC_CHECK_CUDA(launch_kernel(layernorm_kernel<T, NV>, grid, 256, 0, s, x, out, M, d, eps, rows_per_sample, seg_rows, \
-                                seg_rows_per_sample, scale, shift, mod_stride, w, b));                            \
+                                seg_rows_per_sample, scale, shift, mod_stride, w, b, rpw));                       \
     break;
   switch (nv) {
     LC_LN_CASE(1) LC_LN_CASE(2) LC_LN_CASE(3) LC_LN_CASE(4) LC_LN_CASE(5) LC_LN_CASE(6) LC_LN_CASE(7) LC_LN_CASE(8)

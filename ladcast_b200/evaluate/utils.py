@@ -221,50 +221,102 @@ def reshard_members_to_planes(fields_local: torch.Tensor, members, group=None, o
     return out
 
 
-_PEER_VIEWS: dict = {}
+class _DevPtrHolder:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can view it without a copy."""
+
+    def __init__(self, ptr: int, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
-def peer_views(t: torch.Tensor, group=None):
-    """Maps every rank's tensor `t` (same role on each rank, any shape) into this process: returns a list with one
-    tensor per rank — this rank's own `t` and CUDA-IPC views of the others' device memory (one node, peer access over
-    NVLink).  Collective; the mapping is cached per (storage address, size) so a reused output buffer is exchanged once."""
-    import torch.distributed as dist
-    from torch.multiprocessing.reductions import reduce_tensor
+class PeerBuffer:
+    """One fp32 device buffer of `numel` elements per rank, each mapped into every other process of the node
+    (`lc_ipc_alloc` / `lc_ipc_open`: CUDA IPC opened on the reader's own GPU, peer access over NVLink / NVSwitch).
+    `tensor` is this rank's buffer as a torch tensor; `ptrs[q]` is the address at which THIS process sees rank q's buffer.
+    Collective constructor (handles travel through all_gather_object); keep the object alive while kernels use it."""
 
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    key = (t.data_ptr(), tuple(t.shape), t.dtype, id(group))
-    flag = torch.tensor([0 if key in _PEER_VIEWS else 1], device=t.device)
-    dist.all_reduce(flag, group=group)  # any rank without a cached mapping -> everybody re-exchanges handles
-    if int(flag.item()) == 0:
-        return _PEER_VIEWS[key][0]
-    objs = [None] * world
-    dist.all_gather_object(objs, reduce_tensor(t), group=group)
-    views = [t if q == rank else objs[q][0](*objs[q][1]) for q in range(world)]
-    probe = torch.empty(1, device=t.device, dtype=t.dtype)
-    for q, v in enumerate(views):
-        if q == rank:
-            continue
-        if not torch.cuda.can_device_access_peer(t.device.index, v.device.index):
-            raise _lib.LadcastB200Error(f"GPU {t.device.index} cannot access GPU {v.device.index} as a peer")
-        probe.copy_(v.reshape(-1)[:1])  # a device-to-device copy makes torch enable peer access local <-> q
-    torch.cuda.synchronize(t.device)
-    _PEER_VIEWS[key] = (views, t)  # keeps the source alive as long as the mapping is cached
-    return views
+    def __init__(self, numel: int, device: torch.device, group=None):
+        import ctypes
+
+        import torch.distributed as dist
+
+        self._lib = _lib.load()
+        self.device, self.numel = device, int(numel)
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        own, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            _lib.check(self._lib.lc_ipc_alloc(4 * self.numel, ctypes.byref(own), handle), "lc_ipc_alloc")
+        self._own = own.value
+        self._holder = _DevPtrHolder(self._own, (self.numel,))
+        self.tensor = torch.as_tensor(self._holder, device=device)
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.ptrs, self._opened = [], []
+        with torch.cuda.device(device):
+            for q in range(world):
+                if q == rank:
+                    self.ptrs.append(self._own)
+                    continue
+                p = ctypes.c_void_p()
+                hq = (ctypes.c_ubyte * 64).from_buffer_copy(handles[q])
+                _lib.check(self._lib.lc_ipc_open(hq, ctypes.byref(p)), "lc_ipc_open")
+                self.ptrs.append(p.value)
+                self._opened.append(p.value)
+        dist.barrier(group=group)
+        self._group = group
+
+    def release(self):
+        """Collective: unmap the peers' buffers, then (after a barrier) free the own one."""
+        import torch.distributed as dist
+
+        if self._own is None:
+            return
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                self._lib.lc_ipc_close(p)
+        dist.barrier(group=self._group)
+        self.tensor = None
+        with torch.cuda.device(self.device):
+            self._lib.lc_ipc_free(self._own)
+        self._own, self._opened, self.ptrs = None, [], []
+
+
+_PEER_BUFFERS: dict = {}
+
+
+def _peer_buffer(numel: int, device: torch.device, group=None) -> PeerBuffer:
+    """Cached PeerBuffer of at least `numel` elements per rank (the same `numel` must be requested on every rank)."""
+    key = (device.index, id(group))
+    buf = _PEER_BUFFERS.get(key)
+    if buf is None or buf.numel < numel:
+        if buf is not None:
+            buf.release()
+        buf = PeerBuffer(numel, device, group)
+        _PEER_BUFFERS[key] = buf
+    return buf
+
+
+def release_peer_buffers():
+    """Collective: free the cached peer-visible buffers (call before destroying the process group)."""
+    for buf in list(_PEER_BUFFERS.values()):
+        buf.release()
+    _PEER_BUFFERS.clear()
 
 
 @torch.no_grad()
-def _local_sums_peer(views, members, n_planes: int, mine: range, truth_mine: torch.Tensor, lat_weights: torch.Tensor, H, W):
-    """sums/counts [4, len(mine)] of this rank's plane slice with every member read where it lies: views[q] is rank q's
-    [M_q, N, HW] fp32 field block (peer memory for q != rank)."""
+def _local_sums_peer(buf: PeerBuffer, members, n_planes: int, mine: range, truth_mine: torch.Tensor,
+                     lat_weights: torch.Tensor, H, W):
+    """sums/counts [4, len(mine)] of this rank's plane slice with every member read where it lies: rank q's members
+    are the leading [M_q, N, HW] fp32 block of its peer buffer (seen here at buf.ptrs[q])."""
     import ctypes
 
     lib = _lib.load()
     dev = truth_mine.device
     n_mine = len(mine)
     ptrs = []
-    for q, v in enumerate(views):
+    for q, base in enumerate(buf.ptrs):
         for l in range(members[q]):
-            ptrs.append(v.data_ptr() + 4 * (l * n_planes + mine.start) * H * W)
+            ptrs.append(base + 4 * (l * n_planes + mine.start) * H * W)
     arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
     sums = torch.empty((4, n_mine), device=dev, dtype=torch.float64)
     counts = torch.empty((4, n_mine), device=dev, dtype=torch.float64)
@@ -294,10 +346,10 @@ def ensemble_metrics_distributed(fields_local: torch.Tensor, truth: torch.Tensor
     full [C, T] tables (reference assembly: evaluate/evaluate_ens_gpu.py:339-415, gather :462-468).
     `timings` (optional dict) receives CUDA-event milliseconds of the exchange and of the local reduction.
     exchange="p2p" (one node, CUDA): no exchange step at all — the other ranks' field blocks are mapped into this
-    process (`peer_views`) and `lc_metrics_accumulate_ptrs` reads every member of this rank's plane slice in place over
-    NVLink, so the transfer overlaps the reduction pixel by pixel and the gathered copy (a write + a read of
-    M * planes/world * H * W * 4 B per rank) never exists.  `fields_local` must then be fp32-contiguous and must not be
-    overwritten by its owner until the call has returned on every rank (the function ends with a barrier)."""
+    process (`PeerBuffer`: CUDA IPC opened on the reader's GPU) and `lc_metrics_accumulate_ptrs` reads every member of
+    this rank's plane slice in place over NVLink, so the transfer overlaps the reduction pixel by pixel and the gathered
+    copy (a write + a read of M * planes/world * H * W * 4 B per rank) never exists.  Fields that do not already live
+    in the rank's peer buffer are copied into it first (one local device copy, reported as `exchange_ms`)."""
     import torch.distributed as dist
 
     if local_sums_fn is None:
@@ -325,14 +377,17 @@ def ensemble_metrics_distributed(fields_local: torch.Tensor, truth: torch.Tensor
             raise _lib.LadcastB200Error("exchange='p2p' needs CUDA tensors (peer memory over NVLink)")
         if sum(members) > 64:
             raise _lib.LadcastB200Error("exchange='p2p' supports up to 64 members in total")
-        views = peer_views(f if M_r > 0 else torch.zeros(1, device=dev), group)  # a rank without members shares a dummy
+        buf = _peer_buffer(max(members) * N * H * W, dev, group)
+        if ev:
+            ev[0].record()
+        if M_r > 0 and f.data_ptr() != buf.tensor.data_ptr():  # fields produced elsewhere: one local device copy
+            buf.tensor[: f.numel()].copy_(f.reshape(-1))
         torch.cuda.synchronize(dev)
         dist.barrier(group=group)  # every rank's fields are complete before anybody reads them
         if ev:
-            ev[0].record()
             ev[1].record()
         if n_mine:
-            sums_l, counts_l = _local_sums_peer(views, members, N, mine, t_mine, lat_weights, H, W)
+            sums_l, counts_l = _local_sums_peer(buf, members, N, mine, t_mine, lat_weights, H, W)
         else:
             sums_l = counts_l = torch.zeros((4, 0), dtype=torch.float64, device=dev)
         if ev:

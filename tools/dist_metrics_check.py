@@ -6,7 +6,7 @@ import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
-from ladcast_b200.evaluate.utils import ensemble_metrics, ensemble_metrics_distributed
+from ladcast_b200.evaluate.utils import ensemble_metrics, ensemble_metrics_distributed, release_peer_buffers
 from ladcast_b200.pipelines.utils import member_shard
 
 local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -42,6 +42,7 @@ if rank == 0:
     with open("gpurun_out/dist_metrics.jsonl", "a") as f:
         f.write(json.dumps(res) + "\n")
     print(json.dumps(res))
+release_peer_buffers()
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if all_ok else 1)

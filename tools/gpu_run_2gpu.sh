@@ -5,6 +5,7 @@ set -u
 mkdir -p gpurun_out
 N=${N:-2}
 nvidia-smi topo -m 2>/dev/null | head -12 > gpurun_out/topo_${N}gpu.txt
+echo "=== pointer-form kernel on one GPU"; timeout 300 python -m pytest tests/test_metrics_gpu.py -m gpu -q -k pointer 2>&1 | tail -2
 echo "=== dist metrics check ($N GPUs)"
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
   tools/dist_metrics_check.py > gpurun_out/dist_metrics_${N}gpu.log 2>&1; echo "dist check rc=$?"
