@@ -81,8 +81,8 @@ struct lc_denoiser {
   std::vector<DualW> dual;
   std::vector<SingleW> single;
   int mod_dim = 0, kp_in = 96;
-  // RMSNorm(q,k)+RoPE fused into the qkv GEMM epilogue (gemm_tc.cu K_QKV: one pass over tensor memory, values kept as
-  // packed bf16 pairs, staged coalesced stores).  Measured in-step A/B on B200 (375M, B=20), three epilogue forms over
+  // RMSNorm(q,k)+RoPE fused into the qkv GEMM epilogue (gemm_tc.cu K_QKV: two passes over tensor memory, staged
+  // coalesced stores; a one-pass packed-bf16 form measured the same).  Measured in-step A/B on B200 (375M, B=20), three epilogue forms over
   // two rounds: always +0.6 % (477.5 vs 480.5 ms per AR step): the norm / rotation arithmetic of a 128x256 tile on 8
   // epilogue warps (~2x the plain epilogue) exceeds the K=1536 main loop it has to hide under, and the qkv GEMMs give
   // back the 18 ms of the removed HBM-bound kernel (GEMM class 256 -> 275 ms).  Off by default; LADCAST_B200_FUSE_QK=1.

@@ -392,75 +392,6 @@ __device__ __forceinline__ void epilogue_qkv_chunk(const EpiParams& ep, const ui
   }
 }
 
-// Fused qkv epilogue in ONE pass over tensor memory: this warp owns one 128-column head of the tile and each thread a
-// full head row.  Pass over TMEM: bias, sum of squares (fp32), values kept as 64 packed bf16 pairs in registers (the
-// reference's own autocast rounds the projection output to bf16 before the RMSNorm).  Then from registers: q/k heads
-// are normalised and rotated (packed half2 (cos, sin) table), every head is staged and written back as whole 128-byte
-// row segments.  The two-pass form read TMEM twice and its scattered 16-byte stores made the epilogue the K=1536
-// projections' critical path.
-__device__ __forceinline__ void drain_qkv_single_pass(const EpiParams& ep, uint32_t t_addr, int head0, bool is_qk,
-                                                      const float* nw, float* tbuf, int lane, int row, long long orow,
-                                                      int M) {
-  uint8_t* buf = reinterpret_cast<uint8_t*>(tbuf);
-  const bool row_ok = row < M;
-  const int tok = row % ep.rows_per_sample;
-  uint32_t pkd[64];
-  float ss[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {  // one 32-column load in flight at a time: the 64 packed pairs need the registers
-    uint32_t r[32];
-    ptx::tmem_ld32(t_addr + c * 32, r);
-    ptx::tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + head0 + c * 32 + j));
-      const float t0 = __uint_as_float(r[j]) + b4.x, t1 = __uint_as_float(r[j + 1]) + b4.y;
-      const float t2 = __uint_as_float(r[j + 2]) + b4.z, t3 = __uint_as_float(r[j + 3]) + b4.w;
-      ss[0] = fmaf(t0, t0, ss[0]); ss[1] = fmaf(t1, t1, ss[1]); ss[2] = fmaf(t2, t2, ss[2]); ss[3] = fmaf(t3, t3, ss[3]);
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(t0, t1), p1 = __floats2bfloat162_rn(t2, t3);
-      pkd[c * 16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&p0);
-      pkd[c * 16 + (j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&p1);
-    }
-  }
-  if (is_qk) {
-    const float rstd = rsqrtf(((ss[0] + ss[1]) + (ss[2] + ss[3])) * (1.0f / 128.0f) + ep.qk_eps);
-    const uint4* cs = (ep.rope_cs != nullptr && row_ok)
-                          ? reinterpret_cast<const uint4*>(ep.rope_cs + static_cast<long long>(tok) * 64) : nullptr;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {  // 8 features = 4 rotation pairs per step
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(nw + q * 8));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(nw + q * 8 + 4));
-      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-      uint4 c4 = make_uint4(0u, 0u, 0u, 0u);
-      if (cs != nullptr) c4 = __ldg(cs + q);
-      const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pkd[q * 4 + k]));
-        float a = x.x * rstd * wv[2 * k], b = x.y * rstd * wv[2 * k + 1];
-        if (cs != nullptr) {
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&cw[k]));  // (cos, sin)
-          const float ra = a * f.x - b * f.y, rb = b * f.x + a * f.y;
-          a = ra;
-          b = rb;
-        }
-        __nv_bfloat162 o = __floats2bfloat162_rn(a, b);
-        pkd[q * 4 + k] = *reinterpret_cast<uint32_t*>(&o);
-      }
-    }
-  }
-  const StagedRows sr = staged_rows(lane, row, orow, M);
-#pragma unroll
-  for (int g = 0; g < 2; ++g) {  // two groups of 64 columns through the 4 KB staging tile
-#pragma unroll
-    for (int ch = 0; ch < 8; ++ch)
-      staged_put(buf, lane, ch, make_uint4(pkd[g * 32 + ch * 4], pkd[g * 32 + ch * 4 + 1], pkd[g * 32 + ch * 4 + 2],
-                                           pkd[g * 32 + ch * 4 + 3]));
-    staged_writeback(ep, buf, lane, head0 + g * 64, sr);
-  }
-}
-
 __device__ __forceinline__ int epi_kind(const EpiParams& ep) {
   if (ep.qk_cols > 0) return K_QKV;
   if (ep.mode == EPI_NORM_RESID) return K_NORM;
@@ -535,6 +466,8 @@ __device__ __forceinline__ void drain_loop(const EpiParams& ep, uint32_t t_addr,
     ptx::tmem_ld_wait();
     if (c + 1 < NC) ptx::tmem_ld32(t_addr + (c + 1) * 32, r[(c + 1) & 1]);
     const int n0 = n_base + c * 32;
+    if ((KIND == K_GATED || KIND == K_RESID) && ep.prefetch && c + 1 < NC && n0 + 32 < N && row < M)  // next block's lines -> L2
+      ptx::prefetch_l2((KIND == K_GATED ? reinterpret_cast<const float*>(ep.out) + orow * ep.ldo : ep.resid + orow * ep.ldr) + n0 + 32);
     if (n0 < N) epilogue_block<KIND, ACT>(ep, r[c & 1], tbuf, lane, row, orow, sample, n0, M, N);
   }
 }
@@ -562,23 +495,19 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& ep, const ConvLoad
   orow = epi_out_row(ep, row, sample);
 }
 
-// Read-modify-write epilogues (gated fp32 residual, residual + store): pull this warp's slice of the NEXT tile's
-// residual rows (32 rows x BN/2 fp32 columns = 4 lines per lane) into L2 while the current tile is drained.  Each warp
-// walks its 4 column blocks with one DRAM round trip per block; with K = 1536 that chain (not the tensor pipe) set
-// the pace of the out-projections (54 % tensor-active, profiles/r02_kernels.md) — from L2 the round trip is ~3x shorter.
+// Read-modify-write epilogues (gated fp32 residual, residual + store) walk a warp's 4 column blocks with one DRAM round
+// trip per block, and with K = 1536 that chain sets the pace of the out-projections (48-54 % tensor-active,
+// profiles/r02_kernels.md).  Each block's residual lines (one 128-byte line per lane = row) are therefore pulled into
+// L2 one block ahead: the first block of a tile before the wait for its accumulator (here), block c+1 while block c is
+// processed (drain_loop).  (Prefetching the whole NEXT tile instead was measured: +32 % DRAM reads — the lines are
+// evicted again before their use — and the K=1536 out-projection 9 % slower.)
 template <int BN>
-__device__ __forceinline__ void epilogue_prefetch(const EpiParams& ep, const ConvLoad& cv, int kind, int m_blk, int n_blk,
-                                                  int quarter, int half, int lane, int M, int N) {
-  if ((kind != K_GATED && kind != K_RESID) || !ep.prefetch) return;
-  int row, sample;
-  long long orow;
-  epilogue_row(ep, cv, m_blk, quarter, lane, M, row, orow, sample);
-  if (row >= M) return;
+__device__ __forceinline__ void epilogue_prefetch(const EpiParams& ep, int kind, int n_blk, int half, int row, long long orow,
+                                                  int M, int N) {
+  if ((kind != K_GATED && kind != K_RESID) || !ep.prefetch || row >= M) return;
   const float* base = kind == K_GATED ? reinterpret_cast<const float*>(ep.out) + orow * ep.ldo : ep.resid + orow * ep.ldr;
   const int c0 = n_blk * BN + half * (BN / 2);
-#pragma unroll
-  for (int c = 0; c < BN / 2; c += 32)
-    if (c0 + c < N) ptx::prefetch_l2(base + c0 + c);
+  if (c0 < N) ptx::prefetch_l2(base + c0);
 }
 
 // Drain one accumulator stage: this warp's 32 rows x (BN/2) columns, TMEM -> registers -> fused epilogue -> global.
@@ -625,14 +554,11 @@ __device__ __forceinline__ void epilogue_drain(const EpiParams& ep, int kind, in
   }
   if (kind == K_QKV) {
     // this warp owns one 128-column head of the tile: pass 1 = sum of squares per row (q/k heads), pass 2 =
-    // normalise + rotate + store.  TMEM is read twice; the accumulator never leaves the SM in fp32.
+    // normalise + rotate + store (staged).  TMEM is read twice; the accumulator never leaves the SM in fp32.  (A
+    // one-pass form holding the head row as 64 packed bf16 pairs was measured too: same +0.6 % in-step, 130 B of spills.)
     const int head0 = n_blk * BN + half * (BN / 2);
     const bool is_qk = head0 < ep.qk_cols;
     const float* nw = (head0 < ep.qk_cols / 2) ? ep.qk_wq : ep.qk_wk;
-    if (ep.stage_bf16 && (ep.ldo & 7) == 0) {
-      if (head0 < N) drain_qkv_single_pass(ep, t_addr, head0, is_qk, nw, tbuf, lane, row, orow, M);
-      return;
-    }
     float rstd = 1.f;
     uint32_t r[2][32];
     if (is_qk && head0 < N) {
@@ -831,14 +757,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int row, sample;
       long long orow;
       epilogue_row(ep, cv, m_blk, quarter, lane, M, row, orow, sample);
-      if (tile == static_cast<int>(blockIdx.x)) epilogue_prefetch<BN>(ep, cv, kind, m_blk, n_blk, quarter, half, lane, M, N);
+      epilogue_prefetch<BN>(ep, kind, n_blk, half, row, orow, M, N);
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
-      if (tile + static_cast<int>(gridDim.x) < num_tiles) {
-        int m_nx, n_nx;
-        sched.decode(tile + gridDim.x, m_nx, n_nx);
-        epilogue_prefetch<BN>(ep, cv, kind, m_nx, n_nx, quarter, half, lane, M, N);
-      }
       epilogue_drain<BN>(ep, kind, n_blk, quarter, half, lane, tbuf, tbuf_partner, tmem_base, acc, row, orow, sample, M, N);
       ptx::tc_fence_before();
       __syncwarp();
@@ -1021,16 +942,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       int row, sample;
       long long orow;
       epilogue_row(ep, cv, m_blk, quarter, lane, M, row, orow, sample);
-      if (tix == 0) epilogue_prefetch<BN>(ep, cv, kind, m_blk, n_blk, quarter, half, lane, M, N);
+      epilogue_prefetch<BN>(ep, kind, n_blk, half, row, orow, M, N);
       if (trace != nullptr && tix < 64) trace[256 + tix * 4 + 0] = clock64();
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       if (trace != nullptr && tix < 64) trace[256 + tix * 4 + 1] = clock64();
-      if (tile + num_pairs < num_tiles) {
-        int mp_nx, n_nx;
-        sched.decode(tile + num_pairs, mp_nx, n_nx);
-        epilogue_prefetch<BN>(ep, cv, kind, mp_nx * 2 + static_cast<int>(cta_rank), n_nx, quarter, half, lane, M, N);
-      }
+
       epilogue_drain<BN>(ep, kind, n_blk, quarter, half, lane, tbuf, tbuf_partner, tmem_base, acc, row, orow, sample, M, N);
       ptx::tc_fence_before();
       __syncwarp();

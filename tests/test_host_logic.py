@@ -161,6 +161,16 @@ def _dist_worker(rank, world, port, q, n_members=5):
     tabs = ensemble_metrics_distributed(fields[mine].contiguous(), truth, lat_weights=lat_w, local_sums_fn=_oracle_local_sums)
     want = O.ensemble_metrics(fields, truth)
     ok = all(np.allclose(tabs[k].numpy(), want[k].numpy(), rtol=1e-10, atol=1e-12, equal_nan=True) for k in want)
+    # the peer-memory form is CUDA-only (no CPU fallback) and unknown exchange names are rejected, on every rank alike
+    from ladcast_b200 import _lib
+
+    for mode, err in (("p2p", _lib.LadcastB200Error), ("smoke-signals", ValueError)):
+        try:
+            ensemble_metrics_distributed(fields[mine].contiguous(), truth, lat_weights=lat_w, local_sums_fn=_oracle_local_sums,
+                                         exchange=mode)
+            ok = False
+        except err:
+            pass
     q.put((rank, ok))
     dist.destroy_process_group()
 
