@@ -125,7 +125,7 @@ struct EpiParams {
   const float* norm_b = nullptr;
   float norm_eps = 0.f;
   int stage_bf16 = 0;  // CTA-pair kernel, bf16 outputs: rows staged through shared memory, coalesced write-back (LADCAST_B200_EPI_STAGE=0: off)
-  int prefetch = 1;  // read-modify-write epilogues: L2 prefetch of the next tile's residual rows (LADCAST_B200_EPI_PREFETCH=0: off)
+  int prefetch = 0;  // read-modify-write epilogues: L2 prefetch of the next block's residual lines (LADCAST_B200_EPI_PREFETCH=1: on)
   int n_valid = 0;  // EPI_UNPATCHIFY: number of real output channels (<= N)
   // EPI_UNPATCHIFY into a 5-D [B, n_valid, up_T, rows_per_sample] tensor: sample s of this launch is frame
   // (up_frame0 + s) = b * up_T + t and lands in plane (b, n, t).  up_T = 1: plain [samples, n_valid, rows_per_sample].

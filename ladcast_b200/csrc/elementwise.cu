@@ -91,14 +91,16 @@ __device__ __forceinline__ void ln_row(float4 (&v)[NV], int row, int lane, T* __
 constexpr int LN_RPW = 4;  // max rows per warp (8 measured slower: too few blocks for the 9000-row streams); the launcher
                            // picks 4, 2 or 1 per launch so that small row counts (2-3 members per GPU) still fill whole waves
 
-template <typename T, int NV>
-__global__ void __launch_bounds__(256, NV <= 12 ? 2 : 1) layernorm_kernel(const float* __restrict__ x, T* __restrict__ out, int M, int d,
+// Warps per CTA (WPB): 8, two CTAs per SM, up to d = 1536.  d = 2048 needs ~160 registers per thread for the double-
+// buffered row, which allows 384 threads per SM: three 4-warp CTAs (12 warps in flight) instead of one 8-warp CTA.
+template <typename T, int NV, int WPB, int MIN_CTAS>
+__global__ void __launch_bounds__(WPB * 32, MIN_CTAS) layernorm_kernel(const float* __restrict__ x, T* __restrict__ out, int M, int d,
                                                            float eps, int rows_per_sample, int seg_rows,
                                                            int seg_rows_per_sample, const float* __restrict__ scale,
                                                            const float* __restrict__ shift, long long mod_stride,
                                                            const float* __restrict__ w, const float* __restrict__ b, int rpw) {
   pdl_grid_sync();
-  const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * rpw;
+  const int row0 = (blockIdx.x * WPB + (threadIdx.x >> 5)) * rpw;
   const int lane = threadIdx.x & 31;
   if (row0 >= M) return;
   const int nrows = min(rpw, M - row0);
@@ -469,27 +471,40 @@ int layernorm_modulate(const float* x, T* out, int M, int d, float eps, int rows
   LC_REQUIRE(d % 128 == 0 && d <= 2048, "layernorm: d must be a multiple of 128, <= 2048");
   const int nv = d / 128;
   // rows per warp: the largest of 4 / 2 / 1 whose grid fills >= 90 % of its last wave (else the best-filling one)
-  const int slots = num_sms() * (nv <= 12 ? 2 : 1);
+  // LADCAST_B200_LN_WPB=8: the round-1 form for d > 1536 (one 8-warp CTA per SM)
+  static const bool wide8 = [] { const char* e = getenv("LADCAST_B200_LN_WPB"); return e != nullptr && e[0] == '8'; }();
+  const bool small_cta = nv > 12 && !wide8;
+  const int wpb = small_cta ? 4 : 8;
+  const int slots = num_sms() * (nv <= 12 ? 2 : small_cta ? 3 : 1);
   int rpw = LN_RPW;
   double best = -1.0;
   for (int cand = LN_RPW; cand >= 1; cand >>= 1) {
-    const int blocks = ceil_div(M, 8 * cand);
+    const int blocks = ceil_div(M, wpb * cand);
     const double eff = static_cast<double>(blocks) / (static_cast<double>(ceil_div(blocks, slots)) * slots);
     if (eff >= 0.9) { rpw = cand; break; }
     if (eff > best) { best = eff; rpw = cand; }
   }
-  dim3 grid(ceil_div(M, 8 * rpw));
+  dim3 grid(ceil_div(M, wpb * rpw));
   ProfScope ps(PROF_LN, 0.0, static_cast<double>(M) * d * (4 + sizeof(T)), s);
-#define LC_LN_CASE(NV)                                                                                            \
-  case NV:                                                                                                        \
-    LC_CHECK_CUDA(launch_kernel(layernorm_kernel<T, NV>, grid, 256, 0, s, x, out, M, d, eps, rows_per_sample, seg_rows, \
-                                seg_rows_per_sample, scale, shift, mod_stride, w, b, rpw));                       \
+#define LC_LN_LAUNCH(NV, WPB, MINC)                                                                                    \
+  LC_CHECK_CUDA(launch_kernel(layernorm_kernel<T, NV, WPB, MINC>, grid, WPB * 32, 0, s, x, out, M, d, eps, rows_per_sample, \
+                              seg_rows, seg_rows_per_sample, scale, shift, mod_stride, w, b, rpw))
+#define LC_LN_CASE(NV)                   \
+  case NV:                               \
+    LC_LN_LAUNCH(NV, 8, 2);              \
+    break;
+#define LC_LN_CASE_BIG(NV)                                  \
+  case NV:                                                  \
+    if (small_cta) { LC_LN_LAUNCH(NV, 4, 3); }              \
+    else { LC_LN_LAUNCH(NV, 8, 1); }                        \
     break;
   switch (nv) {
     LC_LN_CASE(1) LC_LN_CASE(2) LC_LN_CASE(3) LC_LN_CASE(4) LC_LN_CASE(5) LC_LN_CASE(6) LC_LN_CASE(7) LC_LN_CASE(8)
-    LC_LN_CASE(9) LC_LN_CASE(10) LC_LN_CASE(11) LC_LN_CASE(12) LC_LN_CASE(13) LC_LN_CASE(14) LC_LN_CASE(15)
-    LC_LN_CASE(16)
+    LC_LN_CASE(9) LC_LN_CASE(10) LC_LN_CASE(11) LC_LN_CASE(12) LC_LN_CASE_BIG(13) LC_LN_CASE_BIG(14) LC_LN_CASE_BIG(15)
+    LC_LN_CASE_BIG(16)
   }
+#undef LC_LN_CASE_BIG
+#undef LC_LN_LAUNCH
 #undef LC_LN_CASE
   LC_LAUNCH_CHECK();
   return 0;

@@ -115,3 +115,37 @@ def test_metrics_pointer_form_matches_strided(M):
     with pytest.raises(_lib.LadcastB200Error):
         _lib.check(lib.lc_metrics_accumulate_ptrs(ptrs, _lib.ptr(t_mine), _lib.ptr(lw), 65, n_mine, H, W, _lib.ptr(s1),
                                                   _lib.ptr(c1), _lib.stream()), "lc_metrics_accumulate_ptrs")
+
+
+def test_peer_memory_exchange_world1():
+    """exchange="p2p" end to end in a one-rank NCCL group: PeerBuffer (lc_ipc_alloc, torch view of the raw pointer),
+    fields produced directly in the peer buffer (no staging copy) and elsewhere (one local copy), pointer-form kernel —
+    all equal to ensemble_metrics; the multi-rank case is tools/dist_metrics_check.py (profiles/r02_dist_metrics_2gpu.jsonl)."""
+    import torch.distributed as dist
+
+    from ladcast_b200.evaluate import utils as U
+
+    if dist.is_initialized():
+        pytest.skip("a process group already exists")
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{29650 + os.getpid() % 300}", rank=0, world_size=1,
+                            device_id=torch.device("cuda", 0))
+    try:
+        M, C, T, H, W = 6, 84, 2, 120, 16
+        fields = _seeded((M, C, T, H, W), 410).cuda()
+        truth = _seeded((C, T, H, W), 411).cuda()
+        truth[82, :, 3:6, 2:5] = float("nan")
+        want = U.ensemble_metrics(fields, truth)
+        tm = {}
+        got = U.ensemble_metrics_distributed(fields, truth, exchange="p2p", timings=tm)  # copied into the peer buffer
+        buf = U._peer_buffer(M * C * T * H * W, fields.device)
+        inplace = buf.tensor[: fields.numel()].view(M, C, T, H, W)
+        inplace.copy_(fields * 2.0)
+        got2 = U.ensemble_metrics_distributed(inplace, truth, exchange="p2p")  # already there: read in place
+        want2 = U.ensemble_metrics(fields * 2.0, truth)
+        for k in want:
+            assert torch.allclose(got[k], want[k], rtol=1e-12, atol=0, equal_nan=True), k
+            assert torch.allclose(got2[k], want2[k], rtol=1e-12, atol=0, equal_nan=True), k
+        assert tm["kernel_ms"] > 0
+    finally:
+        U.release_peer_buffers()
+        dist.destroy_process_group()
