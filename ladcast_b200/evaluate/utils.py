@@ -241,28 +241,54 @@ class PeerBuffer:
 
         self._lib = _lib.load()
         self.device, self.numel = device, int(numel)
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-        own, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
-        with torch.cuda.device(device):
-            _lib.check(self._lib.lc_ipc_alloc(4 * self.numel, ctypes.byref(own), handle), "lc_ipc_alloc")
-        self._own = own.value
-        self._holder = _DevPtrHolder(self._own, (self.numel,))
-        self.tensor = torch.as_tensor(self._holder, device=device)
-        handles = [None] * world
-        dist.all_gather_object(handles, bytes(handle), group=group)
-        self.ptrs, self._opened = [], []
-        with torch.cuda.device(device):
-            for q in range(world):
-                if q == rank:
-                    self.ptrs.append(self._own)
-                    continue
-                p = ctypes.c_void_p()
-                hq = (ctypes.c_ubyte * 64).from_buffer_copy(handles[q])
-                _lib.check(self._lib.lc_ipc_open(hq, ctypes.byref(p)), "lc_ipc_open")
-                self.ptrs.append(p.value)
-                self._opened.append(p.value)
-        dist.barrier(group=group)
         self._group = group
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        # Every rank walks through every collective of this constructor even after a local failure, and all ranks
+        # raise together: a rank that bailed out alone would leave the others hanging in the next collective.
+        self._own, self._opened, self.ptrs, self.tensor = None, [], [], None
+        err = None
+        own, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        try:
+            with torch.cuda.device(device):
+                _lib.check(self._lib.lc_ipc_alloc(4 * self.numel, ctypes.byref(own), handle), "lc_ipc_alloc")
+            self._own = own.value
+            self._holder = _DevPtrHolder(self._own, (self.numel,))
+            self.tensor = torch.as_tensor(self._holder, device=device)
+        except Exception as e:  # noqa: BLE001
+            err = e
+        handles = [None] * world
+        dist.all_gather_object(handles, None if err is not None else bytes(handle), group=group)
+        if err is None and any(h is None for h in handles):
+            err = _lib.LadcastB200Error("a peer rank could not allocate its peer-visible buffer")
+        if err is None:
+            try:
+                with torch.cuda.device(device):
+                    for q in range(world):
+                        if q == rank:
+                            self.ptrs.append(self._own)
+                            continue
+                        p = ctypes.c_void_p()
+                        hq = (ctypes.c_ubyte * 64).from_buffer_copy(handles[q])
+                        _lib.check(self._lib.lc_ipc_open(hq, ctypes.byref(p)), "lc_ipc_open")
+                        self.ptrs.append(p.value)
+                        self._opened.append(p.value)
+            except Exception as e:  # noqa: BLE001
+                err = e
+        oks = [None] * world
+        dist.all_gather_object(oks, err is None, group=group)  # doubles as the barrier: every mapping exists before use
+        if not all(oks):
+            self._abandon()
+            raise err if err is not None else _lib.LadcastB200Error("a peer rank could not map the peer-visible buffers")
+
+    def _abandon(self):
+        """Local clean-up after a failed (collective) construction: no further collectives."""
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                self._lib.lc_ipc_close(p)
+            self.tensor = None
+            if self._own is not None:
+                self._lib.lc_ipc_free(self._own)
+        self._own, self._opened, self.ptrs = None, [], []
 
     def release(self):
         """Collective: unmap the peers' buffers, then (after a barrier) free the own one."""
