@@ -311,7 +311,8 @@ _PEER_BUFFERS: dict = {}
 
 
 def _peer_buffer(numel: int, device: torch.device, group=None) -> PeerBuffer:
-    """Cached PeerBuffer of at least `numel` elements per rank (the same `numel` must be requested on every rank)."""
+    """Cached PeerBuffer of at least `numel` elements per rank (the same `numel` must be requested on every rank).
+    Growing the buffer frees the previous one: tensors that view it (e.g. a rollout's `out=`) must be dropped first."""
     key = (device.index, id(group))
     buf = _PEER_BUFFERS.get(key)
     if buf is None or buf.numel < numel:
@@ -407,6 +408,9 @@ def ensemble_metrics_distributed(fields_local: torch.Tensor, truth: torch.Tensor
         if ev:
             ev[0].record()
         if M_r > 0 and f.data_ptr() != buf.tensor.data_ptr():  # fields produced elsewhere: one local device copy
+            lo = buf.tensor.data_ptr()
+            if lo < f.data_ptr() < lo + 4 * buf.numel:  # a view INSIDE the peer buffer but not at its start
+                f = f.clone()
             buf.tensor[: f.numel()].copy_(f.reshape(-1))
         torch.cuda.synchronize(dev)
         dist.barrier(group=group)  # every rank's fields are complete before anybody reads them
