@@ -481,6 +481,351 @@ __global__ void __launch_bounds__(256, 2) linear_attn_kernel(const TI* __restric
   }
 }
 
+// ---------------------------------------------------------------- ReLU linear attention on warp-level tensor-core MMAs
+// Same math as linear_attn_kernel for bf16 tensors, with both products as mma.sync.m16n8k16 (bf16 x bf16 -> fp32):
+//   phase 1  S1[c'][c] = sum_px relu(k[px][c']) * [v | 1][px][c]       M = 32 k-channels, N = 40 (32 v + ones + pad), K = pixels
+//   phase 2  o[px][c]  = sum_c' relu(q[px][c']) * S1[c'][c]             M = pixels, N = 40, K = 32; out = o[:32] / (o[32] + eps)
+// One CTA per (frame, head), 8 warps, each warp walks 16-pixel blocks (cp.async into a private double-buffered tile whose
+// 144-byte rows make every ldmatrix conflict-free; k / v fragments come out of ldmatrix.trans because the pixel index is
+// the contraction index in phase 1).  q, k, v are bf16 in memory already and the MMAs accumulate in fp32, so phase 1 is
+// exactly the SIMT kernel's arithmetic; S1 (fp32) enters phase 2 as hi + lo bf16 halves (two MMAs, relative error 2^-16).
+// The SIMT kernel issues ~130 instructions per pixel and was FMA-issue bound at 0.09 of the HBM roofline; this one
+// issues ~5 and is bound by the loads.
+namespace lamma {
+constexpr int ROW = 72;                 // bf16 per staged pixel row: k 32 | v 32 | one + 7 zeros   (144 B)
+constexpr int TILE = 16 * ROW;          // one 16-pixel block
+constexpr int SB_ROW = 40;              // bf16 per row of the S1 operand tables: 32 k-channels + 8 pad (80 B)
+constexpr int SMEM_BYTES = 8 * 2 * TILE * 2 /*kv / q tiles, reused for the per-warp partials of S1*/ + 2 * 40 * SB_ROW * 2 /*hi, lo*/;
+static_assert(8 * 32 * 33 * 4 <= 8 * 2 * TILE * 2, "the partials of S1 must fit in the staging tiles");
+
+__device__ __forceinline__ void cp16(void* dst, const void* src, bool valid) {
+  const int n = valid ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))),
+               "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(p))));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t x) {
+  const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+  __nv_bfloat162 v = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&x), z);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+}  // namespace lamma
+
+__global__ void __launch_bounds__(256, 3) linear_attn_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ms,
+                                                                 bf16* __restrict__ out, int HW, int heads, float eps) {
+  using namespace lamma;
+  pdl_grid_sync();
+  extern __shared__ __align__(16) uint8_t la_smem[];
+  bf16* tiles = reinterpret_cast<bf16*>(la_smem);                                  // [8 warps][2][16][ROW]
+  bf16* SBhi = reinterpret_cast<bf16*>(la_smem + 8 * 2 * TILE * 2);  // [40 c][SB_ROW]: k-channel contiguous
+  bf16* SBlo = SBhi + 40 * SB_ROW;
+  const int g = blockIdx.x % (2 * heads);
+  const int f = blockIdx.x / (2 * heads);
+  const int scale = g / heads, hg = g % heads;
+  const int C3 = heads * 96;
+  const bf16* src = (scale ? ms : qkv) + static_cast<long long>(f) * HW * C3 + hg * 96;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gi = lane >> 2, ti = lane & 3;        // MMA fragment coordinates
+  const int mi = lane >> 3, mr = lane & 7;        // ldmatrix: matrix index / row this lane addresses
+  bf16* my = tiles + warp * 2 * TILE;
+  const int nblk = (HW + 15) / 16;
+
+  // ------------------------------------------------------------------ phase 1
+  auto stage_kv = [&](int blk, int b) {  // 16 px x (k 64 B | v 64 B): 128 16-byte chunks, 4 per lane
+    bf16* t = my + b * TILE;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ch = j * 32 + lane, px = ch >> 3, c16 = ch & 7;
+      const int p = blk * 16 + px;
+      const bool ok = p < HW;
+      cp16(t + px * ROW + c16 * 8, src + static_cast<long long>(ok ? p : 0) * C3 + 32 + c16 * 8, ok);
+    }
+    if (lane < 16) {  // the column of ones (zero for pixels past the end) + zero pad
+      const bool ok = blk * 16 + lane < HW;
+      *reinterpret_cast<uint4*>(t + lane * ROW + 64) = make_uint4(ok ? 0x00003f80u : 0u, 0u, 0u, 0u);  // bf16 1.0 = 0x3f80
+    }
+    cp_commit();
+  };
+  float acc[2][5][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 5; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+  int buf = 0;
+  if (warp < nblk) stage_kv(warp, 0);
+  for (int blk = warp; blk < nblk; blk += 8) {
+    const bool more = blk + 8 < nblk;
+    if (more) stage_kv(blk + 8, buf ^ 1);
+    if (more) cp_wait<1>(); else cp_wait<0>();
+    __syncwarp();
+    const bf16* t = my + buf * TILE;
+    uint32_t a[2][4], b[6][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {  // A = relu(k)^T: matrices (px 0-7 | 8-15) x (c' 0-7 | 8-15) of this 16-channel slab
+      ldsm4t(a[mt], t + ((mi >> 1) * 8 + mr) * ROW + mt * 16 + (mi & 1) * 8);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[mt][r] = relu_bf16x2(a[mt][r]);
+    }
+#pragma unroll
+    for (int np = 0; np < 3; ++np) {  // B = [v | 1]: two 8-column tiles per ldmatrix (the 6th tile is pad, never used)
+      uint32_t r4[4];
+      const int col = 32 + (np * 2 + (mi >> 1)) * 8;
+      ldsm4t(r4, t + ((mi & 1) * 8 + mr) * ROW + (col < ROW ? col : 64));
+      b[np * 2][0] = r4[0]; b[np * 2][1] = r4[1]; b[np * 2 + 1][0] = r4[2]; b[np * 2 + 1][1] = r4[3];
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 5; ++nt) mma16816(acc[mt][nt], a[mt], b[nt][0], b[nt][1]);
+    __syncwarp();
+    buf ^= 1;
+  }
+  // per-warp partials -> shared memory (the staging tiles are dead now), summed in a fixed order: the result does not
+  // depend on the order in which warps finish (shared-memory atomics would make repeated calls differ in the last bit)
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(la_smem);  // [8 warps][32 c'][33 c]
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 5; ++nt) {
+      if (nt == 4 && ti != 0) continue;  // tile 4 carries only column 32 (the row sums of relu(k))
+      float* r0 = red + (warp * 32 + mt * 16 + gi) * 33 + nt * 8 + 2 * ti;
+      r0[0] = acc[mt][nt][0];
+      r0[8 * 33] = acc[mt][nt][2];
+      if (nt < 4) {
+        r0[1] = acc[mt][nt][1];
+        r0[8 * 33 + 1] = acc[mt][nt][3];
+      }
+    }
+  __syncthreads();
+  for (int i = tid; i < 40 * 32; i += 256) {  // operand tables of phase 2: [c][c'] so that the k index is contiguous
+    const int c = i >> 5, kc = i & 31;
+    float v = 0.f;
+    if (c < 33) {
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += red[(w * 32 + kc) * 33 + c];
+    }
+    const bf16 hi = __float2bfloat16_rn(v);
+    SBhi[c * SB_ROW + kc] = hi;
+    SBlo[c * SB_ROW + kc] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+  __syncthreads();  // tables complete; the partials' memory becomes the q staging tiles again
+  uint32_t bh[5][4], bl[5][4];  // per 8-column tile: {b0, b1} of k-step 0, {b0, b1} of k-step 1
+#pragma unroll
+  for (int nt = 0; nt < 5; ++nt) {
+    ldsm4(bh[nt], SBhi + (nt * 8 + mr) * SB_ROW + mi * 8);
+    ldsm4(bl[nt], SBlo + (nt * 8 + mr) * SB_ROW + mi * 8);
+  }
+
+  // ------------------------------------------------------------------ phase 2
+  auto stage_q = [&](int blk, int b) {  // 16 px x 64 B: 64 chunks, 2 per lane; rows reuse the 144-byte pitch
+    bf16* t = my + b * TILE;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int ch = j * 32 + lane, px = ch >> 2, c16 = ch & 3;
+      const int p = blk * 16 + px;
+      const bool ok = p < HW;
+      cp16(t + px * ROW + c16 * 8, src + static_cast<long long>(ok ? p : 0) * C3 + c16 * 8, ok);
+    }
+    cp_commit();
+  };
+  const int Co = 2 * heads * 32;
+  buf = 0;
+  if (warp < nblk) stage_q(warp, 0);
+  for (int blk = warp; blk < nblk; blk += 8) {
+    const bool more = blk + 8 < nblk;
+    if (more) stage_q(blk + 8, buf ^ 1);
+    if (more) cp_wait<1>(); else cp_wait<0>();
+    __syncwarp();
+    const bf16* t = my + buf * TILE;
+    float o[5][4];
+#pragma unroll
+    for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[nt][c] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {  // A = relu(q): matrices (px 0-7 | 8-15) x (c' 0-7 | 8-15) of this 16-channel k-step
+      uint32_t a[4];
+      ldsm4(a, t + ((mi & 1) * 8 + mr) * ROW + ks * 16 + (mi >> 1) * 8);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = relu_bf16x2(a[r]);
+#pragma unroll
+      for (int nt = 0; nt < 5; ++nt) {
+        mma16816(o[nt], a, bh[nt][ks * 2], bh[nt][ks * 2 + 1]);
+        mma16816(o[nt], a, bl[nt][ks * 2], bl[nt][ks * 2 + 1]);
+      }
+    }
+    // denominator = column 32 = tile 4, column 0: held by the ti == 0 lane of each row quad
+    const float d0 = __shfl_sync(0xffffffffu, o[4][0], lane & ~3), d8 = __shfl_sync(0xffffffffu, o[4][2], lane & ~3);
+    const float i0 = 1.0f / (d0 + eps), i8 = 1.0f / (d8 + eps);
+    const int p0 = blk * 16 + gi, p8 = p0 + 8;
+    bf16* op = out + static_cast<long long>(f) * HW * Co + g * 32 + 2 * ti;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      if (p0 < HW)
+        *reinterpret_cast<__nv_bfloat162*>(op + static_cast<long long>(p0) * Co + nt * 8) = __floats2bfloat162_rn(o[nt][0] * i0, o[nt][1] * i0);
+      if (p8 < HW)
+        *reinterpret_cast<__nv_bfloat162*>(op + static_cast<long long>(p8) * Co + nt * 8) = __floats2bfloat162_rn(o[nt][2] * i8, o[nt][3] * i8);
+    }
+    __syncwarp();
+    buf ^= 1;
+  }
+}
+
+// ---------------------------------------------------------------- fused multiscale projection, grouped 1x1 on mma.sync
+// Phase A (5x5 depthwise sphere conv, sliding window) as in multiscale_fused_kernel; its fp32 results are split into
+// bf16 hi + lo halves and stored pixel-major ([64 px][128 channels], 272-byte rows: conflict-free for the 8-byte stores
+// of phase A and for ldmatrix).  Phase B (grouped 32 -> 32 1x1: 55 % of the kernel's FMAs) runs as m16n8k16 MMAs per
+// (group, 32-pixel half): x_hi w_hi + x_lo w_hi + x_hi w_lo, i.e. fp32-class products (relative error 2^-16) for a
+// sixth of the SIMT form's instructions.
+namespace msmma {
+constexpr int XROW = 136;  // bf16 per pixel row: 128 channels + 8 pad
+constexpr int WROW = 40;   // bf16 per weight row: 32 inputs + 8 pad
+constexpr int SMEM_BYTES = 2 * 64 * XROW * 2 + 2 * 4 * 32 * WROW * 2;
+}  // namespace msmma
+
+__global__ void __launch_bounds__(256, 3) multiscale_fused_mma_kernel(const bf16* __restrict__ in, const float* __restrict__ w5,
+                                                                      const float* __restrict__ wg, bf16* __restrict__ out,
+                                                                      int n, int H, int W, int C) {
+  using namespace lamma;
+  using namespace msmma;
+  pdl_grid_sync();
+  extern __shared__ __align__(16) uint8_t ms_smem[];
+  bf16* xh = reinterpret_cast<bf16*>(ms_smem);  // [64 px][XROW]
+  bf16* xl = xh + 64 * XROW;
+  bf16* wh = xl + 64 * XROW;                    // [4 groups][32 outputs][WROW]: input index contiguous
+  bf16* wl = wh + 4 * 32 * WROW;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ncb = (C + 127) / 128;
+  const int cb = (blockIdx.x % ncb) * 128;
+  const int fy = blockIdx.x / ncb;
+  const int y = fy % H, f = fy / H;
+  for (int i = tid; i < 4096; i += 256) {  // grouped weights [o][k] -> bf16 hi / lo
+    const int g = i >> 10, o = (i >> 5) & 31, k = i & 31;
+    float v = 0.f;
+    if (cb + g * 32 < C) v = wg[(static_cast<long long>(cb) + g * 32 + o) * 32 + k];
+    const bf16 hi = __float2bfloat16_rn(v);
+    wh[(g * 32 + o) * WROW + k] = hi;
+    wl[(g * 32 + o) * WROW + k] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+  const int c = cb + lane * 4;
+  const bool c_ok = c < C;
+  const bf16* base = in + static_cast<long long>(f) * H * W * C + c;
+  const int g = warp & 3, half = warp >> 2;
+  const bool g_ok = cb + g * 32 < C;
+  const int gi = lane >> 2, ti = lane & 3, mi = lane >> 3, mr = lane & 7;
+  for (int seg = 0; seg < W; seg += 64) {
+    __syncthreads();  // weights staged / previous segment's phase B done with xh / xl
+    // ---- phase A
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {
+      const int xloc = (it * 8 + warp) * 4;
+      const int x0 = seg + xloc;
+      float4 acc[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c_ok && x0 < W) {
+        int con[8];
+        col_offsets<8>(con, x0, 2, W, C, false);
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky) {
+          int sy;
+          bool rolled;
+          sphere_row(y + ky, 2, H, sy, rolled);
+          const bool flip = (y == 0 && ky < 2) || (y == H - 1 && ky >= 3);
+          float4 wr[5];
+#pragma unroll
+          for (int kx = 0; kx < 5; ++kx)
+            wr[kx] = __ldg(reinterpret_cast<const float4*>(w5 + (ky * 5 + (flip ? 4 - kx : kx)) * C + c));
+          const bf16* rowp = base + static_cast<long long>(sy) * W * C;
+          int co[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) co[j] = con[j];
+          if (rolled) col_offsets<8>(co, x0, 2, W, C, true);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 v = ld4<bf16>(rowp + co[j]);
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) {
+              const int o = j - kx;
+              if (o >= 0 && o < 4) fma4(acc[o], wr[kx], v);
+            }
+          }
+        }
+      }
+      // (pixels past the row end / channels past C: zeros, so that no stale bits ever reach the tensor pipe)
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[o].x, acc[o].y), h1 = __floats2bfloat162_rn(acc[o].z, acc[o].w);
+        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+        const __nv_bfloat162 l0 = __floats2bfloat162_rn(acc[o].x - f0.x, acc[o].y - f0.y);
+        const __nv_bfloat162 l1 = __floats2bfloat162_rn(acc[o].z - f1.x, acc[o].w - f1.y);
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+        lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
+        *reinterpret_cast<uint2*>(xh + (xloc + o) * XROW + lane * 4) = hv;
+        *reinterpret_cast<uint2*>(xl + (xloc + o) * XROW + lane * 4) = lv;
+      }
+    }
+    __syncthreads();
+    // ---- phase B: this warp = (group g, 32-pixel half): two 16-pixel M tiles x four 8-output N tiles x two k-steps
+    if (!g_ok || seg + half * 32 >= W) continue;
+    uint32_t bh[4][4], bl[4][4];  // per 8-output tile: {b0, b1} of k-step 0, {b0, b1} of k-step 1 (reloaded per segment:
+                                  // keeping them across phase A spills)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      ldsm4(bh[nt], wh + (g * 32 + nt * 8 + mr) * WROW + mi * 8);
+      ldsm4(bl[nt], wl + (g * 32 + nt * 8 + mr) * WROW + mi * 8);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int prow = half * 32 + mt * 16;
+      float d[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d[nt][q] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t ah[4], al[4];
+        const int off = (prow + (mi & 1) * 8 + mr) * XROW + g * 32 + ks * 16 + (mi >> 1) * 8;
+        ldsm4(ah, xh + off);
+        ldsm4(al, xl + off);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          mma16816(d[nt], ah, bh[nt][ks * 2], bh[nt][ks * 2 + 1]);
+          mma16816(d[nt], al, bh[nt][ks * 2], bh[nt][ks * 2 + 1]);
+          mma16816(d[nt], ah, bl[nt][ks * 2], bl[nt][ks * 2 + 1]);
+        }
+      }
+      const int p0 = seg + prow + gi, p8 = p0 + 8;
+      bf16* op = out + (static_cast<long long>(f) * H + y) * W * C + cb + g * 32 + 2 * ti;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        if (p0 < W) *reinterpret_cast<__nv_bfloat162*>(op + static_cast<long long>(p0) * C + nt * 8) = __floats2bfloat162_rn(d[nt][0], d[nt][1]);
+        if (p8 < W) *reinterpret_cast<__nv_bfloat162*>(op + static_cast<long long>(p8) * C + nt * 8) = __floats2bfloat162_rn(d[nt][2], d[nt][3]);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- channel RMSNorm (+residual) on [P, C] rows
 // y = x_in * rsqrt(mean(x_in^2) + eps) * w + b ; if resid: resid += y (in place) and the result is also written as T.
 template <typename TY, typename T>
@@ -691,21 +1036,65 @@ int dwconv3_glu(const T* in, const float* w, const float* bias, T* out, int n, i
   return 0;
 }
 template <typename T>
+int multiscale_launch(const T* in, const float* w5, const float* wg, T* out, int n, int H, int W, int C, unsigned nblk,
+                      cudaStream_t s) {
+  LC_CHECK_CUDA(launch_kernel(multiscale_fused_kernel<T>, nblk, 256, 0, s, in, w5, wg, out, n, H, W, C));
+  return 0;
+}
+template <>
+int multiscale_launch<bf16>(const bf16* in, const float* w5, const float* wg, bf16* out, int n, int H, int W, int C,
+                            unsigned nblk, cudaStream_t s) {
+  // LADCAST_B200_MULTISCALE=mma: grouped 1x1 on warp-level MMAs (off until measured); default: the SIMT kernel
+  static const bool mma = [] { const char* e = getenv("LADCAST_B200_MULTISCALE"); return e != nullptr && e[0] == 'm'; }();
+  if (!mma || C % 32 != 0) {
+    LC_CHECK_CUDA(launch_kernel(multiscale_fused_kernel<bf16>, nblk, 256, 0, s, in, w5, wg, out, n, H, W, C));
+    return 0;
+  }
+  static PerDevice<bool> attr_set;
+  if (!attr_set.here()) {
+    LC_CHECK_CUDA(cudaFuncSetAttribute(multiscale_fused_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, msmma::SMEM_BYTES));
+    attr_set.here() = true;
+  }
+  LC_CHECK_CUDA(launch_kernel(multiscale_fused_mma_kernel, nblk, 256, msmma::SMEM_BYTES, s, in, w5, wg, out, n, H, W, C));
+  return 0;
+}
+template <typename T>
 int multiscale_fused(const T* in, const float* w5, const float* wg, T* out, int n, int H, int W, int C, cudaStream_t s) {
   LC_REQUIRE(C % 32 == 0, "multiscale projection: channels must be a multiple of 32");
   const long long nblk = static_cast<long long>(n) * H * ((C + 127) / 128);
   LC_REQUIRE(nblk < (1ll << 31), "multiscale projection: too many image rows per call");
   // algorithmic: read qkv [P, C] once, write the multiscale branch [P, C]
   ProfScope ps(PROF_DEC_MS, 2.0 * n * H * W * C * (25.0 + 32.0), static_cast<double>(n) * H * W * C * 2.0 * sizeof(T), s);
-  LC_CHECK_CUDA(launch_kernel(multiscale_fused_kernel<T>, static_cast<unsigned>(nblk), 256, 0, s, in, w5, wg, out, n, H, W, C));
+  LC_TRY(multiscale_launch<T>(in, w5, wg, out, n, H, W, C, static_cast<unsigned>(nblk), s));
   LC_LAUNCH_CHECK();
+  return 0;
+}
+template <typename T>
+int linear_attn_launch(const T* qkv, const T* ms, T* out, int n, int HW, int heads, float eps, cudaStream_t s) {
+  LC_CHECK_CUDA(launch_kernel(linear_attn_kernel<T, T>, n * 2 * heads, 256, 0, s, qkv, ms, out, HW, heads, eps));
+  return 0;
+}
+template <>
+int linear_attn_launch<bf16>(const bf16* qkv, const bf16* ms, bf16* out, int n, int HW, int heads, float eps, cudaStream_t s) {
+  // LADCAST_B200_LINATTN=simt: the register-tiled SIMT kernel (also what the FP32 validation mode runs)
+  static const bool simt = [] { const char* e = getenv("LADCAST_B200_LINATTN"); return e != nullptr && e[0] == 's'; }();
+  if (simt) {
+    LC_CHECK_CUDA(launch_kernel(linear_attn_kernel<bf16, bf16>, n * 2 * heads, 256, 0, s, qkv, ms, out, HW, heads, eps));
+    return 0;
+  }
+  static PerDevice<bool> attr_set;
+  if (!attr_set.here()) {
+    LC_CHECK_CUDA(cudaFuncSetAttribute(linear_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lamma::SMEM_BYTES));
+    attr_set.here() = true;
+  }
+  LC_CHECK_CUDA(launch_kernel(linear_attn_mma_kernel, n * 2 * heads, 256, lamma::SMEM_BYTES, s, qkv, ms, out, HW, heads, eps));
   return 0;
 }
 template <typename T>
 int linear_attention(const T* qkv, const T* ms, T* out, int n, int HW, int heads, float eps, cudaStream_t s) {
   // algorithmic: k, v read once (phase 1), q read once (phase 2) of both scales, output [P, 2*heads*32] written
   ProfScope ps(PROF_DEC_LINATTN, 0.0, static_cast<double>(n) * HW * heads * (2 * 96 + 2 * 32) * sizeof(T), s);
-  LC_CHECK_CUDA(launch_kernel(linear_attn_kernel<T, T>, n * 2 * heads, 256, 0, s, qkv, ms, out, HW, heads, eps));
+  LC_TRY(linear_attn_launch<T>(qkv, ms, out, n, HW, heads, eps, s));
   LC_LAUNCH_CHECK();
   return 0;
 }
