@@ -47,14 +47,14 @@ MODEL_CFG = {
 TENSOR_CLASSES = ("gemm_tc", "attention_tc", "sphere_conv_tc")
 CLASS_KERNELS = {
     "gemm_tc": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05 bf16 GEMM, CTA-pair; denoiser linears + decoder 1x1)",
-    "attention_tc": "attention_tc_kernel (tcgen05 flash attention, D=128)",
+    "attention_tc": "attention_tc_persistent_kernel (tcgen05 flash attention, D=128, persistent, split P hand-over)",
     "sphere_conv_tc": "gemm_tc2_kernel in implicit-GEMM 3x3 sphere-conv mode (DC-AE)",
     "layernorm": "layernorm_kernel (LayerNorm + AdaLN modulation, fp32 in / bf16 out)",
     "qk_norm_rope": "qk_norm_rope_bf16_kernel (per-head RMSNorm(q,k) + RoPE, in place)",
     "scheduler": "dpmpp2m_kernel / scale_kernel / latent_feedback_kernel (fused scheduler step, AR feedback)",
     "dec_rmsnorm": "rmsnorm_rows_kernel (DC-AE channel RMSNorm + residual)",
-    "dec_multiscale": "multiscale_fused_kernel (DC-AE 5x5 depthwise + grouped 1x1)",
-    "dec_linear_attn": "linear_attn_kernel (DC-AE ReLU linear attention)",
+    "dec_multiscale": "multiscale_fused_mma_kernel (DC-AE 5x5 depthwise on the FMA pipe + grouped 1x1 on mma.sync)",
+    "dec_linear_attn": "linear_attn_mma_kernel (DC-AE ReLU linear attention on mma.sync)",
     "dec_dwconv_glu": "dwconv3_glu_kernel (DC-AE depthwise 3x3 + GLU)",
     "dec_pixel_shuffle": "pixel_shuffle_kernel (+ shortcut)",
     "dec_pad": "pad_from_* / halo_fill / in_shortcut kernels (sphere padding)",
